@@ -1,0 +1,89 @@
+// Implicit-GEMM convolution on sm_100a: plan structures shared by the tcgen05 kernel (conv_gemm.cu), the
+// SIMT cross-check kernel (conv_simt.cu) and the network executor (model.cu).
+//
+// One plan covers every conv-like layer of the reference's two backbones and deconv head
+// (reference: lib/models/backbones/HRnet.py:22-98,197-242,341-429; lib/models/backbones/Resnet.py:21-29,96-135;
+//  lib/models/full_net.py:194-216,78):
+//   GEMM rows   = a grid (B, Hm, Wm) of "row pixels", tiled in boxes of bw x bh x bn = 128 pixels
+//   GEMM K      = taps x Cin; tap t reads the source grid at (h + dh[t], w + dw[t]) through tensor map
+//                 map[t] (maps differ only for stride-2 convs: one per input parity)
+//   GEMM cols   = Cout (per phase; deconvs run 4 sub-pixel phases as gridDim.z)
+//   epilogue    = v = acc*scale[c] + bias[c] + sum(pre[i]) + sum(upsampled up[i]);  relu;  v += post
+//   output px   = (n, h*os + oh0 + ph, w*os + ow0 + pw) in a (B, Hout, Wout, Cout) bf16 NHWC tensor
+#pragma once
+#include "hrp_common.cuh"
+
+namespace hrp {
+
+constexpr int kMaxTaps = 16;
+constexpr int kTileM = 128;
+
+struct ConvParams {
+  int B, Hm, Wm;          // row-pixel grid
+  int bw, bh, bn;         // tile box (bw*bh*bn == 128)
+  int tiles_w, tiles_h, tiles_n;
+  int Hs, Ws, Cin;        // source grid seen by the taps (per parity map for stride 2) + stored channels
+  int Hout, Wout, Cout;   // output tensor
+  int os, oh0, ow0;       // output pixel stride / offset
+  int nphase;             // 1, or 4 for ConvTranspose2d(k4,s2,p1): phase z = (ph,pw) shifts taps and output
+  int ntaps, ck, cpt;     // taps, channels per k-block (16/32/64), k-blocks per tap (Cin/ck)
+  int n_tile, cout_pad;   // N tile (multiple of 16, <= 256); weight rows per phase (multiple of n_tile)
+  int ktot;               // ntaps*Cin
+  int8_t tap_dh[kMaxTaps], tap_dw[kMaxTaps], tap_map[kMaxTaps];
+  // epilogue
+  const float* scale;     // [Cout] folded BN scale (1 if none)
+  const float* bias;      // [Cout] folded BN shift (+ conv bias)
+  const bf16* pre[3];     // same-resolution addends, (B,Hout,Wout,Cout)
+  const bf16* up[3];      // low-resolution addends, (B,Hout>>s,Wout>>s,Cout), nearest upsample by 2^s
+  int up_shift[3];
+  const bf16* post;       // added after the ReLU (HRNet cls head, HRnet.py:558-560)
+  int relu;
+  bf16* out;              // (B,Hout,Wout,Cout) bf16, may be null when only pooled output is wanted
+  float* pool_out;        // optional (B,Cout) fp32: mean over the Hout*Wout pixels of post-activation values
+  float pool_scale;       // 1/(Hout*Wout)
+  // raw pointers for the SIMT cross-check path
+  const bf16* in;         // (B,Hin,Win,Cin) source tensor base
+  const bf16* w;          // (nphase*cout_pad, ktot) packed weights
+  int Hin, Win, src_sh, src_sw;  // full input dims and source-grid stride (2 for parity maps)
+};
+
+struct ConvMaps {
+  CUtensorMap a[4];
+  CUtensorMap b;
+};
+
+struct ConvPlan {
+  ConvParams p;
+  ConvMaps maps;
+  dim3 grid;
+  int smem_bytes;
+  int stages;
+  double flops;  // 2*MACs of the reference layer (algorithmic, not padded)
+};
+
+// Layer description used to build a plan.
+enum ConvKind { kConv = 0, kDeconvK4S2P1 = 1, kStemS2D = 2 };
+
+struct ConvLayerDesc {
+  int kind;              // ConvKind
+  int B, Hin, Win, Cin;  // input NHWC (Cin = stored channels, multiple of 16). For kStemS2D the input is the
+                         // space-to-depth tensor (B, H/2, W/2, 16) and kh/kw/pad describe the ORIGINAL conv.
+  int Cout;
+  int kh, kw, stride, pad;
+  int relu;
+};
+
+// Host-side weight packing: reference layouts -> (nphase*cout_pad, ktot) bf16 K-major.
+//   kConv:          w is (Cout, Cin_ref, kh, kw) fp32 (torch Conv2d)
+//   kDeconvK4S2P1:  w is (Cin_ref, Cout, 4, 4) fp32 (torch ConvTranspose2d)
+//   kStemS2D:       w is (Cout, 3, kh, kw) fp32, conv stride 2; packed for the 2x2 space-to-depth input
+int conv_geometry(const ConvLayerDesc& d, ConvParams* p);  // fills geometry fields (no pointers)
+size_t conv_packed_weight_elems(const ConvParams& p);
+int conv_pack_weights(const ConvLayerDesc& d, const ConvParams& p, int cin_ref, const float* w, uint16_t* out);
+
+// Build tensor maps + launch config.  `in`/`w_packed` are device pointers; epilogue pointers are taken from p.
+int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed);
+int conv_plan_launch(const ConvPlan& plan, cudaStream_t stream);       // tcgen05 path
+int conv_plan_launch_simt(const ConvPlan& plan, cudaStream_t stream);  // cross-check path (tests only)
+
+}  // namespace hrp

@@ -1,0 +1,522 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (see conv.h for the plan model).
+//
+// CTA = 192 threads: warp 0 = TMA producer (one elected lane), warp 1 = TMEM owner + MMA issuer (one elected
+// lane issues tcgen05.mma, M=128, N=n_tile, K=16, bf16 x bf16 -> fp32 in TMEM), warps 2..5 = epilogue
+// (tcgen05.ld 32 lanes x 16 columns, folded-BN scale/shift, residual / upsample-add / post-add, ReLU, bf16
+// NHWC store, optional fp32 global-average-pool accumulation).
+//
+// Shared-memory stage = K extent 64: 64/ck sub-tiles, each a K-major [128 rows x ck] A tile (row = row pixel,
+// written by ONE 4-D tiled TMA box whose out-of-bounds elements are zero-filled: that is the conv padding)
+// and a [n_tile x ck] B tile (2-D TMA over the packed weight matrix).  The TMA swizzle (32/64/128 B = ck*2)
+// matches the UMMA descriptor layout type, so a k-step inside a sub-tile is start address + 32 B.
+#include "conv.h"
+#include "launch_count.h"
+
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+namespace hrp {
+
+// ------------------------------------------------------------------------------------------------------
+// device
+// ------------------------------------------------------------------------------------------------------
+constexpr int kNumThreads = 192;
+constexpr int kStageABytes = kTileM * 64 * 2;  // 16 KiB of A per stage regardless of ck
+
+struct __align__(8) PipeBarriers {
+  uint64_t full[8];
+  uint64_t empty[8];
+  uint64_t tmem_full;
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+template <int CK>
+__global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_constant__ ConvMaps maps,
+                                                                const __grid_constant__ ConvParams p,
+                                                                int stages) {
+  constexpr int SUB = 64 / CK;                 // sub-tiles (k-blocks) per stage
+  constexpr int A_SUB_BYTES = kTileM * CK * 2;
+  constexpr int KSTEPS = CK / 16;              // tcgen05.mma K=16 steps per sub-tile
+  constexpr uint32_t LAYOUT = (CK == 64) ? 2u : (CK == 32) ? 4u : 6u;  // SW128 / SW64 / SW32
+  constexpr uint32_t SBO = 8 * CK * 2;         // 8 rows of CK bf16
+
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  const int n_tile = p.n_tile;
+  const int b_sub_bytes = n_tile * CK * 2;
+  const int stage_bytes = kStageABytes + n_tile * 128;
+  PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(smem + (size_t)stages * stage_bytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile coordinates
+  int t = blockIdx.x;
+  const int tw = t % p.tiles_w;
+  t /= p.tiles_w;
+  const int th = t % p.tiles_h;
+  const int tn = t / p.tiles_h;
+  const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
+  const int n_blk = blockIdx.y;
+  const int phase = blockIdx.z;
+  const int ph = phase >> 1, pw = phase & 1;  // deconv sub-pixel phase (0,0) when nphase == 1
+
+  const int nkb = p.ntaps * p.cpt;
+  const int n_iters = (nkb + SUB - 1) / SUB;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.a[0]);
+    tma_prefetch_desc(&maps.b);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], 1);
+    }
+    mbar_init(&bars->tmem_full, 1);
+    fence_mbar_init();
+  }
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < n_tile) tmem_cols <<= 1;
+  if (warp == 1) {
+    tmem_alloc(&bars->tmem_base, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      for (int it = 0; it < n_iters; ++it) {
+        const int s = it % stages;
+        const uint32_t par = (it / stages) & 1;
+        mbar_wait(&bars->empty[s], par ^ 1);
+        const int nsub = min(SUB, nkb - it * SUB);
+        mbar_expect_tx(&bars->full[s], (uint32_t)(nsub * (A_SUB_BYTES + b_sub_bytes)));
+        uint8_t* sa = smem + (size_t)s * stage_bytes;
+        uint8_t* sb = sa + kStageABytes;
+        for (int j = 0; j < nsub; ++j) {
+          const int kb = it * SUB + j;
+          const int tap = kb / p.cpt;
+          const int cc = kb - tap * p.cpt;
+          tma_load_4d(sa + j * A_SUB_BYTES, &maps.a[p.tap_map[tap]], &bars->full[s], cc * CK,
+                      w0 + p.tap_dw[tap] + pw, h0 + p.tap_dh[tap] + ph, n0);
+          tma_load_2d(sb + j * b_sub_bytes, &maps.b, &bars->full[s], kb * CK,
+                      phase * p.cout_pad + n_blk * n_tile);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc_bf16(kTileM, (uint32_t)n_tile);
+    for (int it = 0; it < n_iters; ++it) {
+      const int s = it % stages;
+      const uint32_t par = (it / stages) & 1;
+      mbar_wait(&bars->full[s], par);
+      tc_fence_after();
+      if (elect_one()) {
+        const int nsub = min(SUB, nkb - it * SUB);
+        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t sb = sa + kStageABytes;
+        for (int j = 0; j < nsub; ++j) {
+#pragma unroll
+          for (int k = 0; k < KSTEPS; ++k) {
+            const uint64_t adesc = make_kmajor_desc(sa + j * A_SUB_BYTES + k * 32, SBO, LAYOUT);
+            const uint64_t bdesc = make_kmajor_desc(sb + j * b_sub_bytes + k * 32, SBO, LAYOUT);
+            umma_bf16_ss(tmem_base, adesc, bdesc, idesc, (it | j | k) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&bars->empty[s]);                       // frees the smem stage when the MMAs retire
+        if (it == n_iters - 1) umma_commit(&bars->tmem_full);  // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 <-> TMEM lane quarters warp%4) =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int wi = row % p.bw;
+    const int hi = (row / p.bw) % p.bh;
+    const int ni = row / (p.bw * p.bh);
+    const int n = n0 + ni, h = h0 + hi, w = w0 + wi;
+    const bool valid = (n < p.B) && (h < p.Hm) && (w < p.Wm);
+    const int oh = h * p.os + p.oh0 + ph, ow = w * p.os + p.ow0 + pw;
+    const size_t opix = ((size_t)n * p.Hout + oh) * p.Wout + ow;
+    const int c_base = n_blk * n_tile;
+
+    mbar_wait(&bars->tmem_full, 0);
+    tc_fence_after();
+
+    for (int c0 = 0; c0 < n_tile; c0 += 16) {
+      uint32_t acc[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
+      tmem_ld_wait();
+      const int c = c_base + c0;
+      if (c >= p.Cout) continue;  // warp-uniform (padded weight rows)
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + c + i));
+        const float4 bi = __ldg(reinterpret_cast<const float4*>(p.bias + c + i));
+        v[i + 0] = fmaf(__uint_as_float(acc[i + 0]), sc.x, bi.x);
+        v[i + 1] = fmaf(__uint_as_float(acc[i + 1]), sc.y, bi.y);
+        v[i + 2] = fmaf(__uint_as_float(acc[i + 2]), sc.z, bi.z);
+        v[i + 3] = fmaf(__uint_as_float(acc[i + 3]), sc.w, bi.w);
+      }
+      if (valid) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          if (p.pre[a] != nullptr) {
+            const uint4* src = reinterpret_cast<const uint4*>(p.pre[a] + opix * p.Cout + c);
+            const uint4 x0 = __ldg(src), x1 = __ldg(src + 1);
+            const uint32_t xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              v[2 * i] += bf16lo_to_f32(xs[i]);
+              v[2 * i + 1] += bf16hi_to_f32(xs[i]);
+            }
+          }
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          if (p.up[a] != nullptr) {
+            const int sh = p.up_shift[a];
+            const size_t upix = ((size_t)n * (p.Hout >> sh) + (oh >> sh)) * (p.Wout >> sh) + (ow >> sh);
+            const uint4* src = reinterpret_cast<const uint4*>(p.up[a] + upix * p.Cout + c);
+            const uint4 x0 = __ldg(src), x1 = __ldg(src + 1);
+            const uint32_t xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              v[2 * i] += bf16lo_to_f32(xs[i]);
+              v[2 * i + 1] += bf16hi_to_f32(xs[i]);
+            }
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (p.post != nullptr) {
+          const uint4* src = reinterpret_cast<const uint4*>(p.post + opix * p.Cout + c);
+          const uint4 x0 = __ldg(src), x1 = __ldg(src + 1);
+          const uint32_t xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            v[2 * i] += bf16lo_to_f32(xs[i]);
+            v[2 * i + 1] += bf16hi_to_f32(xs[i]);
+          }
+        }
+        if (p.out != nullptr) {
+          uint4 o0, o1;
+          o0.x = pack_bf16x2(v[0], v[1]);
+          o0.y = pack_bf16x2(v[2], v[3]);
+          o0.z = pack_bf16x2(v[4], v[5]);
+          o0.w = pack_bf16x2(v[6], v[7]);
+          o1.x = pack_bf16x2(v[8], v[9]);
+          o1.y = pack_bf16x2(v[10], v[11]);
+          o1.z = pack_bf16x2(v[12], v[13]);
+          o1.w = pack_bf16x2(v[14], v[15]);
+          uint4* dst = reinterpret_cast<uint4*>(p.out + opix * p.Cout + c);
+          dst[0] = o0;
+          dst[1] = o1;
+        }
+      }
+      if (p.pool_out != nullptr) {
+        // global average pool: rows of one image inside this warp are contiguous runs of lanes; reduce the
+        // whole warp when it maps to one image (host guarantees bw*bh >= 32 or bw*bh*bn rows per image >= 32)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float x = valid ? v[i] : 0.f;
+          x += __shfl_xor_sync(0xffffffffu, x, 16);
+          x += __shfl_xor_sync(0xffffffffu, x, 8);
+          x += __shfl_xor_sync(0xffffffffu, x, 4);
+          x += __shfl_xor_sync(0xffffffffu, x, 2);
+          x += __shfl_xor_sync(0xffffffffu, x, 1);
+          v[i] = x;
+        }
+        const int n_warp = n0 + (q * 32) / (p.bw * p.bh);
+        float mine = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) mine = (lane == i) ? v[i] : mine;
+        if (lane < 16 && n_warp < p.B) atomicAdd(p.pool_out + (size_t)n_warp * p.Cout + c + lane, mine * p.pool_scale);
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host: geometry, weight packing, tensor maps, launch
+// ------------------------------------------------------------------------------------------------------
+static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+static int posmod(int a, int b) { return ((a % b) + b) % b; }
+
+int conv_geometry(const ConvLayerDesc& d, ConvParams* pp) {
+  ConvParams& p = *pp;
+  memset(&p, 0, sizeof(p));
+  HRP_REQUIRE(d.B > 0 && d.Hin > 0 && d.Win > 0 && d.Cout > 0, "conv dims must be positive");
+  HRP_REQUIRE(d.Cin == 16 || d.Cin == 32 || d.Cin % 64 == 0, "stored Cin must be 16, 32 or a multiple of 64");
+  HRP_REQUIRE(d.Cout % 16 == 0, "Cout must be a multiple of 16");
+  p.B = d.B;
+  p.Cin = d.Cin;
+  p.Cout = d.Cout;
+  p.Hin = d.Hin;
+  p.Win = d.Win;
+  p.src_sh = p.src_sw = 1;
+  p.nphase = 1;
+  p.os = 1;
+  p.relu = d.relu;
+  p.ck = std::min(d.Cin, 64);
+  p.cpt = d.Cin / p.ck;
+  if (d.kind == kConv) {
+    HRP_REQUIRE(d.stride == 1 || d.stride == 2, "conv stride must be 1 or 2");
+    HRP_REQUIRE(d.kh * d.kw <= kMaxTaps, "too many taps");
+    p.Hout = (d.Hin + 2 * d.pad - d.kh) / d.stride + 1;
+    p.Wout = (d.Win + 2 * d.pad - d.kw) / d.stride + 1;
+    p.Hm = p.Hout;
+    p.Wm = p.Wout;
+    p.ntaps = d.kh * d.kw;
+    if (d.stride == 1) {
+      p.Hs = d.Hin;
+      p.Ws = d.Win;
+      for (int i = 0; i < d.kh; ++i)
+        for (int j = 0; j < d.kw; ++j) {
+          p.tap_dh[i * d.kw + j] = (int8_t)(i - d.pad);
+          p.tap_dw[i * d.kw + j] = (int8_t)(j - d.pad);
+          p.tap_map[i * d.kw + j] = 0;
+        }
+    } else {
+      HRP_REQUIRE(d.Hin % 2 == 0 && d.Win % 2 == 0, "stride-2 conv needs even input size");
+      p.Hs = d.Hin / 2;
+      p.Ws = d.Win / 2;
+      p.src_sh = p.src_sw = 2;
+      HRP_REQUIRE(p.Hout == p.Hs && p.Wout == p.Ws, "unsupported stride-2 geometry");
+      for (int i = 0; i < d.kh; ++i)
+        for (int j = 0; j < d.kw; ++j) {
+          const int rh = i - d.pad, rw = j - d.pad;
+          const int hp = posmod(rh, 2), wp = posmod(rw, 2);
+          p.tap_dh[i * d.kw + j] = (int8_t)floordiv(rh, 2);
+          p.tap_dw[i * d.kw + j] = (int8_t)floordiv(rw, 2);
+          p.tap_map[i * d.kw + j] = (int8_t)(hp * 2 + wp);
+        }
+    }
+  } else if (d.kind == kDeconvK4S2P1) {
+    p.Hout = d.Hin * 2;
+    p.Wout = d.Win * 2;
+    p.Hm = d.Hin;
+    p.Wm = d.Win;
+    p.Hs = d.Hin;
+    p.Ws = d.Win;
+    p.os = 2;
+    p.nphase = 4;
+    p.ntaps = 4;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        p.tap_dh[a * 2 + b] = (int8_t)(-a);  // + ph in the kernel
+        p.tap_dw[a * 2 + b] = (int8_t)(-b);  // + pw in the kernel
+        p.tap_map[a * 2 + b] = 0;
+      }
+  } else if (d.kind == kStemS2D) {
+    HRP_REQUIRE(d.Cin == 16 && d.stride == 2, "s2d stem expects the 16-channel space-to-depth input");
+    // d.Hin/d.Win are the s2d dims (H/2, W/2); output of the original stride-2 conv has the same size
+    const int Horig = d.Hin * 2, Worig = d.Win * 2;
+    p.Hout = (Horig + 2 * d.pad - d.kh) / 2 + 1;
+    p.Wout = (Worig + 2 * d.pad - d.kw) / 2 + 1;
+    HRP_REQUIRE(p.Hout == d.Hin && p.Wout == d.Win, "unsupported stem geometry");
+    p.Hm = p.Hout;
+    p.Wm = p.Wout;
+    p.Hs = d.Hin;
+    p.Ws = d.Win;
+    const int dh_lo = floordiv(-d.pad, 2), dh_hi = floordiv(d.kh - 1 - d.pad, 2);
+    const int dw_lo = floordiv(-d.pad, 2), dw_hi = floordiv(d.kw - 1 - d.pad, 2);
+    const int nh = dh_hi - dh_lo + 1, nw = dw_hi - dw_lo + 1;
+    HRP_REQUIRE(nh * nw <= kMaxTaps, "too many s2d taps");
+    p.ntaps = nh * nw;
+    for (int a = 0; a < nh; ++a)
+      for (int b = 0; b < nw; ++b) {
+        p.tap_dh[a * nw + b] = (int8_t)(dh_lo + a);
+        p.tap_dw[a * nw + b] = (int8_t)(dw_lo + b);
+        p.tap_map[a * nw + b] = 0;
+      }
+  } else {
+    set_error("unknown conv kind");
+    return HRP_ERR_INVALID;
+  }
+  p.ktot = p.ntaps * p.Cin;
+  // M tile box
+  p.bw = std::min(p.Wm, kTileM);
+  // round bw down to a power of two so that bw*bh*bn == 128 exactly
+  int bw = 1;
+  while (bw * 2 <= p.bw) bw *= 2;
+  p.bw = bw;
+  int bh = 1;
+  while (bh * 2 <= std::min(p.Hm, kTileM / p.bw)) bh *= 2;
+  p.bh = bh;
+  p.bn = kTileM / (p.bw * p.bh);
+  p.tiles_w = (p.Wm + p.bw - 1) / p.bw;
+  p.tiles_h = (p.Hm + p.bh - 1) / p.bh;
+  p.tiles_n = (p.B + p.bn - 1) / p.bn;
+  // N tile
+  const int n_tiles = (p.Cout + 255) / 256;
+  p.n_tile = (((p.Cout + n_tiles - 1) / n_tiles) + 15) / 16 * 16;
+  p.cout_pad = n_tiles * p.n_tile;
+  p.pool_scale = 1.f / (float)(p.Hout * p.Wout);
+  return HRP_OK;
+}
+
+size_t conv_packed_weight_elems(const ConvParams& p) { return (size_t)p.nphase * p.cout_pad * p.ktot; }
+
+int conv_pack_weights(const ConvLayerDesc& d, const ConvParams& p, int cin_ref, const float* w, uint16_t* out) {
+  const size_t total = conv_packed_weight_elems(p);
+  memset(out, 0, total * sizeof(uint16_t));
+  if (d.kind == kConv) {
+    HRP_REQUIRE(cin_ref <= p.Cin, "reference Cin exceeds stored Cin");
+    for (int co = 0; co < p.Cout; ++co)
+      for (int ci = 0; ci < cin_ref; ++ci)
+        for (int i = 0; i < d.kh; ++i)
+          for (int j = 0; j < d.kw; ++j) {
+            const float v = w[(((size_t)co * cin_ref + ci) * d.kh + i) * d.kw + j];
+            out[(size_t)co * p.ktot + (size_t)(i * d.kw + j) * p.Cin + ci] = f32_to_bf16_bits(v);
+          }
+  } else if (d.kind == kDeconvK4S2P1) {
+    HRP_REQUIRE(cin_ref <= p.Cin, "reference Cin exceeds stored Cin");
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw)
+        for (int co = 0; co < p.Cout; ++co)
+          for (int a = 0; a < 2; ++a)
+            for (int b = 0; b < 2; ++b) {
+              const int kh = 1 - ph + 2 * a, kw = 1 - pw + 2 * b;
+              uint16_t* dst = out + ((size_t)(ph * 2 + pw) * p.cout_pad + co) * p.ktot + (size_t)(a * 2 + b) * p.Cin;
+              for (int ci = 0; ci < cin_ref; ++ci)
+                dst[ci] = f32_to_bf16_bits(w[(((size_t)ci * p.Cout + co) * 4 + kh) * 4 + kw]);
+            }
+  } else if (d.kind == kStemS2D) {
+    HRP_REQUIRE(cin_ref == 3, "stem conv expects 3 input channels");
+    for (int co = 0; co < p.Cout; ++co)
+      for (int t = 0; t < p.ntaps; ++t)
+        for (int hp = 0; hp < 2; ++hp)
+          for (int wp = 0; wp < 2; ++wp) {
+            const int i = 2 * p.tap_dh[t] + hp + d.pad, j = 2 * p.tap_dw[t] + wp + d.pad;
+            if (i < 0 || i >= d.kh || j < 0 || j >= d.kw) continue;
+            for (int ci = 0; ci < 3; ++ci) {
+              const float v = w[(((size_t)co * 3 + ci) * d.kh + i) * d.kw + j];
+              out[(size_t)co * p.ktot + (size_t)t * 16 + (hp * 2 + wp) * 3 + ci] = f32_to_bf16_bits(v);
+            }
+          }
+  }
+  return HRP_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, int ck) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return HRP_ERR_CUDA;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUtensorMapSwizzle sw = (ck == 64)   ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : (ck == 32) ? CU_TENSOR_MAP_SWIZZLE_64B
+                                             : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+                  reinterpret_cast<const cuuint64_t*>(dims), reinterpret_cast<const cuuint64_t*>(strides_bytes),
+                  reinterpret_cast<const cuuint32_t*>(box), estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return HRP_ERR_CUDA;
+  }
+  return HRP_OK;
+}
+
+static void set_smem_attr_once() {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaFuncSetAttribute(conv_gemm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+}
+
+int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed) {
+  ConvParams& p = plan->p;
+  HRP_REQUIRE(in != nullptr && w_packed != nullptr, "null tensor");
+  HRP_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0,
+              "tensors must be 16-byte aligned");
+  p.in = in;
+  p.w = w_packed;
+  // A maps: one per input parity for stride-2 sources, else a single map
+  const int nmaps = (p.src_sh == 2) ? 4 : 1;
+  for (int m = 0; m < nmaps; ++m) {
+    const int hp = m >> 1, wp = m & 1;
+    const bf16* base = in + ((size_t)hp * p.Win + wp) * p.Cin;
+    uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.Ws, (uint64_t)p.Hs, (uint64_t)p.B};
+    uint64_t strides[3] = {(uint64_t)p.src_sw * p.Cin * 2, (uint64_t)p.src_sh * p.Win * p.Cin * 2,
+                           (uint64_t)p.Hin * p.Win * p.Cin * 2};
+    uint32_t box[4] = {(uint32_t)p.ck, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+    int rc = encode_map(&plan->maps.a[m], base, 4, dims, strides, box, p.ck);
+    if (rc != HRP_OK) return rc;
+  }
+  for (int m = nmaps; m < 4; ++m) plan->maps.a[m] = plan->maps.a[0];
+  {
+    uint64_t dims[2] = {(uint64_t)p.ktot, (uint64_t)p.nphase * p.cout_pad};
+    uint64_t strides[1] = {(uint64_t)p.ktot * 2};
+    uint32_t box[2] = {(uint32_t)p.ck, (uint32_t)p.n_tile};
+    int rc = encode_map(&plan->maps.b, w_packed, 2, dims, strides, box, p.ck);
+    if (rc != HRP_OK) return rc;
+  }
+  if (p.pool_out != nullptr)
+    HRP_REQUIRE(p.bw * p.bh >= 32, "pooled epilogue needs >= 32 rows per image in a tile");
+  const int stage_bytes = kStageABytes + p.n_tile * 128;
+  const int sub = 64 / p.ck;
+  const int n_iters = (p.ntaps * p.cpt + sub - 1) / sub;
+  int stages = std::max(2, std::min(6, (100 * 1024) / stage_bytes));
+  stages = std::max(1, std::min(stages, n_iters));
+  plan->stages = stages;
+  plan->smem_bytes = stages * stage_bytes + (int)sizeof(PipeBarriers) + 1024;
+  plan->grid = dim3((unsigned)(p.tiles_w * p.tiles_h * p.tiles_n), (unsigned)(p.cout_pad / p.n_tile),
+                    (unsigned)p.nphase);
+  return HRP_OK;
+}
+
+int conv_plan_launch(const ConvPlan& plan, cudaStream_t stream) {
+  set_smem_attr_once();
+  const ConvParams& p = plan.p;
+  if (p.ck == 64)
+    conv_gemm_kernel<64><<<plan.grid, kNumThreads, plan.smem_bytes, stream>>>(plan.maps, p, plan.stages);
+  else if (p.ck == 32)
+    conv_gemm_kernel<32><<<plan.grid, kNumThreads, plan.smem_bytes, stream>>>(plan.maps, p, plan.stages);
+  else
+    conv_gemm_kernel<16><<<plan.grid, kNumThreads, plan.smem_bytes, stream>>>(plan.maps, p, plan.stages);
+  count_launch();
+  HRP_CUDA_CHECK(cudaGetLastError());
+  return HRP_OK;
+}
+
+}  // namespace hrp

@@ -1,0 +1,156 @@
+// Memory-bound layout kernels around the conv stack: input packing (fp32 NCHW -> bf16 NHWC space-to-depth),
+// max-pool, NCHW<->NHWC bridges.  All are coalesced on the NHWC side and vectorised to 16 B per thread.
+#include "hrp_common.cuh"
+#include "launch_count.h"
+
+namespace hrp {
+
+// (B,3,H,W) fp32 -> (B,H/2,W/2,16) bf16; channel = (hp*2+wp)*3 + c; 12..15 = 0.
+// One thread per s2d pixel: reads 3 channels x 2 rows x 2 adjacent floats (float2, coalesced along W),
+// writes 32 contiguous bytes.
+__global__ void pack_input_s2d_kernel(const float* __restrict__ x, uint4* __restrict__ out, int B, int H, int W) {
+  const int Ws = W >> 1, Hs = H >> 1;
+  const size_t total = (size_t)B * Hs * Ws;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ws = (int)(i % Ws);
+    const int hs = (int)((i / Ws) % Hs);
+    const int n = (int)(i / ((size_t)Ws * Hs));
+    float v[16];
+#pragma unroll
+    for (int k = 12; k < 16; ++k) v[k] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int hp = 0; hp < 2; ++hp) {
+        const float2 t = __ldg(reinterpret_cast<const float2*>(x + (((size_t)n * 3 + c) * H + (2 * hs + hp)) * W + 2 * ws));
+        v[(hp * 2 + 0) * 3 + c] = t.x;
+        v[(hp * 2 + 1) * 3 + c] = t.y;
+      }
+    }
+    uint4 o0, o1;
+    o0.x = pack_bf16x2(v[0], v[1]);
+    o0.y = pack_bf16x2(v[2], v[3]);
+    o0.z = pack_bf16x2(v[4], v[5]);
+    o0.w = pack_bf16x2(v[6], v[7]);
+    o1.x = pack_bf16x2(v[8], v[9]);
+    o1.y = pack_bf16x2(v[10], v[11]);
+    o1.z = pack_bf16x2(v[12], v[13]);
+    o1.w = pack_bf16x2(v[14], v[15]);
+    out[2 * i] = o0;
+    out[2 * i + 1] = o1;
+  }
+}
+
+// MaxPool2d(kernel 3, stride 2, pad 1) on bf16 NHWC; thread = (output pixel, 8-channel group)
+__global__ void maxpool3x3s2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W,
+                                    int C8) {
+  const int Ho = H >> 1, Wo = W >> 1;
+  const size_t total = (size_t)B * Ho * Wo * C8;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % C8);
+    size_t pix = i / C8;
+    const int wo = (int)(pix % Wo);
+    const int ho = (int)((pix / Wo) % Ho);
+    const int n = (int)(pix / ((size_t)Wo * Ho));
+    float m[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+#pragma unroll
+    for (int dh = -1; dh <= 1; ++dh) {
+      const int h = 2 * ho + dh;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int dw = -1; dw <= 1; ++dw) {
+        const int w = 2 * wo + dw;
+        if (w < 0 || w >= W) continue;
+        const uint4 t = __ldg(in + (((size_t)n * H + h) * W + w) * C8 + cg);
+        const uint32_t xs[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          m[2 * k] = fmaxf(m[2 * k], bf16lo_to_f32(xs[k]));
+          m[2 * k + 1] = fmaxf(m[2 * k + 1], bf16hi_to_f32(xs[k]));
+        }
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16x2(m[0], m[1]);
+    o.y = pack_bf16x2(m[2], m[3]);
+    o.z = pack_bf16x2(m[4], m[5]);
+    o.w = pack_bf16x2(m[6], m[7]);
+    out[i] = o;
+  }
+}
+
+// generic bridges (operator-level shims / tests): smem-tiled transpose of a (C x HW) slab per image
+__global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, int C, int HW,
+                                             int Cpad) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int c = c0 + r, p = p0 + threadIdx.x;
+    tile[r][threadIdx.x] = (c < C && p < HW) ? in[((size_t)n * C + c) * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int p = p0 + r, c = c0 + threadIdx.x;
+    if (p < HW && c < Cpad) out[((size_t)n * HW + p) * Cpad + c] = __float2bfloat16_rn(tile[threadIdx.x][r]);
+  }
+}
+
+__global__ void nhwc_bf16_to_nchw_f32_kernel(const bf16* __restrict__ in, float* __restrict__ out, int C, int HW,
+                                             int Cpad) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int p = p0 + r, c = c0 + threadIdx.x;
+    tile[r][threadIdx.x] = (p < HW && c < C) ? __bfloat162float(in[((size_t)n * HW + p) * Cpad + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int c = c0 + r, p = p0 + threadIdx.x;
+    if (c < C && p < HW) out[((size_t)n * C + c) * HW + p] = tile[threadIdx.x][r];
+  }
+}
+
+int launch_pack_input_s2d(const float* x, void* out, int B, int H, int W, cudaStream_t s) {
+  HRP_REQUIRE(H % 2 == 0 && W % 2 == 0, "input size must be even");
+  const size_t total = (size_t)B * (H / 2) * (W / 2);
+  const int threads = 256;
+  const int blocks = (int)std::min<size_t>((total + threads - 1) / threads, 148 * 16);
+  pack_input_s2d_kernel<<<blocks, threads, 0, s>>>(x, reinterpret_cast<uint4*>(out), B, H, W);
+  count_launch();
+  HRP_CUDA_CHECK(cudaGetLastError());
+  return HRP_OK;
+}
+
+int launch_maxpool3x3s2(const void* in, void* out, int B, int H, int W, int C, cudaStream_t s) {
+  HRP_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool needs C%8==0 and even H,W");
+  const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 8);
+  const int threads = 256;
+  const int blocks = (int)std::min<size_t>((total + threads - 1) / threads, 148 * 16);
+  maxpool3x3s2_kernel<<<blocks, threads, 0, s>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), B,
+                                                 H, W, C / 8);
+  count_launch();
+  HRP_CUDA_CHECK(cudaGetLastError());
+  return HRP_OK;
+}
+
+int launch_nchw_f32_to_nhwc_bf16(const float* in, void* out, int B, int C, int H, int W, int Cpad, cudaStream_t s) {
+  dim3 grid((H * W + 31) / 32, (Cpad + 31) / 32, B), block(32, 8);
+  nchw_f32_to_nhwc_bf16_kernel<<<grid, block, 0, s>>>(in, reinterpret_cast<bf16*>(out), C, H * W, Cpad);
+  count_launch();
+  HRP_CUDA_CHECK(cudaGetLastError());
+  return HRP_OK;
+}
+
+int launch_nhwc_bf16_to_nchw_f32(const void* in, float* out, int B, int C, int H, int W, int Cpad, cudaStream_t s) {
+  dim3 grid((H * W + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  nhwc_bf16_to_nchw_f32_kernel<<<grid, block, 0, s>>>(reinterpret_cast<const bf16*>(in), out, C, H * W, Cpad);
+  count_launch();
+  HRP_CUDA_CHECK(cudaGetLastError());
+  return HRP_OK;
+}
+
+}  // namespace hrp

@@ -1,0 +1,173 @@
+"""tcgen05 implicit-GEMM convolution vs a plain PyTorch fp32 reference of the same op (on the same
+bf16-rounded operands), plus the SIMT cross-check kernel.  Shapes cover every conv class of the two backbones
+and the deconv head."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf16_round(t):
+    return t.to(torch.bfloat16).float()
+
+
+def _nhwc(x_nchw, cpad=None):
+    B, C, H, W = x_nchw.shape
+    cpad = cpad or C
+    out = torch.zeros(B, H, W, cpad, dtype=torch.bfloat16, device=x_nchw.device)
+    out[..., :C] = x_nchw.permute(0, 2, 3, 1).to(torch.bfloat16)
+    return out.contiguous()
+
+
+def _report(name, got, ref, tol_rel=2.0 ** -7, tol_abs=2e-2):
+    got = got.float()
+    err = (got - ref).abs()
+    lim = tol_abs + tol_rel * ref.abs()
+    bad = err > lim
+    nbad = int(bad.sum())
+    if nbad:
+        idx = bad.nonzero()[:8].tolist()
+        rows_bad = bad.reshape(bad.shape[0], -1, bad.shape[-1]).any(-1).sum().item()
+        chans_bad = bad.reshape(-1, bad.shape[-1]).any(0).nonzero().flatten()[:32].tolist()
+        msg = (f"{name}: {nbad}/{bad.numel()} mismatches, max err {err.max().item():.4g}, "
+               f"ref absmax {ref.abs().max().item():.4g}, got absmax {got.abs().max().item():.4g}, "
+               f"bad pixels {rows_bad}, first bad idx {idx}, bad channels {chans_bad}")
+        vals = [(got[tuple(i)].item(), ref[tuple(i)].item()) for i in idx[:4]]
+        raise AssertionError(msg + f" samples(got,ref)={vals}")
+    return err.max().item()
+
+
+CASES = [
+    # name, B, Cin, H, W, Cout, k, stride, pad
+    ("gemm_1x1_64", 2, 64, 64, 64, 64, 1, 1, 0),
+    ("gemm_1x1_256_to_64", 2, 256, 64, 64, 64, 1, 1, 0),
+    ("gemm_1x1_64_to_256", 1, 64, 64, 64, 256, 1, 1, 0),
+    ("conv3_64_16x16", 3, 64, 16, 16, 64, 3, 1, 1),
+    ("conv3_32_64x64_sw64", 2, 32, 64, 64, 32, 3, 1, 1),
+    ("conv3_128_16x16", 2, 128, 16, 16, 128, 3, 1, 1),
+    ("conv3_256_8x8_bn2", 3, 256, 8, 8, 256, 3, 1, 1),
+    ("conv3_s2_64_to_128", 2, 64, 32, 32, 128, 3, 2, 1),
+    ("conv3_s2_32_to_64", 2, 32, 64, 64, 64, 3, 2, 1),
+    ("conv1_s2_256_to_512", 2, 256, 32, 32, 512, 1, 2, 0),
+    ("final_1x1_256_to_448", 1, 256, 64, 64, 448, 1, 1, 0),
+    ("gemm_1024_to_2048_8x8", 3, 1024, 8, 8, 2048, 1, 1, 0),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_conv_vs_torch(case, hrp_lib):
+    from horopose_b200 import ops
+    name, B, Cin, H, W, Cout, k, stride, pad = case
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    import zlib
+    g = torch.Generator().manual_seed(zlib.crc32(name.encode()) % 1000)
+    x = _bf16_round(torch.randn(B, Cin, H, W, generator=g)).cuda()
+    w = _bf16_round(torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5)
+    scale = (torch.rand(Cout, generator=g) + 0.5)
+    bias = torch.randn(Cout, generator=g) * 0.1
+    op = ops.ConvOp(_nhwc(x), w, stride=stride, pad=pad, relu=True, scale=scale, bias=bias)
+    ref = F.conv2d(x, w.cuda(), stride=stride, padding=pad)
+    ref = torch.relu(ref * scale.cuda()[None, :, None, None] + bias.cuda()[None, :, None, None])
+    ref = ref.permute(0, 2, 3, 1).contiguous()
+    got_simt = op.run(ops.IMPL_SIMT_CHECK).clone()
+    torch.cuda.synchronize()
+    _report(name + "[simt]", got_simt, ref)
+    op.out.zero_()
+    got = op.run(ops.IMPL_TCGEN05)
+    torch.cuda.synchronize()
+    _report(name + "[tcgen05]", got, ref)
+
+
+def test_epilogue_addends(hrp_lib):
+    """pre (residual), nearest-upsampled addends (HRNet fuse, HRnet.py:197-208,254-263) and post-ReLU addend
+    (cls head, HRnet.py:558-560)."""
+    from horopose_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    B, C, H, W = 2, 64, 32, 32
+    x = _bf16_round(torch.randn(B, C, H, W, generator=g)).cuda()
+    w = _bf16_round(torch.randn(C, C, 3, 3, generator=g) / (C * 9) ** 0.5)
+    res = _bf16_round(torch.randn(B, C, H, W, generator=g)).cuda()
+    up1 = _bf16_round(torch.randn(B, C, H // 2, W // 2, generator=g)).cuda()
+    up2 = _bf16_round(torch.randn(B, C, H // 4, W // 4, generator=g)).cuda()
+    post = _bf16_round(torch.randn(B, C, H, W, generator=g)).cuda()
+    op = ops.ConvOp(_nhwc(x), w, stride=1, pad=1, relu=True, pre=[_nhwc(res)],
+                    up=[(_nhwc(up1), 1), (_nhwc(up2), 2)], post=_nhwc(post))
+    ref = F.conv2d(x, w.cuda(), padding=1) + res
+    ref = ref + F.interpolate(up1, scale_factor=2, mode="nearest") + F.interpolate(up2, scale_factor=4, mode="nearest")
+    ref = (torch.relu(ref) + post).permute(0, 2, 3, 1).contiguous()
+    got = op.run()
+    torch.cuda.synchronize()
+    _report("addends", got, ref)
+
+
+def test_pooled_epilogue(hrp_lib):
+    """conv + BN + ReLU + global average pool in the epilogue (HRnet.py:562-568)."""
+    from horopose_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    B, Cin, Cout = 3, 128, 256
+    x = _bf16_round(torch.randn(B, Cin, 8, 8, generator=g)).cuda()
+    w = _bf16_round(torch.randn(Cout, Cin, 1, 1, generator=g) / Cin ** 0.5)
+    op = ops.ConvOp(_nhwc(x), w, relu=True, pool=True, write_out=False)
+    ref = torch.relu(F.conv2d(x, w.cuda())).mean(dim=(2, 3))
+    got = op.run()
+    torch.cuda.synchronize()
+    assert torch.allclose(got, ref, rtol=1e-4, atol=1e-4), (got - ref).abs().max()
+
+
+@pytest.mark.parametrize("cin,hin", [(256, 8), (64, 16)])
+def test_deconv_k4s2p1(cin, hin, hrp_lib):
+    """ConvTranspose2d(k4,s2,p1)+BN+ReLU as four sub-pixel phases (full_net.py:194-216)."""
+    from horopose_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    B, Cout = 2, 64
+    x = _bf16_round(torch.randn(B, cin, hin, hin, generator=g)).cuda()
+    w = _bf16_round(torch.randn(cin, Cout, 4, 4, generator=g) / (cin * 4) ** 0.5)
+    scale = torch.rand(Cout, generator=g) + 0.5
+    bias = torch.randn(Cout, generator=g) * 0.1
+    op = ops.ConvOp(_nhwc(x), w, kind=ops.DECONV_K4S2P1, relu=True, scale=scale, bias=bias)
+    ref = F.conv_transpose2d(x, w.cuda(), stride=2, padding=1)
+    ref = torch.relu(ref * scale.cuda()[None, :, None, None] + bias.cuda()[None, :, None, None])
+    ref = ref.permute(0, 2, 3, 1).contiguous()
+    got_simt = op.run(ops.IMPL_SIMT_CHECK).clone()
+    torch.cuda.synchronize()
+    _report("deconv[simt]", got_simt, ref)
+    op.out.zero_()
+    got = op.run()
+    torch.cuda.synchronize()
+    _report("deconv[tcgen05]", got, ref)
+
+
+@pytest.mark.parametrize("k,pad", [(7, 3), (3, 1)])
+def test_stem_s2d(k, pad, hrp_lib):
+    """Stride-2 stem convs with C_in=3 through the space-to-depth input packing
+    (Resnet.py:21 k7 s2 p3; HRnet.py:284 k3 s2 p1)."""
+    from horopose_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    B, H = 2, 64
+    x = torch.rand(B, 3, H, H, generator=g).cuda()
+    w = _bf16_round(torch.randn(64, 3, k, k, generator=g) / (3 * k * k) ** 0.5)
+    xs = ops.pack_input_s2d(x)
+    op = ops.ConvOp(xs, w, kind=ops.STEM_S2D, stride=2, pad=pad, relu=True)
+    ref = torch.relu(F.conv2d(_bf16_round(x), w.cuda(), stride=2, padding=pad)).permute(0, 2, 3, 1).contiguous()
+    got_simt = op.run(ops.IMPL_SIMT_CHECK).clone()
+    torch.cuda.synchronize()
+    _report("stem[simt]", got_simt, ref)
+    op.out.zero_()
+    got = op.run()
+    torch.cuda.synchronize()
+    _report("stem[tcgen05]", got, ref)
+
+
+def test_maxpool_and_bridges(hrp_lib):
+    from horopose_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    x = _bf16_round(torch.randn(2, 64, 32, 32, generator=g)).cuda()
+    xn = ops.nchw_to_nhwc_bf16(x)
+    assert torch.equal(xn.float(), x.permute(0, 2, 3, 1))
+    back = ops.nhwc_bf16_to_nchw(xn)
+    assert torch.equal(back, x)
+    mp = ops.maxpool3x3s2(xn)
+    ref = F.max_pool2d(x, 3, 2, 1).permute(0, 2, 3, 1)
+    assert torch.equal(mp.float(), ref)
