@@ -1,0 +1,188 @@
+"""Generate the committed fixtures from the REAL reference (run in the build container only).
+
+  python tests/golden/make_golden.py --calibrate   # fixtures/bn_stats.npz (BN running stats of the synthetic recipe)
+  python tests/golden/make_golden.py               # tests/golden/*.npz (reference outputs on seeded inputs)
+
+Inputs and weights are regenerated from seeds by horopose_b200.synth on every machine; only the small OUTPUT
+tensors of the reference are stored.  The reference is imported from /root/reference through
+oracle/ref_harness.py (sandbox + stubs, no reference source is copied).
+"""
+import argparse
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+import horopose_b200  # noqa: E402,F401
+from horopose_b200 import arch, synth  # noqa: E402
+from oracle import horopose_oracle as O  # noqa: E402
+from oracle import ref_harness  # noqa: E402
+
+GOLDEN = Path(__file__).resolve().parent
+torch.set_grad_enabled(False)
+
+HEATMAP_STRESS_GAIN = 10.0  # "peaky heatmap" variant
+
+
+def heatmap_logits(robot_type: str, batch: int, seed: int = 3, gain: float = 1.0) -> torch.Tensor:
+    nkpt = arch.ROBOTS[robot_type][1]
+    u = synth.uniform01("heatmap_" + robot_type, batch * nkpt * 64 * 64 * 64, seed)
+    x = torch.from_numpy((u - np.float32(0.5)) * np.float32(6.0 * gain))
+    return x.reshape(batch, nkpt * 64, 64, 64)
+
+
+def calibrate():
+    """BN running statistics = batch statistics of the synthetic-weight nets on 8 seeded random images, layer by
+    layer (equivalent to the train-mode calibration pass of SURVEY.md fact 7), rounded to fp16-representable
+    values so the fixture is compact and exact."""
+    sd = synth.full_state_dict("panda", with_bn_stats=False)
+    robot = O.OracleRobot("panda", str(synth.URDF_PATHS["panda"]))
+    x_reg, x_root, k, K = synth.inputs(8, seed=7)
+    stats = {}
+
+    def calib(name, mean, var):
+        mean = mean.half().float()
+        var = var.clamp_min(1e-3).half().float()
+        key = name.replace("rootnet_backbone.", "B.", 1)
+        stats[key + ".running_mean"] = mean.numpy().astype(np.float16)
+        stats[key + ".running_var"] = var.numpy().astype(np.float16)
+        return mean, var
+
+    out = O.full_forward(sd, robot, x_reg, x_root, k, K, calib=calib)
+    np.savez_compressed(synth.BN_STATS_PATH, **stats)
+    print("wrote", synth.BN_STATS_PATH, len(stats), "arrays,", synth.BN_STATS_PATH.stat().st_size, "bytes")
+    print("calibration-pass depth:", out[4].flatten().tolist())
+
+
+def to_np(t):
+    return t.detach().cpu().numpy()
+
+
+def golden_full(ns, robot_type: str, batch: int = 2):
+    sd = synth.full_state_dict(robot_type)
+    model = ref_harness.build_full_model(ns, robot_type)
+    model.load_state_dict(sd, strict=True)   # proves the key/shape schema of horopose_b200.arch
+    x_reg, x_root, k, K = synth.inputs(batch, seed=11)
+    outs = model(x_reg, x_root, k, K)
+    names = ["pose", "rot", "trans", "root_uv", "depth", "uvd", "xyz_int", "xyz_fk"]
+    data = {n: to_np(o) for n, o in zip(names, outs)}
+    # activation summaries for fault localisation (mean |x| of a few stages through forward hooks)
+    taps = {}
+
+    def hook(name):
+        def fn(_m, _i, o):
+            taps[name] = float(o.abs().mean())
+        return fn
+
+    hs = [model.reg_backbone.layer1.register_forward_hook(hook("reg_backbone.layer1")),
+          model.reg_backbone.layer4.register_forward_hook(hook("reg_backbone.layer4")),
+          model.rootnet_backbone.layer1.register_forward_hook(hook("rootnet_backbone.layer1")),
+          model.rootnet_backbone.final_feat_layer.register_forward_hook(hook("rootnet_backbone.final_feat")),
+          model.deconv_layers.register_forward_hook(hook("deconv")),
+          model.final_layer.register_forward_hook(hook("heatmap"))]
+    model(x_reg, x_root, k, K)
+    for h in hs:
+        h.remove()
+    for n, v in taps.items():
+        data["tap_absmean." + n] = np.float32(v)
+    np.savez(GOLDEN / f"full_{robot_type}.npz", **data)
+    # oracle agreement, printed for the record
+    robot = O.OracleRobot(robot_type, str(synth.URDF_PATHS[robot_type]))
+    o = O.full_forward(sd, robot, x_reg, x_root, k, K)
+    print(f"[full {robot_type}] oracle vs reference max|diff|:",
+          {n: float((a - b).abs().max()) for n, a, b in zip(names, o, outs)})
+    print("   depth", data["depth"].flatten(), "pose[0]", data["pose"][0][:4], "taps", taps)
+
+
+def golden_depthnet(ns, batch: int = 2):
+    sd = synth.depthnet_state_dict()
+    model = ref_harness.build_depthnet(ns)
+    model.load_state_dict(sd, strict=True)
+    _, x_root, k, _ = synth.inputs(batch, seed=11)
+    out = model(x_root, k)
+    np.savez(GOLDEN / "depthnet.npz", depth_mm=to_np(out))
+    o = O.depthnet_forward(sd, x_root, k)
+    print("[depthnet] oracle vs reference max|diff| (mm):", float((o - out).abs().max()), to_np(out).flatten())
+
+
+def golden_fk(ns, robot_type: str, batch: int = 64):
+    robot = ns.urdf_robot.URDFRobot(robot_type)
+    q, rot, trans = synth.fk_inputs(robot_type, batch)
+    _, _, _, K = synth.inputs(batch, seed=5)
+    data = {
+        "link_names": np.array(robot.link_names),
+        "actuated_joint_names": np.array([j.name for j in robot.robot.actuated_joints]),
+        "offsets": to_np(robot.offsets.squeeze(0).squeeze(-1)),
+        "keypoints": to_np(robot.get_keypoints(q, rot, trans)),
+        "keypoints_only_fk": to_np(robot.get_keypoints_only_fk(q)),
+    }
+    nk = len(robot.link_names)
+    for root in sorted({0, 3, nk - 1}):
+        data[f"keypoints_root{root}"] = to_np(robot.get_keypoints_root(q, rot, trans, root=root))
+        data[f"only_fk_root{root}"] = to_np(robot.get_keypoints_only_fk_at_specific_root(q, root=root))
+        data[f"rotation_root{root}"] = to_np(robot.get_rotation_at_specific_root(q, rot, trans, root=root))
+    fk = robot.robot.link_fk_batch(q, use_names=True)
+    data["all_link_names"] = np.array(list(fk.keys()))
+    data["all_link_fk"] = to_np(torch.stack(list(fk.values()), dim=1))
+    data["proj_tensor"] = to_np(ns.transforms.point_projection_from_3d_tensor(K, torch.from_numpy(data["keypoints"])))
+    data["proj_numpy"] = ns.transforms.point_projection_from_3d(to_np(K), data["keypoints"]).astype(np.float32)
+    # quaternion rotation input (urdf_robot.py:89-90)
+    quat = synth.sym_uniform("fk_quat_" + robot_type, (batch, 4), 1.0, 2)
+    data["keypoints_quat"] = to_np(robot.get_keypoints(q, quat, trans))
+    np.savez(GOLDEN / f"fk_{robot_type}.npz", **data)
+    orob = O.OracleRobot(robot_type, str(synth.URDF_PATHS[robot_type]))
+    d = (orob.get_keypoints_root(q, rot, trans, root=3) - torch.from_numpy(data["keypoints_root3"])).abs().max()
+    print(f"[fk {robot_type}] oracle vs reference max|diff|: {float(d):.3g}; links {list(robot.link_names)[:3]}...")
+
+
+def golden_integral(ns, robot_type: str, batch: int = 2):
+    dof, nkpt, ref = arch.ROBOTS[robot_type]
+    data = {}
+    for tag, gain in (("", 1.0), ("_peaky", HEATMAP_STRESS_GAIN)):
+        hm = heatmap_logits(robot_type, batch, gain=gain)
+        _, _, k, K = synth.inputs(batch, seed=13)
+        root_trans = torch.zeros(batch, 3)
+        root_trans[:, 2] = synth.range_uniform("root_z", (batch,), 0.8, 2.5, 13)
+        layer = ns.integral.HeatmapIntegralPose(backbone="resnet50", num_joints=nkpt, depth_dim=64, height_dim=64,
+                                                width_dim=64, norm_type="softmax", image_size=256.0,
+                                                bbox_3d_shape=[1300, 1300, 1300], rootid=ref, fixroot=True)
+        uvd, xyz = layer(hm, root_trans=root_trans, K=K)
+        data["uvd" + tag], data["xyz" + tag] = to_np(uvd), to_np(xyz)
+        root_uv = (uvd[:, ref, :2] + 0.5) * 256.0
+        data["trans" + tag] = to_np(ns.transforms.uvz2xyz_singlepoint(root_uv, root_trans[:, 2:3], K))
+        ou, ox = O.heatmap_integral(hm, nkpt, K, root_trans, ref)
+        print(f"[integral {robot_type}{tag}] oracle vs reference:", float((ou - uvd).abs().max()),
+              float((ox - xyz).abs().max()))
+    np.savez(GOLDEN / f"integral_{robot_type}.npz", **data)
+
+
+def golden_geometry(ns):
+    r6 = synth.sym_uniform("rot6d", (64, 6), 1.0, 4)
+    R = ns.geometries.rot6d_to_rotmat(r6)
+    quat = synth.sym_uniform("quat", (64, 4), 1.0, 4)
+    np.savez(GOLDEN / "geometry.npz", rot6d_to_rotmat=to_np(R), rotmat_to_rot6d=to_np(ns.geometries.rotmat_to_rot6d(R)),
+             quat_to_rotmat=to_np(ns.geometries.quat_to_rotmat(quat)))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--calibrate", action="store_true")
+    args = ap.parse_args()
+    if args.calibrate:
+        calibrate()
+        return
+    ns = ref_harness.setup({k: str(v) for k, v in synth.URDF_PATHS.items()})
+    golden_geometry(ns)
+    for r in ("panda", "kuka", "baxter"):
+        golden_fk(ns, r)
+        golden_integral(ns, r)
+    golden_depthnet(ns)
+    for r in ("panda", "kuka", "baxter"):
+        golden_full(ns, r)
+
+
+if __name__ == "__main__":
+    main()
