@@ -2,6 +2,7 @@
 #include "../../include/hrp.h"
 
 #include "conv.h"
+#include "head.h"
 #include "launch_count.h"
 #include "ops.h"
 
@@ -15,6 +16,11 @@ std::atomic<int64_t> g_launch_count{0};
 }  // namespace hrp
 
 using namespace hrp;
+
+struct hrp_robot {
+  RobotTable host;
+  RobotTable* dev = nullptr;
+};
 
 struct hrp_conv {
   ConvLayerDesc desc;
@@ -128,6 +134,136 @@ int hrp_nhwc_bf16_to_nchw_f32(const void* in, float* out, int32_t B, int32_t C, 
                               void* stream) {
   HRP_REQUIRE(in != nullptr && out != nullptr && B > 0 && Cpad >= C, "bad argument");
   return launch_nhwc_bf16_to_nchw_f32(in, out, B, C, H, W, Cpad, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int hrp_robot_create(const hrp_link_row* rows, int32_t n_links, const int32_t* kp_link, const double* kp_offset,
+                     int32_t nkpt, int32_t dof, hrp_robot** out) {
+  HRP_REQUIRE(rows != nullptr && kp_link != nullptr && kp_offset != nullptr && out != nullptr, "null argument");
+  HRP_REQUIRE(n_links > 0 && n_links <= kMaxLinks, "link count out of range (prune the tree to keypoint ancestors)");
+  HRP_REQUIRE(nkpt > 0 && nkpt <= kMaxKpt && dof > 0 && dof <= kMaxDof, "keypoint / dof count out of range");
+  hrp_robot* r = new (std::nothrow) hrp_robot();
+  HRP_REQUIRE(r != nullptr, "out of host memory");
+  RobotTable& t = r->host;
+  memset(&t, 0, sizeof(t));
+  t.n_links = n_links;
+  t.nkpt = nkpt;
+  t.dof = dof;
+  for (int i = 0; i < n_links; ++i) {
+    const hrp_link_row& row = rows[i];
+    if (!(row.parent < i && row.parent >= -1) || row.jtype < 0 || row.jtype > 2 || row.qcol >= dof ||
+        (row.jtype != 0 && row.qcol < 0)) {
+      delete r;
+      set_error("invalid link row " + std::to_string(i));
+      return HRP_ERR_INVALID;
+    }
+    t.parent[i] = row.parent;
+    t.jtype[i] = row.jtype;
+    t.qcol[i] = row.qcol;
+    t.qmul[i] = (float)row.qmul;
+    t.qoff[i] = (float)row.qoff;
+    for (int e = 0; e < 12; ++e) t.origin[i][e] = (float)row.origin[e];
+    for (int a = 0; a < 3; ++a) t.axis[i][a] = (float)row.axis[a];
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) t.axis_outer[i][a * 3 + b] = (float)(row.axis[a] * row.axis[b]);
+  }
+  for (int k = 0; k < nkpt; ++k) {
+    if (kp_link[k] < 0 || kp_link[k] >= n_links) {
+      delete r;
+      set_error("keypoint link index out of range");
+      return HRP_ERR_INVALID;
+    }
+    t.kp_link[k] = kp_link[k];
+    for (int a = 0; a < 3; ++a) t.kp_off[k][a] = (float)kp_offset[k * 3 + a];
+  }
+  cudaError_t e = cudaMalloc(&r->dev, sizeof(RobotTable));
+  if (e == cudaSuccess) e = cudaMemcpy(r->dev, &t, sizeof(RobotTable), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    if (r->dev) cudaFree(r->dev);
+    delete r;
+    set_error(std::string("robot table upload failed: ") + cudaGetErrorString(e));
+    return HRP_ERR_CUDA;
+  }
+  *out = r;
+  return HRP_OK;
+}
+
+void hrp_robot_destroy(hrp_robot* robot) {
+  if (robot == nullptr) return;
+  if (robot->dev) cudaFree(robot->dev);
+  delete robot;
+}
+
+int hrp_fk(hrp_robot* robot, const float* q, const float* rot, int32_t rot_dim, const float* trans, int32_t root,
+           int32_t use_b2c, float* out_xyz, float* out_rot, int32_t B, void* stream) {
+  HRP_REQUIRE(robot != nullptr && q != nullptr && B > 0, "bad argument");
+  HRP_REQUIRE(out_xyz != nullptr || out_rot != nullptr, "an output is required");
+  HRP_REQUIRE(root >= 0 && root < robot->host.nkpt, "root keypoint out of range");
+  HRP_REQUIRE(out_rot == nullptr || use_b2c, "rotation output needs the base-to-camera transform");
+  if (use_b2c && rot_dim == 9) {
+    set_error("9-D (SVD) rotation input is outside the hot path (no shipped config uses it)");
+    return HRP_ERR_UNSUPPORTED;
+  }
+  FkParams p;
+  p.B = B;
+  p.rot_dim = rot_dim;
+  p.root = root;
+  p.use_b2c = use_b2c;
+  p.q = q;
+  p.rot = rot;
+  p.trans = trans;
+  p.robot = robot->dev;
+  p.pts = out_xyz;
+  p.rot_out = out_rot;
+  return launch_fk(p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int hrp_project(const float* K, const float* pts, float* uv, int32_t B, int32_t N, void* stream) {
+  return launch_project(K, pts, uv, B, N, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int hrp_head_workspace_bytes(int32_t B, int32_t nkpt, int64_t* bytes) {
+  HRP_REQUIRE(B > 0 && nkpt > 0 && nkpt <= kMaxKpt && bytes != nullptr, "bad argument");
+  const int chunks = head_default_chunks(B);
+  *bytes = (int64_t)(((size_t)B * sizeof(unsigned int) + 255) / 256 * 256 +
+                     head_partials_elems(B, nkpt, chunks) * sizeof(float));
+  return HRP_OK;
+}
+
+int hrp_head(const hrp_head_args* a, void* stream) {
+  HRP_REQUIRE(a != nullptr, "null argument");
+  HRP_REQUIRE(a->workspace != nullptr, "workspace is required");
+  int64_t need = 0;
+  int rc = hrp_head_workspace_bytes(a->B, a->nkpt, &need);
+  if (rc != HRP_OK) return rc;
+  HRP_REQUIRE(a->workspace_bytes >= need, "workspace too small");
+  HRP_REQUIRE(a->root_depth != nullptr, "root depth is required");
+  HRP_REQUIRE(a->robot == nullptr || a->robot->host.nkpt == a->nkpt, "robot keypoint count mismatch");
+  HeadParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = a->B;
+  p.nkpt = a->nkpt;
+  p.ref_kpt = a->ref_kpt;
+  p.fix_root = a->fix_root;
+  p.image_size = a->image_size;
+  p.depth_factor = a->depth_factor;
+  p.heatmap = reinterpret_cast<const bf16*>(a->heatmap);
+  p.chunks = head_default_chunks(a->B);
+  p.counters = reinterpret_cast<unsigned int*>(a->workspace);
+  p.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(a->workspace) +
+                                        ((size_t)a->B * sizeof(unsigned int) + 255) / 256 * 256);
+  p.K = a->K;
+  p.depth_in = a->root_depth;
+  p.pose_in = a->pose;
+  p.rot_in = a->rot;
+  p.robot = (a->robot != nullptr && a->pose != nullptr && a->rot != nullptr) ? a->robot->dev : nullptr;
+  p.trans = a->trans;
+  p.root_uv = a->root_uv;
+  p.uvd = a->uvd;
+  p.xyz_int = a->xyz_int;
+  p.xyz_fk = a->xyz_fk;
+  p.uv_int = a->uv_int;
+  p.uv_fk = a->uv_fk;
+  return launch_head(p, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

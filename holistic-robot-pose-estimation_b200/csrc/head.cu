@@ -1,0 +1,597 @@
+// Fused head kernel (memory-bound): one streaming pass over the bf16 heatmap logits computes the 3-D
+// soft-argmax of every keypoint; the last CTA of each image then finishes the sample on chip: uvd -> xyz,
+// root depth (2048-dot), root translation, collapsed pose/rot regressors, URDF forward kinematics and
+// projections.  Also the standalone FK / projection / pooling kernels behind URDFRobot and
+// point_projection_from_3d (head.h lists the reference lines).
+#include "head.h"
+#include "launch_count.h"
+
+namespace hrp {
+
+// ------------------------------------------------------------------------------------------------------
+// small rigid-transform helpers; a 3x4 matrix lives at T[e*stride], e = row*4+col
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rigid_mul(const float* a, int sa, const float* b, int sb, float* c, int sc) {
+  // c = a * b for [R t; 0 0 0 1] matrices (the bottom row contributes exactly as in a full 4x4 product)
+  float r[12];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float a0 = a[(i * 4 + 0) * sa], a1 = a[(i * 4 + 1) * sa], a2 = a[(i * 4 + 2) * sa], a3 = a[(i * 4 + 3) * sa];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float v = a0 * b[(0 * 4 + j) * sb];
+      v = fmaf(a1, b[(1 * 4 + j) * sb], v);
+      v = fmaf(a2, b[(2 * 4 + j) * sb], v);
+      if (j == 3) v += a3;
+      r[i * 4 + j] = v;
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 12; ++e) c[e * sc] = r[e];
+}
+
+__device__ __forceinline__ void rigid_inverse(const float* a, int sa, float* c) {
+  // [R t]^-1 = [R^T, -R^T t]
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) c[i * 4 + j] = a[(j * 4 + i) * sa];
+    c[i * 4 + 3] = -(a[(0 * 4 + i) * sa] * a[3 * sa] + a[(1 * 4 + i) * sa] * a[7 * sa] + a[(2 * 4 + i) * sa] * a[11 * sa]);
+  }
+}
+
+// rot6d -> rotation matrix whose ROWS are x, y, z (geometries.py:100-115)
+__device__ __forceinline__ void rot6d_to_rows(const float* r, float* R) {
+  const float n1 = sqrtf(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+  const float x0 = r[0] / n1, x1 = r[1] / n1, x2 = r[2] / n1;
+  float z0 = x1 * r[5] - x2 * r[4], z1 = x2 * r[3] - x0 * r[5], z2 = x0 * r[4] - x1 * r[3];
+  const float n2 = sqrtf(z0 * z0 + z1 * z1 + z2 * z2);
+  z0 /= n2;
+  z1 /= n2;
+  z2 /= n2;
+  const float y0 = z1 * x2 - z2 * x1, y1 = z2 * x0 - z0 * x2, y2 = z0 * x1 - z1 * x0;
+  R[0] = x0; R[1] = x1; R[2] = x2;
+  R[3] = y0; R[4] = y1; R[5] = y2;
+  R[6] = z0; R[7] = z1; R[8] = z2;
+}
+
+// quaternion (w,x,y,z) -> rotation matrix (geometries.py:21-41)
+__device__ __forceinline__ void quat_to_rows(const float* qv, float* R) {
+  const float nrm = sqrtf(qv[0] * qv[0] + qv[1] * qv[1] + qv[2] * qv[2] + qv[3] * qv[3]) + 1e-9f;
+  const float w = qv[0] / nrm, x = qv[1] / nrm, y = qv[2] / nrm, z = qv[3] / nrm;
+  const float w2 = w * w, x2 = x * x, y2 = y * y, z2 = z * z;
+  const float wx = w * x, wy = w * y, wz = w * z, xy = x * y, xz = x * z, yz = y * z;
+  R[0] = w2 + x2 - y2 - z2; R[1] = 2 * xy - 2 * wz;     R[2] = 2 * wy + 2 * xz;
+  R[3] = 2 * wz + 2 * xy;   R[4] = w2 - x2 + y2 - z2;   R[5] = 2 * yz - 2 * wx;
+  R[6] = 2 * xz - 2 * wy;   R[7] = 2 * wx + 2 * yz;     R[8] = w2 - x2 - y2 + z2;
+}
+
+// rotation matrix -> quaternion (geometries.py:63-82)
+__device__ __forceinline__ void rows_to_quat(const float* R, float* qo) {
+  float w = sqrtf(fmaxf(1.0f + R[0] + R[4] + R[8], 0.f)) / 2.0f;
+  w = fmaxf(w, 1e-8f);
+  const float w4 = 4.0f * w;
+  float x = (R[7] - R[5]) / w4, y = (R[2] - R[6]) / w4, z = (R[3] - R[1]) / w4;
+  float mag = fmaxf(sqrtf(w * w + x * x + y * y + z * z), 1e-8f);
+  qo[0] = w / mag; qo[1] = x / mag; qo[2] = y / mag; qo[3] = z / mag;
+}
+
+// Tree forward kinematics: T_link = T_parent * (O_j * M_j(q))  (urdf.py:3116-3140)
+__device__ void fk_tree(const RobotTable* __restrict__ rb, const float* __restrict__ q, float* T, int stride) {
+  const int nl = rb->n_links;
+  for (int i = 0; i < nl; ++i) {
+    float* Ti = T + (size_t)i * 12 * stride;
+    const int par = rb->parent[i];
+    if (par < 0) {
+#pragma unroll
+      for (int e = 0; e < 12; ++e) Ti[e * stride] = (e == 0 || e == 5 || e == 10) ? 1.f : 0.f;
+      continue;
+    }
+    float child[12];
+    const float* O = rb->origin[i];
+    const int jt = rb->jtype[i];
+    if (jt == 0) {
+#pragma unroll
+      for (int e = 0; e < 12; ++e) child[e] = O[e];
+    } else {
+      const float cfg = rb->qmul[i] * q[rb->qcol[i]] + rb->qoff[i];
+      if (jt == 1) {  // Rodrigues, urdf.py:2447-2462
+        float s, c;
+        sincosf(cfg, &s, &c);
+        const float* ax = rb->axis[i];
+        const float* oo = rb->axis_outer[i];
+        const float omc = 1.0f - c;
+        float M[9];
+        M[0] = (c + oo[0] * omc);
+        M[1] = (oo[1] * omc) + (-ax[2]) * s;
+        M[2] = (oo[2] * omc) + ax[1] * s;
+        M[3] = (oo[3] * omc) + ax[2] * s;
+        M[4] = (c + oo[4] * omc);
+        M[5] = (oo[5] * omc) + (-ax[0]) * s;
+        M[6] = (oo[6] * omc) + (-ax[1]) * s;
+        M[7] = (oo[7] * omc) + ax[0] * s;
+        M[8] = (c + oo[8] * omc);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc)
+            child[r * 4 + cc] = fmaf(O[r * 4 + 2], M[6 + cc], fmaf(O[r * 4 + 1], M[3 + cc], O[r * 4 + 0] * M[cc]));
+          child[r * 4 + 3] = O[r * 4 + 3];
+        }
+      } else {  // prismatic, urdf.py:2388-2390
+        const float* ax = rb->axis[i];
+        const float t0 = ax[0] * cfg, t1 = ax[1] * cfg, t2 = ax[2] * cfg;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          child[r * 4 + 0] = O[r * 4 + 0];
+          child[r * 4 + 1] = O[r * 4 + 1];
+          child[r * 4 + 2] = O[r * 4 + 2];
+          child[r * 4 + 3] = fmaf(O[r * 4 + 2], t2, fmaf(O[r * 4 + 1], t1, O[r * 4 + 0] * t0)) + O[r * 4 + 3];
+        }
+      }
+    }
+    rigid_mul(T + (size_t)par * 12 * stride, stride, child, 1, Ti, stride);
+  }
+}
+
+// keypoints from link transforms: pts = (b2c * [Troot^-1 *] T_link) applied to the link offset
+// (urdf_robot.py:100-104,195-198).  b2c == nullptr -> only_fk variants.
+__device__ void fk_keypoints(const RobotTable* __restrict__ rb, const float* T, int stride, const float* b2c, int root,
+                             float* __restrict__ pts) {
+  float Tinv[12];
+  if (root > 0) rigid_inverse(T + (size_t)rb->kp_link[root] * 12 * stride, stride, Tinv);
+  for (int k = 0; k < rb->nkpt; ++k) {
+    float X[12], Y[12];
+    const float* Tl = T + (size_t)rb->kp_link[k] * 12 * stride;
+    if (root > 0) {
+      rigid_mul(Tinv, 1, Tl, stride, X, 1);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 12; ++e) X[e] = Tl[e * stride];
+    }
+    if (b2c != nullptr) {
+      rigid_mul(b2c, 1, X, 1, Y, 1);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 12; ++e) Y[e] = X[e];
+    }
+    const float o0 = rb->kp_off[k][0], o1 = rb->kp_off[k][1], o2 = rb->kp_off[k][2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+      pts[k * 3 + r] = fmaf(Y[r * 4 + 2], o2, fmaf(Y[r * 4 + 1], o1, Y[r * 4 + 0] * o0)) + Y[r * 4 + 3];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// standalone FK kernel: one thread per sample, link transforms in shared memory ([element][thread] layout)
+// ------------------------------------------------------------------------------------------------------
+constexpr int kFkThreads = 32;
+
+__global__ void __launch_bounds__(kFkThreads) fk_kernel(const FkParams p) {
+  extern __shared__ float fk_smem[];
+  const int b = blockIdx.x * kFkThreads + threadIdx.x;
+  if (b >= p.B) return;
+  const RobotTable* rb = p.robot;
+  float* T = fk_smem + threadIdx.x;
+  float q[kMaxDof];
+  for (int i = 0; i < rb->dof; ++i) q[i] = p.q[(size_t)b * rb->dof + i];
+  fk_tree(rb, q, T, kFkThreads);
+  float b2c[12];
+  if (p.use_b2c) {
+    float R[9];
+    if (p.rot_dim == 6) rot6d_to_rows(p.rot + (size_t)b * 6, R);
+    else quat_to_rows(p.rot + (size_t)b * 4, R);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      b2c[r * 4 + 0] = R[r * 3 + 0];
+      b2c[r * 4 + 1] = R[r * 3 + 1];
+      b2c[r * 4 + 2] = R[r * 3 + 2];
+      b2c[r * 4 + 3] = p.trans[(size_t)b * 3 + r];
+    }
+  }
+  if (p.pts != nullptr) {
+    float pts[kMaxKpt * 3];
+    fk_keypoints(rb, T, kFkThreads, p.use_b2c ? b2c : nullptr, p.root, pts);
+    for (int i = 0; i < rb->nkpt * 3; ++i) p.pts[(size_t)b * rb->nkpt * 3 + i] = pts[i];
+  }
+  if (p.rot_out != nullptr) {  // get_rotation_at_specific_root, urdf_robot.py:113-138: rotation of b2c * T_root
+    float Y[12];
+    rigid_mul(b2c, 1, T + (size_t)rb->kp_link[p.root] * 12 * kFkThreads, kFkThreads, Y, 1);
+    if (p.rot_dim == 6) {
+      for (int i = 0; i < 6; ++i) p.rot_out[(size_t)b * 6 + i] = Y[(i / 3) * 4 + (i % 3)];
+    } else {
+      const float R[9] = {Y[0], Y[1], Y[2], Y[4], Y[5], Y[6], Y[8], Y[9], Y[10]};
+      rows_to_quat(R, p.rot_out + (size_t)b * 4);
+    }
+  }
+}
+
+int launch_fk(const FkParams& p, cudaStream_t s) {
+  HRP_REQUIRE(p.B > 0 && p.q != nullptr && p.robot != nullptr, "bad FK arguments");
+  HRP_REQUIRE(!p.use_b2c || (p.rot != nullptr && p.trans != nullptr), "rotation / translation required");
+  HRP_REQUIRE(!p.use_b2c || p.rot_dim == 6 || p.rot_dim == 4, "rotation must be 6-D or a quaternion");
+  const int smem = kMaxLinks * 12 * kFkThreads * (int)sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(fk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr = true;
+  }
+  fk_kernel<<<(p.B + kFkThreads - 1) / kFkThreads, kFkThreads, smem, s>>>(p);
+  count_launch();
+  HRP_CUDA_CHECK(cudaGetLastError());
+  return HRP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// pinhole projection: uv = (K p)[:2] / (K p)[2]   (transforms.py:7-21)
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void project_point(const float* __restrict__ K, float x, float y, float z, float* uv) {
+  const float v0 = fmaf(K[2], z, fmaf(K[1], y, K[0] * x));
+  const float v1 = fmaf(K[5], z, fmaf(K[4], y, K[3] * x));
+  const float v2 = fmaf(K[8], z, fmaf(K[7], y, K[6] * x));
+  uv[0] = v0 / v2;
+  uv[1] = v1 / v2;
+}
+
+__global__ void project_kernel(const float* __restrict__ K, const float* __restrict__ pts, float* __restrict__ uv, int B,
+                               int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * N) return;
+  const int b = i / N;
+  float k[9];
+#pragma unroll
+  for (int e = 0; e < 9; ++e) k[e] = __ldg(K + (size_t)b * 9 + e);
+  float o[2];
+  project_point(k, pts[(size_t)i * 3], pts[(size_t)i * 3 + 1], pts[(size_t)i * 3 + 2], o);
+  uv[(size_t)i * 2] = o[0];
+  uv[(size_t)i * 2 + 1] = o[1];
+}
+
+int launch_project(const float* K, const float* pts, float* uv, int B, int N, cudaStream_t s) {
+  HRP_REQUIRE(K != nullptr && pts != nullptr && uv != nullptr && B > 0 && N > 0, "bad projection arguments");
+  project_kernel<<<(B * N + 127) / 128, 128, 0, s>>>(K, pts, uv, B, N);
+  count_launch();
+  HRP_CUDA_CHECK(cudaGetLastError());
+  return HRP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// global average pool of a bf16 NHWC tensor -> fp32 (B,C)   (full_net.py:79,294)
+// ------------------------------------------------------------------------------------------------------
+__global__ void pool_mean_kernel(const bf16* __restrict__ in, float* __restrict__ out, int HW, int C) {
+  const int b = blockIdx.y;
+  const int c2 = blockIdx.x * blockDim.x + threadIdx.x;  // channel pair
+  if (c2 * 2 >= C) return;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(in + (size_t)b * HW * C) + c2;
+  float s0 = 0.f, s1 = 0.f;
+  for (int pix = 0; pix < HW; ++pix) {
+    const uint32_t v = __ldg(src + (size_t)pix * (C / 2));
+    s0 += bf16lo_to_f32(v);
+    s1 += bf16hi_to_f32(v);
+  }
+  const float inv = 1.0f / (float)HW;
+  out[(size_t)b * C + 2 * c2] = s0 * inv;
+  out[(size_t)b * C + 2 * c2 + 1] = s1 * inv;
+}
+
+int launch_pool_mean(const bf16* in, float* out, int B, int HW, int C, cudaStream_t s) {
+  HRP_REQUIRE(C % 2 == 0, "pool: even channel count required");
+  dim3 grid((C / 2 + 127) / 128, B);
+  pool_mean_kernel<<<grid, 128, 0, s>>>(in, out, HW, C);
+  count_launch();
+  HRP_CUDA_CHECK(cudaGetLastError());
+  return HRP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// fused head
+// ------------------------------------------------------------------------------------------------------
+constexpr int kHeadMaxThreads = 576;
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct HeadSmem {
+  float part[kHeadMaxThreads][5];
+  float uvd[kMaxKpt][3];
+  float reg_a[kMaxDof + 6];
+  float red[32];
+  float T[kMaxLinks * 12];
+  float pts[kMaxKpt * 3];
+  float depth;
+  int is_last;
+};
+
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < nw; ++i) t += red[i];
+  return t;
+}
+
+__device__ __noinline__ void head_finalize(const HeadParams& p, HeadSmem& sm, int b) {
+  const int tid = threadIdx.x;
+  const int nk = p.nkpt;
+  const RobotTable* rb = p.robot;
+  // (a) merge the per-chunk partial sums of every keypoint -> uvd (integral.py:114-135)
+  if (tid < nk) {
+    float M = -INFINITY;
+    for (int c = 0; c < p.chunks; ++c) M = fmaxf(M, __ldcg(p.partials + (((size_t)b * p.chunks + c) * nk + tid) * 5));
+    float S = 0.f, Sx = 0.f, Sy = 0.f, Sz = 0.f;
+    for (int c = 0; c < p.chunks; ++c) {
+      const float* pp = p.partials + (((size_t)b * p.chunks + c) * nk + tid) * 5;
+      const float f = exp2f(__ldcg(pp) - M);
+      S = fmaf(__ldcg(pp + 1), f, S);
+      Sx = fmaf(__ldcg(pp + 2), f, Sx);
+      Sy = fmaf(__ldcg(pp + 3), f, Sy);
+      Sz = fmaf(__ldcg(pp + 4), f, Sz);
+    }
+    float u = (Sx / S) / 64.0f - 0.5f, v = (Sy / S) / 64.0f - 0.5f, d = (Sz / S) / 64.0f - 0.5f;
+    if (p.fix_root && tid == p.ref_kpt) d = 0.0f;
+    sm.uvd[tid][0] = u;
+    sm.uvd[tid][1] = v;
+    sm.uvd[tid][2] = d;
+  }
+  // (b) root depth (full_net.py:271-287)
+  if (p.depth_in != nullptr) {
+    if (tid == 0) sm.depth = p.depth_in[b];
+  } else {
+    float acc = 0.f;
+    for (int i = tid; i < 2048; i += blockDim.x) acc = fmaf(__ldcg(p.feat + (size_t)b * 2048 + i), __ldg(p.depth_w + i), acc);
+    acc = block_sum(acc, sm.red);
+    if (tid == 0) sm.depth = ((acc + p.depth_b) * p.k_value[b]) / 1000.0f;
+  }
+  // (c) collapsed regressors: a = Wx * xf + c  (rows = dof, then 6)
+  const int dof = rb->dof;
+  if (p.xf != nullptr) {
+    const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+    const float4* x4 = reinterpret_cast<const float4*>(p.xf + (size_t)b * 2048);
+    for (int r = warp; r < dof + 6; r += nw) {
+      const RegressorTable* rt = (r < dof) ? p.reg_pose : p.reg_rot;
+      const int rr = (r < dof) ? r : r - dof;
+      const float4* w4 = reinterpret_cast<const float4*>(rt->Wx + (size_t)rr * 2048);
+      float acc = 0.f;
+      for (int i = lane; i < 512; i += 32) {
+        const float4 a = __ldg(w4 + i);
+        const float4 x = __ldcg(x4 + i);
+        acc = fmaf(a.x, x.x, acc);
+        acc = fmaf(a.y, x.y, acc);
+        acc = fmaf(a.z, x.z, acc);
+        acc = fmaf(a.w, x.w, acc);
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (lane == 0) sm.reg_a[r] = acc + rt->c[rr];
+    }
+  }
+  __syncthreads();
+  if (tid != 0) return;
+  // (d) everything per-sample and tiny: one thread
+  const float* K = p.K + (size_t)b * 9;
+  const float fx = K[0], fy = K[4], cx = K[2], cy = K[5];
+  const float ifx = (float)(1.0 / (double)fx), ify = (float)(1.0 / (double)fy);      // transforms.py:147-162
+  const float icx = (float)(-(double)cx / (double)fx), icy = (float)(-(double)cy / (double)fy);
+  const float z_root = sm.depth;
+  if (p.depth != nullptr) p.depth[b] = z_root;
+  for (int k = 0; k < nk; ++k) {  // uvd_to_xyz, transforms.py:33-73
+    const float u = sm.uvd[k][0], v = sm.uvd[k][1], d = sm.uvd[k][2];
+    const float upx = (u + 0.5f) * p.image_size, vpx = (v + 0.5f) * p.image_size;
+    const float az = d * p.depth_factor + z_root;
+    const float x = (ifx * upx + icx) * az, y = (ify * vpx + icy) * az, zz = az;
+    if (p.uvd != nullptr) {
+      p.uvd[((size_t)b * nk + k) * 3 + 0] = u;
+      p.uvd[((size_t)b * nk + k) * 3 + 1] = v;
+      p.uvd[((size_t)b * nk + k) * 3 + 2] = d;
+    }
+    if (p.xyz_int != nullptr) {
+      p.xyz_int[((size_t)b * nk + k) * 3 + 0] = x;
+      p.xyz_int[((size_t)b * nk + k) * 3 + 1] = y;
+      p.xyz_int[((size_t)b * nk + k) * 3 + 2] = zz;
+    }
+    if (p.uv_int != nullptr) project_point(K, x, y, zz, p.uv_int + ((size_t)b * nk + k) * 2);
+  }
+  // root uv and translation (full_net.py:298,305; transforms.py:133-143)
+  const float ru = (sm.uvd[p.ref_kpt][0] + 0.5f) * p.image_size, rv = (sm.uvd[p.ref_kpt][1] + 0.5f) * p.image_size;
+  float tr[3];
+  tr[0] = ifx * (ru * z_root) + icx * z_root;
+  tr[1] = ify * (rv * z_root) + icy * z_root;
+  tr[2] = z_root;
+  if (p.root_uv != nullptr) {
+    p.root_uv[(size_t)b * 2] = ru;
+    p.root_uv[(size_t)b * 2 + 1] = rv;
+  }
+  if (p.trans != nullptr) {
+    p.trans[(size_t)b * 3] = tr[0];
+    p.trans[(size_t)b * 3 + 1] = tr[1];
+    p.trans[(size_t)b * 3 + 2] = tr[2];
+  }
+  if (rb == nullptr) return;
+  // pose / rot (full_net.py:308-378)
+  float pose[kMaxDof], rot[6];
+  if (p.xf != nullptr) {
+    for (int i = 0; i < dof; ++i) pose[i] = p.init_pose[(p.init_batched ? (size_t)b * dof : 0) + i];
+    for (int i = 0; i < 6; ++i) rot[i] = p.init_rot[(p.init_batched ? (size_t)b * 6 : 0) + i];
+    for (int it = 0; it < p.reg_pose->n_iter; ++it) {
+      float nx[kMaxDof];
+      for (int i = 0; i < dof; ++i) {
+        float dlt = sm.reg_a[i];
+        for (int j = 0; j < dof; ++j) dlt = fmaf(p.reg_pose->A[i][j], pose[j], dlt);
+        nx[i] = pose[i] + dlt;
+      }
+      for (int i = 0; i < dof; ++i) pose[i] = nx[i];
+    }
+    for (int it = 0; it < p.reg_rot->n_iter; ++it) {
+      float nx[6];
+      for (int i = 0; i < 6; ++i) {
+        float dlt = sm.reg_a[dof + i];
+        for (int j = 0; j < 6; ++j) dlt = fmaf(p.reg_rot->A[i][j], rot[j], dlt);
+        nx[i] = rot[i] + dlt;
+      }
+      for (int i = 0; i < 6; ++i) rot[i] = nx[i];
+    }
+  } else if (p.pose_in != nullptr) {
+    for (int i = 0; i < dof; ++i) pose[i] = p.pose_in[(size_t)b * dof + i];
+    for (int i = 0; i < 6; ++i) rot[i] = p.rot_in[(size_t)b * 6 + i];
+  } else {
+    return;
+  }
+  if (p.pose != nullptr)
+    for (int i = 0; i < dof; ++i) p.pose[(size_t)b * dof + i] = pose[i];
+  if (p.rot != nullptr)
+    for (int i = 0; i < 6; ++i) p.rot[(size_t)b * 6 + i] = rot[i];
+  // FK (full_net.py:380-383)
+  fk_tree(rb, pose, sm.T, 1);
+  float R[9], b2c[12];
+  rot6d_to_rows(rot, R);
+  for (int r = 0; r < 3; ++r) {
+    b2c[r * 4 + 0] = R[r * 3 + 0];
+    b2c[r * 4 + 1] = R[r * 3 + 1];
+    b2c[r * 4 + 2] = R[r * 3 + 2];
+    b2c[r * 4 + 3] = tr[r];
+  }
+  fk_keypoints(rb, sm.T, 1, b2c, p.ref_kpt, sm.pts);
+  for (int k = 0; k < nk; ++k) {
+    if (p.xyz_fk != nullptr)
+      for (int r = 0; r < 3; ++r) p.xyz_fk[((size_t)b * nk + k) * 3 + r] = sm.pts[k * 3 + r];
+    if (p.uv_fk != nullptr)
+      project_point(K, sm.pts[k * 3], sm.pts[k * 3 + 1], sm.pts[k * 3 + 2], p.uv_fk + ((size_t)b * nk + k) * 2);
+  }
+}
+
+__global__ void __launch_bounds__(kHeadMaxThreads) head_kernel(const __grid_constant__ HeadParams p) {
+  __shared__ HeadSmem sm;
+  const int C = p.nkpt * 64;
+  const int vpp = C >> 3;                 // 16-byte vectors per pixel
+  const int ppi = blockDim.x / vpp;       // pixels per iteration
+  const int b = blockIdx.x / p.chunks, chunk = blockIdx.x - b * p.chunks;
+  const int ppc = 4096 / p.chunks;        // pixels per chunk
+  const int v = threadIdx.x % vpp, slot = threadIdx.x / vpp;
+  const float dbase = (float)((v & 7) * 8);
+  const uint4* base = reinterpret_cast<const uint4*>(p.heatmap + ((size_t)b * 4096 + (size_t)chunk * ppc) * C) + v;
+
+  float m = -INFINITY, S = 0.f, Sx = 0.f, Sy = 0.f, Sz = 0.f;
+  constexpr int UNROLL = 4;
+  for (int pix0 = slot; pix0 < ppc; pix0 += ppi * UNROLL) {
+    uint4 raw[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int pix = pix0 + u * ppi;
+      if (pix < ppc) raw[u] = ld_stream(base + (size_t)pix * vpp);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int pix = pix0 + u * ppi;
+      if (pix >= ppc) continue;
+      const int gp = chunk * ppc + pix;
+      const float fw = (float)(gp & 63), fh = (float)(gp >> 6);
+      float t[8];
+      t[0] = bf16lo_to_f32(raw[u].x) * kLog2e; t[1] = bf16hi_to_f32(raw[u].x) * kLog2e;
+      t[2] = bf16lo_to_f32(raw[u].y) * kLog2e; t[3] = bf16hi_to_f32(raw[u].y) * kLog2e;
+      t[4] = bf16lo_to_f32(raw[u].z) * kLog2e; t[5] = bf16hi_to_f32(raw[u].z) * kLog2e;
+      t[6] = bf16lo_to_f32(raw[u].w) * kLog2e; t[7] = bf16hi_to_f32(raw[u].w) * kLog2e;
+      const float vmax = fmaxf(fmaxf(fmaxf(t[0], t[1]), fmaxf(t[2], t[3])), fmaxf(fmaxf(t[4], t[5]), fmaxf(t[6], t[7])));
+      if (vmax > m) {  // online-softmax rescale (rare after the first few pixels)
+        const float f = exp2f(m - vmax);
+        S *= f; Sx *= f; Sy *= f; Sz *= f;
+        m = vmax;
+      }
+      float s8 = 0.f, sz8 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float e = exp2f(t[i] - m);
+        s8 += e;
+        sz8 = fmaf(e, dbase + (float)i, sz8);
+      }
+      S += s8;
+      Sx = fmaf(s8, fw, Sx);
+      Sy = fmaf(s8, fh, Sy);
+      Sz += sz8;
+    }
+  }
+  sm.part[threadIdx.x][0] = m;
+  sm.part[threadIdx.x][1] = S;
+  sm.part[threadIdx.x][2] = Sx;
+  sm.part[threadIdx.x][3] = Sy;
+  sm.part[threadIdx.x][4] = Sz;
+  __syncthreads();
+  if ((int)threadIdx.x < p.nkpt) {  // merge the 8*ppi contributors of keypoint k
+    const int k = threadIdx.x;
+    float M = -INFINITY;
+    for (int s = 0; s < ppi; ++s)
+      for (int j = 0; j < 8; ++j) M = fmaxf(M, sm.part[s * vpp + k * 8 + j][0]);
+    float a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+    for (int s = 0; s < ppi; ++s)
+      for (int j = 0; j < 8; ++j) {
+        const float* pp = sm.part[s * vpp + k * 8 + j];
+        const float f = (pp[0] == -INFINITY) ? 0.f : exp2f(pp[0] - M);
+        a1 = fmaf(pp[1], f, a1);
+        a2 = fmaf(pp[2], f, a2);
+        a3 = fmaf(pp[3], f, a3);
+        a4 = fmaf(pp[4], f, a4);
+      }
+    float* dst = p.partials + (((size_t)b * p.chunks + chunk) * p.nkpt + k) * 5;
+    __stcg(dst, M);
+    __stcg(dst + 1, a1);
+    __stcg(dst + 2, a2);
+    __stcg(dst + 3, a3);
+    __stcg(dst + 4, a4);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int ticket = atomicAdd(p.counters + b, 1u);
+    sm.is_last = (ticket == (unsigned int)p.chunks - 1u);
+    if (sm.is_last) p.counters[b] = 0u;  // self-reset for the next launch
+  }
+  __syncthreads();
+  if (!sm.is_last) return;
+  __threadfence();
+  head_finalize(p, sm, b);
+}
+
+int head_default_chunks(int B) {
+  // enough CTAs to cover 148 SMs x ~8 resident CTAs a few times over, power of two <= 64
+  int chunks = 64;
+  while (chunks > 4 && (long)B * chunks > 148L * 8 * 4) chunks >>= 1;
+  return chunks;
+}
+
+size_t head_partials_elems(int B, int nkpt, int chunks) { return (size_t)B * chunks * nkpt * 5; }
+
+int launch_head(const HeadParams& p, cudaStream_t s) {
+  HRP_REQUIRE(p.B > 0 && p.nkpt > 0 && p.nkpt <= kMaxKpt, "bad head dims");
+  HRP_REQUIRE(p.heatmap != nullptr && p.K != nullptr && p.partials != nullptr && p.counters != nullptr,
+              "head: null tensor");
+  HRP_REQUIRE(p.chunks > 0 && 4096 % p.chunks == 0, "chunks must divide 4096");
+  HRP_REQUIRE(p.depth_in != nullptr || (p.feat != nullptr && p.depth_w != nullptr && p.k_value != nullptr),
+              "head: a root-depth source is required");
+  HRP_REQUIRE(p.ref_kpt >= 0 && p.ref_kpt < p.nkpt, "reference keypoint out of range");
+  const int vpp = p.nkpt * 8;
+  int ppi = 1;
+  while ((vpp * ppi) % 32 != 0 || vpp * ppi < 192) ++ppi;
+  const int threads = vpp * ppi;
+  HRP_REQUIRE(threads <= kHeadMaxThreads, "too many keypoints for the head kernel");
+  head_kernel<<<p.B * p.chunks, threads, 0, s>>>(p);
+  count_launch();
+  HRP_CUDA_CHECK(cudaGetLastError());
+  return HRP_OK;
+}
+
+}  // namespace hrp

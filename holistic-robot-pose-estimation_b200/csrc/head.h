@@ -1,0 +1,92 @@
+// Head of the HoRoPose forward: heatmap soft-argmax, uvd->xyz, root translation, collapsed pose/rot regressors,
+// URDF forward kinematics and pinhole projection (reference: lib/utils/integral.py:97-145,
+// lib/utils/transforms.py:11-21,33-73,133-162, lib/models/full_net.py:271-287,305-383,
+// lib/utils/urdf_robot.py:82-199, lib/utils/urdfpytorch/urdf.py:2344-2396,2427-2462,3061-3149).
+#pragma once
+#include "hrp_common.cuh"
+
+namespace hrp {
+
+constexpr int kMaxLinks = 32;
+constexpr int kMaxKpt = 32;
+constexpr int kMaxDof = 16;
+
+// Flat kinematic table (links in parent-before-child order, pruned to the ancestors of the keypoint links).
+struct RobotTable {
+  int n_links, nkpt, dof, pad0;
+  int parent[kMaxLinks];      // -1 for the base
+  int jtype[kMaxLinks];       // 0 fixed, 1 revolute/continuous, 2 prismatic
+  int qcol[kMaxLinks];        // -1: joint not driven
+  float qmul[kMaxLinks], qoff[kMaxLinks];
+  float origin[kMaxLinks][12];  // rows 0..2 of the 4x4 joint origin, fp32 (urdf.py:2383 casts to q's dtype)
+  float axis[kMaxLinks][3];     // unit axis (urdf.py:2169,2446)
+  float axis_outer[kMaxLinks][9];  // outer(axis,axis) computed in fp64 then cast (urdf.py:2453-2456)
+  int kp_link[kMaxKpt];
+  float kp_off[kMaxKpt][3];
+};
+
+// Collapsed iterative regressor (full_net.py:318-331,365-378 are affine maps: no activation, dropout = identity):
+//   delta(p) = Wx * xf + A * p + c ;   p <- p + delta(p)   n_iter times.
+struct RegressorTable {
+  int dim, n_iter;
+  const float* Wx;   // device [dim][2048]
+  float A[kMaxDof][kMaxDof];
+  float c[kMaxDof];
+};
+
+struct HeadParams {
+  int B, nkpt, ref_kpt, fix_root;
+  float image_size, depth_factor;
+  // soft-argmax input: bf16 heatmap logits, pixel-major (B, 64*64, nkpt*64): channel = k*64 + d
+  const bf16* heatmap;
+  int chunks;               // CTAs per image
+  float* partials;          // workspace (B, chunks, nkpt, 5)
+  unsigned int* counters;   // workspace (B) zero-initialised; self-resetting
+  const float* K;           // (B,3,3)
+  // root depth: either depth_in (B) [m], or gamma = depth_w . feat + depth_b ; depth = gamma*k_value/1000
+  const float* depth_in;
+  const float* feat;        // (B,2048) fp32 pooled HRNet feature
+  const float* depth_w;     // (2048)
+  float depth_b;
+  const float* k_value;     // (B)
+  // regressors: either pose_in/rot_in, or xf (B,2048) with the collapsed tables
+  const float* pose_in;     // (B,dof)
+  const float* rot_in;      // (B,6)
+  const float* xf;          // (B,2048) fp32 pooled ResNet feature
+  const float* init_pose;   // (dof) or (B,dof) when init_batched
+  const float* init_rot;    // (6)
+  int init_batched;
+  const RobotTable* robot;  // device
+  const RegressorTable* reg_pose;  // device
+  const RegressorTable* reg_rot;   // device
+  // outputs (fp32)
+  float* pose;      // (B,dof)
+  float* rot;       // (B,6)
+  float* trans;     // (B,3)
+  float* root_uv;   // (B,2)
+  float* depth;     // (B,1)
+  float* uvd;       // (B,nkpt,3)
+  float* xyz_int;   // (B,nkpt,3)
+  float* xyz_fk;    // (B,nkpt,3)
+  float* uv_int;    // (B,nkpt,2) optional projections with K (scripts/test.py:179)
+  float* uv_fk;     // (B,nkpt,2) optional
+};
+
+int launch_head(const HeadParams& p, cudaStream_t s);
+size_t head_partials_elems(int B, int nkpt, int chunks);
+int head_default_chunks(int B);
+
+struct FkParams {
+  int B, rot_dim, root, use_b2c;
+  const float* q;      // (B,dof)
+  const float* rot;    // (B,rot_dim) or null
+  const float* trans;  // (B,3) or null
+  const RobotTable* robot;
+  float* pts;          // (B,nkpt,3) or null
+  float* rot_out;      // (B,rot_dim) rotation at `root` (get_rotation_at_specific_root) or null
+};
+int launch_fk(const FkParams& p, cudaStream_t s);
+int launch_project(const float* K, const float* pts, float* uv, int B, int N, cudaStream_t s);
+int launch_pool_mean(const bf16* in, float* out, int B, int HW, int C, cudaStream_t s);
+
+}  // namespace hrp

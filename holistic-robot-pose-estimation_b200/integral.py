@@ -1,0 +1,102 @@
+"""Drop-in for `HeatmapIntegralPose` (lib/utils/integral.py:76-186) on top of the fused head kernel.
+
+forward(out, K=..., root_trans=...) takes the reference's heatmap-logit tensor (B, nkpt*64, 64, 64) (channel =
+k*64 + d) and returns (pred_uvd_jts (B,nkpt,3), pred_xyz_jts (B,nkpt,3)).  The logits are bridged to the kernel's
+pixel-major bf16 layout (one extra pass; inside the full model the final conv writes that layout directly).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib, ops
+from ._lib import check
+
+
+class HeadArgs(C.Structure):
+    _fields_ = [("B", C.c_int32), ("nkpt", C.c_int32), ("ref_kpt", C.c_int32), ("fix_root", C.c_int32),
+                ("image_size", C.c_float), ("depth_factor", C.c_float),
+                ("heatmap", C.c_void_p), ("K", C.c_void_p), ("root_depth", C.c_void_p), ("robot", C.c_void_p),
+                ("pose", C.c_void_p), ("rot", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+                ("uvd", C.c_void_p), ("xyz_int", C.c_void_p), ("root_uv", C.c_void_p), ("trans", C.c_void_p),
+                ("xyz_fk", C.c_void_p), ("uv_int", C.c_void_p), ("uv_fk", C.c_void_p)]
+
+
+_workspaces = {}
+
+
+def _workspace(device, B, nkpt):
+    need = C.c_int64(0)
+    check(_lib.lib().hrp_head_workspace_bytes(B, nkpt, C.byref(need)))
+    key = (device, B, nkpt)
+    ws = _workspaces.get(key)
+    if ws is None:
+        ws = torch.zeros(need.value, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def run_head(heatmap_nhwc, K, root_depth, *, nkpt, ref_kpt, fix_root=True, image_size=256.0, depth_factor=1.3,
+             robot=None, pose=None, rot=None, want_uv=False):
+    """heatmap_nhwc: (B,64,64,nkpt*64) bf16 CUDA.  Returns dict of fp32 CUDA tensors."""
+    assert heatmap_nhwc.is_cuda and heatmap_nhwc.dtype == torch.bfloat16 and heatmap_nhwc.is_contiguous()
+    B = heatmap_nhwc.shape[0]
+    dev = heatmap_nhwc.device
+    K = K.detach().to(device=dev, dtype=torch.float32).contiguous()
+    root_depth = root_depth.detach().to(device=dev, dtype=torch.float32).contiguous().view(-1)
+    out = {n: torch.empty(B, *shape, dtype=torch.float32, device=dev) for n, shape in
+           (("uvd", (nkpt, 3)), ("xyz_int", (nkpt, 3)), ("root_uv", (2,)), ("trans", (3,)))}
+    a = HeadArgs()
+    a.B, a.nkpt, a.ref_kpt, a.fix_root = B, nkpt, ref_kpt, int(fix_root)
+    a.image_size, a.depth_factor = float(image_size), float(depth_factor)
+    a.heatmap, a.K, a.root_depth = heatmap_nhwc.data_ptr(), K.data_ptr(), root_depth.data_ptr()
+    keep = [K, root_depth]
+    if robot is not None and pose is not None:
+        pose = pose.detach().to(device=dev, dtype=torch.float32).contiguous()
+        rot = rot.detach().to(device=dev, dtype=torch.float32).contiguous()
+        keep += [pose, rot]
+        a.robot, a.pose, a.rot = robot.handle(), pose.data_ptr(), rot.data_ptr()
+        out["xyz_fk"] = torch.empty(B, nkpt, 3, dtype=torch.float32, device=dev)
+        a.xyz_fk = out["xyz_fk"].data_ptr()
+        if want_uv:
+            out["uv_fk"] = torch.empty(B, nkpt, 2, dtype=torch.float32, device=dev)
+            a.uv_fk = out["uv_fk"].data_ptr()
+    if want_uv:
+        out["uv_int"] = torch.empty(B, nkpt, 2, dtype=torch.float32, device=dev)
+        a.uv_int = out["uv_int"].data_ptr()
+    ws = _workspace(dev, B, nkpt)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    a.uvd, a.xyz_int = out["uvd"].data_ptr(), out["xyz_int"].data_ptr()
+    a.root_uv, a.trans = out["root_uv"].data_ptr(), out["trans"].data_ptr()
+    with torch.cuda.device(dev):
+        check(_lib.lib().hrp_head(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return out
+
+
+class HeatmapIntegralPose(torch.nn.Module):
+    def __init__(self, backbone, **kwargs):
+        super().__init__()
+        self.backbone_name = backbone
+        self.norm_type = kwargs["norm_type"]
+        if self.norm_type != "softmax":
+            raise NotImplementedError("only norm_type='softmax' is on the hot path (integral.py:45-54)")
+        self.num_joints = kwargs["num_joints"]
+        self.depth_dim, self.height_dim, self.width_dim = kwargs["depth_dim"], kwargs["height_dim"], kwargs["width_dim"]
+        if (self.depth_dim, self.height_dim, self.width_dim) != (64, 64, 64):
+            raise NotImplementedError("the fused head is specialised for 64x64x64 heatmaps (full_net.py:64-66)")
+        self.rootid = kwargs.get("rootid", 0)
+        self.fixroot = kwargs.get("fixroot", False)
+        bbox_3d_shape = kwargs.get("bbox_3d_shape", (2300, 2300, 2300))
+        self.bbox_3d_shape = torch.tensor(bbox_3d_shape).float()
+        self.depth_factor = self.bbox_3d_shape[2] * 1e-3   # integral.py:91-93 (an fp32 tensor product)
+        self.image_size = kwargs["image_size"]
+
+    def forward(self, out, flip_test=False, **kwargs):
+        K, root_trans = kwargs["K"], kwargs["root_trans"]
+        if not out.is_cuda:
+            raise _lib.HrpError("horopose_b200 has no CPU path: tensors must live on a CUDA device")
+        hm = ops.nchw_to_nhwc_bf16(out.detach().float().contiguous(), cpad=out.shape[1])
+        r = run_head(hm, K, root_trans[:, 2].to(out.device), nkpt=self.num_joints, ref_kpt=self.rootid,
+                     fix_root=self.fixroot, image_size=float(self.image_size), depth_factor=float(self.depth_factor))
+        return r["uvd"], r["xyz_int"]

@@ -93,6 +93,70 @@ int hrp_nchw_f32_to_nhwc_bf16(const float* in, void* out, int32_t B, int32_t C, 
 int hrp_nhwc_bf16_to_nchw_f32(const void* in, float* out, int32_t B, int32_t C, int32_t H, int32_t W,
                               int32_t Cpad, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Robot kinematic table + forward kinematics + projection.
+ * Replaces URDFRobot.get_keypoints / get_keypoints_root / get_keypoints_only_fk[_at_specific_root] /
+ * get_rotation_at_specific_root / get_TWL (lib/utils/urdf_robot.py:82-199), URDF.link_fk_batch
+ * (lib/utils/urdfpytorch/urdf.py:3061-3149, Joint.get_child_poses :2344-2396, _rotation_matrices :2427-2462)
+ * and point_projection_from_3d[_tensor] (lib/utils/transforms.py:7-21).
+ * The host parses the URDF (host logic, no arithmetic) and hands over a flat table: links in
+ * parent-before-child order, pruned to the ancestors of the keypoint links.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct hrp_robot hrp_robot;
+
+typedef struct hrp_link_row {
+  int32_t parent;      /* index of the parent link, -1 for the base */
+  int32_t jtype;       /* 0 fixed, 1 revolute/continuous, 2 prismatic */
+  int32_t qcol;        /* column of q driving the joint (mimic joints point at their master), -1 if none */
+  int32_t pad;
+  double qmul, qoff;   /* cfg = qmul * q[qcol] + qoff */
+  double origin[16];   /* 4x4 joint origin, row-major, float64 as parsed from the URDF */
+  double axis[3];      /* unit joint axis */
+} hrp_link_row;
+
+int hrp_robot_create(const hrp_link_row* rows, int32_t n_links, const int32_t* kp_link, const double* kp_offset,
+                     int32_t nkpt, int32_t dof, hrp_robot** out);
+void hrp_robot_destroy(hrp_robot* robot);
+/* q (B,dof); rot (B,rot_dim), rot_dim 6 (Zhou et al.) or 4 (w,x,y,z); trans (B,3); all device fp32.
+ * use_b2c=0 -> "only_fk" variants (rot/trans ignored).  root>0 -> keypoints relative to keypoint `root`
+ * (get_keypoints_root).  out_xyz (B,nkpt,3) and/or out_rot (B,rot_dim) (get_rotation_at_specific_root). */
+int hrp_fk(hrp_robot* robot, const float* q, const float* rot, int32_t rot_dim, const float* trans, int32_t root,
+           int32_t use_b2c, float* out_xyz, float* out_rot, int32_t B, void* stream);
+/* K (B,3,3), pts (B,N,3) -> uv (B,N,2), device fp32 */
+int hrp_project(const float* K, const float* pts, float* uv, int32_t B, int32_t N, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused head: 3-D heatmap soft-argmax -> uvd -> xyz, root translation, FK and projections in one kernel.
+ * Replaces HeatmapIntegralPose.forward (lib/utils/integral.py:97-145), uvd_to_xyz / uvz2xyz_singlepoint /
+ * get_intrinsic_matrix_batch (lib/utils/transforms.py:33-73,133-162) and the FK call of
+ * RootNetwithRegInt.forward (lib/models/full_net.py:297-305,380-383).
+ * heatmap: device bf16 logits, pixel-major (B, 64*64, nkpt*64) with channel = k*64 + d -- the layout the final
+ * 1x1 convolution writes (use hrp_nchw_f32_to_nhwc_bf16 to bridge from the reference's NCHW fp32 tensor).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct hrp_head_args {
+  int32_t B, nkpt, ref_kpt, fix_root;
+  float image_size;        /* 256 */
+  float depth_factor;      /* bbox_3d_shape[2] * 1e-3 */
+  const void* heatmap;
+  const float* K;          /* (B,3,3) */
+  const float* root_depth; /* (B) metres */
+  const hrp_robot* robot;  /* may be NULL: no FK outputs */
+  const float* pose;       /* (B,dof) joint angles for the FK, or NULL */
+  const float* rot;        /* (B,6) */
+  void* workspace;         /* device, hrp_head_workspace_bytes(), zero-initialised once by the caller */
+  int64_t workspace_bytes;
+  float* uvd;              /* (B,nkpt,3) */
+  float* xyz_int;          /* (B,nkpt,3) */
+  float* root_uv;          /* (B,2) */
+  float* trans;            /* (B,3) */
+  float* xyz_fk;           /* (B,nkpt,3) or NULL */
+  float* uv_int;           /* (B,nkpt,2) or NULL: projection of xyz_int with K */
+  float* uv_fk;            /* (B,nkpt,2) or NULL */
+} hrp_head_args;
+
+int hrp_head_workspace_bytes(int32_t B, int32_t nkpt, int64_t* bytes);
+int hrp_head(const hrp_head_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,140 @@
+"""CUDA head path (FK, projection, fused soft-argmax head) vs the committed reference outputs and the CPU oracle."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests" / "golden"))
+pytestmark = pytest.mark.gpu
+GOLDEN = ROOT / "tests" / "golden"
+ROBOT_TYPES = ["panda", "kuka", "baxter"]
+
+
+def _rel(a, b):
+    """max |a-b| / max |b| -- the 'relative' of the north-star FK / projection bar (1e-5)."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-12)
+
+
+@pytest.mark.parametrize("rt", ROBOT_TYPES)
+def test_fk_and_projection_vs_reference_golden(rt, hrp_lib):
+    """FK + projection in fp32 within 1e-5 relative of the reference's own outputs (BASELINE.json north_star)."""
+    from horopose_b200 import synth
+    from horopose_b200.robot import URDFRobot, point_projection_from_3d, point_projection_from_3d_tensor
+    g = np.load(GOLDEN / f"fk_{rt}.npz")
+    robot = URDFRobot(rt)
+    assert robot.link_names == list(g["link_names"])
+    np.testing.assert_allclose(robot.offsets.squeeze(0).squeeze(-1).numpy(), g["offsets"], rtol=1e-7)
+    q, rot, trans = (t.cuda() for t in synth.fk_inputs(rt, 64))
+    TOL = 1e-5
+    assert _rel(robot.get_keypoints(q, rot, trans).cpu(), g["keypoints"]) < TOL
+    assert _rel(robot.get_keypoints_only_fk(q).cpu(), g["keypoints_only_fk"]) < TOL
+    nk = len(robot.link_names)
+    for root in sorted({0, 3, nk - 1}):
+        assert _rel(robot.get_keypoints_root(q, rot, trans, root=root).cpu(), g[f"keypoints_root{root}"]) < TOL, root
+        assert _rel(robot.get_keypoints_only_fk_at_specific_root(q, root=root).cpu(), g[f"only_fk_root{root}"]) < TOL
+        assert _rel(robot.get_rotation_at_specific_root(q, rot, trans, root=root).cpu(), g[f"rotation_root{root}"]) < TOL
+    quat = synth.sym_uniform("fk_quat_" + rt, (64, 4), 1.0, 2).cuda()
+    assert _rel(robot.get_keypoints(q, quat, trans).cpu(), g["keypoints_quat"]) < TOL
+    # projection: keypoints with z < 0.2 m are excluded (pure conditioning)
+    _, _, _, K = synth.inputs(64, seed=5)
+    pts = torch.from_numpy(g["keypoints"])
+    uv = point_projection_from_3d_tensor(K.cuda(), pts.cuda()).cpu().numpy()
+    ok = g["keypoints"][..., 2] > 0.2
+    assert ok.sum() > 0.5 * ok.size
+    assert _rel(uv[ok], g["proj_tensor"][ok]) < TOL
+    uv_np = point_projection_from_3d(K.numpy(), g["keypoints"])
+    assert _rel(uv_np[ok], g["proj_numpy"][ok]) < TOL
+    # properties: root=0 equals get_keypoints; the root keypoint maps to the translation
+    assert torch.equal(robot.get_keypoints_root(q, rot, trans, root=0), robot.get_keypoints(q, rot, trans))
+    kr = robot.get_keypoints_root(q, rot, trans, root=3)
+    np.testing.assert_allclose(kr[:, 3].cpu().numpy(), trans.cpu().numpy(), atol=2e-6)
+
+
+def test_fk_large_batch_vs_oracle(hrp_lib):
+    """B=4096 (the FK micro-KAT size) against the oracle; ragged tail (B not a multiple of the CTA size)."""
+    from horopose_b200 import synth
+    from horopose_b200.robot import URDFRobot
+    from oracle import horopose_oracle as O
+    for rt, B in (("panda", 4096), ("baxter", 1000 + 13)):
+        q, rot, trans = synth.fk_inputs(rt, B, seed=21)
+        robot = URDFRobot(rt)
+        ref = O.OracleRobot(rt, str(synth.URDF_PATHS[rt])).get_keypoints_root(q, rot, trans, root=3)
+        got = robot.get_keypoints_root(q.cuda(), rot.cuda(), trans.cuda(), root=3).cpu()
+        assert _rel(got, ref) < 1e-5
+
+
+def test_fk_rejects_unsupported(hrp_lib):
+    from horopose_b200 import _lib, synth
+    from horopose_b200.robot import URDFRobot
+    robot = URDFRobot("panda")
+    q, rot, trans = (t.cuda() for t in synth.fk_inputs("panda", 4))
+    with pytest.raises(_lib.HrpError):
+        robot.get_keypoints(q, torch.zeros(4, 9).cuda(), trans)   # 9-D SVD rotations are outside the hot path
+    with pytest.raises(_lib.HrpError):
+        robot.get_keypoints(q.cpu(), rot.cpu(), trans.cpu())       # no CPU fallback
+
+
+@pytest.mark.parametrize("rt", ROBOT_TYPES)
+def test_heatmap_integral_vs_reference_golden(rt, hrp_lib):
+    """HeatmapIntegralPose drop-in: bf16 heatmap hand-off, fp32 accumulation (SURVEY.md section 9 finding 3)."""
+    from horopose_b200 import arch, synth
+    from horopose_b200.integral import HeatmapIntegralPose
+    from make_golden import HEATMAP_STRESS_GAIN, heatmap_logits
+    g = np.load(GOLDEN / f"integral_{rt}.npz")
+    dof, nkpt, ref = arch.ROBOTS[rt]
+    layer = HeatmapIntegralPose(backbone="resnet50", num_joints=nkpt, depth_dim=64, height_dim=64, width_dim=64,
+                                norm_type="softmax", image_size=256.0, bbox_3d_shape=[1300, 1300, 1300], rootid=ref,
+                                fixroot=True)
+    for tag, gain in (("", 1.0), ("_peaky", HEATMAP_STRESS_GAIN)):
+        hm = heatmap_logits(rt, 2, gain=gain)
+        _, _, k, K = synth.inputs(2, seed=13)
+        root_trans = torch.zeros(2, 3)
+        root_trans[:, 2] = synth.range_uniform("root_z", (2,), 0.8, 2.5, 13)
+        uvd, xyz = layer(hm.cuda(), root_trans=root_trans.cuda(), K=K.cuda())
+        # the logits are rounded to bf16 on hand-off: 0.02 px / 0.1 mm budget (measured ~7e-4 px in the survey)
+        assert np.abs(uvd.cpu().numpy() - g["uvd" + tag]).max() * 256 < 0.02, tag
+        assert np.abs(xyz.cpu().numpy() - g["xyz" + tag]).max() < 1e-4, tag
+        assert float(uvd[:, ref, 2].abs().max()) == 0.0
+
+
+def test_fused_head_exact_on_bf16_logits(hrp_lib):
+    """With logits that are exactly representable in bf16 the fused head must match the fp32 oracle to fp32
+    round-off, including root translation, FK and the projections (all fp32 islands)."""
+    from horopose_b200 import arch, ops, synth
+    from horopose_b200.integral import run_head
+    from horopose_b200.robot import URDFRobot
+    from make_golden import heatmap_logits
+    from oracle import horopose_oracle as O
+    for rt, B in (("panda", 3), ("baxter", 2)):
+        dof, nkpt, ref = arch.ROBOTS[rt]
+        hm = heatmap_logits(rt, B, seed=9, gain=2.0).to(torch.bfloat16).float()
+        _, _, k, K = synth.inputs(B, seed=17)
+        depth = synth.range_uniform("hz", (B,), 0.8, 2.5, 17)
+        q, rot, _ = synth.fk_inputs(rt, B, seed=17)
+        root_trans = torch.zeros(B, 3)
+        root_trans[:, 2] = depth
+        uvd_ref, xyz_ref = O.heatmap_integral(hm, nkpt, K, root_trans, ref)
+        root_uv_ref = (uvd_ref[:, ref, :2] + 0.5) * 256.0
+        trans_ref = O.uvz2xyz_singlepoint(root_uv_ref, depth.view(-1, 1), K)
+        orob = O.OracleRobot(rt, str(synth.URDF_PATHS[rt]))
+        fk_ref = orob.get_keypoints_root(q, rot, trans_ref, root=ref) if ref else orob.get_keypoints(q, rot, trans_ref)
+        hm_nhwc = ops.nchw_to_nhwc_bf16(hm.cuda(), cpad=nkpt * 64)
+        r = run_head(hm_nhwc, K.cuda(), depth.cuda(), nkpt=nkpt, ref_kpt=ref, robot=URDFRobot(rt), pose=q.cuda(),
+                     rot=rot.cuda(), want_uv=True)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(r["uvd"].cpu().numpy(), uvd_ref.numpy(), atol=3e-6)
+        np.testing.assert_allclose(r["xyz_int"].cpu().numpy(), xyz_ref.numpy(), atol=1e-5)
+        np.testing.assert_allclose(r["root_uv"].cpu().numpy(), root_uv_ref.numpy(), atol=1e-3)
+        np.testing.assert_allclose(r["trans"].cpu().numpy(), trans_ref.numpy(), atol=1e-5)
+        np.testing.assert_allclose(r["xyz_fk"].cpu().numpy(), fk_ref.numpy(), atol=1e-5)
+        uv_int_ref = O.point_projection_from_3d(K, xyz_ref)
+        np.testing.assert_allclose(r["uv_int"].cpu().numpy(), uv_int_ref.numpy(), atol=2e-3)
+        # run twice: the per-image completion counters must self-reset
+        r2 = run_head(hm_nhwc, K.cuda(), depth.cuda(), nkpt=nkpt, ref_kpt=ref, robot=URDFRobot(rt), pose=q.cuda(),
+                      rot=rot.cuda())
+        assert torch.equal(r2["uvd"], r["uvd"])
