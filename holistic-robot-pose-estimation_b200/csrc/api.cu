@@ -187,6 +187,14 @@ int hrp_robot_create(const hrp_link_row* rows, int32_t n_links, const int32_t* k
   return HRP_OK;
 }
 
+// internal accessors for model.cu (not part of include/hrp.h)
+const void* hrp_robot_device_table(const hrp_robot* robot) { return robot ? robot->dev : nullptr; }
+int hrp_robot_dims(const hrp_robot* robot, int32_t* nkpt, int32_t* dof) {
+  *nkpt = robot->host.nkpt;
+  *dof = robot->host.dof;
+  return HRP_OK;
+}
+
 void hrp_robot_destroy(hrp_robot* robot) {
   if (robot == nullptr) return;
   if (robot->dev) cudaFree(robot->dev);
@@ -264,6 +272,12 @@ int hrp_head(const hrp_head_args* a, void* stream) {
   p.uv_int = a->uv_int;
   p.uv_fk = a->uv_fk;
   return launch_head(p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int hrp_copy_device(void* dst, const void* src, int64_t bytes, void* stream) {
+  HRP_REQUIRE(dst != nullptr && src != nullptr && bytes >= 0, "bad argument");
+  HRP_CUDA_CHECK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, reinterpret_cast<cudaStream_t>(stream)));
+  return HRP_OK;
 }
 
 }  // extern "C"

@@ -82,6 +82,7 @@ size_t conv_packed_weight_elems(const ConvParams& p);
 int conv_pack_weights(const ConvLayerDesc& d, const ConvParams& p, int cin_ref, const float* w, uint16_t* out);
 
 // Build tensor maps + launch config.  `in`/`w_packed` are device pointers; epilogue pointers are taken from p.
+void conv_init();  // one-time kernel attribute setup (call outside stream capture)
 int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed);
 int conv_plan_launch(const ConvPlan& plan, cudaStream_t stream);       // tcgen05 path
 int conv_plan_launch_simt(const ConvPlan& plan, cudaStream_t stream);  // cross-check path (tests only)

@@ -464,6 +464,8 @@ static void set_smem_attr_once() {
   });
 }
 
+void conv_init() { set_smem_attr_once(); }
+
 int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed) {
   ConvParams& p = plan->p;
   HRP_REQUIRE(in != nullptr && w_packed != nullptr, "null tensor");

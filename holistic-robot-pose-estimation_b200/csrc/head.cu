@@ -284,6 +284,37 @@ int launch_pool_mean(const bf16* in, float* out, int B, int HW, int C, cudaStrea
 }
 
 // ------------------------------------------------------------------------------------------------------
+// standalone root-depth head (RootNet.forward, depth_net.py:121-125): out = (w . feat + b) * k_value * out_scale
+// ------------------------------------------------------------------------------------------------------
+__global__ void depth_kernel(const float* __restrict__ feat, const float* __restrict__ w, float b, const float* __restrict__ k,
+                             float* __restrict__ out, float out_scale) {
+  __shared__ float red[32];
+  const int n = blockIdx.x;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) acc = fmaf(feat[(size_t)n * 2048 + i], __ldg(w + i), acc);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    out[n] = ((t + b) * k[n]) * out_scale;
+  }
+}
+
+int launch_depth(const float* feat, const float* w, float b, const float* k, float* out, int B, float out_scale,
+                 cudaStream_t s) {
+  depth_kernel<<<B, 256, 0, s>>>(feat, w, b, k, out, out_scale);
+  count_launch();
+  HRP_CUDA_CHECK(cudaGetLastError());
+  return HRP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
 // fused head
 // ------------------------------------------------------------------------------------------------------
 constexpr int kHeadMaxThreads = 576;
@@ -356,8 +387,8 @@ __device__ __noinline__ void head_finalize(const HeadParams& p, HeadSmem& sm, in
     if (tid == 0) sm.depth = ((acc + p.depth_b) * p.k_value[b]) / 1000.0f;
   }
   // (c) collapsed regressors: a = Wx * xf + c  (rows = dof, then 6)
-  const int dof = rb->dof;
-  if (p.xf != nullptr) {
+  const int dof = (rb != nullptr) ? rb->dof : 0;
+  if (p.xf != nullptr && rb != nullptr) {
     const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
     const float4* x4 = reinterpret_cast<const float4*>(p.xf + (size_t)b * 2048);
     for (int r = warp; r < dof + 6; r += nw) {

@@ -87,6 +87,8 @@ struct FkParams {
 };
 int launch_fk(const FkParams& p, cudaStream_t s);
 int launch_project(const float* K, const float* pts, float* uv, int B, int N, cudaStream_t s);
+int launch_depth(const float* feat, const float* w, float b, const float* k, float* out, int B, float out_scale,
+                 cudaStream_t s);
 int launch_pool_mean(const bf16* in, float* out, int B, int HW, int C, cudaStream_t s);
 
 }  // namespace hrp

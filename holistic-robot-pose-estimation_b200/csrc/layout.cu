@@ -2,6 +2,9 @@
 // max-pool, NCHW<->NHWC bridges.  All are coalesced on the NHWC side and vectorised to 16 B per thread.
 #include "hrp_common.cuh"
 #include "launch_count.h"
+#include "ops.h"
+
+#include <algorithm>
 
 namespace hrp {
 
@@ -114,6 +117,54 @@ __global__ void nhwc_bf16_to_nchw_f32_kernel(const bf16* __restrict__ in, float*
   }
 }
 
+
+// HRNet fuse for the highest-resolution branch (no conv lands on it): out = relu(pre + sum_i upsample(up_i))
+// (HRnet.py:254-263 with i == 0); thread = (pixel, 8-channel group)
+__global__ void fuse_add_kernel(const FuseAddParams p) {
+  const int C8 = p.C >> 3;
+  const size_t total = (size_t)p.B * p.H * p.W * C8;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % C8);
+    const size_t pix = i / C8;
+    const int w = (int)(pix % p.W);
+    const int h = (int)((pix / p.W) % p.H);
+    const int n = (int)(pix / ((size_t)p.W * p.H));
+    float v[8];
+    {
+      const uint4 t = __ldg(reinterpret_cast<const uint4*>(p.pre) + i);
+      const uint32_t xs[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        v[2 * k] = bf16lo_to_f32(xs[k]);
+        v[2 * k + 1] = bf16hi_to_f32(xs[k]);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      if (p.up[a] == nullptr) continue;
+      const int sh = p.up_shift[a];
+      const size_t upix = ((size_t)n * (p.H >> sh) + (h >> sh)) * (p.W >> sh) + (w >> sh);
+      const uint4 t = __ldg(reinterpret_cast<const uint4*>(p.up[a]) + upix * C8 + cg);
+      const uint32_t xs[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        v[2 * k] += bf16lo_to_f32(xs[k]);
+        v[2 * k + 1] += bf16hi_to_f32(xs[k]);
+      }
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]);
+    o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]);
+    o.w = pack_bf16x2(v[6], v[7]);
+    reinterpret_cast<uint4*>(p.out)[i] = o;
+  }
+}
+
 int launch_pack_input_s2d(const float* x, void* out, int B, int H, int W, cudaStream_t s) {
   HRP_REQUIRE(H % 2 == 0 && W % 2 == 0, "input size must be even");
   const size_t total = (size_t)B * (H / 2) * (W / 2);
@@ -148,6 +199,17 @@ int launch_nchw_f32_to_nhwc_bf16(const float* in, void* out, int B, int C, int H
 int launch_nhwc_bf16_to_nchw_f32(const void* in, float* out, int B, int C, int H, int W, int Cpad, cudaStream_t s) {
   dim3 grid((H * W + 31) / 32, (C + 31) / 32, B), block(32, 8);
   nhwc_bf16_to_nchw_f32_kernel<<<grid, block, 0, s>>>(reinterpret_cast<const bf16*>(in), out, C, H * W, Cpad);
+  count_launch();
+  HRP_CUDA_CHECK(cudaGetLastError());
+  return HRP_OK;
+}
+
+int launch_fuse_add(const FuseAddParams& p, cudaStream_t s) {
+  HRP_REQUIRE(p.C % 8 == 0 && p.pre != nullptr && p.out != nullptr, "fuse_add: bad arguments");
+  const size_t total = (size_t)p.B * p.H * p.W * (p.C / 8);
+  const int threads = 256;
+  const int blocks = (int)std::min<size_t>((total + threads - 1) / threads, 148 * 16);
+  fuse_add_kernel<<<blocks, threads, 0, s>>>(p);
   count_launch();
   HRP_CUDA_CHECK(cudaGetLastError());
   return HRP_OK;

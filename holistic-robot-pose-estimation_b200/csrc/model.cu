@@ -1,0 +1,970 @@
+// Whole-network executor: RootNetwithRegInt (ResNet-50 + deconv head + HRNet-w32 root-depth net) and the
+// standalone RootNet depthnet, as a static program of planned kernels per batch-chunk size, captured once into
+// a CUDA graph with one capture stream per independent lane (4 HRNet branches + the ResNet/deconv path).
+//
+// Reference topology restated from lib/models/full_net.py:239-397, lib/models/backbones/Resnet.py:56-135,
+// lib/models/backbones/HRnet.py:101-265,341-429,499-570 (+ configs/hrnet_w32.yaml:54-93) and
+// lib/models/depth_net.py:92-137.  Weights arrive by reference state-dict key (hrp_model_set_tensor).
+#include "../../include/hrp.h"
+
+#include "conv.h"
+#include "head.h"
+#include "launch_count.h"
+#include "ops.h"
+
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace hrp {
+
+namespace {
+
+constexpr int kNumLanes = 5;  // lanes 0..3: HRNet branches (lane 0 also stem / layer1 / cls head); lane 4: ResNet path
+constexpr int kLaneRN = 4;
+constexpr int kImg = 256;
+
+struct HostTensor {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+};
+
+struct ConvWeights {
+  bf16* w = nullptr;
+  float* scale = nullptr;
+  float* bias = nullptr;
+};
+
+struct Act {
+  int H = 0, W = 0, C = 0;
+  bf16* ptr = nullptr;
+  int producer = -1;  // op index
+};
+
+struct Epi {
+  int pre[3] = {-1, -1, -1};
+  int up[3] = {-1, -1, -1};
+  int up_shift[3] = {0, 0, 0};
+  int post = -1;
+};
+
+enum OpKind { OP_CONV = 0, OP_MAXPOOL = 1, OP_FUSEADD = 2, OP_MEMSET = 3 };
+
+struct Op {
+  int kind = OP_CONV;
+  int lane = 0;
+  ConvPlan conv;
+  FuseAddParams fuse;
+  const void* mp_in = nullptr;
+  void* mp_out = nullptr;
+  int mp_B = 0, mp_H = 0, mp_W = 0, mp_C = 0;
+  void* ms_ptr = nullptr;
+  size_t ms_bytes = 0;
+  std::vector<int> reads;  // activation ids
+  int writes = -1;
+  bool cross_lane_consumer = false;
+  cudaEvent_t done = nullptr;
+};
+
+}  // namespace
+
+struct Plan {
+  int B = 0;
+  std::vector<Act> acts;
+  std::vector<Op> ops;
+  std::map<std::string, int> taps;
+  std::vector<void*> owned;
+  bf16* s2d_reg = nullptr;
+  bf16* s2d_root = nullptr;
+  float* feat = nullptr;     // (B,2048) pooled HRNet feature
+  float* xf = nullptr;       // (B,2048) pooled ResNet feature
+  int heatmap = -1;          // activation id
+  void* head_ws = nullptr;
+  int head_chunks = 0;
+  cudaStream_t stream = nullptr;         // launch stream of this replica (when inflight > 1)
+  cudaStream_t cap[kNumLanes] = {};
+  cudaEvent_t fork_ev = nullptr, join_ev[kNumLanes] = {};
+  cudaEvent_t done_ev = nullptr;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  int n_kernels = 0;
+  double flops = 0;
+
+  ~Plan() {
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    for (auto& op : ops)
+      if (op.done) cudaEventDestroy(op.done);
+    for (int l = 0; l < kNumLanes; ++l) {
+      if (cap[l]) cudaStreamDestroy(cap[l]);
+      if (join_ev[l]) cudaEventDestroy(join_ev[l]);
+    }
+    if (fork_ev) cudaEventDestroy(fork_ev);
+    if (done_ev) cudaEventDestroy(done_ev);
+    if (stream) cudaStreamDestroy(stream);
+    for (void* p : owned) cudaFree(p);
+  }
+};
+
+}  // namespace hrp
+
+using namespace hrp;
+
+struct hrp_robot;  // defined in api.cu
+extern "C" const void* hrp_robot_device_table(const hrp_robot* robot);
+extern "C" int hrp_robot_dims(const hrp_robot* robot, int32_t* nkpt, int32_t* dof);
+
+struct hrp_model {
+  hrp_model_desc desc;
+  bool finalized = false;
+  std::map<std::string, HostTensor> host;
+  std::map<std::string, ConvWeights> wcache;
+  std::vector<void*> owned;
+  const hrp_robot* robot = nullptr;
+  RegressorTable* reg_pose = nullptr;
+  RegressorTable* reg_rot = nullptr;
+  float* depth_w = nullptr;
+  float depth_b = 0.f;
+  float* init_pose = nullptr;
+  float* init_rot = nullptr;
+  std::map<std::pair<int, int>, std::unique_ptr<Plan>> plans;  // (batch, replica)
+  Plan* last_plan = nullptr;
+  cudaEvent_t fork_ev = nullptr;
+  int device = 0;
+  bool use_graph = true;
+  bool use_simt = false;
+  std::string prefix_root;  // "rootnet_backbone." (full) or "backbone." (depthnet)
+
+  ~hrp_model() {
+    plans.clear();
+    for (void* p : owned) cudaFree(p);
+    if (fork_ev) cudaEventDestroy(fork_ev);
+  }
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------
+// weights
+// ------------------------------------------------------------------------------------------------------
+int dev_upload(hrp_model* m, const void* src, size_t bytes, void** out) {
+  void* p = nullptr;
+  HRP_CUDA_CHECK(cudaMalloc(&p, bytes));
+  m->owned.push_back(p);
+  HRP_CUDA_CHECK(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice));
+  *out = p;
+  return HRP_OK;
+}
+
+const HostTensor* find(const hrp_model* m, const std::string& key) {
+  auto it = m->host.find(key);
+  return it == m->host.end() ? nullptr : &it->second;
+}
+
+#define HRP_NEED(ptr, key)                                                   \
+  do {                                                                       \
+    if ((ptr) == nullptr) {                                                  \
+      set_error(std::string("missing tensor in state dict: ") + (key));      \
+      return HRP_ERR_STATE;                                                  \
+    }                                                                        \
+  } while (0)
+
+// fold conv bias + BatchNorm (eval) into per-channel scale / shift, pack the weights, upload (cached per conv)
+int get_weights(hrp_model* m, const std::string& conv, const std::string& bn, const ConvLayerDesc& d,
+                const ConvParams& geo, ConvWeights* out) {
+  auto it = m->wcache.find(conv);
+  if (it != m->wcache.end()) {
+    *out = it->second;
+    return HRP_OK;
+  }
+  const HostTensor* w = find(m, conv + ".weight");
+  HRP_NEED(w, conv + ".weight");
+  HRP_REQUIRE(w->shape.size() == 4, "conv weight must be 4-D: " + conv);
+  int cin_ref, cout_ref;
+  if (d.kind == kDeconvK4S2P1) {
+    cin_ref = (int)w->shape[0];
+    cout_ref = (int)w->shape[1];
+    HRP_REQUIRE(w->shape[2] == 4 && w->shape[3] == 4, "deconv kernel must be 4x4: " + conv);
+  } else {
+    cout_ref = (int)w->shape[0];
+    cin_ref = (int)w->shape[1];
+    HRP_REQUIRE(w->shape[2] == d.kh && w->shape[3] == d.kw, "conv kernel size mismatch: " + conv);
+  }
+  HRP_REQUIRE(cout_ref == d.Cout, "conv Cout mismatch: " + conv);
+  HRP_REQUIRE(d.kind == kStemS2D ? cin_ref == 3 : cin_ref == d.Cin, "conv Cin mismatch: " + conv);
+  std::vector<uint16_t> packed(conv_packed_weight_elems(geo));
+  int rc = conv_pack_weights(d, geo, cin_ref, w->data.data(), packed.data());
+  if (rc != HRP_OK) return rc;
+  std::vector<float> scale(d.Cout, 1.f), bias(d.Cout, 0.f);
+  const HostTensor* cb = find(m, conv + ".bias");
+  if (!bn.empty()) {
+    const HostTensor *g = find(m, bn + ".weight"), *b = find(m, bn + ".bias"), *mu = find(m, bn + ".running_mean"),
+                     *var = find(m, bn + ".running_var");
+    HRP_NEED(g, bn + ".weight");
+    HRP_NEED(b, bn + ".bias");
+    HRP_NEED(mu, bn + ".running_mean");
+    HRP_NEED(var, bn + ".running_var");
+    HRP_REQUIRE((int)g->data.size() == d.Cout && (int)var->data.size() == d.Cout, "BN size mismatch: " + bn);
+    for (int c = 0; c < d.Cout; ++c) {
+      const double s = (double)g->data[c] / std::sqrt((double)var->data[c] + 1e-5);
+      double sh = (double)b->data[c] - (double)mu->data[c] * s;
+      if (cb != nullptr) sh += (double)cb->data[c] * s;
+      scale[c] = (float)s;
+      bias[c] = (float)sh;
+    }
+  } else if (cb != nullptr) {
+    for (int c = 0; c < d.Cout; ++c) bias[c] = cb->data[c];
+  }
+  ConvWeights cw;
+  rc = dev_upload(m, packed.data(), packed.size() * 2, reinterpret_cast<void**>(&cw.w));
+  if (rc != HRP_OK) return rc;
+  rc = dev_upload(m, scale.data(), scale.size() * 4, reinterpret_cast<void**>(&cw.scale));
+  if (rc != HRP_OK) return rc;
+  rc = dev_upload(m, bias.data(), bias.size() * 4, reinterpret_cast<void**>(&cw.bias));
+  if (rc != HRP_OK) return rc;
+  m->wcache[conv] = cw;
+  *out = cw;
+  return HRP_OK;
+}
+
+// Collapse one iterative regressor (three affine layers, no activation) into delta(p) = Wx*xf + A*p + c, in fp64.
+int build_regressor(hrp_model* m, const std::string& fc1, const std::string& fc2, const std::string& dec, int dim,
+                    RegressorTable** out) {
+  const HostTensor *W1 = find(m, fc1 + ".weight"), *b1 = find(m, fc1 + ".bias"), *W2 = find(m, fc2 + ".weight"),
+                   *b2 = find(m, fc2 + ".bias"), *W3 = find(m, dec + ".weight"), *b3 = find(m, dec + ".bias");
+  HRP_NEED(W1, fc1 + ".weight");
+  HRP_NEED(b1, fc1 + ".bias");
+  HRP_NEED(W2, fc2 + ".weight");
+  HRP_NEED(b2, fc2 + ".bias");
+  HRP_NEED(W3, dec + ".weight");
+  HRP_NEED(b3, dec + ".bias");
+  const int hid = 1024, nx = 2048, in1 = nx + dim;
+  HRP_REQUIRE(W1->shape.size() == 2 && W1->shape[0] == hid && W1->shape[1] == in1, "unexpected shape: " + fc1);
+  HRP_REQUIRE(W2->shape.size() == 2 && W2->shape[0] == hid && W2->shape[1] == hid, "unexpected shape: " + fc2);
+  HRP_REQUIRE(W3->shape.size() == 2 && W3->shape[0] == dim && W3->shape[1] == hid, "unexpected shape: " + dec);
+  std::vector<double> W32((size_t)dim * hid, 0.0);
+  for (int i = 0; i < dim; ++i)
+    for (int k = 0; k < hid; ++k) {
+      const double a = W3->data[(size_t)i * hid + k];
+      const float* row = &W2->data[(size_t)k * hid];
+      double* dst = &W32[(size_t)i * hid];
+      for (int j = 0; j < hid; ++j) dst[j] += a * (double)row[j];
+    }
+  std::vector<double> Wfull((size_t)dim * in1, 0.0);
+  for (int i = 0; i < dim; ++i)
+    for (int k = 0; k < hid; ++k) {
+      const double a = W32[(size_t)i * hid + k];
+      const float* row = &W1->data[(size_t)k * in1];
+      double* dst = &Wfull[(size_t)i * in1];
+      for (int j = 0; j < in1; ++j) dst[j] += a * (double)row[j];
+    }
+  RegressorTable t;
+  memset(&t, 0, sizeof(t));
+  t.dim = dim;
+  t.n_iter = m->desc.n_iter;
+  std::vector<float> Wx((size_t)dim * nx);
+  for (int i = 0; i < dim; ++i) {
+    for (int j = 0; j < nx; ++j) Wx[(size_t)i * nx + j] = (float)Wfull[(size_t)i * in1 + j];
+    for (int j = 0; j < dim; ++j) t.A[i][j] = (float)Wfull[(size_t)i * in1 + nx + j];
+    double c = b3->data[i];
+    for (int k = 0; k < hid; ++k) c += W32[(size_t)i * hid + k] * (double)b1->data[k] + (double)W3->data[(size_t)i * hid + k] * (double)b2->data[k];
+    t.c[i] = (float)c;
+  }
+  float* wx_dev = nullptr;
+  int rc = dev_upload(m, Wx.data(), Wx.size() * 4, reinterpret_cast<void**>(&wx_dev));
+  if (rc != HRP_OK) return rc;
+  t.Wx = wx_dev;
+  return dev_upload(m, &t, sizeof(t), reinterpret_cast<void**>(out));
+}
+
+// ------------------------------------------------------------------------------------------------------
+// program builder
+// ------------------------------------------------------------------------------------------------------
+struct Builder {
+  hrp_model* m;
+  Plan* pl;
+  int rc = HRP_OK;
+
+  int new_act(int H, int W, int C) {
+    Act a;
+    a.H = H;
+    a.W = W;
+    a.C = C;
+    void* p = nullptr;
+    if (rc == HRP_OK) {
+      cudaError_t e = cudaMalloc(&p, (size_t)pl->B * H * W * C * sizeof(bf16));
+      if (e != cudaSuccess) {
+        set_error(std::string("activation allocation failed: ") + cudaGetErrorString(e));
+        rc = HRP_ERR_CUDA;
+      } else {
+        pl->owned.push_back(p);
+      }
+    }
+    a.ptr = reinterpret_cast<bf16*>(p);
+    pl->acts.push_back(a);
+    return (int)pl->acts.size() - 1;
+  }
+
+  // conv + (bias) + BN + addends + ReLU; returns the output activation id (or -1 when only pooled)
+  int conv(int lane, const std::string& name, const std::string& bn, int in, int cout, int k, int stride, int pad,
+           bool relu, const Epi& epi = Epi(), int kind = kConv, bool write_out = true, float* pool_out = nullptr,
+           const bf16* raw_in = nullptr, int raw_H = 0, int raw_W = 0, int raw_C = 0) {
+    if (rc != HRP_OK) return -1;
+    ConvLayerDesc d;
+    d.kind = kind;
+    d.B = pl->B;
+    if (raw_in != nullptr) {
+      d.Hin = raw_H;
+      d.Win = raw_W;
+      d.Cin = raw_C;
+    } else {
+      d.Hin = pl->acts[in].H;
+      d.Win = pl->acts[in].W;
+      d.Cin = pl->acts[in].C;
+    }
+    d.Cout = cout;
+    d.kh = d.kw = k;
+    d.stride = stride;
+    d.pad = pad;
+    d.relu = relu ? 1 : 0;
+    Op op;
+    op.kind = OP_CONV;
+    op.lane = lane;
+    rc = conv_geometry(d, &op.conv.p);
+    if (rc != HRP_OK) return -1;
+    ConvWeights cw;
+    rc = get_weights(m, name, bn, d, op.conv.p, &cw);
+    if (rc != HRP_OK) return -1;
+    ConvParams& p = op.conv.p;
+    int out = -1;
+    if (write_out) {
+      out = new_act(p.Hout, p.Wout, cout);
+      if (rc != HRP_OK) return -1;
+      p.out = pl->acts[out].ptr;
+    }
+    p.scale = cw.scale;
+    p.bias = cw.bias;
+    p.pool_out = pool_out;
+    if (in >= 0) op.reads.push_back(in);
+    for (int i = 0; i < 3; ++i) {
+      if (epi.pre[i] >= 0) {
+        const Act& a = pl->acts[epi.pre[i]];
+        if (a.H != p.Hout || a.W != p.Wout || a.C != cout) {
+          set_error("internal: pre addend shape mismatch at " + name);
+          rc = HRP_ERR_STATE;
+          return -1;
+        }
+        p.pre[i] = a.ptr;
+        op.reads.push_back(epi.pre[i]);
+      }
+      if (epi.up[i] >= 0) {
+        const Act& a = pl->acts[epi.up[i]];
+        if ((a.H << epi.up_shift[i]) != p.Hout || a.C != cout) {
+          set_error("internal: up addend shape mismatch at " + name);
+          rc = HRP_ERR_STATE;
+          return -1;
+        }
+        p.up[i] = a.ptr;
+        p.up_shift[i] = epi.up_shift[i];
+        op.reads.push_back(epi.up[i]);
+      }
+    }
+    if (epi.post >= 0) {
+      p.post = pl->acts[epi.post].ptr;
+      op.reads.push_back(epi.post);
+    }
+    rc = conv_plan_finalize(&op.conv, raw_in != nullptr ? raw_in : pl->acts[in].ptr, cw.w);
+    if (rc != HRP_OK) return -1;
+    // algorithmic FLOPs of the reference layer (2*MACs, unpadded)
+    {
+      const ConvParams& q = op.conv.p;
+      double macs;
+      if (kind == kDeconvK4S2P1) macs = (double)pl->B * q.Hout * q.Wout * 4.0 * q.Cin * cout;
+      else if (kind == kStemS2D) macs = (double)pl->B * q.Hout * q.Wout * (double)k * k * 3.0 * cout;
+      else macs = (double)pl->B * q.Hout * q.Wout * (double)k * k * q.Cin * cout;
+      op.conv.flops = 2.0 * macs;
+      pl->flops += op.conv.flops;
+    }
+    op.writes = out;
+    pl->ops.push_back(op);
+    if (out >= 0) pl->acts[out].producer = (int)pl->ops.size() - 1;
+    return out;
+  }
+
+  int maxpool(int lane, int in) {
+    if (rc != HRP_OK) return -1;
+    const Act a = pl->acts[in];
+    const int out = new_act(a.H / 2, a.W / 2, a.C);
+    if (rc != HRP_OK) return -1;
+    Op op;
+    op.kind = OP_MAXPOOL;
+    op.lane = lane;
+    op.mp_in = a.ptr;
+    op.mp_out = pl->acts[out].ptr;
+    op.mp_B = pl->B;
+    op.mp_H = a.H;
+    op.mp_W = a.W;
+    op.mp_C = a.C;
+    op.reads.push_back(in);
+    op.writes = out;
+    pl->ops.push_back(op);
+    pl->acts[out].producer = (int)pl->ops.size() - 1;
+    return out;
+  }
+
+  int fuse_add(int lane, int pre, const Epi& epi) {
+    if (rc != HRP_OK) return -1;
+    const Act a = pl->acts[pre];
+    const int out = new_act(a.H, a.W, a.C);
+    if (rc != HRP_OK) return -1;
+    Op op;
+    op.kind = OP_FUSEADD;
+    op.lane = lane;
+    memset(&op.fuse, 0, sizeof(op.fuse));
+    op.fuse.pre = a.ptr;
+    op.fuse.out = pl->acts[out].ptr;
+    op.fuse.B = pl->B;
+    op.fuse.H = a.H;
+    op.fuse.W = a.W;
+    op.fuse.C = a.C;
+    op.fuse.relu = 1;
+    op.reads.push_back(pre);
+    for (int i = 0; i < 3; ++i)
+      if (epi.up[i] >= 0) {
+        op.fuse.up[i] = pl->acts[epi.up[i]].ptr;
+        op.fuse.up_shift[i] = epi.up_shift[i];
+        op.reads.push_back(epi.up[i]);
+      }
+    op.writes = out;
+    pl->ops.push_back(op);
+    pl->acts[out].producer = (int)pl->ops.size() - 1;
+    return out;
+  }
+
+  void memset_op(int lane, void* ptr, size_t bytes) {
+    Op op;
+    op.kind = OP_MEMSET;
+    op.lane = lane;
+    op.ms_ptr = ptr;
+    op.ms_bytes = bytes;
+    pl->ops.push_back(op);
+  }
+
+  // Bottleneck (Resnet.py:96-135, HRnet.py:60-98): 1x1 -> 3x3(stride) -> 1x1 (+ residual / downsample) -> ReLU
+  int bottleneck(int lane, const std::string& n, int x, int planes, int stride, int post = -1, float* pool_out = nullptr) {
+    int t = conv(lane, n + ".conv1", n + ".bn1", x, planes, 1, 1, 0, true);
+    t = conv(lane, n + ".conv2", n + ".bn2", t, planes, 3, stride, 1, true);
+    int res = x;
+    if (find(m, n + ".downsample.0.weight") != nullptr || m->wcache.count(n + ".downsample.0") != 0)
+      res = conv(lane, n + ".downsample.0", n + ".downsample.1", x, planes * 4, 1, stride, 0, false);
+    Epi e;
+    e.pre[0] = res;
+    e.post = post;
+    return conv(lane, n + ".conv3", n + ".bn3", t, planes * 4, 1, 1, 0, true, e, kConv, true, pool_out);
+  }
+
+  // BasicBlock (HRnet.py:28-57)
+  int basic(int lane, const std::string& n, int x, int c) {
+    int t = conv(lane, n + ".conv1", n + ".bn1", x, c, 3, 1, 1, true);
+    Epi e;
+    e.pre[0] = x;
+    return conv(lane, n + ".conv2", n + ".bn2", t, c, 3, 1, 1, true, e);
+  }
+
+  void tap(const std::string& name, int act) { pl->taps[name] = act; }
+
+  // ResNet-50 trunk (Resnet.py:56-67) on the s2d-packed input; returns the (B,8,8,2048) activation
+  int resnet50(const std::string& pre, const bf16* s2d, float* pool_out) {
+    const int lane = kLaneRN;
+    int x = conv(lane, pre + "conv1", pre + "bn1", -1, 64, 7, 2, 3, true, Epi(), kStemS2D, true, nullptr, s2d, kImg / 2,
+                 kImg / 2, 16);
+    tap(pre + "stem", x);
+    x = maxpool(lane, x);
+    const int planes[4] = {64, 128, 256, 512}, blocks[4] = {3, 4, 6, 3};
+    for (int li = 0; li < 4; ++li) {
+      for (int b = 0; b < blocks[li]; ++b) {
+        const bool last = (li == 3 && b == blocks[li] - 1);
+        x = bottleneck(lane, pre + "layer" + std::to_string(li + 1) + "." + std::to_string(b), x, planes[li],
+                       (b == 0 && li > 0) ? 2 : 1, -1, last ? pool_out : nullptr);
+      }
+      tap(pre + "layer" + std::to_string(li + 1), x);
+    }
+    return x;
+  }
+
+  // HRNet-w32 with classification head, pooled feature only (HRnet.py:499-570, generate_hm=False)
+  void hrnet32(const std::string& pre, const bf16* s2d, float* pool_out) {
+    const int C[4] = {32, 64, 128, 256};
+    int x = conv(0, pre + "conv1", pre + "bn1", -1, 64, 3, 2, 1, true, Epi(), kStemS2D, true, nullptr, s2d, kImg / 2,
+                 kImg / 2, 16);
+    x = conv(0, pre + "conv2", pre + "bn2", x, 64, 3, 2, 1, true);
+    for (int b = 0; b < 4; ++b) x = bottleneck(0, pre + "layer1." + std::to_string(b), x, 64, 1);
+    tap(pre + "layer1", x);
+    std::vector<int> ys;
+    ys.push_back(conv(0, pre + "transition1.0.0", pre + "transition1.0.1", x, C[0], 3, 1, 1, true));
+    ys.push_back(conv(1, pre + "transition1.1.0.0", pre + "transition1.1.0.1", x, C[1], 3, 2, 1, true));
+    const int nmods[3] = {1, 4, 3};
+    for (int stage = 2; stage <= 4; ++stage) {
+      const int nb = stage;
+      if (stage > 2) {  // HRnet.py:516-521,524-529: the new branch comes from the previous stage's LAST output
+        const std::string t = pre + "transition" + std::to_string(stage - 1) + "." + std::to_string(nb - 1) + ".0";
+        ys.push_back(conv(nb - 1, t + ".0", t + ".1", ys.back(), C[nb - 1], 3, 2, 1, true));
+      }
+      for (int mod = 0; mod < nmods[stage - 2]; ++mod) {
+        const std::string mn = pre + "stage" + std::to_string(stage) + "." + std::to_string(mod);
+        std::vector<int> xs(nb);
+        for (int br = 0; br < nb; ++br) {
+          int v = ys[br];
+          for (int blk = 0; blk < 4; ++blk)
+            v = basic(br, mn + ".branches." + std::to_string(br) + "." + std::to_string(blk), v, C[br]);
+          xs[br] = v;
+        }
+        // fuse (HRnet.py:254-263): y_i = relu(sum_j f_ij(x_j)); everything is summed in fp32 in ONE epilogue
+        std::vector<int> fused(nb);
+        for (int i = 0; i < nb; ++i) {
+          Epi e;
+          int nup = 0, npre = 0;
+          e.pre[npre++] = xs[i];
+          for (int j = i + 1; j < nb; ++j) {  // 1x1 conv + BN at the low resolution, upsampled in the consumer
+            const std::string f = mn + ".fuse_layers." + std::to_string(i) + "." + std::to_string(j);
+            e.up[nup] = conv(j, f + ".0", f + ".1", xs[j], C[i], 1, 1, 0, false);
+            e.up_shift[nup] = j - i;
+            ++nup;
+          }
+          if (i == 0) {
+            fused[i] = fuse_add(0, xs[0], e);
+            continue;
+          }
+          for (int j = 0; j < i; ++j) {  // chains of stride-2 3x3 convs; the last chain carries the summation
+            const std::string f = mn + ".fuse_layers." + std::to_string(i) + "." + std::to_string(j);
+            int t = xs[j];
+            for (int k = 0; k < i - j - 1; ++k)
+              t = conv(i, f + "." + std::to_string(k) + ".0", f + "." + std::to_string(k) + ".1", t, C[j], 3, 2, 1, true);
+            const std::string lastc = f + "." + std::to_string(i - j - 1);
+            if (j < i - 1) {
+              e.pre[npre++] = conv(i, lastc + ".0", lastc + ".1", t, C[i], 3, 2, 1, false);
+            } else {
+              fused[i] = conv(i, lastc + ".0", lastc + ".1", t, C[i], 3, 2, 1, true, e);
+            }
+          }
+        }
+        ys = fused;
+      }
+      for (int i = 0; i < nb; ++i) tap(pre + "stage" + std::to_string(stage) + ".out" + std::to_string(i), ys[i]);
+    }
+    // classification head (HRnet.py:557-568)
+    const int head_ch[4] = {32, 64, 128, 256};
+    int y = bottleneck(0, pre + "incre_modules.0.0", ys[0], head_ch[0], 1);
+    for (int i = 0; i < 3; ++i) {
+      const std::string dn = pre + "downsamp_modules." + std::to_string(i);
+      const int d = conv(0, dn + ".0", dn + ".1", y, head_ch[i + 1] * 4, 3, 2, 1, true);
+      y = bottleneck(0, pre + "incre_modules." + std::to_string(i + 1) + ".0", ys[i + 1], head_ch[i + 1], 1, d);
+    }
+    tap(pre + "cls_y", y);
+    conv(0, pre + "final_feat_layer.0", pre + "final_feat_layer.1", y, 2048, 1, 1, 0, true, Epi(), kConv, false, pool_out);
+  }
+};
+
+int launch_op(const hrp_model* m, const Op& op, cudaStream_t s) {
+  switch (op.kind) {
+    case OP_CONV:
+      return m->use_simt ? conv_plan_launch_simt(op.conv, s) : conv_plan_launch(op.conv, s);
+    case OP_MAXPOOL:
+      return launch_maxpool3x3s2(op.mp_in, op.mp_out, op.mp_B, op.mp_H, op.mp_W, op.mp_C, s);
+    case OP_FUSEADD:
+      return launch_fuse_add(op.fuse, s);
+    case OP_MEMSET:
+      HRP_CUDA_CHECK(cudaMemsetAsync(op.ms_ptr, 0, op.ms_bytes, s));
+      return HRP_OK;
+  }
+  return HRP_ERR_STATE;
+}
+
+int capture_plan(hrp_model* m, Plan* pl) {
+  // cross-lane dependencies -> events
+  for (size_t i = 0; i < pl->ops.size(); ++i)
+    for (int a : pl->ops[i].reads) {
+      const int prod = pl->acts[a].producer;
+      if (prod >= 0 && pl->ops[prod].lane != pl->ops[i].lane) pl->ops[prod].cross_lane_consumer = true;
+    }
+  for (auto& op : pl->ops)
+    if (op.cross_lane_consumer) HRP_CUDA_CHECK(cudaEventCreateWithFlags(&op.done, cudaEventDisableTiming));
+  for (int l = 0; l < kNumLanes; ++l) {
+    HRP_CUDA_CHECK(cudaStreamCreateWithFlags(&pl->cap[l], cudaStreamNonBlocking));
+    HRP_CUDA_CHECK(cudaEventCreateWithFlags(&pl->join_ev[l], cudaEventDisableTiming));
+  }
+  HRP_CUDA_CHECK(cudaEventCreateWithFlags(&pl->fork_ev, cudaEventDisableTiming));
+  HRP_CUDA_CHECK(cudaEventCreateWithFlags(&pl->done_ev, cudaEventDisableTiming));
+  HRP_CUDA_CHECK(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+  pl->n_kernels = 0;
+  for (auto& op : pl->ops)
+    if (op.kind != OP_MEMSET) ++pl->n_kernels;
+  if (!m->use_graph) return HRP_OK;
+
+  const int64_t launches_before = g_launch_count.load();
+  HRP_CUDA_CHECK(cudaStreamBeginCapture(pl->cap[0], cudaStreamCaptureModeThreadLocal));
+  int rc = HRP_OK;
+  do {
+    if (cudaEventRecord(pl->fork_ev, pl->cap[0]) != cudaSuccess) { rc = HRP_ERR_CUDA; break; }
+    for (int l = 1; l < kNumLanes && rc == HRP_OK; ++l)
+      if (cudaStreamWaitEvent(pl->cap[l], pl->fork_ev, 0) != cudaSuccess) rc = HRP_ERR_CUDA;
+    for (size_t i = 0; i < pl->ops.size() && rc == HRP_OK; ++i) {
+      Op& op = pl->ops[i];
+      for (int a : op.reads) {
+        const int prod = pl->acts[a].producer;
+        if (prod >= 0 && pl->ops[prod].lane != op.lane)
+          if (cudaStreamWaitEvent(pl->cap[op.lane], pl->ops[prod].done, 0) != cudaSuccess) rc = HRP_ERR_CUDA;
+      }
+      if (rc != HRP_OK) break;
+      rc = launch_op(m, op, pl->cap[op.lane]);
+      if (rc == HRP_OK && op.cross_lane_consumer)
+        if (cudaEventRecord(op.done, pl->cap[op.lane]) != cudaSuccess) rc = HRP_ERR_CUDA;
+    }
+    for (int l = 1; l < kNumLanes && rc == HRP_OK; ++l) {
+      if (cudaEventRecord(pl->join_ev[l], pl->cap[l]) != cudaSuccess) rc = HRP_ERR_CUDA;
+      if (rc == HRP_OK && cudaStreamWaitEvent(pl->cap[0], pl->join_ev[l], 0) != cudaSuccess) rc = HRP_ERR_CUDA;
+    }
+  } while (0);
+  cudaError_t e = cudaStreamEndCapture(pl->cap[0], &pl->graph);
+  g_launch_count.store(launches_before);  // captured launches are counted per replay instead
+  if (rc != HRP_OK || e != cudaSuccess) {
+    if (rc == HRP_OK || rc == HRP_ERR_CUDA)
+      set_error(std::string("CUDA graph capture failed: ") + cudaGetErrorString(e != cudaSuccess ? e : cudaGetLastError()));
+    return HRP_ERR_CUDA;
+  }
+  HRP_CUDA_CHECK(cudaGraphInstantiate(&pl->exec, pl->graph, 0));
+  return HRP_OK;
+}
+
+int build_plan(hrp_model* m, int B, Plan** out_plan, int replica) {
+  std::unique_ptr<Plan> pl(new Plan());
+  pl->B = B;
+  Builder b{m, pl.get()};
+  auto dmalloc = [&](size_t bytes, void** p) -> int {
+    HRP_CUDA_CHECK(cudaMalloc(p, bytes));
+    pl->owned.push_back(*p);
+    return HRP_OK;
+  };
+  const size_t s2d_bytes = (size_t)B * (kImg / 2) * (kImg / 2) * 16 * sizeof(bf16);
+  int rc = dmalloc(s2d_bytes, reinterpret_cast<void**>(&pl->s2d_root));
+  if (rc != HRP_OK) return rc;
+  rc = dmalloc((size_t)B * 2048 * 4, reinterpret_cast<void**>(&pl->feat));
+  if (rc != HRP_OK) return rc;
+  b.memset_op(0, pl->feat, (size_t)B * 2048 * 4);
+  const bool full = (m->desc.kind == HRP_MODEL_FULL);
+  if (full) {
+    rc = dmalloc(s2d_bytes, reinterpret_cast<void**>(&pl->s2d_reg));
+    if (rc != HRP_OK) return rc;
+    rc = dmalloc((size_t)B * 2048 * 4, reinterpret_cast<void**>(&pl->xf));
+    if (rc != HRP_OK) return rc;
+    b.memset_op(kLaneRN, pl->xf, (size_t)B * 2048 * 4);
+  }
+  b.hrnet32(m->prefix_root, pl->s2d_root, pl->feat);
+  if (full && b.rc == HRP_OK) {
+    int x = b.resnet50("reg_backbone.", pl->s2d_reg, pl->xf);
+    const int dc[3] = {256, 256, 256};
+    for (int i = 0; i < 3 && b.rc == HRP_OK; ++i)
+      x = b.conv(kLaneRN, "deconv_layers." + std::to_string(3 * i), "deconv_layers." + std::to_string(3 * i + 1), x, dc[i],
+                 4, 2, 1, true, Epi(), kDeconvK4S2P1);
+    b.tap("deconv", x);
+    x = b.conv(kLaneRN, "final_layer", "", x, m->desc.nkpt * 64, 1, 1, 0, false);
+    b.tap("heatmap", x);
+    pl->heatmap = x;
+    if (b.rc == HRP_OK) {
+      pl->head_chunks = head_default_chunks(B);
+      const size_t ws = ((size_t)B * 4 + 255) / 256 * 256 + head_partials_elems(B, m->desc.nkpt, pl->head_chunks) * 4;
+      rc = dmalloc(ws, &pl->head_ws);
+      if (rc != HRP_OK) return rc;
+      HRP_CUDA_CHECK(cudaMemset(pl->head_ws, 0, ws));
+    }
+  }
+  if (b.rc != HRP_OK) return b.rc;
+  rc = capture_plan(m, pl.get());
+  if (rc != HRP_OK) return rc;
+  *out_plan = pl.get();
+  m->plans[std::make_pair(B, replica)] = std::move(pl);
+  return HRP_OK;
+}
+
+int get_plan(hrp_model* m, int B, int replica, Plan** out) {
+  auto it = m->plans.find(std::make_pair(B, replica));
+  if (it != m->plans.end()) {
+    *out = it->second.get();
+    return HRP_OK;
+  }
+  return build_plan(m, B, out, replica);
+}
+
+int run_plan_body(hrp_model* m, Plan* pl, cudaStream_t s) {
+  if (m->use_graph) {
+    HRP_CUDA_CHECK(cudaGraphLaunch(pl->exec, s));
+    count_launch(pl->n_kernels);
+    return HRP_OK;
+  }
+  for (auto& op : pl->ops) {
+    int rc = launch_op(m, op, s);
+    if (rc != HRP_OK) return rc;
+  }
+  return HRP_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int hrp_model_create(const hrp_model_desc* desc, hrp_model** out) {
+  HRP_REQUIRE(desc != nullptr && out != nullptr, "null argument");
+  HRP_REQUIRE(desc->kind == HRP_MODEL_FULL || desc->kind == HRP_MODEL_DEPTHNET, "unknown model kind");
+  if (desc->kind == HRP_MODEL_FULL) {
+    HRP_REQUIRE(desc->nkpt > 0 && desc->nkpt <= kMaxKpt && desc->dof > 0 && desc->dof <= kMaxDof, "bad nkpt / dof");
+    HRP_REQUIRE(desc->ref_kpt >= 0 && desc->ref_kpt < desc->nkpt, "reference keypoint out of range");
+    HRP_REQUIRE(desc->n_iter >= 0 && desc->n_iter <= 16, "n_iter out of range");
+  }
+  HRP_REQUIRE(desc->chunk > 0 && desc->chunk <= 1024, "chunk must be in 1..1024");
+  HRP_REQUIRE(desc->inflight >= 1 && desc->inflight <= 4, "inflight must be in 1..4");
+  hrp_model* m = new (std::nothrow) hrp_model();
+  HRP_REQUIRE(m != nullptr, "out of host memory");
+  m->desc = *desc;
+  m->prefix_root = (desc->kind == HRP_MODEL_FULL) ? "rootnet_backbone." : "backbone.";
+  cudaGetDevice(&m->device);
+  const char* e = getenv("HRP_NO_GRAPH");
+  m->use_graph = !(e != nullptr && e[0] == '1');
+  e = getenv("HRP_CONV_IMPL");
+  m->use_simt = (e != nullptr && std::string(e) == "simt");
+  *out = m;
+  return HRP_OK;
+}
+
+void hrp_model_destroy(hrp_model* model) { delete model; }
+
+int hrp_model_set_tensor(hrp_model* model, const char* name, const float* data, const int64_t* shape, int32_t ndim) {
+  HRP_REQUIRE(model != nullptr && name != nullptr && data != nullptr && ndim >= 0 && ndim <= 8, "bad argument");
+  HRP_REQUIRE(shape != nullptr || ndim == 0, "null shape");
+  if (model->finalized) {
+    set_error("hrp_model_set_tensor after hrp_model_finalize");
+    return HRP_ERR_STATE;
+  }
+  HostTensor t;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    HRP_REQUIRE(shape[i] > 0, "non-positive dimension");
+    t.shape.push_back(shape[i]);
+    n *= (size_t)shape[i];
+  }
+  t.data.assign(data, data + n);
+  model->host[name] = std::move(t);
+  return HRP_OK;
+}
+
+int hrp_model_set_robot(hrp_model* model, const hrp_robot* robot) {
+  HRP_REQUIRE(model != nullptr && robot != nullptr, "null argument");
+  int32_t nkpt = 0, dof = 0;
+  hrp_robot_dims(robot, &nkpt, &dof);
+  HRP_REQUIRE(nkpt == model->desc.nkpt && dof == model->desc.dof, "robot table does not match the model (nkpt / dof)");
+  model->robot = robot;
+  return HRP_OK;
+}
+
+int hrp_model_finalize(hrp_model* m) {
+  HRP_REQUIRE(m != nullptr, "null model");
+  if (m->finalized) return HRP_OK;
+  HRP_CUDA_CHECK(cudaSetDevice(m->device));
+  const HostTensor* dw = find(m, "depth_layer.weight");
+  const HostTensor* db = find(m, "depth_layer.bias");
+  HRP_NEED(dw, "depth_layer.weight");
+  HRP_NEED(db, "depth_layer.bias");
+  HRP_REQUIRE(dw->data.size() == 2048 && db->data.size() == 1, "depth_layer must map 2048 -> 1 (multi_kp is off-path)");
+  int rc = dev_upload(m, dw->data.data(), 2048 * 4, reinterpret_cast<void**>(&m->depth_w));
+  if (rc != HRP_OK) return rc;
+  m->depth_b = db->data[0];
+  if (m->desc.kind == HRP_MODEL_FULL) {
+    if (m->robot == nullptr) {
+      set_error("hrp_model_set_robot must be called before hrp_model_finalize");
+      return HRP_ERR_STATE;
+    }
+    rc = build_regressor(m, "fc_pose_1", "fc_pose_2", "decpose", m->desc.dof, &m->reg_pose);
+    if (rc != HRP_OK) return rc;
+    rc = build_regressor(m, "fc_rot_1", "fc_rot_2", "decrot", 6, &m->reg_rot);
+    if (rc != HRP_OK) return rc;
+    const HostTensor *ip = find(m, "init_pose"), *ir = find(m, "init_rot");
+    HRP_NEED(ip, "init_pose");
+    HRP_NEED(ir, "init_rot");
+    HRP_REQUIRE((int)ip->data.size() == m->desc.dof && ir->data.size() == 6, "init_pose / init_rot size mismatch");
+    rc = dev_upload(m, ip->data.data(), ip->data.size() * 4, reinterpret_cast<void**>(&m->init_pose));
+    if (rc != HRP_OK) return rc;
+    rc = dev_upload(m, ir->data.data(), 24, reinterpret_cast<void**>(&m->init_rot));
+    if (rc != HRP_OK) return rc;
+  }
+  HRP_CUDA_CHECK(cudaEventCreateWithFlags(&m->fork_ev, cudaEventDisableTiming));
+  conv_init();  // function attributes must be set outside of stream capture
+  // build the plan(s) of the nominal chunk now: packs every weight once and validates the state dict
+  for (int r = 0; r < m->desc.inflight; ++r) {
+    Plan* pl = nullptr;
+    rc = get_plan(m, m->desc.chunk, r, &pl);
+    if (rc != HRP_OK) return rc;
+  }
+  m->host.clear();  // packed copies live on the device now
+  m->finalized = true;
+  return HRP_OK;
+}
+
+static int forward_impl(hrp_model* m, const float* x_reg, const float* x_root, const float* k_value, const float* K,
+                        const float* init_pose, const float* init_rot, int32_t B, const hrp_outputs* out,
+                        float* depth_mm, cudaStream_t user) {
+  if (!m->finalized) {
+    set_error("forward before hrp_model_finalize");
+    return HRP_ERR_STATE;
+  }
+  HRP_CUDA_CHECK(cudaSetDevice(m->device));
+  const bool full = (m->desc.kind == HRP_MODEL_FULL);
+  const int chunk = m->desc.chunk;
+  const int nchunks = (B + chunk - 1) / chunk;
+  const bool multi = (m->desc.inflight > 1 && nchunks > 1);
+  const size_t img = (size_t)3 * kImg * kImg;
+  if (multi) HRP_CUDA_CHECK(cudaEventRecord(m->fork_ev, user));
+  std::vector<Plan*> used;
+  for (int c = 0; c < nchunks; ++c) {
+    const int b0 = c * chunk;
+    const int nb = std::min(chunk, B - b0);
+    const int replica = multi ? (c % m->desc.inflight) : 0;
+    Plan* pl = nullptr;
+    int rc = get_plan(m, nb, replica, &pl);
+    if (rc != HRP_OK) return rc;
+    m->last_plan = pl;
+    cudaStream_t s = multi ? pl->stream : user;
+    if (multi && std::find(used.begin(), used.end(), pl) == used.end()) {
+      HRP_CUDA_CHECK(cudaStreamWaitEvent(s, m->fork_ev, 0));
+      used.push_back(pl);
+    }
+    rc = launch_pack_input_s2d(x_root + b0 * img, pl->s2d_root, nb, kImg, kImg, s);
+    if (rc != HRP_OK) return rc;
+    if (full) {
+      rc = launch_pack_input_s2d(x_reg + b0 * img, pl->s2d_reg, nb, kImg, kImg, s);
+      if (rc != HRP_OK) return rc;
+    }
+    rc = run_plan_body(m, pl, s);
+    if (rc != HRP_OK) return rc;
+    if (!full) {
+      rc = launch_depth(pl->feat, m->depth_w, m->depth_b, k_value + b0, depth_mm + b0, nb, 1.0f, s);
+      if (rc != HRP_OK) return rc;
+      continue;
+    }
+    const int nk = m->desc.nkpt, dof = m->desc.dof;
+    HeadParams hp;
+    memset(&hp, 0, sizeof(hp));
+    hp.B = nb;
+    hp.nkpt = nk;
+    hp.ref_kpt = m->desc.ref_kpt;
+    hp.fix_root = m->desc.fix_root;
+    hp.image_size = m->desc.image_size;
+    hp.depth_factor = m->desc.depth_factor;
+    hp.heatmap = pl->acts[pl->heatmap].ptr;
+    hp.chunks = pl->head_chunks;
+    hp.counters = reinterpret_cast<unsigned int*>(pl->head_ws);
+    hp.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(pl->head_ws) + ((size_t)nb * 4 + 255) / 256 * 256);
+    hp.K = K + (size_t)b0 * 9;
+    hp.feat = pl->feat;
+    hp.depth_w = m->depth_w;
+    hp.depth_b = m->depth_b;
+    hp.k_value = k_value + b0;
+    hp.xf = pl->xf;
+    hp.init_pose = (init_pose != nullptr) ? init_pose + (size_t)b0 * dof : m->init_pose;
+    hp.init_rot = (init_rot != nullptr) ? init_rot + (size_t)b0 * 6 : m->init_rot;
+    hp.init_batched = (init_pose != nullptr) ? 1 : 0;
+    HRP_REQUIRE((init_pose == nullptr) == (init_rot == nullptr), "init_pose and init_rot must be given together");
+    hp.robot = reinterpret_cast<const RobotTable*>(hrp_robot_device_table(m->robot));
+    hp.reg_pose = m->reg_pose;
+    hp.reg_rot = m->reg_rot;
+    hp.pose = out->pose ? out->pose + (size_t)b0 * dof : nullptr;
+    hp.rot = out->rot ? out->rot + (size_t)b0 * 6 : nullptr;
+    hp.trans = out->trans ? out->trans + (size_t)b0 * 3 : nullptr;
+    hp.root_uv = out->root_uv ? out->root_uv + (size_t)b0 * 2 : nullptr;
+    hp.depth = out->depth ? out->depth + b0 : nullptr;
+    hp.uvd = out->uvd ? out->uvd + (size_t)b0 * nk * 3 : nullptr;
+    hp.xyz_int = out->xyz_int ? out->xyz_int + (size_t)b0 * nk * 3 : nullptr;
+    hp.xyz_fk = out->xyz_fk ? out->xyz_fk + (size_t)b0 * nk * 3 : nullptr;
+    hp.uv_int = out->uv_int ? out->uv_int + (size_t)b0 * nk * 2 : nullptr;
+    hp.uv_fk = out->uv_fk ? out->uv_fk + (size_t)b0 * nk * 2 : nullptr;
+    rc = launch_head(hp, s);
+    if (rc != HRP_OK) return rc;
+  }
+  if (multi)
+    for (Plan* pl : used) {
+      HRP_CUDA_CHECK(cudaEventRecord(pl->done_ev, pl->stream));
+      HRP_CUDA_CHECK(cudaStreamWaitEvent(user, pl->done_ev, 0));
+    }
+  return HRP_OK;
+}
+
+int hrp_model_forward(hrp_model* model, const float* x_reg, const float* x_root, const float* k_value, const float* K,
+                      const float* init_pose, const float* init_rot, int32_t B, const hrp_outputs* out, void* stream) {
+  HRP_REQUIRE(model != nullptr && x_reg != nullptr && x_root != nullptr && k_value != nullptr && K != nullptr &&
+                  out != nullptr && B > 0,
+              "bad argument");
+  HRP_REQUIRE(model->desc.kind == HRP_MODEL_FULL, "not a full model handle");
+  return forward_impl(model, x_reg, x_root, k_value, K, init_pose, init_rot, B, out, nullptr,
+                      reinterpret_cast<cudaStream_t>(stream));
+}
+
+int hrp_model_depthnet_forward(hrp_model* model, const float* x, const float* k_value, int32_t B, float* depth_mm,
+                               void* stream) {
+  HRP_REQUIRE(model != nullptr && x != nullptr && k_value != nullptr && depth_mm != nullptr && B > 0, "bad argument");
+  HRP_REQUIRE(model->desc.kind == HRP_MODEL_DEPTHNET, "not a depthnet handle");
+  return forward_impl(model, nullptr, x, k_value, nullptr, nullptr, nullptr, B, nullptr, depth_mm,
+                      reinterpret_cast<cudaStream_t>(stream));
+}
+
+int hrp_model_activation(hrp_model* model, const char* name, const void** ptr, int32_t* B, int32_t* H, int32_t* W,
+                         int32_t* C) {
+  HRP_REQUIRE(model != nullptr && name != nullptr && ptr != nullptr, "bad argument");
+  if (model->last_plan == nullptr) {
+    set_error("no forward has run yet");
+    return HRP_ERR_STATE;
+  }
+  Plan* pl = model->last_plan;
+  if (std::string(name) == "feat" || std::string(name) == "xf") {
+    *ptr = (std::string(name) == "feat") ? (const void*)pl->feat : (const void*)pl->xf;
+    *B = pl->B;
+    *H = *W = 1;
+    *C = -2048;  // negative: fp32 vector, not a bf16 NHWC tensor
+    return HRP_OK;
+  }
+  auto it = pl->taps.find(name);
+  if (it == pl->taps.end()) {
+    set_error(std::string("unknown activation tap: ") + name);
+    return HRP_ERR_INVALID;
+  }
+  const Act& a = pl->acts[it->second];
+  *ptr = a.ptr;
+  *B = pl->B;
+  *H = a.H;
+  *W = a.W;
+  *C = a.C;
+  return HRP_OK;
+}
+
+int hrp_model_stats(const hrp_model* model, int32_t batch, double* flops, int32_t* kernels, int64_t* activation_bytes) {
+  HRP_REQUIRE(model != nullptr, "null model");
+  for (auto& kv : model->plans)
+    if (kv.first.first == batch) {
+      const Plan* pl = kv.second.get();
+      if (flops) *flops = pl->flops;
+      if (kernels) *kernels = pl->n_kernels + ((model->desc.kind == HRP_MODEL_FULL) ? 3 : 2);
+      if (activation_bytes) {
+        int64_t t = 0;
+        for (auto& a : pl->acts) t += (int64_t)pl->B * a.H * a.W * a.C * 2;
+        *activation_bytes = t;
+      }
+      return HRP_OK;
+    }
+  set_error("no plan for this batch size yet");
+  return HRP_ERR_STATE;
+}
+
+}  // extern "C"

@@ -2,6 +2,14 @@
 #pragma once
 #include "hrp_common.cuh"
 namespace hrp {
+struct FuseAddParams {
+  const bf16* pre;
+  const bf16* up[3];
+  int up_shift[3];
+  bf16* out;
+  int B, H, W, C, relu;
+};
+int launch_fuse_add(const FuseAddParams& p, cudaStream_t s);
 int launch_pack_input_s2d(const float* x, void* out, int B, int H, int W, cudaStream_t s);
 int launch_maxpool3x3s2(const void* in, void* out, int B, int H, int W, int C, cudaStream_t s);
 int launch_nchw_f32_to_nhwc_bf16(const float* in, void* out, int B, int C, int H, int W, int Cpad, cudaStream_t s);

@@ -157,6 +157,66 @@ typedef struct hrp_head_args {
 int hrp_head_workspace_bytes(int32_t B, int32_t nkpt, int64_t* bytes);
 int hrp_head(const hrp_head_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Whole-network inference.
+ * Replaces RootNetwithRegInt.forward (lib/models/full_net.py:239-397; construction :38-192 and
+ * get_rootNetwithRegInt_model :401-435 incl. the backbone.* -> rootnet_backbone.* remap :423-427) and
+ * RootNet.forward (lib/models/depth_net.py:92-137) for the shipped configuration family:
+ * backbone_name=resnet50, rootnet_backbone_name=hrnet32, rotation_dim=6, fix_root, no add_fc / multi_kp /
+ * reg_joint_map / direct_reg_rot / rot_iterative_matmul (configs/{panda,kuka,baxter}/{full,depthnet}.yaml).
+ * Weights are ingested by their reference state_dict key.
+ * Call order: create -> set_tensor (every key) -> [set_robot] -> finalize -> forward*.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct hrp_model hrp_model;
+enum { HRP_MODEL_FULL = 0, HRP_MODEL_DEPTHNET = 1 };
+
+typedef struct hrp_model_desc {
+  int32_t kind;          /* HRP_MODEL_FULL | HRP_MODEL_DEPTHNET */
+  int32_t dof, nkpt;     /* panda 8/7, kuka 7/8, baxter 15/17 (full_net.py:42-51); ignored for the depthnet */
+  int32_t ref_kpt;       /* reference_keypoint_id (configs/<robot>/full.yaml) */
+  int32_t n_iter;        /* iterations of the pose / rot regressors (4) */
+  int32_t fix_root;      /* args.fix_root */
+  float image_size;      /* 256 */
+  float depth_factor;    /* bbox_3d_shape[2] * 1e-3 */
+  int32_t chunk;         /* images per pass through the network (L2-sized sub-batch) */
+  int32_t inflight;      /* number of chunk replicas executing concurrently (1..4) */
+} hrp_model_desc;
+
+/* device fp32 outputs; any pointer may be NULL.  Shapes as returned by the reference forward (8-tuple). */
+typedef struct hrp_outputs {
+  float* pose;     /* (B,dof) */
+  float* rot;      /* (B,6) */
+  float* trans;    /* (B,3) */
+  float* root_uv;  /* (B,2) */
+  float* depth;    /* (B,1) metres */
+  float* uvd;      /* (B,nkpt,3) */
+  float* xyz_int;  /* (B,nkpt,3) */
+  float* xyz_fk;   /* (B,nkpt,3) */
+  float* uv_int;   /* (B,nkpt,2) projection of xyz_int with K (scripts/test.py:179) -- extra */
+  float* uv_fk;    /* (B,nkpt,2) projection of xyz_fk with K -- extra */
+} hrp_outputs;
+
+int hrp_model_create(const hrp_model_desc* desc, hrp_model** out);
+void hrp_model_destroy(hrp_model* model);
+/* data: host fp32, copied.  Integer buffers (num_batches_tracked) need not be passed. */
+int hrp_model_set_tensor(hrp_model* model, const char* name, const float* data, const int64_t* shape, int32_t ndim);
+int hrp_model_set_robot(hrp_model* model, const hrp_robot* robot);   /* robot must outlive the model */
+int hrp_model_finalize(hrp_model* model);
+/* x_reg, x_root: device fp32 (B,3,256,256) in [0,1]; k_value (B); K (B,3,3); init_pose (B,dof) / init_rot (B,6)
+ * or NULL for the registered buffers. */
+int hrp_model_forward(hrp_model* model, const float* x_reg, const float* x_root, const float* k_value, const float* K,
+                      const float* init_pose, const float* init_rot, int32_t B, const hrp_outputs* out, void* stream);
+/* RootNet.forward: x (B,3,256,256), k_value (B) -> depth in millimetres (B,1) */
+int hrp_model_depthnet_forward(hrp_model* model, const float* x, const float* k_value, int32_t B, float* depth_mm,
+                               void* stream);
+/* test / profiling hooks: named intermediate activation of the most recently used plan (bf16 NHWC device
+ * pointer; C < 0 means an fp32 (B,|C|) vector), and per-plan statistics */
+int hrp_model_activation(hrp_model* model, const char* name, const void** ptr, int32_t* B, int32_t* H, int32_t* W,
+                         int32_t* C);
+/* asynchronous device-to-device copy on `stream` (used by the shims to snapshot activations) */
+int hrp_copy_device(void* dst, const void* src, int64_t bytes, void* stream);
+int hrp_model_stats(const hrp_model* model, int32_t batch, double* flops, int32_t* kernels, int64_t* activation_bytes);
+
 #ifdef __cplusplus
 }
 #endif
