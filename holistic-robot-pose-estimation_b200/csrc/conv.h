@@ -27,7 +27,8 @@ struct ConvParams {
   int os, oh0, ow0;       // output pixel stride / offset
   int nphase;             // 1, or 4 for ConvTranspose2d(k4,s2,p1): phase z = (ph,pw) shifts taps and output
   int ntaps, ck, cpt;     // taps, channels per k-block (16/32/64), k-blocks per tap (Cin/ck)
-  int n_tile, cout_pad;   // N tile (multiple of 16, <= 256); weight rows per phase (multiple of n_tile)
+  int n_tile, cout_pad;   // N tile (multiple of 32, <= 256); weight rows per phase (multiple of n_tile)
+  int cko;                // channels per TMA-store block of the epilogue (64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B)
   int ktot;               // ntaps*Cin
   int8_t tap_dh[kMaxTaps], tap_dw[kMaxTaps], tap_map[kMaxTaps];
   // epilogue
@@ -48,8 +49,9 @@ struct ConvParams {
 };
 
 struct ConvMaps {
-  CUtensorMap a[4];
-  CUtensorMap b;
+  CUtensorMap a[4];  // input: one per stride-2 parity (else a[0])
+  CUtensorMap b;     // packed weights
+  CUtensorMap o[4];  // output: one per deconv phase (else o[0])
 };
 
 struct ConvPlan {

@@ -35,7 +35,7 @@ struct __align__(8) PipeBarriers {
 template <int CK>
 __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_constant__ ConvMaps maps,
                                                                 const __grid_constant__ ConvParams p,
-                                                                int stages) {
+                                                                int stages, int bar_offset) {
   constexpr int SUB = 64 / CK;                 // sub-tiles (k-blocks) per stage
   constexpr int A_SUB_BYTES = kTileM * CK * 2;
   constexpr int KSTEPS = CK / 16;              // tcgen05.mma K=16 steps per sub-tile
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
   const int n_tile = p.n_tile;
   const int b_sub_bytes = n_tile * CK * 2;
   const int stage_bytes = kStageABytes + n_tile * 128;
-  PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(smem + (size_t)stages * stage_bytes);
+  PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(smem + bar_offset);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -219,9 +219,15 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
           o1.y = pack_bf16x2(v[10], v[11]);
           o1.z = pack_bf16x2(v[12], v[13]);
           o1.w = pack_bf16x2(v[14], v[15]);
-          uint4* dst = reinterpret_cast<uint4*>(p.out + opix * p.Cout + c);
-          dst[0] = o0;
-          dst[1] = o1;
+          // stage into the (now idle) pipeline buffers in the TMA-store box layout: column blocks of cko channels,
+          // 128 rows each, 16-byte chunks XOR-swizzled exactly as the output tensor map expects
+          const int cko = p.cko;
+          const int blk = c0 / cko;
+          const int ch0 = (c0 - blk * cko) >> 3;  // first 16-byte chunk of this thread inside the row
+          const int sw = (cko == 64) ? (row & 7) : ((row >> 1) & 3);
+          uint8_t* rowp = smem + (size_t)blk * (kTileM * cko * 2) + (size_t)row * (cko * 2);
+          *reinterpret_cast<uint4*>(rowp + (((ch0 + 0) ^ sw) << 4)) = o0;
+          *reinterpret_cast<uint4*>(rowp + (((ch0 + 1) ^ sw) << 4)) = o1;
         }
       }
       if (p.pool_out != nullptr) {
@@ -245,6 +251,23 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
       }
     }
     tc_fence_before();
+    if (p.out != nullptr) {
+      // generic-proxy smem writes -> visible to the async proxy, then ONE thread issues the TMA stores
+      // (rows / channels outside the tensor are clipped by the TMA unit: ragged tiles need no predicates)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 2 && elect_one()) {
+        const int cko = p.cko;
+        const int nblk = n_tile / cko;
+        for (int j = 0; j < nblk; ++j) {
+          const int cj = c_base + j * cko;
+          if (cj >= p.Cout) break;
+          tma_store_4d(smem + (size_t)j * (kTileM * cko * 2), &maps.o[phase], cj, w0, h0, n0);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
+    }
   }
 
   __syncthreads();
@@ -265,7 +288,7 @@ int conv_geometry(const ConvLayerDesc& d, ConvParams* pp) {
   memset(&p, 0, sizeof(p));
   HRP_REQUIRE(d.B > 0 && d.Hin > 0 && d.Win > 0 && d.Cout > 0, "conv dims must be positive");
   HRP_REQUIRE(d.Cin == 16 || d.Cin == 32 || d.Cin % 64 == 0, "stored Cin must be 16, 32 or a multiple of 64");
-  HRP_REQUIRE(d.Cout % 16 == 0, "Cout must be a multiple of 16");
+  HRP_REQUIRE(d.Cout % 32 == 0, "Cout must be a multiple of 32");
   p.B = d.B;
   p.Cin = d.Cin;
   p.Cout = d.Cout;
@@ -367,8 +390,9 @@ int conv_geometry(const ConvLayerDesc& d, ConvParams* pp) {
   p.tiles_n = (p.B + p.bn - 1) / p.bn;
   // N tile
   const int n_tiles = (p.Cout + 255) / 256;
-  p.n_tile = (((p.Cout + n_tiles - 1) / n_tiles) + 15) / 16 * 16;
+  p.n_tile = (((p.Cout + n_tiles - 1) / n_tiles) + 31) / 32 * 32;
   p.cout_pad = n_tiles * p.n_tile;
+  p.cko = (p.n_tile % 64 == 0) ? 64 : 32;  // channel block of the TMA-store epilogue
   p.pool_scale = 1.f / (float)(p.Hout * p.Wout);
   return HRP_OK;
 }
@@ -495,13 +519,31 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed) {
   }
   if (p.pool_out != nullptr)
     HRP_REQUIRE(p.bw * p.bh >= 32, "pooled epilogue needs >= 32 rows per image in a tile");
+  if (p.out != nullptr) {
+    // output maps for the TMA-store epilogue: one per deconv phase (stride-2 interleaved pixels), else one
+    HRP_REQUIRE((reinterpret_cast<uintptr_t>(p.out) & 15) == 0, "output must be 16-byte aligned");
+    for (int ph = 0; ph < p.nphase; ++ph) {
+      const int oh = p.oh0 + (ph >> 1), ow = p.ow0 + (ph & 1);
+      const bf16* base = p.out + ((size_t)oh * p.Wout + ow) * p.Cout;
+      uint64_t dims[4] = {(uint64_t)p.Cout, (uint64_t)p.Wm, (uint64_t)p.Hm, (uint64_t)p.B};
+      uint64_t strides[3] = {(uint64_t)p.os * p.Cout * 2, (uint64_t)p.os * p.Wout * p.Cout * 2,
+                             (uint64_t)p.Hout * p.Wout * p.Cout * 2};
+      uint32_t box[4] = {(uint32_t)p.cko, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+      int rc = encode_map(&plan->maps.o[ph], base, 4, dims, strides, box, p.cko);
+      if (rc != HRP_OK) return rc;
+    }
+    for (int ph = p.nphase; ph < 4; ++ph) plan->maps.o[ph] = plan->maps.o[0];
+  }
   const int stage_bytes = kStageABytes + p.n_tile * 128;
   const int sub = 64 / p.ck;
   const int n_iters = (p.ntaps * p.cpt + sub - 1) / sub;
-  int stages = std::max(2, std::min(6, (100 * 1024) / stage_bytes));
+  // shallow per-CTA pipelines, several CTAs per SM: small tiles are latency-bound, not smem-bound
+  const int budget = (p.n_tile <= 64) ? 56 * 1024 : (p.n_tile <= 128) ? 72 * 1024 : 100 * 1024;
+  int stages = std::max(2, budget / stage_bytes);
   stages = std::max(1, std::min(stages, n_iters));
   plan->stages = stages;
-  plan->smem_bytes = stages * stage_bytes + (int)sizeof(PipeBarriers) + 1024;
+  const int staging = (p.out != nullptr) ? kTileM * p.n_tile * 2 : 0;
+  plan->smem_bytes = std::max(stages * stage_bytes, staging) + (int)sizeof(PipeBarriers) + 1024;
   plan->grid = dim3((unsigned)(p.tiles_w * p.tiles_h * p.tiles_n), (unsigned)(p.cout_pad / p.n_tile),
                     (unsigned)p.nphase);
   return HRP_OK;
@@ -510,12 +552,13 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed) {
 int conv_plan_launch(const ConvPlan& plan, cudaStream_t stream) {
   set_smem_attr_once();
   const ConvParams& p = plan.p;
+  const int bar_offset = plan.smem_bytes - (int)sizeof(PipeBarriers) - 1024;
   if (p.ck == 64)
-    conv_gemm_kernel<64><<<plan.grid, kNumThreads, plan.smem_bytes, stream>>>(plan.maps, p, plan.stages);
+    conv_gemm_kernel<64><<<plan.grid, kNumThreads, plan.smem_bytes, stream>>>(plan.maps, p, plan.stages, bar_offset);
   else if (p.ck == 32)
-    conv_gemm_kernel<32><<<plan.grid, kNumThreads, plan.smem_bytes, stream>>>(plan.maps, p, plan.stages);
+    conv_gemm_kernel<32><<<plan.grid, kNumThreads, plan.smem_bytes, stream>>>(plan.maps, p, plan.stages, bar_offset);
   else
-    conv_gemm_kernel<16><<<plan.grid, kNumThreads, plan.smem_bytes, stream>>>(plan.maps, p, plan.stages);
+    conv_gemm_kernel<16><<<plan.grid, kNumThreads, plan.smem_bytes, stream>>>(plan.maps, p, plan.stages, bar_offset);
   count_launch();
   HRP_CUDA_CHECK(cudaGetLastError());
   return HRP_OK;

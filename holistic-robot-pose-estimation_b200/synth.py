@@ -13,6 +13,9 @@ Recipe (one per robot, backbones shared):
   * BatchNorm running statistics: calibrated ONCE on seeded random images with the oracle and committed as
     fixtures/bn_stats.npz (tests/golden/make_golden.py) -- random-init nets explode in eval mode otherwise
     (SURVEY.md fact 7);
+  * regression heads with the reference's own init scales (nn.Linear default for fc_*, xavier gain 0.01 for
+    decpose / decrot, full_net.py:95-100,129-134; depth_layer normal std 1e-3, :174-177): the bf16 noise of the
+    2048-d features reaches pose / rot / depth through these weights, so their scale sets the parity margin;
   * depth_layer.bias = 2.0 so that depth = gamma*k/1000 is a plausible 0.7..2.5 m.
 """
 from __future__ import annotations
@@ -80,14 +83,15 @@ def _fill(spec, seed: int, with_bn_stats: bool):
             else:
                 fan_in = shape[1] * shape[2] * shape[3]
             gain = 1.0
-            if key == "depth_layer.weight":
-                sd[key] = sym_uniform(key, shape, 0.01, seed)
+            if key == "depth_layer.weight":  # reference: normal(std=0.001), full_net.py:174-177
+                sd[key] = sym_uniform(key, shape, 0.001, seed)
                 continue
             sd[key] = sym_uniform(key, shape, gain * float(np.sqrt(2.0 / fan_in)), seed)
-        elif len(shape) == 2 and leaf == "weight":  # linear
-            std = float(np.sqrt(1.0 / shape[1]))
-            if base in ("decpose", "decrot"):
-                std *= 0.1  # reference uses xavier gain 0.01 (full_net.py:100,134); keep updates small but visible
+        elif len(shape) == 2 and leaf == "weight":  # linear: the reference's own init scales
+            if base in ("decpose", "decrot"):  # xavier_uniform(gain=0.01), full_net.py:100,134
+                std = 0.01 * float(np.sqrt(2.0 / (shape[0] + shape[1])))
+            else:  # nn.Linear default: U(+-1/sqrt(fan_in))
+                std = float(np.sqrt(1.0 / (3.0 * shape[1])))
             sd[key] = sym_uniform(key, shape, std, seed)
         elif leaf == "weight":  # BN gamma
             g = range_uniform(key, shape, 0.5, 1.5, seed)
@@ -97,7 +101,9 @@ def _fill(spec, seed: int, with_bn_stats: bool):
                 sd[key] = torch.full(shape, 2.0)
             elif (base + ".running_mean") in spec:  # BN beta
                 sd[key] = range_uniform(key, shape, -0.2, 0.2, seed)
-            else:  # conv / linear bias
+            elif len(spec.get(base + ".weight", ())) == 2:  # linear bias: U(+-1/sqrt(fan_in)) like nn.Linear
+                sd[key] = sym_uniform(key, shape, float(np.sqrt(1.0 / (3.0 * spec[base + ".weight"][1]))), seed)
+            else:  # conv bias
                 sd[key] = sym_uniform(key, shape, 0.05, seed)
         else:
             raise KeyError(key)

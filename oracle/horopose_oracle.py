@@ -413,23 +413,12 @@ def depthnet_forward(sd, x, k_value, calib=None):
     return gamma * k_value.view(-1, 1)
 
 
-def full_forward(sd, robot: OracleRobot, x_reg, x_root, k_value, K, n_iter=4, calib=None, taps=None,
-                 init_pose=None, init_rot=None):
-    """RootNetwithRegInt.forward, full_net.py:239-397 (resnet50 + hrnet32, rotation_dim 6, fix_root True)."""
-    dof, nkpt, ref = ROBOTS[robot.robot_type]
-    B = x_reg.shape[0]
+def full_features(sd, x_reg, x_root, calib=None, taps=None):
+    """The convolutional part of RootNetwithRegInt.forward (full_net.py:251-296): pooled HRNet feature (B,2048),
+    ResNet trunk output (B,2048,8,8) and the heatmap logits (B,nkpt*64,64,64)."""
     x_reg, x_root = x_reg.float(), x_root.float()
-    init_pose = sd["init_pose"].expand(B, -1) if init_pose is None else init_pose
-    init_rot = sd["init_rot"].expand(B, -1) if init_rot is None else init_rot
-    # A. root depth, full_net.py:251-287
     feat = hrnet32_forward(sd, x_root, "rootnet_backbone.", calib, taps)
-    gamma = F.conv2d(feat[:, :, None, None], sd["depth_layer.weight"], sd["depth_layer.bias"]).view(-1, 1)
-    pred_depth = (gamma * k_value.view(-1, 1)).reshape(B, 1) / 1000.0
-    root_trans = torch.zeros(B, 3)
-    root_trans[:, 2:3] = pred_depth
-    # B. keypoints, full_net.py:291-298
     x_out = resnet50_forward(sd, x_reg, "reg_backbone.", calib, taps)
-    xf = F.avg_pool2d(x_out, 8, stride=1)
     c = _Ctx(sd, "", calib, taps)
     out = x_out
     for i in range(3):
@@ -438,7 +427,23 @@ def full_forward(sd, robot: OracleRobot, x_reg, x_root, k_value, K, n_iter=4, ca
     c.tap("deconv", out)
     out = F.conv2d(out, sd["final_layer.weight"], sd["final_layer.bias"])
     c.tap("heatmap", out)
-    pred_uvd, pred_xyz_int = heatmap_integral(out, nkpt, K, root_trans, ref)
+    return feat, x_out, out
+
+
+def full_head(sd, robot: OracleRobot, feat, x_out, heat, k_value, K, n_iter=4, init_pose=None, init_rot=None):
+    """Everything after the convolutions (full_net.py:271-287,294,297-397), fp32."""
+    dof, nkpt, ref = ROBOTS[robot.robot_type]
+    B = feat.shape[0]
+    init_pose = sd["init_pose"].expand(B, -1) if init_pose is None else init_pose
+    init_rot = sd["init_rot"].expand(B, -1) if init_rot is None else init_rot
+    # A. root depth, full_net.py:271-287
+    gamma = F.conv2d(feat[:, :, None, None], sd["depth_layer.weight"], sd["depth_layer.bias"]).view(-1, 1)
+    pred_depth = (gamma * k_value.view(-1, 1)).reshape(B, 1) / 1000.0
+    root_trans = torch.zeros(B, 3)
+    root_trans[:, 2:3] = pred_depth
+    # B. keypoints, full_net.py:294-298
+    xf = F.avg_pool2d(x_out, 8, stride=1)
+    pred_uvd, pred_xyz_int = heatmap_integral(heat, nkpt, K, root_trans, ref)
     pred_root_uv = (pred_uvd[:, ref, :2] + 0.5) * 256.0
     # C. root translation, full_net.py:305
     pred_trans = uvz2xyz_singlepoint(pred_root_uv, pred_depth, K)
@@ -461,3 +466,10 @@ def full_forward(sd, robot: OracleRobot, x_reg, x_root, k_value, K, n_iter=4, ca
     else:
         xyz_fk = robot.get_keypoints_root(pose, rot, pred_trans, root=ref)
     return pose, rot, pred_trans, pred_root_uv, pred_depth, pred_uvd, pred_xyz_int, xyz_fk
+
+
+def full_forward(sd, robot: OracleRobot, x_reg, x_root, k_value, K, n_iter=4, calib=None, taps=None,
+                 init_pose=None, init_rot=None):
+    """RootNetwithRegInt.forward, full_net.py:239-397 (resnet50 + hrnet32, rotation_dim 6, fix_root True)."""
+    feat, x_out, heat = full_features(sd, x_reg, x_root, calib, taps)
+    return full_head(sd, robot, feat, x_out, heat, k_value, K, n_iter, init_pose, init_rot)
