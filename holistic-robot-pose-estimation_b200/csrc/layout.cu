@@ -44,6 +44,41 @@ __global__ void pack_input_s2d_kernel(const float* __restrict__ x, uint4* __rest
   }
 }
 
+// uint8 variant: fuses the caller-side `images.float() / 255.` of scripts/test.py:83-86 into the packing pass.
+// One thread per s2d pixel; reads 2 bytes (uchar2) per channel-row.
+__global__ void pack_input_s2d_u8_kernel(const uint8_t* __restrict__ x, uint4* __restrict__ out, int B, int H, int W) {
+  const int Ws = W >> 1, Hs = H >> 1;
+  const size_t total = (size_t)B * Hs * Ws;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ws = (int)(i % Ws);
+    const int hs = (int)((i / Ws) % Hs);
+    const int n = (int)(i / ((size_t)Ws * Hs));
+    float v[16];
+#pragma unroll
+    for (int k = 12; k < 16; ++k) v[k] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int hp = 0; hp < 2; ++hp) {
+        const uchar2 t = __ldg(reinterpret_cast<const uchar2*>(x + (((size_t)n * 3 + c) * H + (2 * hs + hp)) * W + 2 * ws));
+        v[(hp * 2 + 0) * 3 + c] = (float)t.x / 255.0f;
+        v[(hp * 2 + 1) * 3 + c] = (float)t.y / 255.0f;
+      }
+    }
+    uint4 o0, o1;
+    o0.x = pack_bf16x2(v[0], v[1]);
+    o0.y = pack_bf16x2(v[2], v[3]);
+    o0.z = pack_bf16x2(v[4], v[5]);
+    o0.w = pack_bf16x2(v[6], v[7]);
+    o1.x = pack_bf16x2(v[8], v[9]);
+    o1.y = pack_bf16x2(v[10], v[11]);
+    o1.z = pack_bf16x2(v[12], v[13]);
+    o1.w = pack_bf16x2(v[14], v[15]);
+    out[2 * i] = o0;
+    out[2 * i + 1] = o1;
+  }
+}
+
 // MaxPool2d(kernel 3, stride 2, pad 1) on bf16 NHWC; thread = (output pixel, 8-channel group)
 __global__ void maxpool3x3s2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W,
                                     int C8) {
@@ -171,6 +206,17 @@ int launch_pack_input_s2d(const float* x, void* out, int B, int H, int W, cudaSt
   const int threads = 256;
   const int blocks = (int)std::min<size_t>((total + threads - 1) / threads, 148 * 16);
   pack_input_s2d_kernel<<<blocks, threads, 0, s>>>(x, reinterpret_cast<uint4*>(out), B, H, W);
+  count_launch();
+  HRP_CUDA_CHECK(cudaGetLastError());
+  return HRP_OK;
+}
+
+int launch_pack_input_s2d_u8(const uint8_t* x, void* out, int B, int H, int W, cudaStream_t s) {
+  HRP_REQUIRE(H % 2 == 0 && W % 2 == 0, "input size must be even");
+  const size_t total = (size_t)B * (H / 2) * (W / 2);
+  const int threads = 256;
+  const int blocks = (int)std::min<size_t>((total + threads - 1) / threads, 148 * 16);
+  pack_input_s2d_u8_kernel<<<blocks, threads, 0, s>>>(x, reinterpret_cast<uint4*>(out), B, H, W);
   count_launch();
   HRP_CUDA_CHECK(cudaGetLastError());
   return HRP_OK;

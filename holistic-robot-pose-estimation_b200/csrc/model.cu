@@ -814,9 +814,13 @@ int hrp_model_finalize(hrp_model* m) {
   return HRP_OK;
 }
 
-static int forward_impl(hrp_model* m, const float* x_reg, const float* x_root, const float* k_value, const float* K,
-                        const float* init_pose, const float* init_rot, int32_t B, const hrp_outputs* out,
-                        float* depth_mm, cudaStream_t user) {
+static int forward_impl(hrp_model* m, const void* x_reg_v, const void* x_root_v, int in_u8, const float* k_value,
+                        const float* K, const float* init_pose, const float* init_rot, int32_t B,
+                        const hrp_outputs* out, float* depth_mm, cudaStream_t user) {
+  const float* x_reg = reinterpret_cast<const float*>(x_reg_v);
+  const float* x_root = reinterpret_cast<const float*>(x_root_v);
+  const uint8_t* x_reg8 = reinterpret_cast<const uint8_t*>(x_reg_v);
+  const uint8_t* x_root8 = reinterpret_cast<const uint8_t*>(x_root_v);
   if (!m->finalized) {
     set_error("forward before hrp_model_finalize");
     return HRP_ERR_STATE;
@@ -842,10 +846,12 @@ static int forward_impl(hrp_model* m, const float* x_reg, const float* x_root, c
       HRP_CUDA_CHECK(cudaStreamWaitEvent(s, m->fork_ev, 0));
       used.push_back(pl);
     }
-    rc = launch_pack_input_s2d(x_root + b0 * img, pl->s2d_root, nb, kImg, kImg, s);
+    rc = in_u8 ? launch_pack_input_s2d_u8(x_root8 + b0 * img, pl->s2d_root, nb, kImg, kImg, s)
+               : launch_pack_input_s2d(x_root + b0 * img, pl->s2d_root, nb, kImg, kImg, s);
     if (rc != HRP_OK) return rc;
     if (full) {
-      rc = launch_pack_input_s2d(x_reg + b0 * img, pl->s2d_reg, nb, kImg, kImg, s);
+      rc = in_u8 ? launch_pack_input_s2d_u8(x_reg8 + b0 * img, pl->s2d_reg, nb, kImg, kImg, s)
+                 : launch_pack_input_s2d(x_reg + b0 * img, pl->s2d_reg, nb, kImg, kImg, s);
       if (rc != HRP_OK) return rc;
     }
     rc = run_plan_body(m, pl, s);
@@ -908,7 +914,18 @@ int hrp_model_forward(hrp_model* model, const float* x_reg, const float* x_root,
                   out != nullptr && B > 0,
               "bad argument");
   HRP_REQUIRE(model->desc.kind == HRP_MODEL_FULL, "not a full model handle");
-  return forward_impl(model, x_reg, x_root, k_value, K, init_pose, init_rot, B, out, nullptr,
+  return forward_impl(model, x_reg, x_root, 0, k_value, K, init_pose, init_rot, B, out, nullptr,
+                      reinterpret_cast<cudaStream_t>(stream));
+}
+
+int hrp_model_forward_u8(hrp_model* model, const uint8_t* x_reg, const uint8_t* x_root, const float* k_value,
+                         const float* K, const float* init_pose, const float* init_rot, int32_t B,
+                         const hrp_outputs* out, void* stream) {
+  HRP_REQUIRE(model != nullptr && x_reg != nullptr && x_root != nullptr && k_value != nullptr && K != nullptr &&
+                  out != nullptr && B > 0,
+              "bad argument");
+  HRP_REQUIRE(model->desc.kind == HRP_MODEL_FULL, "not a full model handle");
+  return forward_impl(model, x_reg, x_root, 1, k_value, K, init_pose, init_rot, B, out, nullptr,
                       reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -916,7 +933,7 @@ int hrp_model_depthnet_forward(hrp_model* model, const float* x, const float* k_
                                void* stream) {
   HRP_REQUIRE(model != nullptr && x != nullptr && k_value != nullptr && depth_mm != nullptr && B > 0, "bad argument");
   HRP_REQUIRE(model->desc.kind == HRP_MODEL_DEPTHNET, "not a depthnet handle");
-  return forward_impl(model, nullptr, x, k_value, nullptr, nullptr, nullptr, B, nullptr, depth_mm,
+  return forward_impl(model, nullptr, x, 0, k_value, nullptr, nullptr, nullptr, B, nullptr, depth_mm,
                       reinterpret_cast<cudaStream_t>(stream));
 }
 

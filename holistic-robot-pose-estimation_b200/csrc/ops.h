@@ -11,6 +11,7 @@ struct FuseAddParams {
 };
 int launch_fuse_add(const FuseAddParams& p, cudaStream_t s);
 int launch_pack_input_s2d(const float* x, void* out, int B, int H, int W, cudaStream_t s);
+int launch_pack_input_s2d_u8(const uint8_t* x, void* out, int B, int H, int W, cudaStream_t s);
 int launch_maxpool3x3s2(const void* in, void* out, int B, int H, int W, int C, cudaStream_t s);
 int launch_nchw_f32_to_nhwc_bf16(const float* in, void* out, int B, int C, int H, int W, int Cpad, cudaStream_t s);
 int launch_nhwc_bf16_to_nchw_f32(const void* in, float* out, int B, int C, int H, int W, int Cpad, cudaStream_t s);

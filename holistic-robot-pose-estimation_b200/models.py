@@ -208,8 +208,12 @@ class RootNetwithRegInt(_EngineModule):
         self._ensure(dev)
         t0 = time.time()
         B = x_reg_input.shape[0]
-        x_reg = x_reg_input.detach().to(torch.float32).contiguous()
-        x_root = x_root_input.detach().to(device=dev, dtype=torch.float32).contiguous()
+        # uint8 images (0..255) are accepted as-is: the engine fuses the caller-side `.float() / 255.`
+        # (scripts/test.py:83-86) into its input-packing kernel
+        u8 = (x_reg_input.dtype == torch.uint8 and x_root_input.dtype == torch.uint8)
+        dt = torch.uint8 if u8 else torch.float32
+        x_reg = x_reg_input.detach().to(dt).contiguous()
+        x_root = x_root_input.detach().to(device=dev, dtype=dt).contiguous()
         k_value = k_value.detach().to(device=dev, dtype=torch.float32).contiguous().view(-1)
         K = K.detach().to(device=dev, dtype=torch.float32).contiguous()
         assert x_reg.shape == (B, 3, 256, 256) and x_root.shape == (B, 3, 256, 256), (x_reg.shape, x_root.shape)
@@ -226,11 +230,11 @@ class RootNetwithRegInt(_EngineModule):
         for n, t in outs.items():
             setattr(o, n, t.data_ptr())
         with torch.cuda.device(dev):
-            check(_lib.lib().hrp_model_forward(self._handle, C.c_void_p(x_reg.data_ptr()), C.c_void_p(x_root.data_ptr()),
-                                               C.c_void_p(k_value.data_ptr()), C.c_void_p(K.data_ptr()),
-                                               C.c_void_p(ip.data_ptr() if ip is not None else 0),
-                                               C.c_void_p(ir.data_ptr() if ir is not None else 0), B, C.byref(o),
-                                               _stream()))
+            fwd = _lib.lib().hrp_model_forward_u8 if u8 else _lib.lib().hrp_model_forward
+            check(fwd(self._handle, C.c_void_p(x_reg.data_ptr()), C.c_void_p(x_root.data_ptr()),
+                      C.c_void_p(k_value.data_ptr()), C.c_void_p(K.data_ptr()),
+                      C.c_void_p(ip.data_ptr() if ip is not None else 0),
+                      C.c_void_p(ir.data_ptr() if ir is not None else 0), B, C.byref(o), _stream()))
         res = (outs["pose"], outs["rot"], outs["trans"], outs["root_uv"], outs["depth"], outs["uvd"], outs["xyz_int"],
                outs["xyz_fk"])
         if test_fps:  # full_net.py:253-289,385-392: wall-clock with a stream sync; the fused engine has one phase

@@ -206,6 +206,11 @@ int hrp_model_finalize(hrp_model* model);
  * or NULL for the registered buffers. */
 int hrp_model_forward(hrp_model* model, const float* x_reg, const float* x_root, const float* k_value, const float* K,
                       const float* init_pose, const float* init_rot, int32_t B, const hrp_outputs* out, void* stream);
+/* Same, with uint8 images (B,3,256,256) in 0..255: fuses the caller-side `images.float() / 255.` of
+ * scripts/test.py:83-86 into the input-packing kernel (4x less host->device traffic). */
+int hrp_model_forward_u8(hrp_model* model, const uint8_t* x_reg, const uint8_t* x_root, const float* k_value,
+                         const float* K, const float* init_pose, const float* init_rot, int32_t B,
+                         const hrp_outputs* out, void* stream);
 /* RootNet.forward: x (B,3,256,256), k_value (B) -> depth in millimetres (B,1) */
 int hrp_model_depthnet_forward(hrp_model* model, const float* x, const float* k_value, int32_t B, float* depth_mm,
                                void* stream);
