@@ -27,6 +27,7 @@ struct ConvParams {
   int os, oh0, ow0;       // output pixel stride / offset
   int nphase;             // 1, or 4 for ConvTranspose2d(k4,s2,p1): phase z = (ph,pw) shifts taps and output
   int ntaps, ck, cpt;     // taps, channels per k-block (16/32/64), k-blocks per tap (Cin/ck)
+  int n_tiles;            // cout_pad / n_tile
   int n_tile, cout_pad;   // N tile (multiple of 32, <= 256); weight rows per phase (multiple of n_tile)
   int cko;                // channels per TMA-store block of the epilogue (64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B)
   int ktot;               // ntaps*Cin
@@ -59,7 +60,9 @@ struct ConvPlan {
   ConvMaps maps;
   dim3 grid;
   int smem_bytes;
+  int bar_offset;  // barriers + scale/shift staging live after the pipeline stages
   int stages;
+  int epi;         // epilogue flavour (EPI_PLAIN / EPI_PRE / EPI_FULL)
   double flops;  // 2*MACs of the reference layer (algorithmic, not padded)
 };
 

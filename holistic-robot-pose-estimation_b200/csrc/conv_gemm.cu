@@ -32,7 +32,24 @@ struct __align__(8) PipeBarriers {
   uint32_t pad;
 };
 
-template <int CK>
+// Epilogue flavours (template parameter EPI): the common case carries no addends and no per-row predicates at all.
+constexpr int EPI_PLAIN = 0;  // y = [relu](acc*scale + bias)
+constexpr int EPI_PRE = 1;    // + up to three same-resolution addends before the ReLU (residual / fuse partials)
+constexpr int EPI_FULL = 2;   // + nearest-upsampled addends, post-ReLU addend, pooled output
+
+__device__ __forceinline__ void add_bf16x8(float* v, const uint4& x) {
+  v[0] += bf16lo_to_f32(x.x); v[1] += bf16hi_to_f32(x.x);
+  v[2] += bf16lo_to_f32(x.y); v[3] += bf16hi_to_f32(x.y);
+  v[4] += bf16lo_to_f32(x.z); v[5] += bf16hi_to_f32(x.z);
+  v[6] += bf16lo_to_f32(x.w); v[7] += bf16hi_to_f32(x.w);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+template <int CK, int EPI>
 __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_constant__ ConvMaps maps,
                                                                 const __grid_constant__ ConvParams p,
                                                                 int stages, int bar_offset) {
@@ -48,20 +65,23 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
   const int b_sub_bytes = n_tile * CK * 2;
   const int stage_bytes = kStageABytes + n_tile * 128;
   PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(smem + bar_offset);
+  float* sb_smem = reinterpret_cast<float*>(bars + 1);  // [2][n_tile] folded-BN scale / shift of this N tile
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // tile coordinates
+  // tile coordinates: the N tile is the fastest-varying block index so that CTAs sharing an A tile run together
   int t = blockIdx.x;
+  const int n_blk = t % p.n_tiles;
+  t /= p.n_tiles;
   const int tw = t % p.tiles_w;
   t /= p.tiles_w;
   const int th = t % p.tiles_h;
   const int tn = t / p.tiles_h;
   const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
-  const int n_blk = blockIdx.y;
   const int phase = blockIdx.z;
   const int ph = phase >> 1, pw = phase & 1;  // deconv sub-pixel phase (0,0) when nphase == 1
+  const int c_base = n_blk * n_tile;
 
   const int nkb = p.ntaps * p.cpt;
   const int n_iters = (nkb + SUB - 1) / SUB;
@@ -81,6 +101,13 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
   if (warp == 1) {
     tmem_alloc(&bars->tmem_base, tmem_cols);
     tmem_relinquish();
+  }
+  if (warp >= 2) {  // stage scale / shift once per CTA (overlaps the TMEM allocation)
+    for (int i = threadIdx.x - 64; i < n_tile; i += 128) {
+      const int c = c_base + i;
+      sb_smem[i] = (c < p.Cout) ? __ldg(p.scale + c) : 0.f;
+      sb_smem[n_tile + i] = (c < p.Cout) ? __ldg(p.bias + c) : 0.f;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -104,8 +131,7 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
           const int cc = kb - tap * p.cpt;
           tma_load_4d(sa + j * A_SUB_BYTES, &maps.a[p.tap_map[tap]], &bars->full[s], cc * CK,
                       w0 + p.tap_dw[tap] + pw, h0 + p.tap_dh[tap] + ph, n0);
-          tma_load_2d(sb + j * b_sub_bytes, &maps.b, &bars->full[s], kb * CK,
-                      phase * p.cout_pad + n_blk * n_tile);
+          tma_load_2d(sb + j * b_sub_bytes, &maps.b, &bars->full[s], kb * CK, phase * p.cout_pad + c_base);
         }
       }
     }
@@ -129,7 +155,7 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
             umma_bf16_ss(tmem_base, adesc, bdesc, idesc, (it | j | k) != 0 ? 1u : 0u);
           }
         }
-        umma_commit(&bars->empty[s]);                       // frees the smem stage when the MMAs retire
+        umma_commit(&bars->empty[s]);                          // frees the smem stage when the MMAs retire
         if (it == n_iters - 1) umma_commit(&bars->tmem_full);  // accumulator complete
       }
       __syncwarp();
@@ -138,126 +164,132 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
     // ===================== epilogue (warps 2..5 <-> TMEM lane quarters warp%4) =====================
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int wi = row % p.bw;
-    const int hi = (row / p.bw) % p.bh;
-    const int ni = row / (p.bw * p.bh);
-    const int n = n0 + ni, h = h0 + hi, w = w0 + wi;
-    const bool valid = (n < p.B) && (h < p.Hm) && (w < p.Wm);
-    const int oh = h * p.os + p.oh0 + ph, ow = w * p.os + p.ow0 + pw;
-    const size_t opix = ((size_t)n * p.Hout + oh) * p.Wout + ow;
-    const int c_base = n_blk * n_tile;
+    // per-row addressing is only needed when addends are read or a pooled output is produced
+    bool valid = true;
+    size_t opix = 0;
+    int n = 0, oh = 0, ow = 0;
+    if (EPI != EPI_PLAIN) {
+      const int wi = row % p.bw;
+      const int hi = (row / p.bw) % p.bh;
+      const int ni = row / (p.bw * p.bh);
+      n = n0 + ni;
+      const int h = h0 + hi, w = w0 + wi;
+      valid = (n < p.B) && (h < p.Hm) && (w < p.Wm);
+      oh = h * p.os + p.oh0 + ph;
+      ow = w * p.os + p.ow0 + pw;
+      opix = ((size_t)n * p.Hout + oh) * p.Wout + ow;
+    }
+    const bf16* pre0 = (EPI != EPI_PLAIN && p.pre[0] != nullptr) ? p.pre[0] + opix * p.Cout + c_base : nullptr;
+    const bf16* pre1 = (EPI != EPI_PLAIN && p.pre[1] != nullptr) ? p.pre[1] + opix * p.Cout + c_base : nullptr;
+    const bf16* pre2 = (EPI != EPI_PLAIN && p.pre[2] != nullptr) ? p.pre[2] + opix * p.Cout + c_base : nullptr;
+    const bf16* upp[3] = {nullptr, nullptr, nullptr};
+    const bf16* postp = nullptr;
+    if (EPI == EPI_FULL) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+        if (p.up[a] != nullptr) {
+          const int sh = p.up_shift[a];
+          const size_t upix = ((size_t)n * (p.Hout >> sh) + (oh >> sh)) * (p.Wout >> sh) + (ow >> sh);
+          upp[a] = p.up[a] + upix * p.Cout + c_base;
+        }
+      if (p.post != nullptr) postp = p.post + opix * p.Cout + c_base;
+    }
+    const bool do_store = (p.out != nullptr);
+    const bool pool = (EPI == EPI_FULL) && (p.pool_out != nullptr);
+    const bool relu_in_cvt = p.relu && !(EPI == EPI_FULL && (postp != nullptr || pool));
+    const bool relu_explicit = p.relu && !relu_in_cvt;
+    const int cko = p.cko;
+    const int sw = (cko == 64) ? (row & 7) : ((row >> 1) & 3);
+    uint8_t* const stage_row = smem + (size_t)row * (cko * 2);
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int c_lim = min(n_tile, p.Cout - c_base);  // channels of this N tile that exist (multiple of 32)
 
     mbar_wait(&bars->tmem_full, 0);
     tc_fence_after();
 
-    for (int c0 = 0; c0 < n_tile; c0 += 16) {
-      uint32_t acc[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
+#pragma unroll 1
+    for (int c0 = 0; c0 < c_lim; c0 += 32) {
+      uint32_t acc[32];
+      tmem_ld32(taddr + (uint32_t)c0, acc);
       tmem_ld_wait();
-      const int c = c_base + c0;
-      if (c >= p.Cout) continue;  // warp-uniform (padded weight rows)
-      float v[16];
 #pragma unroll
-      for (int i = 0; i < 16; i += 4) {
-        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + c + i));
-        const float4 bi = __ldg(reinterpret_cast<const float4*>(p.bias + c + i));
-        v[i + 0] = fmaf(__uint_as_float(acc[i + 0]), sc.x, bi.x);
-        v[i + 1] = fmaf(__uint_as_float(acc[i + 1]), sc.y, bi.y);
-        v[i + 2] = fmaf(__uint_as_float(acc[i + 2]), sc.z, bi.z);
-        v[i + 3] = fmaf(__uint_as_float(acc[i + 3]), sc.w, bi.w);
-      }
-      if (valid) {
+      for (int g = 0; g < 4; ++g) {  // 8 channels at a time
+        const int cg = c0 + g * 8;
+        float v[8];
+        const float4 s0 = *reinterpret_cast<const float4*>(sb_smem + cg);
+        const float4 s1 = *reinterpret_cast<const float4*>(sb_smem + cg + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(sb_smem + n_tile + cg);
+        const float4 b1 = *reinterpret_cast<const float4*>(sb_smem + n_tile + cg + 4);
+        v[0] = fmaf(__uint_as_float(acc[g * 8 + 0]), s0.x, b0.x);
+        v[1] = fmaf(__uint_as_float(acc[g * 8 + 1]), s0.y, b0.y);
+        v[2] = fmaf(__uint_as_float(acc[g * 8 + 2]), s0.z, b0.z);
+        v[3] = fmaf(__uint_as_float(acc[g * 8 + 3]), s0.w, b0.w);
+        v[4] = fmaf(__uint_as_float(acc[g * 8 + 4]), s1.x, b1.x);
+        v[5] = fmaf(__uint_as_float(acc[g * 8 + 5]), s1.y, b1.y);
+        v[6] = fmaf(__uint_as_float(acc[g * 8 + 6]), s1.z, b1.z);
+        v[7] = fmaf(__uint_as_float(acc[g * 8 + 7]), s1.w, b1.w);
+        if (EPI != EPI_PLAIN && valid) {
+          if (pre0 != nullptr) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(pre0 + cg)));
+          if (pre1 != nullptr) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(pre1 + cg)));
+          if (pre2 != nullptr) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(pre2 + cg)));
+          if (EPI == EPI_FULL) {
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          if (p.pre[a] != nullptr) {
-            const uint4* src = reinterpret_cast<const uint4*>(p.pre[a] + opix * p.Cout + c);
-            const uint4 x0 = __ldg(src), x1 = __ldg(src + 1);
-            const uint32_t xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              v[2 * i] += bf16lo_to_f32(xs[i]);
-              v[2 * i + 1] += bf16hi_to_f32(xs[i]);
-            }
+            for (int a = 0; a < 3; ++a)
+              if (upp[a] != nullptr) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(upp[a] + cg)));
           }
         }
+        if (relu_explicit) {
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          if (p.up[a] != nullptr) {
-            const int sh = p.up_shift[a];
-            const size_t upix = ((size_t)n * (p.Hout >> sh) + (oh >> sh)) * (p.Wout >> sh) + (ow >> sh);
-            const uint4* src = reinterpret_cast<const uint4*>(p.up[a] + upix * p.Cout + c);
-            const uint4 x0 = __ldg(src), x1 = __ldg(src + 1);
-            const uint32_t xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              v[2 * i] += bf16lo_to_f32(xs[i]);
-              v[2 * i + 1] += bf16hi_to_f32(xs[i]);
-            }
+          for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (EPI == EPI_FULL && postp != nullptr && valid) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(postp + cg)));
+        if (do_store) {
+          uint4 o;
+          if (relu_in_cvt) {
+            o.x = pack_bf16x2_relu(v[0], v[1]);
+            o.y = pack_bf16x2_relu(v[2], v[3]);
+            o.z = pack_bf16x2_relu(v[4], v[5]);
+            o.w = pack_bf16x2_relu(v[6], v[7]);
+          } else {
+            o.x = pack_bf16x2(v[0], v[1]);
+            o.y = pack_bf16x2(v[2], v[3]);
+            o.z = pack_bf16x2(v[4], v[5]);
+            o.w = pack_bf16x2(v[6], v[7]);
           }
+          // stage into the (now idle) pipeline buffers in the TMA-store box layout: column blocks of cko
+          // channels x 128 rows, 16-byte chunks XOR-swizzled exactly as the output tensor map expects
+          const int blk = cg / cko;
+          const int ch = (cg - blk * cko) >> 3;
+          *reinterpret_cast<uint4*>(stage_row + (size_t)blk * (kTileM * cko * 2) + ((ch ^ sw) << 4)) = o;
         }
-        if (p.relu) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-        }
-        if (p.post != nullptr) {
-          const uint4* src = reinterpret_cast<const uint4*>(p.post + opix * p.Cout + c);
-          const uint4 x0 = __ldg(src), x1 = __ldg(src + 1);
-          const uint32_t xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        if (pool) {
+          // global average pool: the 32 rows of a warp belong to one image (host checks bw*bh >= 32)
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            v[2 * i] += bf16lo_to_f32(xs[i]);
-            v[2 * i + 1] += bf16hi_to_f32(xs[i]);
+            float x = valid ? v[i] : 0.f;
+            x += __shfl_xor_sync(0xffffffffu, x, 16);
+            x += __shfl_xor_sync(0xffffffffu, x, 8);
+            x += __shfl_xor_sync(0xffffffffu, x, 4);
+            x += __shfl_xor_sync(0xffffffffu, x, 2);
+            x += __shfl_xor_sync(0xffffffffu, x, 1);
+            v[i] = x;
           }
-        }
-        if (p.out != nullptr) {
-          uint4 o0, o1;
-          o0.x = pack_bf16x2(v[0], v[1]);
-          o0.y = pack_bf16x2(v[2], v[3]);
-          o0.z = pack_bf16x2(v[4], v[5]);
-          o0.w = pack_bf16x2(v[6], v[7]);
-          o1.x = pack_bf16x2(v[8], v[9]);
-          o1.y = pack_bf16x2(v[10], v[11]);
-          o1.z = pack_bf16x2(v[12], v[13]);
-          o1.w = pack_bf16x2(v[14], v[15]);
-          // stage into the (now idle) pipeline buffers in the TMA-store box layout: column blocks of cko channels,
-          // 128 rows each, 16-byte chunks XOR-swizzled exactly as the output tensor map expects
-          const int cko = p.cko;
-          const int blk = c0 / cko;
-          const int ch0 = (c0 - blk * cko) >> 3;  // first 16-byte chunk of this thread inside the row
-          const int sw = (cko == 64) ? (row & 7) : ((row >> 1) & 3);
-          uint8_t* rowp = smem + (size_t)blk * (kTileM * cko * 2) + (size_t)row * (cko * 2);
-          *reinterpret_cast<uint4*>(rowp + (((ch0 + 0) ^ sw) << 4)) = o0;
-          *reinterpret_cast<uint4*>(rowp + (((ch0 + 1) ^ sw) << 4)) = o1;
-        }
-      }
-      if (p.pool_out != nullptr) {
-        // global average pool: rows of one image inside this warp are contiguous runs of lanes; reduce the
-        // whole warp when it maps to one image (host guarantees bw*bh >= 32 or bw*bh*bn rows per image >= 32)
+          const int n_warp = n0 + (q * 32) / (p.bw * p.bh);
+          float mine = 0.f;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float x = valid ? v[i] : 0.f;
-          x += __shfl_xor_sync(0xffffffffu, x, 16);
-          x += __shfl_xor_sync(0xffffffffu, x, 8);
-          x += __shfl_xor_sync(0xffffffffu, x, 4);
-          x += __shfl_xor_sync(0xffffffffu, x, 2);
-          x += __shfl_xor_sync(0xffffffffu, x, 1);
-          v[i] = x;
+          for (int i = 0; i < 8; ++i) mine = (lane == i) ? v[i] : mine;
+          if (lane < 8 && n_warp < p.B)
+            atomicAdd(p.pool_out + (size_t)n_warp * p.Cout + c_base + cg + lane, mine * p.pool_scale);
         }
-        const int n_warp = n0 + (q * 32) / (p.bw * p.bh);
-        float mine = 0.f;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) mine = (lane == i) ? v[i] : mine;
-        if (lane < 16 && n_warp < p.B) atomicAdd(p.pool_out + (size_t)n_warp * p.Cout + c + lane, mine * p.pool_scale);
       }
     }
     tc_fence_before();
-    if (p.out != nullptr) {
+    if (do_store) {
       // generic-proxy smem writes -> visible to the async proxy, then ONE thread issues the TMA stores
       // (rows / channels outside the tensor are clipped by the TMA unit: ragged tiles need no predicates)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (warp == 2 && elect_one()) {
-        const int cko = p.cko;
         const int nblk = n_tile / cko;
         for (int j = 0; j < nblk; ++j) {
           const int cj = c_base + j * cko;
@@ -389,7 +421,10 @@ int conv_geometry(const ConvLayerDesc& d, ConvParams* pp) {
   p.tiles_h = (p.Hm + p.bh - 1) / p.bh;
   p.tiles_n = (p.B + p.bn - 1) / p.bn;
   // N tile
-  const int n_tiles = (p.Cout + 255) / 256;
+  // N tile: 256 wide for K-heavy (tensor-bound) layers; 128 for short-K layers, whose time is the epilogue and
+  // the output stream: 4 CTAs/SM fit in TMEM instead of 2 and the (small) A tile is re-read from L2
+  const int max_n = (p.ktot <= 256 && p.Cout > 128 && p.Cout % 128 == 0) ? 128 : 256;
+  const int n_tiles = (p.Cout + max_n - 1) / max_n;
   p.n_tile = (((p.Cout + n_tiles - 1) / n_tiles) + 31) / 32 * 32;
   p.cout_pad = n_tiles * p.n_tile;
   p.cko = (p.n_tile % 64 == 0) ? 64 : 32;  // channel block of the TMA-store epilogue
@@ -482,9 +517,12 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t
 static void set_smem_attr_once() {
   static std::once_flag once;
   std::call_once(once, [] {
-    cudaFuncSetAttribute(conv_gemm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(conv_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(conv_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  #define HRP_SET_ATTR(CKV, EPIV) \
+  cudaFuncSetAttribute(conv_gemm_kernel<CKV, EPIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+    HRP_SET_ATTR(16, EPI_PLAIN); HRP_SET_ATTR(16, EPI_PRE); HRP_SET_ATTR(16, EPI_FULL);
+    HRP_SET_ATTR(32, EPI_PLAIN); HRP_SET_ATTR(32, EPI_PRE); HRP_SET_ATTR(32, EPI_FULL);
+    HRP_SET_ATTR(64, EPI_PLAIN); HRP_SET_ATTR(64, EPI_PRE); HRP_SET_ATTR(64, EPI_FULL);
+#undef HRP_SET_ATTR
   });
 }
 
@@ -543,22 +581,33 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed) {
   stages = std::max(1, std::min(stages, n_iters));
   plan->stages = stages;
   const int staging = (p.out != nullptr) ? kTileM * p.n_tile * 2 : 0;
-  plan->smem_bytes = std::max(stages * stage_bytes, staging) + (int)sizeof(PipeBarriers) + 1024;
-  plan->grid = dim3((unsigned)(p.tiles_w * p.tiles_h * p.tiles_n), (unsigned)(p.cout_pad / p.n_tile),
-                    (unsigned)p.nphase);
+  plan->bar_offset = std::max(stages * stage_bytes, staging);
+  plan->smem_bytes = plan->bar_offset + (int)sizeof(PipeBarriers) + 2 * p.n_tile * (int)sizeof(float) + 1024;
+  p.n_tiles = p.cout_pad / p.n_tile;
+  plan->grid = dim3((unsigned)(p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles), 1u, (unsigned)p.nphase);
+  const bool full = p.up[0] || p.up[1] || p.up[2] || p.post || p.pool_out;
+  const bool pre = p.pre[0] || p.pre[1] || p.pre[2];
+  plan->epi = full ? EPI_FULL : (pre ? EPI_PRE : EPI_PLAIN);
   return HRP_OK;
 }
 
 int conv_plan_launch(const ConvPlan& plan, cudaStream_t stream) {
   set_smem_attr_once();
   const ConvParams& p = plan.p;
-  const int bar_offset = plan.smem_bytes - (int)sizeof(PipeBarriers) - 1024;
-  if (p.ck == 64)
-    conv_gemm_kernel<64><<<plan.grid, kNumThreads, plan.smem_bytes, stream>>>(plan.maps, p, plan.stages, bar_offset);
-  else if (p.ck == 32)
-    conv_gemm_kernel<32><<<plan.grid, kNumThreads, plan.smem_bytes, stream>>>(plan.maps, p, plan.stages, bar_offset);
-  else
-    conv_gemm_kernel<16><<<plan.grid, kNumThreads, plan.smem_bytes, stream>>>(plan.maps, p, plan.stages, bar_offset);
+#define HRP_LAUNCH(CKV, EPIV)                                                                              \
+  conv_gemm_kernel<CKV, EPIV><<<plan.grid, kNumThreads, plan.smem_bytes, stream>>>(plan.maps, p, plan.stages, \
+                                                                                     plan.bar_offset)
+#define HRP_LAUNCH_CK(CKV)                                \
+  do {                                                    \
+    if (plan.epi == EPI_PLAIN) HRP_LAUNCH(CKV, EPI_PLAIN); \
+    else if (plan.epi == EPI_PRE) HRP_LAUNCH(CKV, EPI_PRE); \
+    else HRP_LAUNCH(CKV, EPI_FULL);                       \
+  } while (0)
+  if (p.ck == 64) HRP_LAUNCH_CK(64);
+  else if (p.ck == 32) HRP_LAUNCH_CK(32);
+  else HRP_LAUNCH_CK(16);
+#undef HRP_LAUNCH_CK
+#undef HRP_LAUNCH
   count_launch();
   HRP_CUDA_CHECK(cudaGetLastError());
   return HRP_OK;

@@ -57,7 +57,7 @@ struct Op {
   int kind = OP_CONV;
   int lane = 0;
   ConvPlan conv;
-  FuseAddParams fuse;
+  FuseAddParams fuse{};
   const void* mp_in = nullptr;
   void* mp_out = nullptr;
   int mp_B = 0, mp_H = 0, mp_W = 0, mp_C = 0;

@@ -1,0 +1,67 @@
+"""Host-buffer inference: pinned host crops in, host results out, with the host<->device copies overlapped with
+compute (double-buffered sub-batches on a copy stream).  This is the call `bench.py` times as `e2e`.
+
+It plays the role of the reference's eval loop body around the forward (scripts/test.py:83-87,151-152: cast the
+DataLoader's uint8 crops to the device, `/255`, forward, read the predictions back), minus dataset / metrics.
+"""
+from __future__ import annotations
+
+import torch
+
+
+class HostPipeline:
+    def __init__(self, model, sub_batch: int = 128):
+        self.model = model
+        self.sub = int(sub_batch)
+        self.copy_stream = None
+        self._dev = None
+        self._host_out = {}
+
+    def _setup(self, x_reg_h, k_h, K_h):
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        shape = (self.sub,) + tuple(x_reg_h.shape[1:])
+        self._dev = {
+            "reg": [torch.empty(shape, dtype=x_reg_h.dtype, device=dev) for _ in range(2)],
+            "root": [torch.empty(shape, dtype=x_reg_h.dtype, device=dev) for _ in range(2)],
+            "k": [torch.empty(self.sub, dtype=torch.float32, device=dev) for _ in range(2)],
+            "K": [torch.empty(self.sub, 3, 3, dtype=torch.float32, device=dev) for _ in range(2)],
+        }
+        self.ready = [torch.cuda.Event() for _ in range(2)]
+        self.free = [torch.cuda.Event() for _ in range(2)]
+
+    def __call__(self, x_reg_h, x_root_h, k_h, K_h):
+        assert not x_reg_h.is_cuda and x_reg_h.is_pinned(), "HostPipeline expects pinned host tensors"
+        if self._dev is None or self._dev["reg"][0].dtype != x_reg_h.dtype:
+            self._setup(x_reg_h, k_h, K_h)
+        B = x_reg_h.shape[0]
+        main = torch.cuda.current_stream()
+        host_out = None
+        for i, c in enumerate(range(0, B, self.sub)):
+            n = min(self.sub, B - c)
+            slot = i % 2
+            with torch.cuda.stream(self.copy_stream):
+                if i >= 2:
+                    self.copy_stream.wait_event(self.free[slot])
+                elif i == 0:
+                    self.copy_stream.wait_stream(main)
+                self._dev["reg"][slot][:n].copy_(x_reg_h[c:c + n], non_blocking=True)
+                self._dev["root"][slot][:n].copy_(x_root_h[c:c + n], non_blocking=True)
+                self._dev["k"][slot][:n].copy_(k_h[c:c + n], non_blocking=True)
+                self._dev["K"][slot][:n].copy_(K_h[c:c + n], non_blocking=True)
+                self.ready[slot].record(self.copy_stream)
+            main.wait_event(self.ready[slot])
+            outs = self.model(self._dev["reg"][slot][:n], self._dev["root"][slot][:n], self._dev["k"][slot][:n],
+                              self._dev["K"][slot][:n])
+            self.free[slot].record(main)
+            if host_out is None:
+                key = (B, tuple(tuple(o.shape[1:]) for o in outs))
+                host_out = self._host_out.get(key)
+                if host_out is None:
+                    host_out = tuple(torch.empty((B,) + tuple(o.shape[1:]), dtype=torch.float32).pin_memory()
+                                     for o in outs)
+                    self._host_out[key] = host_out
+            for o, h in zip(outs, host_out):
+                h[c:c + n].copy_(o, non_blocking=True)
+        main.synchronize()
+        return host_out

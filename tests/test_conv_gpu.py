@@ -102,6 +102,31 @@ def test_epilogue_addends(hrp_lib):
     _report("addends", got, ref)
 
 
+def test_residual_only_epilogue(hrp_lib):
+    """BasicBlock / Bottleneck tail: conv + BN + residual + ReLU (HRnet.py:41-57), ragged batch tile (B=3 @ 8x8)."""
+    from horopose_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    B, C, H = 3, 256, 8
+    x = _bf16_round(torch.randn(B, C, H, H, generator=g)).cuda()
+    w = _bf16_round(torch.randn(C, C, 3, 3, generator=g) / (C * 9) ** 0.5)
+    res = _bf16_round(torch.randn(B, C, H, H, generator=g)).cuda()
+    res2 = _bf16_round(torch.randn(B, C, H, H, generator=g)).cuda()
+    scale = torch.rand(C, generator=g) + 0.5
+    bias = torch.randn(C, generator=g) * 0.1
+    op = ops.ConvOp(_nhwc(x), w, stride=1, pad=1, relu=True, scale=scale, bias=bias, pre=[_nhwc(res), _nhwc(res2)])
+    ref = F.conv2d(x, w.cuda(), padding=1) * scale.cuda()[None, :, None, None] + bias.cuda()[None, :, None, None]
+    ref = torch.relu(ref + res + res2).permute(0, 2, 3, 1).contiguous()
+    got = op.run()
+    torch.cuda.synchronize()
+    _report("residual", got, ref)
+    # no ReLU variant (HRNet fuse partial sums / downsample branches)
+    op2 = ops.ConvOp(_nhwc(x), w, stride=1, pad=1, relu=False, scale=scale, bias=bias)
+    ref2 = (F.conv2d(x, w.cuda(), padding=1) * scale.cuda()[None, :, None, None] + bias.cuda()[None, :, None, None])
+    got2 = op2.run()
+    torch.cuda.synchronize()
+    _report("norelu", got2, ref2.permute(0, 2, 3, 1).contiguous())
+
+
 def test_pooled_epilogue(hrp_lib):
     """conv + BN + ReLU + global average pool in the epilogue (HRnet.py:562-568)."""
     from horopose_b200 import ops
