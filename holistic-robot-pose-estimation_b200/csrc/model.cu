@@ -56,6 +56,7 @@ enum OpKind { OP_CONV = 0, OP_MAXPOOL = 1, OP_FUSEADD = 2, OP_MEMSET = 3 };
 struct Op {
   int kind = OP_CONV;
   int lane = 0;
+  std::string name;
   ConvPlan conv;
   FuseAddParams fuse{};
   const void* mp_in = nullptr;
@@ -389,6 +390,7 @@ struct Builder {
       pl->flops += op.conv.flops;
     }
     op.writes = out;
+    op.name = name;
     pl->ops.push_back(op);
     if (out >= 0) pl->acts[out].producer = (int)pl->ops.size() - 1;
     return out;
@@ -401,6 +403,7 @@ struct Builder {
     if (rc != HRP_OK) return -1;
     Op op;
     op.kind = OP_MAXPOOL;
+    op.name = "maxpool";
     op.lane = lane;
     op.mp_in = a.ptr;
     op.mp_out = pl->acts[out].ptr;
@@ -422,6 +425,7 @@ struct Builder {
     if (rc != HRP_OK) return -1;
     Op op;
     op.kind = OP_FUSEADD;
+    op.name = "fuse_add";
     op.lane = lane;
     memset(&op.fuse, 0, sizeof(op.fuse));
     op.fuse.pre = a.ptr;
@@ -963,6 +967,56 @@ int hrp_model_activation(hrp_model* model, const char* name, const void** ptr, i
   *H = a.H;
   *W = a.W;
   *C = a.C;
+  return HRP_OK;
+}
+
+int hrp_model_profile(hrp_model* m, int32_t batch, int32_t iters, char* buf, int64_t buflen) {
+  HRP_REQUIRE(m != nullptr && buf != nullptr && buflen > 0 && iters > 0, "bad argument");
+  if (!m->finalized) {
+    set_error("profile before finalize");
+    return HRP_ERR_STATE;
+  }
+  Plan* pl = nullptr;
+  int rc = get_plan(m, batch, 0, &pl);
+  if (rc != HRP_OK) return rc;
+  cudaStream_t s = pl->stream;
+  cudaEvent_t e0, e1;
+  HRP_CUDA_CHECK(cudaEventCreate(&e0));
+  HRP_CUDA_CHECK(cudaEventCreate(&e1));
+  std::string out;
+  char line[512];
+  for (auto& op : pl->ops) {
+    if (op.kind == OP_MEMSET) continue;
+    rc = launch_op(m, op, s);  // warm
+    if (rc != HRP_OK) return rc;
+    HRP_CUDA_CHECK(cudaEventRecord(e0, s));
+    for (int i = 0; i < iters; ++i) {
+      rc = launch_op(m, op, s);
+      if (rc != HRP_OK) return rc;
+    }
+    HRP_CUDA_CHECK(cudaEventRecord(e1, s));
+    HRP_CUDA_CHECK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    HRP_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    const double us = 1e3 * ms / iters;
+    if (op.kind == OP_CONV) {
+      const ConvParams& q = op.conv.p;
+      const double in_b = (double)q.B * q.Hin * q.Win * q.Cin * 2.0, out_b = (double)q.B * q.Hout * q.Wout * q.Cout * 2.0;
+      snprintf(line, sizeof(line), "%s\tconv\t%d\t%dx%d\t%d\t%d\t%dx%d\t%d\t%d\t%d\t%u\t%d\t%.2f\t%.1f\t%.1f\n",
+               op.name.c_str(), op.lane, q.Hin, q.Win, q.Cin, q.Cout, q.Hout, q.Wout, q.ntaps, q.n_tile, op.conv.epi,
+               op.conv.grid.x * op.conv.grid.z, op.conv.stages, us, op.conv.flops / us * 1e-6, (in_b + out_b) / us * 1e-3);
+    } else {
+      snprintf(line, sizeof(line), "%s\tmisc\t%d\t-\t-\t-\t-\t-\t-\t-\t-\t-\t%.2f\t0\t0\n", op.name.c_str(), op.lane, us);
+    }
+    out += line;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if ((int64_t)out.size() + 1 > buflen) {
+    set_error("profile buffer too small: need " + std::to_string(out.size() + 1));
+    return HRP_ERR_INVALID;
+  }
+  memcpy(buf, out.c_str(), out.size() + 1);
   return HRP_OK;
 }
 

@@ -220,6 +220,9 @@ int hrp_model_activation(hrp_model* model, const char* name, const void** ptr, i
                          int32_t* C);
 /* asynchronous device-to-device copy on `stream` (used by the shims to snapshot activations) */
 int hrp_copy_device(void* dst, const void* src, int64_t bytes, void* stream);
+/* per-operation timing of one plan (eager, CUDA events, `iters` back-to-back launches per op): tab-separated text
+ * name, kind, lane, in HxW, Cin, Cout, out HxW, taps, n_tile, epilogue, CTAs, stages, us, TFLOP/s, GB/s */
+int hrp_model_profile(hrp_model* model, int32_t batch, int32_t iters, char* buf, int64_t buflen);
 int hrp_model_stats(const hrp_model* model, int32_t batch, double* flops, int32_t* kernels, int64_t* activation_bytes);
 
 #ifdef __cplusplus
