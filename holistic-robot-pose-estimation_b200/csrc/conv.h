@@ -53,6 +53,16 @@ struct ConvMaps {
   CUtensorMap a[4];  // input: one per stride-2 parity (else a[0])
   CUtensorMap b;     // packed weights
   CUtensorMap o[4];  // output: one per deconv phase (else o[0])
+  CUtensorMap r;     // residual (pre[0]) tile, same geometry as the output (persistent kernel)
+};
+
+struct PersistCfg {
+  int stages;        // smem pipeline depth
+  int nstag;         // output staging buffers (1 or 2)
+  int stag_offset;   // byte offset of the staging buffers
+  int bar_offset;    // byte offset of the barriers (scale/shift follow them)
+  int total_tiles;   // m tiles x n tiles x phases
+  int tmem_cols;     // allocated TMEM columns (power of two >= 2*n_tile)
 };
 
 struct ConvPlan {
@@ -63,6 +73,10 @@ struct ConvPlan {
   int bar_offset;  // barriers + scale/shift staging live after the pipeline stages
   int stages;
   int epi;         // epilogue flavour (EPI_PLAIN / EPI_PRE / EPI_FULL)
+  bool persistent; // persistent kernel (default) vs one-tile-per-CTA kernel (HRP_CONV_V1=1)
+  PersistCfg pcfg;
+  unsigned pgrid;
+  int psmem;
   double flops;  // 2*MACs of the reference layer (algorithmic, not padded)
 };
 

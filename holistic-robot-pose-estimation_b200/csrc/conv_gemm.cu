@@ -310,6 +310,346 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Persistent variant: one CTA per SM loops over output tiles.  The TMA producer runs ahead across tile
+// boundaries, the accumulator is double-buffered in TMEM (MMA of tile i+1 overlaps the epilogue of tile i), the
+// residual tile (pre[0]) is prefetched by TMA into the output staging buffer and updated in place, and eight
+// epilogue warps (two per TMEM lane quarter) drain the accumulators.  Per-tile fixed costs (TMEM allocation,
+// barrier init, descriptor fetch, launch) are paid once per CTA.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kThreadsP = 320;      // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
+constexpr int kEpiThreadsP = 256;
+
+struct __align__(16) PersistBarriers {
+  uint64_t full[8];
+  uint64_t empty[8];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint64_t res_full[2];
+  uint64_t stag_free[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int CK, int EPI>
+__global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __grid_constant__ ConvMaps maps,
+                                                                     const __grid_constant__ ConvParams p,
+                                                                     const PersistCfg cfg) {
+  constexpr int SUB = 64 / CK;
+  constexpr int A_SUB_BYTES = kTileM * CK * 2;
+  constexpr int KSTEPS = CK / 16;
+  constexpr uint32_t LAYOUT = (CK == 64) ? 2u : (CK == 32) ? 4u : 6u;
+  constexpr uint32_t SBO = 8 * CK * 2;
+
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  const int n_tile = p.n_tile;
+  const int b_sub_bytes = n_tile * CK * 2;
+  const int stage_bytes = kStageABytes + n_tile * 128;
+  const int stag_bytes = kTileM * n_tile * 2;
+  const int stages = cfg.stages, nstag = cfg.nstag;
+  uint8_t* const stag_base = smem + cfg.stag_offset;
+  PersistBarriers* bars = reinterpret_cast<PersistBarriers*>(smem + cfg.bar_offset);
+  float* sb_smem = reinterpret_cast<float*>(bars + 1);  // [2][cout_pad] scale / shift of the whole layer
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nkb = p.ntaps * p.cpt;
+  const int n_iters = (nkb + SUB - 1) / SUB;
+  const int cko = p.cko;
+  const int nblk_full = n_tile / cko;
+  const bool has_res = (EPI != EPI_PLAIN) && (p.pre[0] != nullptr) && (p.out != nullptr);
+  const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.a[0]);
+    tma_prefetch_desc(&maps.b);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->tmem_full[i], 1);
+      mbar_init(&bars->tmem_empty[i], kEpiThreadsP);
+      mbar_init(&bars->res_full[i], 1);
+      mbar_init(&bars->stag_free[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&bars->tmem_base, (uint32_t)cfg.tmem_cols);
+    tmem_relinquish();
+  }
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < p.cout_pad; i += kEpiThreadsP) {
+      sb_smem[i] = (i < p.Cout) ? __ldg(p.scale + i) : 0.f;
+      sb_smem[p.cout_pad + i] = (i < p.Cout) ? __ldg(p.bias + i) : 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+#define HRP_DECODE_TILE(tile)                         \
+  int t_ = (tile);                                    \
+  const int n_blk = t_ % p.n_tiles;                   \
+  t_ /= p.n_tiles;                                    \
+  const int phase = t_ / tiles_m;                     \
+  t_ -= phase * tiles_m;                              \
+  const int tw = t_ % p.tiles_w;                      \
+  t_ /= p.tiles_w;                                    \
+  const int th = t_ % p.tiles_h;                      \
+  const int tn = t_ / p.tiles_h;                      \
+  const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn; \
+  const int ph = phase >> 1, pw = phase & 1;          \
+  const int c_base = n_blk * n_tile;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      uint32_t it_g = 0;
+      int li = 0;
+      for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x, ++li) {
+        HRP_DECODE_TILE(tile)
+        (void)th; (void)tw; (void)tn;
+        const int sbuf = li % nstag;
+        const uint32_t spar = (uint32_t)((li / nstag) & 1);
+        auto load_residual = [&]() {
+          mbar_wait(&bars->stag_free[sbuf], spar ^ 1);  // the store that last used this buffer has drained
+          int nb = 0;
+          for (int j = 0; j < nblk_full && c_base + j * cko < p.Cout; ++j) ++nb;
+          mbar_expect_tx(&bars->res_full[sbuf], (uint32_t)(nb * kTileM * cko * 2));
+          for (int j = 0; j < nb; ++j)
+            tma_load_4d(stag_base + (size_t)sbuf * stag_bytes + (size_t)j * (kTileM * cko * 2), &maps.r,
+                        &bars->res_full[sbuf], c_base + j * cko, w0, h0, n0);
+        };
+        if (has_res && nstag == 2) load_residual();
+        for (int it = 0; it < n_iters; ++it, ++it_g) {
+          const int s = it_g % stages;
+          const uint32_t par = (it_g / stages) & 1;
+          mbar_wait(&bars->empty[s], par ^ 1);
+          const int nsub = min(SUB, nkb - it * SUB);
+          mbar_expect_tx(&bars->full[s], (uint32_t)(nsub * (A_SUB_BYTES + b_sub_bytes)));
+          uint8_t* sa = smem + (size_t)s * stage_bytes;
+          uint8_t* sb = sa + kStageABytes;
+          for (int j = 0; j < nsub; ++j) {
+            const int kb = it * SUB + j;
+            const int tap = kb / p.cpt;
+            const int cc = kb - tap * p.cpt;
+            tma_load_4d(sa + j * A_SUB_BYTES, &maps.a[p.tap_map[tap]], &bars->full[s], cc * CK,
+                        w0 + p.tap_dw[tap] + pw, h0 + p.tap_dh[tap] + ph, n0);
+            tma_load_2d(sb + j * b_sub_bytes, &maps.b, &bars->full[s], kb * CK, phase * p.cout_pad + c_base);
+          }
+        }
+        if (has_res && nstag == 1) load_residual();
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc_bf16(kTileM, (uint32_t)n_tile);
+    uint32_t it_g = 0;
+    int li = 0;
+    for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x, ++li) {
+      const int abuf = li & 1;
+      mbar_wait(&bars->tmem_empty[abuf], (uint32_t)(((li >> 1) & 1) ^ 1));  // epilogue drained this accumulator
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(abuf * n_tile);
+      for (int it = 0; it < n_iters; ++it, ++it_g) {
+        const int s = it_g % stages;
+        const uint32_t par = (it_g / stages) & 1;
+        mbar_wait(&bars->full[s], par);
+        tc_fence_after();
+        if (elect_one()) {
+          const int nsub = min(SUB, nkb - it * SUB);
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t sb = sa + kStageABytes;
+          for (int j = 0; j < nsub; ++j) {
+#pragma unroll
+            for (int k = 0; k < KSTEPS; ++k) {
+              const uint64_t adesc = make_kmajor_desc(sa + j * A_SUB_BYTES + k * 32, SBO, LAYOUT);
+              const uint64_t bdesc = make_kmajor_desc(sb + j * b_sub_bytes + k * 32, SBO, LAYOUT);
+              umma_bf16_ss(tacc, adesc, bdesc, idesc, (it | j | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&bars->empty[s]);
+          if (it == n_iters - 1) umma_commit(&bars->tmem_full[abuf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue: warps 2..9, lane quarter = warp % 4, column half = (warp-2)/4 ==========
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const int sw = (cko == 64) ? (row & 7) : ((row >> 1) & 3);
+    const bool do_store = (p.out != nullptr);
+    const bool pool = (EPI == EPI_FULL) && (p.pool_out != nullptr);
+    const bool is_store_thread = (warp == 2) && (lane == 0);
+    int li = 0;
+    for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x, ++li) {
+      HRP_DECODE_TILE(tile)
+      (void)th; (void)tw; (void)tn;
+      const int abuf = li & 1;
+      const int sbuf = li % nstag;
+      const uint32_t spar = (uint32_t)((li / nstag) & 1);
+      bool valid = true;
+      size_t opix = 0;
+      int n = 0, oh = 0, ow = 0;
+      if (EPI != EPI_PLAIN) {
+        const int wi = row % p.bw;
+        const int hi = (row / p.bw) % p.bh;
+        const int ni = row / (p.bw * p.bh);
+        n = n0 + ni;
+        const int h = h0 + hi, w = w0 + wi;
+        valid = (n < p.B) && (h < p.Hm) && (w < p.Wm);
+        oh = h * p.os + p.oh0 + ph;
+        ow = w * p.os + p.ow0 + pw;
+        opix = ((size_t)n * p.Hout + oh) * p.Wout + ow;
+      }
+      const bf16* pre0 = (EPI != EPI_PLAIN && !has_res && p.pre[0] != nullptr) ? p.pre[0] + opix * p.Cout + c_base : nullptr;
+      const bf16* pre1 = (EPI != EPI_PLAIN && p.pre[1] != nullptr) ? p.pre[1] + opix * p.Cout + c_base : nullptr;
+      const bf16* pre2 = (EPI != EPI_PLAIN && p.pre[2] != nullptr) ? p.pre[2] + opix * p.Cout + c_base : nullptr;
+      const bf16* upp[3] = {nullptr, nullptr, nullptr};
+      const bf16* postp = nullptr;
+      if (EPI == EPI_FULL) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+          if (p.up[a] != nullptr) {
+            const int sh = p.up_shift[a];
+            const size_t upix = ((size_t)n * (p.Hout >> sh) + (oh >> sh)) * (p.Wout >> sh) + (ow >> sh);
+            upp[a] = p.up[a] + upix * p.Cout + c_base;
+          }
+        if (p.post != nullptr) postp = p.post + opix * p.Cout + c_base;
+      }
+      const bool relu_in_cvt = p.relu && !(EPI == EPI_FULL && (postp != nullptr || pool));
+      const bool relu_explicit = p.relu && !relu_in_cvt;
+      uint8_t* const stage_row = stag_base + (size_t)sbuf * stag_bytes + (size_t)row * (cko * 2);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * n_tile);
+      const int c_lim = min(n_tile, p.Cout - c_base);
+      const float* sc = sb_smem + c_base;
+      const float* sh_ = sb_smem + p.cout_pad + c_base;
+
+      mbar_wait(&bars->tmem_full[abuf], (uint32_t)((li >> 1) & 1));
+      tc_fence_after();
+      if (do_store) {
+        if (has_res) mbar_wait(&bars->res_full[sbuf], spar);          // residual tile landed in the staging buffer
+        else mbar_wait(&bars->stag_free[sbuf], spar ^ 1);            // previous store from this buffer has drained
+      }
+
+#pragma unroll 1
+      for (int c0 = half * 32; c0 < c_lim; c0 += 64) {
+        uint32_t acc[32];
+        tmem_ld32(taddr + (uint32_t)c0, acc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int cg = c0 + g * 8;
+          float v[8];
+          const float4 s0 = *reinterpret_cast<const float4*>(sc + cg);
+          const float4 s1 = *reinterpret_cast<const float4*>(sc + cg + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(sh_ + cg);
+          const float4 b1 = *reinterpret_cast<const float4*>(sh_ + cg + 4);
+          v[0] = fmaf(__uint_as_float(acc[g * 8 + 0]), s0.x, b0.x);
+          v[1] = fmaf(__uint_as_float(acc[g * 8 + 1]), s0.y, b0.y);
+          v[2] = fmaf(__uint_as_float(acc[g * 8 + 2]), s0.z, b0.z);
+          v[3] = fmaf(__uint_as_float(acc[g * 8 + 3]), s0.w, b0.w);
+          v[4] = fmaf(__uint_as_float(acc[g * 8 + 4]), s1.x, b1.x);
+          v[5] = fmaf(__uint_as_float(acc[g * 8 + 5]), s1.y, b1.y);
+          v[6] = fmaf(__uint_as_float(acc[g * 8 + 6]), s1.z, b1.z);
+          v[7] = fmaf(__uint_as_float(acc[g * 8 + 7]), s1.w, b1.w);
+          const int blk = cg / cko;
+          const int ch = (cg - blk * cko) >> 3;
+          uint4* const sptr = reinterpret_cast<uint4*>(stage_row + (size_t)blk * (kTileM * cko * 2) + ((ch ^ sw) << 4));
+          if (EPI != EPI_PLAIN) {
+            if (has_res) add_bf16x8(v, *sptr);  // residual prefetched by TMA (zero-filled outside the tensor)
+            if (valid) {
+              if (pre0 != nullptr) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(pre0 + cg)));
+              if (pre1 != nullptr) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(pre1 + cg)));
+              if (pre2 != nullptr) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(pre2 + cg)));
+              if (EPI == EPI_FULL) {
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+                  if (upp[a] != nullptr) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(upp[a] + cg)));
+              }
+            }
+          }
+          if (relu_explicit) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (EPI == EPI_FULL && postp != nullptr && valid)
+            add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(postp + cg)));
+          if (do_store) {
+            uint4 o;
+            if (relu_in_cvt) {
+              o.x = pack_bf16x2_relu(v[0], v[1]);
+              o.y = pack_bf16x2_relu(v[2], v[3]);
+              o.z = pack_bf16x2_relu(v[4], v[5]);
+              o.w = pack_bf16x2_relu(v[6], v[7]);
+            } else {
+              o.x = pack_bf16x2(v[0], v[1]);
+              o.y = pack_bf16x2(v[2], v[3]);
+              o.z = pack_bf16x2(v[4], v[5]);
+              o.w = pack_bf16x2(v[6], v[7]);
+            }
+            *sptr = o;
+          }
+          if (pool) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float x = valid ? v[i] : 0.f;
+              x += __shfl_xor_sync(0xffffffffu, x, 16);
+              x += __shfl_xor_sync(0xffffffffu, x, 8);
+              x += __shfl_xor_sync(0xffffffffu, x, 4);
+              x += __shfl_xor_sync(0xffffffffu, x, 2);
+              x += __shfl_xor_sync(0xffffffffu, x, 1);
+              v[i] = x;
+            }
+            const int n_warp = n0 + (q * 32) / (p.bw * p.bh);
+            float mine = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) mine = (lane == i) ? v[i] : mine;
+            if (lane < 8 && n_warp < p.B)
+              atomicAdd(p.pool_out + (size_t)n_warp * p.Cout + c_base + cg + lane, mine * p.pool_scale);
+          }
+        }
+      }
+      // accumulator drained: hand it back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(&bars->tmem_empty[abuf]);
+      if (do_store) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (is_store_thread) {
+          for (int j = 0; j < nblk_full; ++j) {
+            const int cj = c_base + j * cko;
+            if (cj >= p.Cout) break;
+            tma_store_4d(stag_base + (size_t)sbuf * stag_bytes + (size_t)j * (kTileM * cko * 2), &maps.o[phase], cj, w0,
+                         h0, n0);
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          // once the TMA unit has read the staging buffer it can take the next residual / result tile
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          mbar_arrive(&bars->stag_free[sbuf]);
+        }
+      }
+    }
+  }
+#undef HRP_DECODE_TILE
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)cfg.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // host: geometry, weight packing, tensor maps, launch
 // ------------------------------------------------------------------------------------------------------
 static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
@@ -523,6 +863,12 @@ static void set_smem_attr_once() {
     HRP_SET_ATTR(32, EPI_PLAIN); HRP_SET_ATTR(32, EPI_PRE); HRP_SET_ATTR(32, EPI_FULL);
     HRP_SET_ATTR(64, EPI_PLAIN); HRP_SET_ATTR(64, EPI_PRE); HRP_SET_ATTR(64, EPI_FULL);
 #undef HRP_SET_ATTR
+#define HRP_SET_ATTR_P(CKV, EPIV) \
+  cudaFuncSetAttribute(conv_gemm_persistent<CKV, EPIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+    HRP_SET_ATTR_P(16, EPI_PLAIN); HRP_SET_ATTR_P(16, EPI_PRE); HRP_SET_ATTR_P(16, EPI_FULL);
+    HRP_SET_ATTR_P(32, EPI_PLAIN); HRP_SET_ATTR_P(32, EPI_PRE); HRP_SET_ATTR_P(32, EPI_FULL);
+    HRP_SET_ATTR_P(64, EPI_PLAIN); HRP_SET_ATTR_P(64, EPI_PRE); HRP_SET_ATTR_P(64, EPI_FULL);
+#undef HRP_SET_ATTR_P
   });
 }
 
@@ -588,12 +934,75 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed) {
   const bool full = p.up[0] || p.up[1] || p.up[2] || p.post || p.pool_out;
   const bool pre = p.pre[0] || p.pre[1] || p.pre[2];
   plan->epi = full ? EPI_FULL : (pre ? EPI_PRE : EPI_PLAIN);
+
+  // ---- persistent variant (default) ----
+  {
+    static int num_sms = 0;
+    if (num_sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+      if (num_sms <= 0) num_sms = 148;
+    }
+    const char* v1 = getenv("HRP_CONV_V1");
+    plan->persistent = !(v1 != nullptr && v1[0] == '1');
+    PersistCfg& c = plan->pcfg;
+    const bool has_res = (p.pre[0] != nullptr) && (p.out != nullptr);
+    if (has_res) {
+      HRP_REQUIRE(p.nphase == 1 && p.os == 1, "residual addends are not supported on deconvolutions");
+      uint64_t dims[4] = {(uint64_t)p.Cout, (uint64_t)p.Wout, (uint64_t)p.Hout, (uint64_t)p.B};
+      uint64_t strides[3] = {(uint64_t)p.Cout * 2, (uint64_t)p.Wout * p.Cout * 2, (uint64_t)p.Hout * p.Wout * p.Cout * 2};
+      uint32_t box[4] = {(uint32_t)p.cko, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+      int rc = encode_map(&plan->maps.r, p.pre[0], 4, dims, strides, box, p.cko);
+      if (rc != HRP_OK) return rc;
+    } else {
+      plan->maps.r = plan->maps.a[0];
+    }
+    const int stag_bytes = (p.out != nullptr) ? kTileM * p.n_tile * 2 : 0;
+    const int tail = 256 + 2 * p.cout_pad * (int)sizeof(float) + 1024;  // barriers + scale/shift + alignment slack
+    const int avail = 227 * 1024 - tail;
+    int nstag = (stag_bytes > 0 && p.n_tile <= 128) ? 2 : 1;
+    int st = (avail - nstag * stag_bytes) / stage_bytes;
+    if (st < 3 && nstag == 2) {
+      nstag = 1;
+      st = (avail - stag_bytes) / stage_bytes;
+    }
+    HRP_REQUIRE(st >= 1, "layer does not fit in shared memory");
+    c.stages = std::min(8, st);
+    c.nstag = nstag;
+    c.stag_offset = c.stages * stage_bytes;
+    c.bar_offset = c.stag_offset + nstag * stag_bytes;
+    c.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles * p.nphase;
+    int cols = 32;
+    while (cols < 2 * p.n_tile) cols <<= 1;
+    c.tmem_cols = cols;
+    plan->psmem = c.bar_offset + tail;
+    plan->pgrid = (unsigned)std::min(c.total_tiles, num_sms);
+  }
   return HRP_OK;
 }
 
 int conv_plan_launch(const ConvPlan& plan, cudaStream_t stream) {
   set_smem_attr_once();
   const ConvParams& p = plan.p;
+  if (plan.persistent) {
+#define HRP_LAUNCH_P(CKV, EPIV) \
+  conv_gemm_persistent<CKV, EPIV><<<plan.pgrid, kThreadsP, plan.psmem, stream>>>(plan.maps, p, plan.pcfg)
+#define HRP_LAUNCH_P_CK(CKV)                                  \
+  do {                                                        \
+    if (plan.epi == EPI_PLAIN) HRP_LAUNCH_P(CKV, EPI_PLAIN);   \
+    else if (plan.epi == EPI_PRE) HRP_LAUNCH_P(CKV, EPI_PRE);  \
+    else HRP_LAUNCH_P(CKV, EPI_FULL);                         \
+  } while (0)
+    if (p.ck == 64) HRP_LAUNCH_P_CK(64);
+    else if (p.ck == 32) HRP_LAUNCH_P_CK(32);
+    else HRP_LAUNCH_P_CK(16);
+#undef HRP_LAUNCH_P_CK
+#undef HRP_LAUNCH_P
+    count_launch();
+    HRP_CUDA_CHECK(cudaGetLastError());
+    return HRP_OK;
+  }
 #define HRP_LAUNCH(CKV, EPIV)                                                                              \
   conv_gemm_kernel<CKV, EPIV><<<plan.grid, kNumThreads, plan.smem_bytes, stream>>>(plan.maps, p, plan.stages, \
                                                                                      plan.bar_offset)

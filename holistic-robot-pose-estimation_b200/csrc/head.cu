@@ -6,6 +6,8 @@
 #include "head.h"
 #include "launch_count.h"
 
+#include <algorithm>
+
 namespace hrp {
 
 // ------------------------------------------------------------------------------------------------------
@@ -317,11 +319,12 @@ int launch_depth(const float* feat, const float* w, float b, const float* k, flo
 // ------------------------------------------------------------------------------------------------------
 // fused head
 // ------------------------------------------------------------------------------------------------------
-constexpr int kHeadMaxThreads = 576;
+constexpr int kHeadMaxThreads = 320;
+constexpr int kHeadMaxSlots = 8;
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct HeadSmem {
-  float part[kHeadMaxThreads][5];
+  float part[kHeadMaxSlots][kMaxKpt][5];
   float uvd[kMaxKpt][3];
   float reg_a[kMaxDof + 6];
   float red[32];
@@ -506,78 +509,102 @@ __device__ __noinline__ void head_finalize(const HeadParams& p, HeadSmem& sm, in
   }
 }
 
-__global__ void __launch_bounds__(kHeadMaxThreads) head_kernel(const __grid_constant__ HeadParams p) {
+// online-softmax state merge: (m, S, Sx, Sy, Sz) <- combine with (m2, ...), all in the log2 domain
+__device__ __forceinline__ void softmax_merge(float& m, float& S, float& Sx, float& Sy, float& Sz, float m2, float S2,
+                                              float Sx2, float Sy2, float Sz2) {
+  const float M = fmaxf(m, m2);
+  const float f1 = (m == -INFINITY) ? 0.f : exp2f(m - M);
+  const float f2 = (m2 == -INFINITY) ? 0.f : exp2f(m2 - M);
+  S = S * f1 + S2 * f2;
+  Sx = Sx * f1 + Sx2 * f2;
+  Sy = Sy * f1 + Sy2 * f2;
+  Sz = Sz * f1 + Sz2 * f2;
+  m = M;
+}
+
+// Streaming layout: a warp owns a group of 4 keypoints (32 lanes x 16 B = the 512 contiguous bytes those
+// keypoints occupy in a pixel row); lane = (keypoint in group, 8-bin depth vector).  `slots` warps per group
+// walk different pixels.  Every thread keeps a fixed (keypoint, depth vector) -> 5 fp32 accumulators.
+__global__ void __launch_bounds__(kHeadMaxThreads, 3) head_kernel(const __grid_constant__ HeadParams p) {
   __shared__ HeadSmem sm;
-  const int C = p.nkpt * 64;
-  const int vpp = C >> 3;                 // 16-byte vectors per pixel
-  const int ppi = blockDim.x / vpp;       // pixels per iteration
+  const int nk = p.nkpt;
+  const int groups = (nk + 3) >> 2;
+  const int slots = (blockDim.x >> 5) / groups;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kg = warp % groups, slot = warp / groups;
+  const int k = kg * 4 + (lane >> 3);
+  const bool kvalid = (k < nk);
+  const int vec = lane & 7;
+  const int vpp = nk * 8;                 // 16-byte vectors per pixel
   const int b = blockIdx.x / p.chunks, chunk = blockIdx.x - b * p.chunks;
   const int ppc = 4096 / p.chunks;        // pixels per chunk
-  const int v = threadIdx.x % vpp, slot = threadIdx.x / vpp;
-  const float dbase = (float)((v & 7) * 8);
-  const uint4* base = reinterpret_cast<const uint4*>(p.heatmap + ((size_t)b * 4096 + (size_t)chunk * ppc) * C) + v;
+  const float dbase = (float)(vec * 8);
+  const uint4* base =
+      reinterpret_cast<const uint4*>(p.heatmap + ((size_t)b * 4096 + (size_t)chunk * ppc) * (size_t)(nk * 64)) + k * 8 + vec;
 
   float m = -INFINITY, S = 0.f, Sx = 0.f, Sy = 0.f, Sz = 0.f;
   constexpr int UNROLL = 4;
-  for (int pix0 = slot; pix0 < ppc; pix0 += ppi * UNROLL) {
-    uint4 raw[UNROLL];
+  if (kvalid) {
+    for (int pix0 = slot; pix0 < ppc; pix0 += slots * UNROLL) {
+      uint4 raw[UNROLL];
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const int pix = pix0 + u * ppi;
-      if (pix < ppc) raw[u] = ld_stream(base + (size_t)pix * vpp);
-    }
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const int pix = pix0 + u * ppi;
-      if (pix >= ppc) continue;
-      const int gp = chunk * ppc + pix;
-      const float fw = (float)(gp & 63), fh = (float)(gp >> 6);
-      float t[8];
-      t[0] = bf16lo_to_f32(raw[u].x) * kLog2e; t[1] = bf16hi_to_f32(raw[u].x) * kLog2e;
-      t[2] = bf16lo_to_f32(raw[u].y) * kLog2e; t[3] = bf16hi_to_f32(raw[u].y) * kLog2e;
-      t[4] = bf16lo_to_f32(raw[u].z) * kLog2e; t[5] = bf16hi_to_f32(raw[u].z) * kLog2e;
-      t[6] = bf16lo_to_f32(raw[u].w) * kLog2e; t[7] = bf16hi_to_f32(raw[u].w) * kLog2e;
-      const float vmax = fmaxf(fmaxf(fmaxf(t[0], t[1]), fmaxf(t[2], t[3])), fmaxf(fmaxf(t[4], t[5]), fmaxf(t[6], t[7])));
-      if (vmax > m) {  // online-softmax rescale (rare after the first few pixels)
-        const float f = exp2f(m - vmax);
-        S *= f; Sx *= f; Sy *= f; Sz *= f;
-        m = vmax;
+      for (int u = 0; u < UNROLL; ++u) {
+        const int pix = pix0 + u * slots;
+        if (pix < ppc) raw[u] = ld_stream(base + (size_t)pix * vpp);
       }
-      float s8 = 0.f, sz8 = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float e = exp2f(t[i] - m);
-        s8 += e;
-        sz8 = fmaf(e, dbase + (float)i, sz8);
+      for (int u = 0; u < UNROLL; ++u) {
+        const int pix = pix0 + u * slots;
+        if (pix >= ppc) continue;
+        const int gp = chunk * ppc + pix;
+        const float fw = (float)(gp & 63), fh = (float)(gp >> 6);
+        // vector max with packed bf16 ops, then one conversion
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
+        const __nv_bfloat162 mx = __hmax2(__hmax2(h2[0], h2[1]), __hmax2(h2[2], h2[3]));
+        const float vmax = fmaxf(__low2float(mx), __high2float(mx)) * kLog2e;
+        if (vmax > m) {  // online-softmax rescale (rare after the first few pixels)
+          const float f = exp2f(m - vmax);
+          S *= f; Sx *= f; Sy *= f; Sz *= f;
+          m = vmax;
+        }
+        const uint32_t xs[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+        float s8 = 0.f, sz8 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float e0 = exp2f(fmaf(bf16lo_to_f32(xs[i]), kLog2e, -m));
+          const float e1 = exp2f(fmaf(bf16hi_to_f32(xs[i]), kLog2e, -m));
+          s8 += e0 + e1;
+          sz8 = fmaf(e0, dbase + (float)(2 * i), sz8);
+          sz8 = fmaf(e1, dbase + (float)(2 * i + 1), sz8);
+        }
+        S += s8;
+        Sx = fmaf(s8, fw, Sx);
+        Sy = fmaf(s8, fh, Sy);
+        Sz += sz8;
       }
-      S += s8;
-      Sx = fmaf(s8, fw, Sx);
-      Sy = fmaf(s8, fh, Sy);
-      Sz += sz8;
     }
   }
-  sm.part[threadIdx.x][0] = m;
-  sm.part[threadIdx.x][1] = S;
-  sm.part[threadIdx.x][2] = Sx;
-  sm.part[threadIdx.x][3] = Sy;
-  sm.part[threadIdx.x][4] = Sz;
+  // merge the 8 depth-vector lanes of each keypoint, then the pixel slots through shared memory
+#pragma unroll
+  for (int off = 1; off < 8; off <<= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, off), S2 = __shfl_xor_sync(0xffffffffu, S, off);
+    const float Sx2 = __shfl_xor_sync(0xffffffffu, Sx, off), Sy2 = __shfl_xor_sync(0xffffffffu, Sy, off);
+    const float Sz2 = __shfl_xor_sync(0xffffffffu, Sz, off);
+    softmax_merge(m, S, Sx, Sy, Sz, m2, S2, Sx2, Sy2, Sz2);
+  }
+  if (vec == 0 && kvalid) {
+    float* d = sm.part[slot][k];
+    d[0] = m; d[1] = S; d[2] = Sx; d[3] = Sy; d[4] = Sz;
+  }
   __syncthreads();
-  if ((int)threadIdx.x < p.nkpt) {  // merge the 8*ppi contributors of keypoint k
-    const int k = threadIdx.x;
-    float M = -INFINITY;
-    for (int s = 0; s < ppi; ++s)
-      for (int j = 0; j < 8; ++j) M = fmaxf(M, sm.part[s * vpp + k * 8 + j][0]);
-    float a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
-    for (int s = 0; s < ppi; ++s)
-      for (int j = 0; j < 8; ++j) {
-        const float* pp = sm.part[s * vpp + k * 8 + j];
-        const float f = (pp[0] == -INFINITY) ? 0.f : exp2f(pp[0] - M);
-        a1 = fmaf(pp[1], f, a1);
-        a2 = fmaf(pp[2], f, a2);
-        a3 = fmaf(pp[3], f, a3);
-        a4 = fmaf(pp[4], f, a4);
-      }
-    float* dst = p.partials + (((size_t)b * p.chunks + chunk) * p.nkpt + k) * 5;
+  if ((int)threadIdx.x < nk) {
+    const int kk = threadIdx.x;
+    float M = -INFINITY, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+    for (int s = 0; s < slots; ++s) {
+      const float* pp = sm.part[s][kk];
+      softmax_merge(M, a1, a2, a3, a4, pp[0], pp[1], pp[2], pp[3], pp[4]);
+    }
+    float* dst = p.partials + (((size_t)b * p.chunks + chunk) * nk + kk) * 5;
     __stcg(dst, M);
     __stcg(dst + 1, a1);
     __stcg(dst + 2, a2);
@@ -614,11 +641,10 @@ int launch_head(const HeadParams& p, cudaStream_t s) {
   HRP_REQUIRE(p.depth_in != nullptr || (p.feat != nullptr && p.depth_w != nullptr && p.k_value != nullptr),
               "head: a root-depth source is required");
   HRP_REQUIRE(p.ref_kpt >= 0 && p.ref_kpt < p.nkpt, "reference keypoint out of range");
-  const int vpp = p.nkpt * 8;
-  int ppi = 1;
-  while ((vpp * ppi) % 32 != 0 || vpp * ppi < 192) ++ppi;
-  const int threads = vpp * ppi;
-  HRP_REQUIRE(threads <= kHeadMaxThreads, "too many keypoints for the head kernel");
+  const int groups = (p.nkpt + 3) / 4;
+  const int slots = std::max(1, std::min(4, (kHeadMaxThreads / 32) / groups));
+  const int threads = groups * slots * 32;
+  HRP_REQUIRE(threads <= kHeadMaxThreads && slots <= kHeadMaxSlots, "too many keypoints for the head kernel");
   head_kernel<<<p.B * p.chunks, threads, 0, s>>>(p);
   count_launch();
   HRP_CUDA_CHECK(cudaGetLastError());
