@@ -31,6 +31,8 @@ struct ConvParams {
   int n_tile, cout_pad;   // N tile (multiple of 32, <= 256); weight rows per phase (multiple of n_tile)
   int cko;                // channels per TMA-store block of the epilogue (64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B)
   int ktot;               // ntaps*Cin
+  int vsh;                // vertical tap sharing (3x3 s1 p1, tile inside one image): A buffer = bh+2 image rows per dw
+  int vsh_a_bytes, vsh_a_pad, vsh_stage_bytes;
   int8_t tap_dh[kMaxTaps], tap_dw[kMaxTaps], tap_map[kMaxTaps];
   // epilogue
   const float* scale;     // [Cout] folded BN scale (1 if none)
@@ -53,6 +55,7 @@ struct ConvMaps {
   CUtensorMap a[4];  // input: one per stride-2 parity (else a[0])
   CUtensorMap b;     // packed weights
   CUtensorMap o[4];  // output: one per deconv phase (else o[0])
+  CUtensorMap av;    // input with a (bh+2)-row box for vertical tap sharing
   CUtensorMap r;     // residual (pre[0]) tile, same geometry as the output (persistent kernel)
 };
 

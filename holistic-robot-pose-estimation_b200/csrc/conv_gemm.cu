@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   const int n_tile = p.n_tile;
   const int b_sub_bytes = n_tile * CK * 2;
-  const int stage_bytes = kStageABytes + n_tile * 128;
+  const int stage_bytes = p.vsh ? p.vsh_stage_bytes : kStageABytes + n_tile * 128;
   PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(smem + bar_offset);
   float* sb_smem = reinterpret_cast<float*>(bars + 1);  // [2][n_tile] folded-BN scale / shift of this N tile
 
@@ -84,7 +84,9 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
   const int c_base = n_blk * n_tile;
 
   const int nkb = p.ntaps * p.cpt;
-  const int n_iters = (nkb + SUB - 1) / SUB;
+  // vertical tap sharing (3x3 stride-1 convs): one iteration = (channel chunk, dw); its A buffer holds bh+2 image
+  // rows and the three dh taps read 128-row windows of it (window start = dh * one image row: swizzle-aligned)
+  const int n_iters = p.vsh ? 3 * p.cpt : (nkb + SUB - 1) / SUB;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.a[0]);
@@ -121,6 +123,17 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
         const int s = it % stages;
         const uint32_t par = (it / stages) & 1;
         mbar_wait(&bars->empty[s], par ^ 1);
+        if (p.vsh) {
+          const int cc = it / 3, dwi = it - cc * 3;
+          mbar_expect_tx(&bars->full[s], (uint32_t)(p.vsh_a_bytes + 3 * b_sub_bytes));
+          uint8_t* sa = smem + (size_t)s * stage_bytes;
+          uint8_t* sb = sa + p.vsh_a_pad;
+          tma_load_4d(sa, &maps.av, &bars->full[s], cc * CK, w0 + dwi - 1, h0 - 1, n0);
+          for (int dhi = 0; dhi < 3; ++dhi)
+            tma_load_2d(sb + dhi * b_sub_bytes, &maps.b, &bars->full[s], ((dhi * 3 + dwi) * p.cpt + cc) * CK,
+                        phase * p.cout_pad + c_base);
+          continue;
+        }
         const int nsub = min(SUB, nkb - it * SUB);
         mbar_expect_tx(&bars->full[s], (uint32_t)(nsub * (A_SUB_BYTES + b_sub_bytes)));
         uint8_t* sa = smem + (size_t)s * stage_bytes;
@@ -144,8 +157,22 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
       mbar_wait(&bars->full[s], par);
       tc_fence_after();
       if (elect_one()) {
-        const int nsub = min(SUB, nkb - it * SUB);
         const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+        if (p.vsh) {
+          const uint32_t sbv = sa + (uint32_t)p.vsh_a_pad;
+          const uint32_t row_bytes = (uint32_t)(p.bw * CK * 2);  // one image row of the tile
+          for (int dhi = 0; dhi < 3; ++dhi) {
+#pragma unroll
+            for (int k = 0; k < KSTEPS; ++k) {
+              const uint64_t adesc = make_kmajor_desc(sa + dhi * row_bytes + k * 32, SBO, LAYOUT);
+              const uint64_t bdesc = make_kmajor_desc(sbv + dhi * b_sub_bytes + k * 32, SBO, LAYOUT);
+              umma_bf16_ss(tmem_base, adesc, bdesc, idesc, (it | dhi | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&bars->empty[s]);
+          if (it == n_iters - 1) umma_commit(&bars->tmem_full);
+        } else {
+        const int nsub = min(SUB, nkb - it * SUB);
         const uint32_t sb = sa + kStageABytes;
         for (int j = 0; j < nsub; ++j) {
 #pragma unroll
@@ -157,6 +184,7 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
         }
         umma_commit(&bars->empty[s]);                          // frees the smem stage when the MMAs retire
         if (it == n_iters - 1) umma_commit(&bars->tmem_full);  // accumulator complete
+        }
       }
       __syncwarp();
     }
@@ -769,6 +797,18 @@ int conv_geometry(const ConvLayerDesc& d, ConvParams* pp) {
   p.cout_pad = n_tiles * p.n_tile;
   p.cko = (p.n_tile % 64 == 0) ? 64 : 32;  // channel block of the TMA-store epilogue
   p.pool_scale = 1.f / (float)(p.Hout * p.Wout);
+  // vertical tap sharing: 3x3 stride-1 pad-1 convs whose tile lies inside one image
+  const char* vs = getenv("HRP_CONV_VSH");
+  // (default: only where the weights are small -- Cout <= 64 -- so a 3-tap stage still allows several CTAs per SM;
+  //  HRP_CONV_VSH=0 disables it, =2 enables it for every eligible layer)
+  const bool vsh_ok = (d.kind == kConv && d.stride == 1 && d.kh == 3 && d.kw == 3 && d.pad == 1 && p.bn == 1 && p.bw % 8 == 0);
+  const int vsh_mode = (vs != nullptr) ? (vs[0] - '0') : 1;
+  p.vsh = (vsh_ok && (vsh_mode == 2 || (vsh_mode == 1 && p.Cout <= 64))) ? 1 : 0;
+  if (p.vsh) {
+    p.vsh_a_bytes = (p.bh + 2) * p.bw * p.ck * 2;
+    p.vsh_a_pad = (p.vsh_a_bytes + 1023) / 1024 * 1024;
+    p.vsh_stage_bytes = p.vsh_a_pad + 3 * p.n_tile * p.ck * 2;
+  }
   return HRP_OK;
 }
 
@@ -894,6 +934,14 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed) {
     if (rc != HRP_OK) return rc;
   }
   for (int m = nmaps; m < 4; ++m) plan->maps.a[m] = plan->maps.a[0];
+  plan->maps.av = plan->maps.a[0];
+  if (p.vsh) {
+    uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.Ws, (uint64_t)p.Hs, (uint64_t)p.B};
+    uint64_t strides[3] = {(uint64_t)p.Cin * 2, (uint64_t)p.Win * p.Cin * 2, (uint64_t)p.Hin * p.Win * p.Cin * 2};
+    uint32_t box[4] = {(uint32_t)p.ck, (uint32_t)p.bw, (uint32_t)(p.bh + 2), 1u};
+    int rc = encode_map(&plan->maps.av, in, 4, dims, strides, box, p.ck);
+    if (rc != HRP_OK) return rc;
+  }
   {
     uint64_t dims[2] = {(uint64_t)p.ktot, (uint64_t)p.nphase * p.cout_pad};
     uint64_t strides[1] = {(uint64_t)p.ktot * 2};
@@ -918,12 +966,13 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed) {
     }
     for (int ph = p.nphase; ph < 4; ++ph) plan->maps.o[ph] = plan->maps.o[0];
   }
-  const int stage_bytes = kStageABytes + p.n_tile * 128;
+  const int stage_bytes = p.vsh ? p.vsh_stage_bytes : kStageABytes + p.n_tile * 128;
   const int sub = 64 / p.ck;
-  const int n_iters = (p.ntaps * p.cpt + sub - 1) / sub;
+  const int n_iters = p.vsh ? 3 * p.cpt : (p.ntaps * p.cpt + sub - 1) / sub;
   // shallow per-CTA pipelines, several CTAs per SM: small tiles are latency-bound, not smem-bound
   const int budget = (p.n_tile <= 64) ? 56 * 1024 : (p.n_tile <= 128) ? 72 * 1024 : 100 * 1024;
   int stages = std::max(2, budget / stage_bytes);
+  if (p.vsh && 3 * stage_bytes <= 72 * 1024) stages = 3;  // the whole 3-iteration K loop in flight
   stages = std::max(1, std::min(stages, n_iters));
   plan->stages = stages;
   const int staging = (p.out != nullptr) ? kTileM * p.n_tile * 2 : 0;
@@ -944,8 +993,13 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed) {
       cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
       if (num_sms <= 0) num_sms = 148;
     }
-    const char* v1 = getenv("HRP_CONV_V1");
-    plan->persistent = !(v1 != nullptr && v1[0] == '1');
+    // HRP_CONV_PERSISTENT=1 forces the persistent kernel everywhere, =0 the one-tile-per-CTA kernel; by default the
+    // persistent kernel is used where it measured faster on B200: wide short-K layers (the epilogue dominates and
+    // eight epilogue warps + double-buffered accumulators pay off)
+    const char* pe = getenv("HRP_CONV_PERSISTENT");
+    if (pe != nullptr && (pe[0] == '0' || pe[0] == '1')) plan->persistent = (pe[0] == '1');
+    else plan->persistent = (p.n_tile == 128 && p.ktot >= 256 && p.ktot <= 1024 && p.pre[0] == nullptr);
+    if (p.vsh) plan->persistent = false;  // vertical tap sharing lives in the one-tile-per-CTA kernel
     PersistCfg& c = plan->pcfg;
     const bool has_res = (p.pre[0] != nullptr) && (p.out != nullptr);
     if (has_res) {

@@ -82,7 +82,7 @@ def sweep(robot="kuka", B=512):
     to_u8 = lambda t: (t * 255).round().to(torch.uint8).repeat(B // 32, 1, 1, 1).cuda()
     xr, xo = to_u8(x_reg), to_u8(x_root)
     kk, KK = k.repeat(B // 32).cuda(), K.repeat(B // 32, 1, 1).cuda()
-    for chunk, inflight in [(16, 2), (32, 1), (32, 2), (32, 3), (64, 1), (64, 2), (128, 1), (128, 2), (256, 1)]:
+    for chunk, inflight in [(64, 2), (128, 1), (128, 2), (256, 1), (256, 2)]:
         m = make(robot, chunk, inflight)
         for _ in range(2):
             m(xr, xo, kk, KK)
