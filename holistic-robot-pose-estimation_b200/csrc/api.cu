@@ -40,6 +40,7 @@ static ConvLayerDesc to_internal(const hrp_conv_desc* d) {
   o.stride = d->stride;
   o.pad = d->pad;
   o.relu = d->relu;
+  o.has_residual = 0;
   return o;
 }
 
@@ -75,6 +76,7 @@ int hrp_conv_create(const hrp_conv_desc* desc, const void* in_dev, const void* w
   hrp_conv* c = new (std::nothrow) hrp_conv();
   HRP_REQUIRE(c != nullptr, "out of host memory");
   c->desc = to_internal(desc);
+  c->desc.has_residual = (epi->pre[0] != nullptr) ? 1 : 0;
   int rc = conv_geometry(c->desc, &c->plan.p);
   if (rc == HRP_OK) {
     ConvParams& p = c->plan.p;

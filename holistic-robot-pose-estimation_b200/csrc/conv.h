@@ -93,6 +93,7 @@ struct ConvLayerDesc {
   int Cout;
   int kh, kw, stride, pad;
   int relu;
+  int has_residual;      // a same-resolution addend (pre[0]) will be attached: keeps the N tile <= 128
 };
 
 // Host-side weight packing: reference layouts -> (nphase*cout_pad, ktot) bf16 K-major.

@@ -24,10 +24,11 @@ namespace hrp {
 constexpr int kNumThreads = 192;
 constexpr int kStageABytes = kTileM * 64 * 2;  // 16 KiB of A per stage regardless of ck
 
-struct __align__(8) PipeBarriers {
+struct __align__(16) PipeBarriers {
   uint64_t full[8];
   uint64_t empty[8];
   uint64_t tmem_full;
+  uint64_t res_full;
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -83,6 +84,10 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
   const int ph = phase >> 1, pw = phase & 1;  // deconv sub-pixel phase (0,0) when nphase == 1
   const int c_base = n_blk * n_tile;
 
+  // residual (pre[0]) prefetched by TMA into a dedicated staging buffer behind the pipeline stages; without a
+  // residual the staging buffer aliases the (by then idle) stages
+  const bool has_res = (EPI != EPI_PLAIN) && (p.pre[0] != nullptr) && (p.out != nullptr);
+  uint8_t* const stag_base = has_res ? smem + (size_t)stages * stage_bytes : smem;
   const int nkb = p.ntaps * p.cpt;
   // vertical tap sharing (3x3 stride-1 convs): one iteration = (channel chunk, dw); its A buffer holds bh+2 image
   // rows and the three dh taps read 128-row windows of it (window start = dh * one image row: swizzle-aligned)
@@ -96,6 +101,7 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
       mbar_init(&bars->empty[s], 1);
     }
     mbar_init(&bars->tmem_full, 1);
+    mbar_init(&bars->res_full, 1);
     fence_mbar_init();
   }
   uint32_t tmem_cols = 32;
@@ -119,6 +125,13 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
+      if (has_res) {  // residual tile -> dedicated staging buffer, in flight during the whole mainloop
+        int nb = 0;
+        for (int j = 0; j < n_tile / p.cko && c_base + j * p.cko < p.Cout; ++j) ++nb;
+        mbar_expect_tx(&bars->res_full, (uint32_t)(nb * kTileM * p.cko * 2));
+        for (int j = 0; j < nb; ++j)
+          tma_load_4d(stag_base + (size_t)j * (kTileM * p.cko * 2), &maps.r, &bars->res_full, c_base + j * p.cko, w0, h0, n0);
+      }
       for (int it = 0; it < n_iters; ++it) {
         const int s = it % stages;
         const uint32_t par = (it / stages) & 1;
@@ -207,7 +220,7 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
       ow = w * p.os + p.ow0 + pw;
       opix = ((size_t)n * p.Hout + oh) * p.Wout + ow;
     }
-    const bf16* pre0 = (EPI != EPI_PLAIN && p.pre[0] != nullptr) ? p.pre[0] + opix * p.Cout + c_base : nullptr;
+    const bf16* pre0 = (EPI != EPI_PLAIN && !has_res && p.pre[0] != nullptr) ? p.pre[0] + opix * p.Cout + c_base : nullptr;
     const bf16* pre1 = (EPI != EPI_PLAIN && p.pre[1] != nullptr) ? p.pre[1] + opix * p.Cout + c_base : nullptr;
     const bf16* pre2 = (EPI != EPI_PLAIN && p.pre[2] != nullptr) ? p.pre[2] + opix * p.Cout + c_base : nullptr;
     const bf16* upp[3] = {nullptr, nullptr, nullptr};
@@ -228,12 +241,13 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
     const bool relu_explicit = p.relu && !relu_in_cvt;
     const int cko = p.cko;
     const int sw = (cko == 64) ? (row & 7) : ((row >> 1) & 3);
-    uint8_t* const stage_row = smem + (size_t)row * (cko * 2);
+    uint8_t* const stage_row = stag_base + (size_t)row * (cko * 2);
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     const int c_lim = min(n_tile, p.Cout - c_base);  // channels of this N tile that exist (multiple of 32)
 
     mbar_wait(&bars->tmem_full, 0);
     tc_fence_after();
+    if (has_res) mbar_wait(&bars->res_full, 0);
 
 #pragma unroll 1
     for (int c0 = 0; c0 < c_lim; c0 += 32) {
@@ -256,6 +270,10 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
         v[5] = fmaf(__uint_as_float(acc[g * 8 + 5]), s1.y, b1.y);
         v[6] = fmaf(__uint_as_float(acc[g * 8 + 6]), s1.z, b1.z);
         v[7] = fmaf(__uint_as_float(acc[g * 8 + 7]), s1.w, b1.w);
+        const int blk = cg / cko;
+        const int ch = (cg - blk * cko) >> 3;
+        uint4* const sptr = reinterpret_cast<uint4*>(stage_row + (size_t)blk * (kTileM * cko * 2) + ((ch ^ sw) << 4));
+        if (EPI != EPI_PLAIN && has_res) add_bf16x8(v, *sptr);  // TMA-prefetched residual (zero outside the tensor)
         if (EPI != EPI_PLAIN && valid) {
           if (pre0 != nullptr) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(pre0 + cg)));
           if (pre1 != nullptr) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(pre1 + cg)));
@@ -286,9 +304,7 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
           }
           // stage into the (now idle) pipeline buffers in the TMA-store box layout: column blocks of cko
           // channels x 128 rows, 16-byte chunks XOR-swizzled exactly as the output tensor map expects
-          const int blk = cg / cko;
-          const int ch = (cg - blk * cko) >> 3;
-          *reinterpret_cast<uint4*>(stage_row + (size_t)blk * (kTileM * cko * 2) + ((ch ^ sw) << 4)) = o;
+          *sptr = o;
         }
         if (pool) {
           // global average pool: the 32 rows of a warp belong to one image (host checks bw*bh >= 32)
@@ -322,7 +338,7 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
         for (int j = 0; j < nblk; ++j) {
           const int cj = c_base + j * cko;
           if (cj >= p.Cout) break;
-          tma_store_4d(smem + (size_t)j * (kTileM * cko * 2), &maps.o[phase], cj, w0, h0, n0);
+          tma_store_4d(stag_base + (size_t)j * (kTileM * cko * 2), &maps.o[phase], cj, w0, h0, n0);
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -344,7 +360,7 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
 // epilogue warps (two per TMEM lane quarter) drain the accumulators.  Per-tile fixed costs (TMEM allocation,
 // barrier init, descriptor fetch, launch) are paid once per CTA.
 // ------------------------------------------------------------------------------------------------------
-constexpr int kThreadsP = 320;      // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
+constexpr int kThreadsP = 352;      // warp 0 producer, warp 1 MMA, warps 2..9 epilogue, warp 10 TMA-store
 constexpr int kEpiThreadsP = 256;
 
 struct __align__(16) PersistBarriers {
@@ -354,6 +370,7 @@ struct __align__(16) PersistBarriers {
   uint64_t tmem_empty[2];
   uint64_t res_full[2];
   uint64_t stag_free[2];
+  uint64_t stag_ready[2];
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -404,6 +421,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
       mbar_init(&bars->tmem_empty[i], kEpiThreadsP);
       mbar_init(&bars->res_full[i], 1);
       mbar_init(&bars->stag_free[i], 1);
+      mbar_init(&bars->stag_ready[i], kEpiThreadsP);
     }
     fence_mbar_init();
   }
@@ -411,7 +429,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
     tmem_alloc(&bars->tmem_base, (uint32_t)cfg.tmem_cols);
     tmem_relinquish();
   }
-  if (warp >= 2) {
+  if (warp >= 2 && warp < 10) {
     for (int i = threadIdx.x - 64; i < p.cout_pad; i += kEpiThreadsP) {
       sb_smem[i] = (i < p.Cout) ? __ldg(p.scale + i) : 0.f;
       sb_smem[p.cout_pad + i] = (i < p.Cout) ? __ldg(p.bias + i) : 0.f;
@@ -509,6 +527,26 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
         __syncwarp();
       }
     }
+  } else if (warp == 10) {
+    // ===================== TMA-store warp: drains finished staging buffers, never stalls the epilogue ==========
+    if (p.out != nullptr && elect_one()) {
+      int li = 0;
+      for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x, ++li) {
+        HRP_DECODE_TILE(tile)
+        (void)th; (void)tw; (void)tn; (void)ph; (void)pw;
+        const int sbuf = li % nstag;
+        mbar_wait(&bars->stag_ready[sbuf], (uint32_t)((li / nstag) & 1));
+        for (int j = 0; j < nblk_full; ++j) {
+          const int cj = c_base + j * cko;
+          if (cj >= p.Cout) break;
+          tma_store_4d(stag_base + (size_t)sbuf * stag_bytes + (size_t)j * (kTileM * cko * 2), &maps.o[phase], cj, w0,
+                       h0, n0);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem read by the TMA unit: buffer reusable
+        mbar_arrive(&bars->stag_free[sbuf]);
+      }
+    }
   } else {
     // ===================== epilogue: warps 2..9, lane quarter = warp % 4, column half = (warp-2)/4 ==========
     const int q = warp & 3;
@@ -517,7 +555,6 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
     const int sw = (cko == 64) ? (row & 7) : ((row >> 1) & 3);
     const bool do_store = (p.out != nullptr);
     const bool pool = (EPI == EPI_FULL) && (p.pool_out != nullptr);
-    const bool is_store_thread = (warp == 2) && (lane == 0);
     int li = 0;
     for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x, ++li) {
       HRP_DECODE_TILE(tile)
@@ -651,20 +688,9 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
       tc_fence_before();
       mbar_arrive(&bars->tmem_empty[abuf]);
       if (do_store) {
+        // generic-proxy staging writes -> async proxy, then hand the buffer to the store warp
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (is_store_thread) {
-          for (int j = 0; j < nblk_full; ++j) {
-            const int cj = c_base + j * cko;
-            if (cj >= p.Cout) break;
-            tma_store_4d(stag_base + (size_t)sbuf * stag_bytes + (size_t)j * (kTileM * cko * 2), &maps.o[phase], cj, w0,
-                         h0, n0);
-          }
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          // once the TMA unit has read the staging buffer it can take the next residual / result tile
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          mbar_arrive(&bars->stag_free[sbuf]);
-        }
+        mbar_arrive(&bars->stag_ready[sbuf]);
       }
     }
   }
@@ -791,7 +817,7 @@ int conv_geometry(const ConvLayerDesc& d, ConvParams* pp) {
   // N tile
   // N tile: 256 wide for K-heavy (tensor-bound) layers; 128 for short-K layers, whose time is the epilogue and
   // the output stream: 4 CTAs/SM fit in TMEM instead of 2 and the (small) A tile is re-read from L2
-  const int max_n = (p.ktot <= 256 && p.Cout > 128 && p.Cout % 128 == 0) ? 128 : 256;
+  const int max_n = ((p.ktot <= 256 || d.has_residual) && p.Cout > 128 && p.Cout % 128 == 0) ? 128 : 256;
   const int n_tiles = (p.Cout + max_n - 1) / max_n;
   p.n_tile = (((p.Cout + n_tiles - 1) / n_tiles) + 31) / 32 * 32;
   p.cout_pad = n_tiles * p.n_tile;
@@ -802,7 +828,7 @@ int conv_geometry(const ConvLayerDesc& d, ConvParams* pp) {
   // (default: only where the weights are small -- Cout <= 64 -- so a 3-tap stage still allows several CTAs per SM;
   //  HRP_CONV_VSH=0 disables it, =2 enables it for every eligible layer)
   const bool vsh_ok = (d.kind == kConv && d.stride == 1 && d.kh == 3 && d.kw == 3 && d.pad == 1 && p.bn == 1 && p.bw % 8 == 0);
-  const int vsh_mode = (vs != nullptr) ? (vs[0] - '0') : 1;
+  const int vsh_mode = (vs != nullptr) ? (vs[0] - '0') : 0;  // measured slower on B200 (fewer CTAs per SM): opt-in
   p.vsh = (vsh_ok && (vsh_mode == 2 || (vsh_mode == 1 && p.Cout <= 64))) ? 1 : 0;
   if (p.vsh) {
     p.vsh_a_bytes = (p.bh + 2) * p.bw * p.ck * 2;
@@ -976,7 +1002,8 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed) {
   stages = std::max(1, std::min(stages, n_iters));
   plan->stages = stages;
   const int staging = (p.out != nullptr) ? kTileM * p.n_tile * 2 : 0;
-  plan->bar_offset = std::max(stages * stage_bytes, staging);
+  const bool res_v1 = (p.pre[0] != nullptr) && (p.out != nullptr);
+  plan->bar_offset = res_v1 ? stages * stage_bytes + staging : std::max(stages * stage_bytes, staging);
   plan->smem_bytes = plan->bar_offset + (int)sizeof(PipeBarriers) + 2 * p.n_tile * (int)sizeof(float) + 1024;
   p.n_tiles = p.cout_pad / p.n_tile;
   plan->grid = dim3((unsigned)(p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles), 1u, (unsigned)p.nphase);

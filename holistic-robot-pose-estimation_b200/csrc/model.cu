@@ -331,6 +331,7 @@ struct Builder {
     d.stride = stride;
     d.pad = pad;
     d.relu = relu ? 1 : 0;
+    d.has_residual = (epi.pre[0] >= 0) ? 1 : 0;
     Op op;
     op.kind = OP_CONV;
     op.lane = lane;
