@@ -123,55 +123,42 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
   const uint32_t tmem_base = bars->tmem_base;
 
   if (warp == 0) {
-    // ===================== TMA producer (whole warp: one lane per TMA operation) =====================
-    // A single thread sustains only ~1 TMA issue per few hundred cycles; the k-blocks of a stage are independent
-    // operations, so lane j issues operation j and the per-stage issue cost is one instruction, not 2*SUB.
-    if (has_res) {  // residual tile -> dedicated staging buffer, in flight during the whole mainloop
-      int nb = 0;
-      for (int j = 0; j < n_tile / p.cko && c_base + j * p.cko < p.Cout; ++j) ++nb;
-      if (lane == 0) mbar_expect_tx(&bars->res_full, (uint32_t)(nb * kTileM * p.cko * 2));
-      __syncwarp();
-      if (lane < nb)
-        tma_load_4d(stag_base + (size_t)lane * (kTileM * p.cko * 2), &maps.r, &bars->res_full, c_base + lane * p.cko, w0,
-                    h0, n0);
-    }
-    for (int it = 0; it < n_iters; ++it) {
-      const int s = it % stages;
-      const uint32_t par = (it / stages) & 1;
-      uint8_t* sa = smem + (size_t)s * stage_bytes;
-      if (p.vsh) {
-        const int cc = it / 3, dwi = it - cc * 3;
-        if (lane == 0) {
-          mbar_wait(&bars->empty[s], par ^ 1);
-          mbar_expect_tx(&bars->full[s], (uint32_t)(p.vsh_a_bytes + 3 * b_sub_bytes));
-        }
-        __syncwarp();
-        uint8_t* sb = sa + p.vsh_a_pad;
-        if (lane == 0) {
-          tma_load_4d(sa, &maps.av, &bars->full[s], cc * CK, w0 + dwi - 1, h0 - 1, n0);
-        } else if (lane < 4) {
-          const int dhi = lane - 1;
-          tma_load_2d(sb + dhi * b_sub_bytes, &maps.b, &bars->full[s], ((dhi * 3 + dwi) * p.cpt + cc) * CK,
-                      phase * p.cout_pad + c_base);
-        }
-        continue;
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      if (has_res) {  // residual tile -> dedicated staging buffer, in flight during the whole mainloop
+        int nb = 0;
+        for (int j = 0; j < n_tile / p.cko && c_base + j * p.cko < p.Cout; ++j) ++nb;
+        mbar_expect_tx(&bars->res_full, (uint32_t)(nb * kTileM * p.cko * 2));
+        for (int j = 0; j < nb; ++j)
+          tma_load_4d(stag_base + (size_t)j * (kTileM * p.cko * 2), &maps.r, &bars->res_full, c_base + j * p.cko, w0, h0, n0);
       }
-      const int nsub = min(SUB, nkb - it * SUB);
-      if (lane == 0) {
+      for (int it = 0; it < n_iters; ++it) {
+        const int s = it % stages;
+        const uint32_t par = (it / stages) & 1;
         mbar_wait(&bars->empty[s], par ^ 1);
+        if (p.vsh) {
+          const int cc = it / 3, dwi = it - cc * 3;
+          mbar_expect_tx(&bars->full[s], (uint32_t)(p.vsh_a_bytes + 3 * b_sub_bytes));
+          uint8_t* sa = smem + (size_t)s * stage_bytes;
+          uint8_t* sb = sa + p.vsh_a_pad;
+          tma_load_4d(sa, &maps.av, &bars->full[s], cc * CK, w0 + dwi - 1, h0 - 1, n0);
+          for (int dhi = 0; dhi < 3; ++dhi)
+            tma_load_2d(sb + dhi * b_sub_bytes, &maps.b, &bars->full[s], ((dhi * 3 + dwi) * p.cpt + cc) * CK,
+                        phase * p.cout_pad + c_base);
+          continue;
+        }
+        const int nsub = min(SUB, nkb - it * SUB);
         mbar_expect_tx(&bars->full[s], (uint32_t)(nsub * (A_SUB_BYTES + b_sub_bytes)));
-      }
-      __syncwarp();
-      uint8_t* sb = sa + kStageABytes;
-      if (lane < nsub) {
-        const int kb = it * SUB + lane;
-        const int tap = kb / p.cpt;
-        const int cc = kb - tap * p.cpt;
-        tma_load_4d(sa + lane * A_SUB_BYTES, &maps.a[p.tap_map[tap]], &bars->full[s], cc * CK, w0 + p.tap_dw[tap] + pw,
-                    h0 + p.tap_dh[tap] + ph, n0);
-      } else if (lane < 2 * nsub) {
-        const int j = lane - nsub;
-        tma_load_2d(sb + j * b_sub_bytes, &maps.b, &bars->full[s], (it * SUB + j) * CK, phase * p.cout_pad + c_base);
+        uint8_t* sa = smem + (size_t)s * stage_bytes;
+        uint8_t* sb = sa + kStageABytes;
+        for (int j = 0; j < nsub; ++j) {
+          const int kb = it * SUB + j;
+          const int tap = kb / p.cpt;
+          const int cc = kb - tap * p.cpt;
+          tma_load_4d(sa + j * A_SUB_BYTES, &maps.a[p.tap_map[tap]], &bars->full[s], cc * CK,
+                      w0 + p.tap_dw[tap] + pw, h0 + p.tap_dh[tap] + ph, n0);
+          tma_load_2d(sb + j * b_sub_bytes, &maps.b, &bars->full[s], kb * CK, phase * p.cout_pad + c_base);
+        }
       }
     }
   } else if (warp == 1) {
@@ -346,13 +333,15 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
       // (rows / channels outside the tensor are clipped by the TMA unit: ragged tiles need no predicates)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (warp == 2) {  // lane j stores column block j (bulk async-groups are per thread)
-        const int cj = c_base + lane * cko;
-        if (lane < n_tile / cko && cj < p.Cout) {
-          tma_store_4d(stag_base + (size_t)lane * (kTileM * cko * 2), &maps.o[phase], cj, w0, h0, n0);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      if (warp == 2 && elect_one()) {
+        const int nblk = n_tile / cko;
+        for (int j = 0; j < nblk; ++j) {
+          const int cj = c_base + j * cko;
+          if (cj >= p.Cout) break;
+          tma_store_4d(stag_base + (size_t)j * (kTileM * cko * 2), &maps.o[phase], cj, w0, h0, n0);
         }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       }
     }
   }
@@ -466,50 +455,44 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
   const int c_base = n_blk * n_tile;
 
   if (warp == 0) {
-    // ===================== TMA producer (whole warp: one lane per TMA operation) =====================
-    uint32_t it_g = 0;
-    int li = 0;
-    for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x, ++li) {
-      HRP_DECODE_TILE(tile)
-      (void)th; (void)tw; (void)tn;
-      const int sbuf = li % nstag;
-      const uint32_t spar = (uint32_t)((li / nstag) & 1);
-      auto load_residual = [&]() {
-        int nb = 0;
-        for (int j = 0; j < nblk_full && c_base + j * cko < p.Cout; ++j) ++nb;
-        if (lane == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      uint32_t it_g = 0;
+      int li = 0;
+      for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x, ++li) {
+        HRP_DECODE_TILE(tile)
+        (void)th; (void)tw; (void)tn;
+        const int sbuf = li % nstag;
+        const uint32_t spar = (uint32_t)((li / nstag) & 1);
+        auto load_residual = [&]() {
           mbar_wait(&bars->stag_free[sbuf], spar ^ 1);  // the store that last used this buffer has drained
+          int nb = 0;
+          for (int j = 0; j < nblk_full && c_base + j * cko < p.Cout; ++j) ++nb;
           mbar_expect_tx(&bars->res_full[sbuf], (uint32_t)(nb * kTileM * cko * 2));
-        }
-        __syncwarp();
-        if (lane < nb)
-          tma_load_4d(stag_base + (size_t)sbuf * stag_bytes + (size_t)lane * (kTileM * cko * 2), &maps.r,
-                      &bars->res_full[sbuf], c_base + lane * cko, w0, h0, n0);
-      };
-      if (has_res && nstag == 2) load_residual();
-      for (int it = 0; it < n_iters; ++it, ++it_g) {
-        const int s = it_g % stages;
-        const uint32_t par = (it_g / stages) & 1;
-        const int nsub = min(SUB, nkb - it * SUB);
-        if (lane == 0) {
+          for (int j = 0; j < nb; ++j)
+            tma_load_4d(stag_base + (size_t)sbuf * stag_bytes + (size_t)j * (kTileM * cko * 2), &maps.r,
+                        &bars->res_full[sbuf], c_base + j * cko, w0, h0, n0);
+        };
+        if (has_res && nstag == 2) load_residual();
+        for (int it = 0; it < n_iters; ++it, ++it_g) {
+          const int s = it_g % stages;
+          const uint32_t par = (it_g / stages) & 1;
           mbar_wait(&bars->empty[s], par ^ 1);
+          const int nsub = min(SUB, nkb - it * SUB);
           mbar_expect_tx(&bars->full[s], (uint32_t)(nsub * (A_SUB_BYTES + b_sub_bytes)));
+          uint8_t* sa = smem + (size_t)s * stage_bytes;
+          uint8_t* sb = sa + kStageABytes;
+          for (int j = 0; j < nsub; ++j) {
+            const int kb = it * SUB + j;
+            const int tap = kb / p.cpt;
+            const int cc = kb - tap * p.cpt;
+            tma_load_4d(sa + j * A_SUB_BYTES, &maps.a[p.tap_map[tap]], &bars->full[s], cc * CK,
+                        w0 + p.tap_dw[tap] + pw, h0 + p.tap_dh[tap] + ph, n0);
+            tma_load_2d(sb + j * b_sub_bytes, &maps.b, &bars->full[s], kb * CK, phase * p.cout_pad + c_base);
+          }
         }
-        __syncwarp();
-        uint8_t* sa = smem + (size_t)s * stage_bytes;
-        uint8_t* sb = sa + kStageABytes;
-        if (lane < nsub) {
-          const int kb = it * SUB + lane;
-          const int tap = kb / p.cpt;
-          const int cc = kb - tap * p.cpt;
-          tma_load_4d(sa + lane * A_SUB_BYTES, &maps.a[p.tap_map[tap]], &bars->full[s], cc * CK,
-                      w0 + p.tap_dw[tap] + pw, h0 + p.tap_dh[tap] + ph, n0);
-        } else if (lane < 2 * nsub) {
-          const int j = lane - nsub;
-          tma_load_2d(sb + j * b_sub_bytes, &maps.b, &bars->full[s], (it * SUB + j) * CK, phase * p.cout_pad + c_base);
-        }
+        if (has_res && nstag == 1) load_residual();
       }
-      if (has_res && nstag == 1) load_residual();
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -546,22 +529,22 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
     }
   } else if (warp == 10) {
     // ===================== TMA-store warp: drains finished staging buffers, never stalls the epilogue ==========
-    if (p.out != nullptr) {
+    if (p.out != nullptr && elect_one()) {
       int li = 0;
       for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x, ++li) {
         HRP_DECODE_TILE(tile)
         (void)th; (void)tw; (void)tn; (void)ph; (void)pw;
         const int sbuf = li % nstag;
         mbar_wait(&bars->stag_ready[sbuf], (uint32_t)((li / nstag) & 1));
-        const int cj = c_base + lane * cko;
-        if (lane < nblk_full && cj < p.Cout) {  // lane j stores column block j
-          tma_store_4d(stag_base + (size_t)sbuf * stag_bytes + (size_t)lane * (kTileM * cko * 2), &maps.o[phase], cj, w0,
+        for (int j = 0; j < nblk_full; ++j) {
+          const int cj = c_base + j * cko;
+          if (cj >= p.Cout) break;
+          tma_store_4d(stag_base + (size_t)sbuf * stag_bytes + (size_t)j * (kTileM * cko * 2), &maps.o[phase], cj, w0,
                        h0, n0);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem read by the TMA unit
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->stag_free[sbuf]);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem read by the TMA unit: buffer reusable
+        mbar_arrive(&bars->stag_free[sbuf]);
       }
     }
   } else {
