@@ -119,6 +119,12 @@ int hrp_conv_run(hrp_conv* conv, int32_t impl, void* stream) {
 
 void hrp_conv_destroy(hrp_conv* conv) { delete conv; }
 
+int hrp_conv_set_timeline(hrp_conv* conv, long long* dev_buf) {
+  HRP_REQUIRE(conv != nullptr, "null conv handle");
+  conv->plan.p.timeline = dev_buf;
+  return HRP_OK;
+}
+
 int hrp_pack_input_s2d(const float* x_nchw, void* out_s2d, int32_t B, int32_t H, int32_t W, void* stream) {
   HRP_REQUIRE(x_nchw != nullptr && out_s2d != nullptr && B > 0, "bad argument");
   return launch_pack_input_s2d(x_nchw, out_s2d, B, H, W, reinterpret_cast<cudaStream_t>(stream));

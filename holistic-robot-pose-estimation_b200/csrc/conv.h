@@ -22,6 +22,7 @@ struct ConvParams {
   int B, Hm, Wm;          // row-pixel grid
   int bw, bh, bn;         // tile box (bw*bh*bn == 128)
   int tiles_w, tiles_h, tiles_n;
+  int tw_shift, th_shift, bw_shift, bh_shift;  // log2 of tiles_w, tiles_h, bw, bh
   int Hs, Ws, Cin;        // source grid seen by the taps (per parity map for stride 2) + stored channels
   int Hout, Wout, Cout;   // output tensor
   int os, oh0, ow0;       // output pixel stride / offset
@@ -49,6 +50,7 @@ struct ConvParams {
   const bf16* in;         // (B,Hin,Win,Cin) source tensor base
   const bf16* w;          // (nphase*cout_pad, ktot) packed weights
   int Hin, Win, src_sh, src_sw;  // full input dims and source-grid stride (2 for parity maps)
+  long long* timeline;    // debug: per-role clock64 stamps of the first CTAs (null in production)
 };
 
 struct ConvMaps {
@@ -66,6 +68,7 @@ struct PersistCfg {
   int bar_offset;    // byte offset of the barriers (scale/shift follow them)
   int total_tiles;   // m tiles x n tiles x phases
   int tmem_cols;     // allocated TMEM columns (power of two >= 2*n_tile)
+  int tw_shift, th_shift;  // log2 of tiles_w / tiles_h (tile decode without divisions)
 };
 
 struct ConvPlan {

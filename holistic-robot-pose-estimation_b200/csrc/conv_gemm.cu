@@ -33,6 +33,11 @@ struct __align__(16) PipeBarriers {
   uint32_t pad;
 };
 
+// debug timeline: slot = (cta * 64 + tile_local * 8 + event) for the first 8 CTAs / 8 tiles
+__device__ __forceinline__ void tl_stamp(long long* tl, int tile_local, int ev) {
+  if (tl != nullptr && blockIdx.x < 8 && tile_local < 8) tl[(blockIdx.x * 8 + tile_local) * 16 + ev] = clock64();
+}
+
 // Epilogue flavours (template parameter EPI): the common case carries no addends and no per-row predicates at all.
 constexpr int EPI_PLAIN = 0;  // y = [relu](acc*scale + bias)
 constexpr int EPI_PRE = 1;    // + up to three same-resolution addends before the ReLU (residual / fuse partials)
@@ -73,12 +78,16 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
 
   // tile coordinates: the N tile is the fastest-varying block index so that CTAs sharing an A tile run together
   int t = blockIdx.x;
-  const int n_blk = t % p.n_tiles;
-  t /= p.n_tiles;
-  const int tw = t % p.tiles_w;
-  t /= p.tiles_w;
-  const int th = t % p.tiles_h;
-  const int tn = t / p.tiles_h;
+  int n_blk = 0;
+  if (p.n_tiles > 1) {
+    const int q_ = t / p.n_tiles;
+    n_blk = t - q_ * p.n_tiles;
+    t = q_;
+  }
+  const int tw = t & (p.tiles_w - 1);   // tiles_w, tiles_h, bw, bh are powers of two
+  t >>= p.tw_shift;
+  const int th = t & (p.tiles_h - 1);
+  const int tn = t >> p.th_shift;
   const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
   const int phase = blockIdx.z;
   const int ph = phase >> 1, pw = phase & 1;  // deconv sub-pixel phase (0,0) when nphase == 1
@@ -132,41 +141,46 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
         for (int j = 0; j < nb; ++j)
           tma_load_4d(stag_base + (size_t)j * (kTileM * p.cko * 2), &maps.r, &bars->res_full, c_base + j * p.cko, w0, h0, n0);
       }
+      // running counters instead of div/mod: this single thread's scalar latency IS the producer's throughput
+      int s = 0, tap = 0, cc = 0;
+      uint32_t par = 0;
+      const int brow = phase * p.cout_pad + c_base;
       for (int it = 0; it < n_iters; ++it) {
-        const int s = it % stages;
-        const uint32_t par = (it / stages) & 1;
         mbar_wait(&bars->empty[s], par ^ 1);
-        if (p.vsh) {
-          const int cc = it / 3, dwi = it - cc * 3;
-          mbar_expect_tx(&bars->full[s], (uint32_t)(p.vsh_a_bytes + 3 * b_sub_bytes));
-          uint8_t* sa = smem + (size_t)s * stage_bytes;
-          uint8_t* sb = sa + p.vsh_a_pad;
-          tma_load_4d(sa, &maps.av, &bars->full[s], cc * CK, w0 + dwi - 1, h0 - 1, n0);
-          for (int dhi = 0; dhi < 3; ++dhi)
-            tma_load_2d(sb + dhi * b_sub_bytes, &maps.b, &bars->full[s], ((dhi * 3 + dwi) * p.cpt + cc) * CK,
-                        phase * p.cout_pad + c_base);
-          continue;
-        }
-        const int nsub = min(SUB, nkb - it * SUB);
-        mbar_expect_tx(&bars->full[s], (uint32_t)(nsub * (A_SUB_BYTES + b_sub_bytes)));
         uint8_t* sa = smem + (size_t)s * stage_bytes;
-        uint8_t* sb = sa + kStageABytes;
-        for (int j = 0; j < nsub; ++j) {
-          const int kb = it * SUB + j;
-          const int tap = kb / p.cpt;
-          const int cc = kb - tap * p.cpt;
-          tma_load_4d(sa + j * A_SUB_BYTES, &maps.a[p.tap_map[tap]], &bars->full[s], cc * CK,
-                      w0 + p.tap_dw[tap] + pw, h0 + p.tap_dh[tap] + ph, n0);
-          tma_load_2d(sb + j * b_sub_bytes, &maps.b, &bars->full[s], kb * CK, phase * p.cout_pad + c_base);
+        if (p.vsh) {
+          const int cch = it / 3, dwi = it - cch * 3;
+          mbar_expect_tx(&bars->full[s], (uint32_t)(p.vsh_a_bytes + 3 * b_sub_bytes));
+          uint8_t* sb = sa + p.vsh_a_pad;
+          tma_load_4d(sa, &maps.av, &bars->full[s], cch * CK, w0 + dwi - 1, h0 - 1, n0);
+          for (int dhi = 0; dhi < 3; ++dhi)
+            tma_load_2d(sb + dhi * b_sub_bytes, &maps.b, &bars->full[s], ((dhi * 3 + dwi) * p.cpt + cch) * CK, brow);
+        } else {
+          const int nsub = min(SUB, nkb - it * SUB);
+          mbar_expect_tx(&bars->full[s], (uint32_t)(nsub * (A_SUB_BYTES + b_sub_bytes)));
+          uint8_t* sb = sa + kStageABytes;
+          for (int j = 0; j < nsub; ++j) {
+            tma_load_4d(sa + j * A_SUB_BYTES, &maps.a[p.tap_map[tap]], &bars->full[s], cc * CK,
+                        w0 + p.tap_dw[tap] + pw, h0 + p.tap_dh[tap] + ph, n0);
+            tma_load_2d(sb + j * b_sub_bytes, &maps.b, &bars->full[s], (it * SUB + j) * CK, brow);
+            if (++cc == p.cpt) {
+              cc = 0;
+              ++tap;
+            }
+          }
+        }
+        if (++s == stages) {
+          s = 0;
+          par ^= 1;
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     const uint32_t idesc = make_idesc_bf16(kTileM, (uint32_t)n_tile);
+    int s = 0;
+    uint32_t par = 0;
     for (int it = 0; it < n_iters; ++it) {
-      const int s = it % stages;
-      const uint32_t par = (it / stages) & 1;
       mbar_wait(&bars->full[s], par);
       tc_fence_after();
       if (elect_one()) {
@@ -200,6 +214,10 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
         }
       }
       __syncwarp();
+      if (++s == stages) {
+        s = 0;
+        par ^= 1;
+      }
     }
   } else {
     // ===================== epilogue (warps 2..5 <-> TMEM lane quarters warp%4) =====================
@@ -210,9 +228,9 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
     size_t opix = 0;
     int n = 0, oh = 0, ow = 0;
     if (EPI != EPI_PLAIN) {
-      const int wi = row % p.bw;
-      const int hi = (row / p.bw) % p.bh;
-      const int ni = row / (p.bw * p.bh);
+      const int wi = row & (p.bw - 1);
+      const int hi = (row >> p.bw_shift) & (p.bh - 1);
+      const int ni = row >> (p.bw_shift + p.bh_shift);
       n = n0 + ni;
       const int h = h0 + hi, w = w0 + wi;
       valid = (n < p.B) && (h < p.Hm) && (w < p.Wm);
@@ -318,7 +336,7 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
             x += __shfl_xor_sync(0xffffffffu, x, 1);
             v[i] = x;
           }
-          const int n_warp = n0 + (q * 32) / (p.bw * p.bh);
+          const int n_warp = n0 + ((q * 32) >> (p.bw_shift + p.bh_shift));
           float mine = 0.f;
 #pragma unroll
           for (int i = 0; i < 8; ++i) mine = (lane == i) ? v[i] : mine;
@@ -440,30 +458,41 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
-#define HRP_DECODE_TILE(tile)                         \
-  int t_ = (tile);                                    \
-  const int n_blk = t_ % p.n_tiles;                   \
-  t_ /= p.n_tiles;                                    \
-  const int phase = t_ / tiles_m;                     \
-  t_ -= phase * tiles_m;                              \
-  const int tw = t_ % p.tiles_w;                      \
-  t_ /= p.tiles_w;                                    \
-  const int th = t_ % p.tiles_h;                      \
-  const int tn = t_ / p.tiles_h;                      \
-  const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn; \
-  const int ph = phase >> 1, pw = phase & 1;          \
+  // tile -> (n tile, phase, w/h/n tile) with shifts: tiles_w and tiles_h are powers of two by construction
+#define HRP_DECODE_TILE(tile)                                          \
+  int t_ = (tile);                                                     \
+  int n_blk = 0;                                                       \
+  if (p.n_tiles > 1) {                                                 \
+    const int q_ = t_ / p.n_tiles;                                     \
+    n_blk = t_ - q_ * p.n_tiles;                                       \
+    t_ = q_;                                                           \
+  }                                                                    \
+  int phase = 0;                                                       \
+  if (p.nphase > 1) {                                                  \
+    phase = t_ / tiles_m;                                              \
+    t_ -= phase * tiles_m;                                             \
+  }                                                                    \
+  const int tw = t_ & (p.tiles_w - 1);                                 \
+  t_ >>= cfg.tw_shift;                                                 \
+  const int th = t_ & (p.tiles_h - 1);                                 \
+  const int tn = t_ >> cfg.th_shift;                                   \
+  const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;            \
+  const int ph = phase >> 1, pw = phase & 1;                           \
   const int c_base = n_blk * n_tile;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      uint32_t it_g = 0;
+      int s = 0;
+      uint32_t par = 0;
       int li = 0;
       for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x, ++li) {
         HRP_DECODE_TILE(tile)
         (void)th; (void)tw; (void)tn;
-        const int sbuf = li % nstag;
-        const uint32_t spar = (uint32_t)((li / nstag) & 1);
+        const int sbuf = (nstag == 2) ? (li & 1) : 0;
+        const uint32_t spar = (uint32_t)(((nstag == 2) ? (li >> 1) : li) & 1);
+        const int brow = phase * p.cout_pad + c_base;
+        int tap = 0, cc = 0;
         auto load_residual = [&]() {
           mbar_wait(&bars->stag_free[sbuf], spar ^ 1);  // the store that last used this buffer has drained
           int nb = 0;
@@ -474,41 +503,48 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
                         &bars->res_full[sbuf], c_base + j * cko, w0, h0, n0);
         };
         if (has_res && nstag == 2) load_residual();
-        for (int it = 0; it < n_iters; ++it, ++it_g) {
-          const int s = it_g % stages;
-          const uint32_t par = (it_g / stages) & 1;
+        tl_stamp(p.timeline, li, 0);
+        for (int it = 0; it < n_iters; ++it) {
           mbar_wait(&bars->empty[s], par ^ 1);
+          if (it == 0) tl_stamp(p.timeline, li, 1);
           const int nsub = min(SUB, nkb - it * SUB);
           mbar_expect_tx(&bars->full[s], (uint32_t)(nsub * (A_SUB_BYTES + b_sub_bytes)));
           uint8_t* sa = smem + (size_t)s * stage_bytes;
           uint8_t* sb = sa + kStageABytes;
           for (int j = 0; j < nsub; ++j) {
-            const int kb = it * SUB + j;
-            const int tap = kb / p.cpt;
-            const int cc = kb - tap * p.cpt;
             tma_load_4d(sa + j * A_SUB_BYTES, &maps.a[p.tap_map[tap]], &bars->full[s], cc * CK,
                         w0 + p.tap_dw[tap] + pw, h0 + p.tap_dh[tap] + ph, n0);
-            tma_load_2d(sb + j * b_sub_bytes, &maps.b, &bars->full[s], kb * CK, phase * p.cout_pad + c_base);
+            tma_load_2d(sb + j * b_sub_bytes, &maps.b, &bars->full[s], (it * SUB + j) * CK, brow);
+            if (++cc == p.cpt) {
+              cc = 0;
+              ++tap;
+            }
+          }
+          if (++s == stages) {
+            s = 0;
+            par ^= 1;
           }
         }
+        tl_stamp(p.timeline, li, 2);
         if (has_res && nstag == 1) load_residual();
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     const uint32_t idesc = make_idesc_bf16(kTileM, (uint32_t)n_tile);
-    uint32_t it_g = 0;
+    int s = 0;
+    uint32_t par = 0;
     int li = 0;
     for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x, ++li) {
       const int abuf = li & 1;
       mbar_wait(&bars->tmem_empty[abuf], (uint32_t)(((li >> 1) & 1) ^ 1));  // epilogue drained this accumulator
       tc_fence_after();
+      if (lane == 0) tl_stamp(p.timeline, li, 3);
       const uint32_t tacc = tmem_base + (uint32_t)(abuf * n_tile);
-      for (int it = 0; it < n_iters; ++it, ++it_g) {
-        const int s = it_g % stages;
-        const uint32_t par = (it_g / stages) & 1;
+      for (int it = 0; it < n_iters; ++it) {
         mbar_wait(&bars->full[s], par);
         tc_fence_after();
+        if (lane == 0 && it == 0) tl_stamp(p.timeline, li, 4);
         if (elect_one()) {
           const int nsub = min(SUB, nkb - it * SUB);
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
@@ -524,7 +560,12 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
           umma_commit(&bars->empty[s]);
           if (it == n_iters - 1) umma_commit(&bars->tmem_full[abuf]);
         }
+        if (lane == 0 && it == n_iters - 1) tl_stamp(p.timeline, li, 5);
         __syncwarp();
+        if (++s == stages) {
+          s = 0;
+          par ^= 1;
+        }
       }
     }
   } else if (warp == 10) {
@@ -534,8 +575,9 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
       for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x, ++li) {
         HRP_DECODE_TILE(tile)
         (void)th; (void)tw; (void)tn; (void)ph; (void)pw;
-        const int sbuf = li % nstag;
-        mbar_wait(&bars->stag_ready[sbuf], (uint32_t)((li / nstag) & 1));
+        const int sbuf = (nstag == 2) ? (li & 1) : 0;
+        mbar_wait(&bars->stag_ready[sbuf], (uint32_t)(((nstag == 2) ? (li >> 1) : li) & 1));
+        tl_stamp(p.timeline, li, 10);
         for (int j = 0; j < nblk_full; ++j) {
           const int cj = c_base + j * cko;
           if (cj >= p.Cout) break;
@@ -543,7 +585,9 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
                        h0, n0);
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        tl_stamp(p.timeline, li, 11);
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem read by the TMA unit: buffer reusable
+        tl_stamp(p.timeline, li, 12);
         mbar_arrive(&bars->stag_free[sbuf]);
       }
     }
@@ -560,15 +604,15 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
       HRP_DECODE_TILE(tile)
       (void)th; (void)tw; (void)tn;
       const int abuf = li & 1;
-      const int sbuf = li % nstag;
-      const uint32_t spar = (uint32_t)((li / nstag) & 1);
+      const int sbuf = (nstag == 2) ? (li & 1) : 0;
+      const uint32_t spar = (uint32_t)(((nstag == 2) ? (li >> 1) : li) & 1);
       bool valid = true;
       size_t opix = 0;
       int n = 0, oh = 0, ow = 0;
       if (EPI != EPI_PLAIN) {
-        const int wi = row % p.bw;
-        const int hi = (row / p.bw) % p.bh;
-        const int ni = row / (p.bw * p.bh);
+        const int wi = row & (p.bw - 1);
+        const int hi = (row >> p.bw_shift) & (p.bh - 1);
+        const int ni = row >> (p.bw_shift + p.bh_shift);
         n = n0 + ni;
         const int h = h0 + hi, w = w0 + wi;
         valid = (n < p.B) && (h < p.Hm) && (w < p.Wm);
@@ -599,12 +643,15 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
       const float* sc = sb_smem + c_base;
       const float* sh_ = sb_smem + p.cout_pad + c_base;
 
+      if (warp == 2 && lane == 0) tl_stamp(p.timeline, li, 6);
       mbar_wait(&bars->tmem_full[abuf], (uint32_t)((li >> 1) & 1));
       tc_fence_after();
+      if (warp == 2 && lane == 0) tl_stamp(p.timeline, li, 7);
       if (do_store) {
         if (has_res) mbar_wait(&bars->res_full[sbuf], spar);          // residual tile landed in the staging buffer
         else mbar_wait(&bars->stag_free[sbuf], spar ^ 1);            // previous store from this buffer has drained
       }
+      if (warp == 2 && lane == 0) tl_stamp(p.timeline, li, 8);
 
 #pragma unroll 1
       for (int c0 = half * 32; c0 < c_lim; c0 += 64) {
@@ -675,7 +722,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
               x += __shfl_xor_sync(0xffffffffu, x, 1);
               v[i] = x;
             }
-            const int n_warp = n0 + (q * 32) / (p.bw * p.bh);
+            const int n_warp = n0 + ((q * 32) >> (p.bw_shift + p.bh_shift));
             float mine = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) mine = (lane == i) ? v[i] : mine;
@@ -687,6 +734,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
       // accumulator drained: hand it back to the MMA warp
       tc_fence_before();
       mbar_arrive(&bars->tmem_empty[abuf]);
+      if (warp == 2 && lane == 0) tl_stamp(p.timeline, li, 9);
       if (do_store) {
         // generic-proxy staging writes -> async proxy, then hand the buffer to the store warp
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -814,6 +862,13 @@ int conv_geometry(const ConvLayerDesc& d, ConvParams* pp) {
   p.tiles_w = (p.Wm + p.bw - 1) / p.bw;
   p.tiles_h = (p.Hm + p.bh - 1) / p.bh;
   p.tiles_n = (p.B + p.bn - 1) / p.bn;
+  auto ilog2 = [](int v) { int sft = 0; while ((1 << sft) < v) ++sft; return sft; };
+  p.tw_shift = ilog2(p.tiles_w);
+  p.th_shift = ilog2(p.tiles_h);
+  p.bw_shift = ilog2(p.bw);
+  p.bh_shift = ilog2(p.bh);
+  HRP_REQUIRE((1 << p.tw_shift) == p.tiles_w && (1 << p.th_shift) == p.tiles_h,
+              "spatial sizes must give power-of-two tile counts");
   // N tile
   // N tile: 256 wide for K-heavy (tensor-bound) layers; 128 for short-K layers, whose time is the epilogue and
   // the output stream: 4 CTAs/SM fit in TMEM instead of 2 and the (small) A tile is re-read from L2
@@ -1054,6 +1109,11 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed) {
     c.stag_offset = c.stages * stage_bytes;
     c.bar_offset = c.stag_offset + nstag * stag_bytes;
     c.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles * p.nphase;
+    c.tw_shift = 0;
+    while ((1 << c.tw_shift) < p.tiles_w) ++c.tw_shift;
+    c.th_shift = 0;
+    while ((1 << c.th_shift) < p.tiles_h) ++c.th_shift;
+    HRP_REQUIRE((1 << c.tw_shift) == p.tiles_w && (1 << c.th_shift) == p.tiles_h, "tile counts must be powers of two");
     int cols = 32;
     while (cols < 2 * p.n_tile) cols <<= 1;
     c.tmem_cols = cols;

@@ -77,6 +77,8 @@ int hrp_conv_create(const hrp_conv_desc* desc, const void* in_dev, const void* w
 int hrp_conv_out_shape(const hrp_conv* conv, int32_t* Hout, int32_t* Wout);
 int hrp_conv_run(hrp_conv* conv, int32_t impl, void* stream);
 void hrp_conv_destroy(hrp_conv* conv);
+/* debug: device buffer of 8 CTAs x 8 tiles x 16 int64 clock64() stamps per pipeline role, or NULL to disable */
+int hrp_conv_set_timeline(hrp_conv* conv, long long* dev_buf);
 
 /* ------------------------------------------------------------------------------------------------
  * Input / layout kernels.
