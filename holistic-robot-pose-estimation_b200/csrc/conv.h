@@ -69,6 +69,9 @@ struct PersistCfg {
   int total_tiles;   // m tiles x n tiles x phases
   int tmem_cols;     // allocated TMEM columns (power of two >= 2*n_tile)
   int tw_shift, th_shift;  // log2 of tiles_w / tiles_h (tile decode without divisions)
+  int vsh;           // vertical tap sharing: one (bh+2)-row A buffer per (channel chunk, dw)
+  int wres;          // packed weights of the (single) N tile resident in shared memory
+  int a_bytes, a_region, stage_bytes, pipe_offset;
 };
 
 struct ConvPlan {

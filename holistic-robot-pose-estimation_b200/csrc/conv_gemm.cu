@@ -389,6 +389,7 @@ struct __align__(16) PersistBarriers {
   uint64_t res_full[2];
   uint64_t stag_free[2];
   uint64_t stag_ready[2];
+  uint64_t w_full;
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -411,9 +412,12 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   const int n_tile = p.n_tile;
   const int b_sub_bytes = n_tile * CK * 2;
-  const int stage_bytes = kStageABytes + n_tile * 128;
+  const int stage_bytes = cfg.stage_bytes;      // A region (+ B region unless the weights are resident)
+  const int a_region = cfg.a_region;
   const int stag_bytes = kTileM * n_tile * 2;
   const int stages = cfg.stages, nstag = cfg.nstag;
+  const bool vsh = cfg.vsh != 0, wres = cfg.wres != 0;
+  uint8_t* const pipe_base = smem + cfg.pipe_offset;  // resident weights (if any) live in front of the stages
   uint8_t* const stag_base = smem + cfg.stag_offset;
   PersistBarriers* bars = reinterpret_cast<PersistBarriers*>(smem + cfg.bar_offset);
   float* sb_smem = reinterpret_cast<float*>(bars + 1);  // [2][cout_pad] scale / shift of the whole layer
@@ -421,7 +425,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nkb = p.ntaps * p.cpt;
-  const int n_iters = (nkb + SUB - 1) / SUB;
+  const int n_iters = vsh ? 3 * p.cpt : (nkb + SUB - 1) / SUB;
   const int cko = p.cko;
   const int nblk_full = n_tile / cko;
   const bool has_res = (EPI != EPI_PLAIN) && (p.pre[0] != nullptr) && (p.out != nullptr);
@@ -441,6 +445,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
       mbar_init(&bars->stag_free[i], 1);
       mbar_init(&bars->stag_ready[i], kEpiThreadsP);
     }
+    mbar_init(&bars->w_full, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -483,6 +488,10 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
+      if (wres) {  // the whole (single) N tile of packed weights stays in shared memory for the CTA's lifetime
+        mbar_expect_tx(&bars->w_full, (uint32_t)(nkb * b_sub_bytes));
+        for (int kb = 0; kb < nkb; ++kb) tma_load_2d(smem + (size_t)kb * b_sub_bytes, &maps.b, &bars->w_full, kb * CK, 0);
+      }
       int s = 0;
       uint32_t par = 0;
       int li = 0;
@@ -492,7 +501,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
         const int sbuf = (nstag == 2) ? (li & 1) : 0;
         const uint32_t spar = (uint32_t)(((nstag == 2) ? (li >> 1) : li) & 1);
         const int brow = phase * p.cout_pad + c_base;
-        int tap = 0, cc = 0;
+        int tap = 0, cc = 0, dwi = 0;
         auto load_residual = [&]() {
           mbar_wait(&bars->stag_free[sbuf], spar ^ 1);  // the store that last used this buffer has drained
           int nb = 0;
@@ -507,17 +516,30 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
         for (int it = 0; it < n_iters; ++it) {
           mbar_wait(&bars->empty[s], par ^ 1);
           if (it == 0) tl_stamp(p.timeline, li, 1);
-          const int nsub = min(SUB, nkb - it * SUB);
-          mbar_expect_tx(&bars->full[s], (uint32_t)(nsub * (A_SUB_BYTES + b_sub_bytes)));
-          uint8_t* sa = smem + (size_t)s * stage_bytes;
-          uint8_t* sb = sa + kStageABytes;
-          for (int j = 0; j < nsub; ++j) {
-            tma_load_4d(sa + j * A_SUB_BYTES, &maps.a[p.tap_map[tap]], &bars->full[s], cc * CK,
-                        w0 + p.tap_dw[tap] + pw, h0 + p.tap_dh[tap] + ph, n0);
-            tma_load_2d(sb + j * b_sub_bytes, &maps.b, &bars->full[s], (it * SUB + j) * CK, brow);
-            if (++cc == p.cpt) {
-              cc = 0;
-              ++tap;
+          uint8_t* sa = pipe_base + (size_t)s * stage_bytes;
+          uint8_t* sb = sa + a_region;
+          if (vsh) {
+            // one (channel chunk, dw) per iteration: an A buffer of bh+2 image rows serves the three dh taps
+            mbar_expect_tx(&bars->full[s], (uint32_t)(cfg.a_bytes + (wres ? 0 : 3 * b_sub_bytes)));
+            tma_load_4d(sa, &maps.av, &bars->full[s], cc * CK, w0 + dwi - 1, h0 - 1, n0);
+            if (!wres)
+              for (int dhi = 0; dhi < 3; ++dhi)
+                tma_load_2d(sb + dhi * b_sub_bytes, &maps.b, &bars->full[s], ((dhi * 3 + dwi) * p.cpt + cc) * CK, brow);
+            if (++dwi == 3) {
+              dwi = 0;
+              ++cc;
+            }
+          } else {
+            const int nsub = min(SUB, nkb - it * SUB);
+            mbar_expect_tx(&bars->full[s], (uint32_t)(nsub * (A_SUB_BYTES + (wres ? 0 : b_sub_bytes))));
+            for (int j = 0; j < nsub; ++j) {
+              tma_load_4d(sa + j * A_SUB_BYTES, &maps.a[p.tap_map[tap]], &bars->full[s], cc * CK,
+                          w0 + p.tap_dw[tap] + pw, h0 + p.tap_dh[tap] + ph, n0);
+              if (!wres) tma_load_2d(sb + j * b_sub_bytes, &maps.b, &bars->full[s], (it * SUB + j) * CK, brow);
+              if (++cc == p.cpt) {
+                cc = 0;
+                ++tap;
+              }
             }
           }
           if (++s == stages) {
@@ -530,41 +552,74 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    const uint32_t idesc = make_idesc_bf16(kTileM, (uint32_t)n_tile);
-    int s = 0;
-    uint32_t par = 0;
-    int li = 0;
-    for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x, ++li) {
-      const int abuf = li & 1;
-      mbar_wait(&bars->tmem_empty[abuf], (uint32_t)(((li >> 1) & 1) ^ 1));  // epilogue drained this accumulator
-      tc_fence_after();
-      if (lane == 0) tl_stamp(p.timeline, li, 3);
-      const uint32_t tacc = tmem_base + (uint32_t)(abuf * n_tile);
-      for (int it = 0; it < n_iters; ++it) {
-        mbar_wait(&bars->full[s], par);
+    // ===================== MMA issuer: ONE thread runs the whole loop (scalar latency = issue rate) ==========
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(kTileM, (uint32_t)n_tile);
+      // descriptor = constant high word + (smem byte address >> 4) in the low word
+      const uint32_t desc_hi = (uint32_t)(make_kmajor_desc(0, SBO, LAYOUT) >> 32);
+      const uint32_t desc_lo0 = (uint32_t)make_kmajor_desc(0, SBO, LAYOUT);
+      const uint32_t pipe_addr = smem_u32(pipe_base);
+      const uint32_t wres_addr = smem_u32(smem);
+      const uint32_t row_units = (uint32_t)(p.bw * CK * 2) >> 4;   // one image row of the tile, in 16-byte units
+      const uint32_t bsub_units = (uint32_t)b_sub_bytes >> 4;
+      auto mk = [&](uint32_t addr_units) -> uint64_t {
+        return ((uint64_t)desc_hi << 32) | (uint64_t)(desc_lo0 + (addr_units & 0x3fffu));
+      };
+      if (wres) mbar_wait(&bars->w_full, 0);
+      int s = 0;
+      uint32_t par = 0;
+      int li = 0;
+      for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x, ++li) {
+        const int abuf = li & 1;
+        mbar_wait(&bars->tmem_empty[abuf], (uint32_t)(((li >> 1) & 1) ^ 1));  // epilogue drained this accumulator
         tc_fence_after();
-        if (lane == 0 && it == 0) tl_stamp(p.timeline, li, 4);
-        if (elect_one()) {
-          const int nsub = min(SUB, nkb - it * SUB);
-          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint32_t sb = sa + kStageABytes;
-          for (int j = 0; j < nsub; ++j) {
+        tl_stamp(p.timeline, li, 3);
+        const uint32_t tacc = tmem_base + (uint32_t)(abuf * n_tile);
+        int cc = 0, dwi = 0;
+        uint32_t acc_flag = 0;
+        for (int it = 0; it < n_iters; ++it) {
+          mbar_wait(&bars->full[s], par);
+          tc_fence_after();
+          if (it == 0) tl_stamp(p.timeline, li, 4);
+          const uint32_t sa = (pipe_addr + (uint32_t)(s * stage_bytes)) >> 4;
+          const uint32_t sb = sa + ((uint32_t)a_region >> 4);
+          if (vsh) {
 #pragma unroll
-            for (int k = 0; k < KSTEPS; ++k) {
-              const uint64_t adesc = make_kmajor_desc(sa + j * A_SUB_BYTES + k * 32, SBO, LAYOUT);
-              const uint64_t bdesc = make_kmajor_desc(sb + j * b_sub_bytes + k * 32, SBO, LAYOUT);
-              umma_bf16_ss(tacc, adesc, bdesc, idesc, (it | j | k) != 0 ? 1u : 0u);
+            for (int dhi = 0; dhi < 3; ++dhi) {
+              const uint32_t a0 = sa + dhi * row_units;
+              const uint32_t b0 = wres ? (wres_addr >> 4) + (uint32_t)((dhi * 3 + dwi) * p.cpt + cc) * bsub_units
+                                       : sb + dhi * bsub_units;
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k) {
+                umma_bf16_ss(tacc, mk(a0 + 2 * k), mk(b0 + 2 * k), idesc, acc_flag);
+                acc_flag = 1;
+              }
+            }
+            if (++dwi == 3) {
+              dwi = 0;
+              ++cc;
+            }
+          } else {
+            const int nsub = min(SUB, nkb - it * SUB);
+            for (int j = 0; j < nsub; ++j) {
+              const uint32_t a0 = sa + (uint32_t)j * (A_SUB_BYTES >> 4);
+              const uint32_t b0 = wres ? (wres_addr >> 4) + (uint32_t)(it * SUB + j) * bsub_units : sb + j * bsub_units;
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k) {
+                umma_bf16_ss(tacc, mk(a0 + 2 * k), mk(b0 + 2 * k), idesc, acc_flag);
+                acc_flag = 1;
+              }
             }
           }
           umma_commit(&bars->empty[s]);
-          if (it == n_iters - 1) umma_commit(&bars->tmem_full[abuf]);
-        }
-        if (lane == 0 && it == n_iters - 1) tl_stamp(p.timeline, li, 5);
-        __syncwarp();
-        if (++s == stages) {
-          s = 0;
-          par ^= 1;
+          if (it == n_iters - 1) {
+            umma_commit(&bars->tmem_full[abuf]);
+            tl_stamp(p.timeline, li, 5);
+          }
+          if (++s == stages) {
+            s = 0;
+            par ^= 1;
+          }
         }
       }
     }
@@ -1081,7 +1136,6 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed) {
     const char* pe = getenv("HRP_CONV_PERSISTENT");
     if (pe != nullptr && (pe[0] == '0' || pe[0] == '1')) plan->persistent = (pe[0] == '1');
     else plan->persistent = (p.n_tile == 128 && p.ktot >= 256 && p.ktot <= 1024 && p.pre[0] == nullptr);
-    if (p.vsh) plan->persistent = false;  // vertical tap sharing lives in the one-tile-per-CTA kernel
     PersistCfg& c = plan->pcfg;
     const bool has_res = (p.pre[0] != nullptr) && (p.out != nullptr);
     if (has_res) {
@@ -1097,16 +1151,39 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed) {
     const int stag_bytes = (p.out != nullptr) ? kTileM * p.n_tile * 2 : 0;
     const int tail = 256 + 2 * p.cout_pad * (int)sizeof(float) + 1024;  // barriers + scale/shift + alignment slack
     const int avail = 227 * 1024 - tail;
+    const int b_sub = p.n_tile * p.ck * 2;
+    // vertical tap sharing + resident weights: in the persistent kernel the producer thread's issue rate is the
+    // limit for small tiles, so fewer TMA operations per tile is what counts (HRP_CONV_PVSH=0 / HRP_CONV_WRES=0 disable)
+    const char* e1 = getenv("HRP_CONV_PVSH");
+    const char* e2 = getenv("HRP_CONV_WRES");
+    const bool vsh_ok = (p.nphase == 1 && p.src_sh == 1 && p.ntaps == 9 && p.tap_dh[0] == -1 && p.tap_dw[0] == -1 &&
+                         p.tap_dh[8] == 1 && p.tap_dw[8] == 1 && p.bn == 1 && p.Hs == p.Hm && p.Ws == p.Wm);
+    c.vsh = (vsh_ok && !(e1 != nullptr && e1[0] == '0')) ? 1 : 0;
+    const int wbytes = p.ntaps * p.cpt * b_sub;
+    c.wres = (p.n_tiles == 1 && p.nphase == 1 && wbytes <= 80 * 1024 && !(e2 != nullptr && e2[0] == '0')) ? 1 : 0;
+    c.a_bytes = c.vsh ? (p.bh + 2) * p.bw * p.ck * 2 : kStageABytes;
+    c.a_region = (c.a_bytes + 1023) / 1024 * 1024;
+    const int b_region = c.wres ? 0 : (c.vsh ? 3 * b_sub : p.n_tile * 128);
+    c.stage_bytes = c.a_region + b_region;
+    c.pipe_offset = c.wres ? (wbytes + 1023) / 1024 * 1024 : 0;
+    if (c.vsh) {
+      uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.Ws, (uint64_t)p.Hs, (uint64_t)p.B};
+      uint64_t strides[3] = {(uint64_t)p.Cin * 2, (uint64_t)p.Win * p.Cin * 2, (uint64_t)p.Hin * p.Win * p.Cin * 2};
+      uint32_t box[4] = {(uint32_t)p.ck, (uint32_t)p.bw, (uint32_t)(p.bh + 2), 1u};
+      int rc = encode_map(&plan->maps.av, in, 4, dims, strides, box, p.ck);
+      if (rc != HRP_OK) return rc;
+    }
+    const int pipe_avail = avail - c.pipe_offset;
     int nstag = (stag_bytes > 0 && p.n_tile <= 128) ? 2 : 1;
-    int st = (avail - nstag * stag_bytes) / stage_bytes;
+    int st = (pipe_avail - nstag * stag_bytes) / c.stage_bytes;
     if (st < 3 && nstag == 2) {
       nstag = 1;
-      st = (avail - stag_bytes) / stage_bytes;
+      st = (pipe_avail - stag_bytes) / c.stage_bytes;
     }
     HRP_REQUIRE(st >= 1, "layer does not fit in shared memory");
     c.stages = std::min(8, st);
     c.nstag = nstag;
-    c.stag_offset = c.stages * stage_bytes;
+    c.stag_offset = c.pipe_offset + c.stages * c.stage_bytes;
     c.bar_offset = c.stag_offset + nstag * stag_bytes;
     c.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles * p.nphase;
     c.tw_shift = 0;
