@@ -72,6 +72,7 @@ struct PersistCfg {
   int vsh;           // vertical tap sharing: one (bh+2)-row A buffer per (channel chunk, dw)
   int wres;          // packed weights of the (single) N tile resident in shared memory
   int a_bytes, a_region, stage_bytes, pipe_offset;
+  int ksplit;        // accumulators per tile: K steps round-robin over them to hide the dependent-MMA latency
 };
 
 struct ConvPlan {

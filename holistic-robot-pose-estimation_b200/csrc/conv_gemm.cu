@@ -417,6 +417,8 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
   const int stag_bytes = kTileM * n_tile * 2;
   const int stages = cfg.stages, nstag = cfg.nstag;
   const bool vsh = cfg.vsh != 0, wres = cfg.wres != 0;
+  const int ksplit = cfg.ksplit;               // accumulators per tile (1, 2 or 4)
+  const uint32_t ksmask = (uint32_t)ksplit - 1u;
   uint8_t* const pipe_base = smem + cfg.pipe_offset;  // resident weights (if any) live in front of the stages
   uint8_t* const stag_base = smem + cfg.stag_offset;
   PersistBarriers* bars = reinterpret_cast<PersistBarriers*>(smem + cfg.bar_offset);
@@ -555,16 +557,15 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
     // ===================== MMA issuer: ONE thread runs the whole loop (scalar latency = issue rate) ==========
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(kTileM, (uint32_t)n_tile);
-      // descriptor = constant high word + (smem byte address >> 4) in the low word
-      const uint32_t desc_hi = (uint32_t)(make_kmajor_desc(0, SBO, LAYOUT) >> 32);
-      const uint32_t desc_lo0 = (uint32_t)make_kmajor_desc(0, SBO, LAYOUT);
-      const uint32_t pipe_addr = smem_u32(pipe_base);
-      const uint32_t wres_addr = smem_u32(smem);
+      // descriptor = constant 64-bit base + (smem byte address >> 4): one 64-bit add per operand, no masking needed
+      // because shared-memory addresses stay below 2^18
+      const uint64_t dbase = make_kmajor_desc(0, SBO, LAYOUT);
+      const uint32_t pipe_units = smem_u32(pipe_base) >> 4;
+      const uint32_t wres_units = smem_u32(smem) >> 4;
+      const uint32_t stage_units = (uint32_t)stage_bytes >> 4;
+      const uint32_t aregion_units = (uint32_t)a_region >> 4;
       const uint32_t row_units = (uint32_t)(p.bw * CK * 2) >> 4;   // one image row of the tile, in 16-byte units
       const uint32_t bsub_units = (uint32_t)b_sub_bytes >> 4;
-      auto mk = [&](uint32_t addr_units) -> uint64_t {
-        return ((uint64_t)desc_hi << 32) | (uint64_t)(desc_lo0 + (addr_units & 0x3fffu));
-      };
       if (wres) mbar_wait(&bars->w_full, 0);
       int s = 0;
       uint32_t par = 0;
@@ -574,25 +575,28 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
         mbar_wait(&bars->tmem_empty[abuf], (uint32_t)(((li >> 1) & 1) ^ 1));  // epilogue drained this accumulator
         tc_fence_after();
         tl_stamp(p.timeline, li, 3);
-        const uint32_t tacc = tmem_base + (uint32_t)(abuf * n_tile);
+        // dependent tcgen05.mma into ONE accumulator are latency-bound (~130 cycles each) when N is small: round-robin
+        // the K steps over `ksplit` accumulators (summed by the epilogue) so independent chains overlap
+        const uint32_t tacc0 = tmem_base + (uint32_t)(abuf * ksplit * n_tile);
         int cc = 0, dwi = 0;
-        uint32_t acc_flag = 0;
+        uint32_t mi = 0;
         for (int it = 0; it < n_iters; ++it) {
           mbar_wait(&bars->full[s], par);
           tc_fence_after();
           if (it == 0) tl_stamp(p.timeline, li, 4);
-          const uint32_t sa = (pipe_addr + (uint32_t)(s * stage_bytes)) >> 4;
-          const uint32_t sb = sa + ((uint32_t)a_region >> 4);
+          const uint64_t a_it = dbase + (uint64_t)(pipe_units + (uint32_t)s * stage_units);
+          const uint64_t b_it = a_it + aregion_units;
           if (vsh) {
+            const uint64_t bw_it = dbase + (uint64_t)(wres_units + (uint32_t)(dwi * p.cpt + cc) * bsub_units);
 #pragma unroll
             for (int dhi = 0; dhi < 3; ++dhi) {
-              const uint32_t a0 = sa + dhi * row_units;
-              const uint32_t b0 = wres ? (wres_addr >> 4) + (uint32_t)((dhi * 3 + dwi) * p.cpt + cc) * bsub_units
-                                       : sb + dhi * bsub_units;
+              const uint64_t ad = a_it + (uint64_t)(dhi * row_units);
+              const uint64_t bd = wres ? bw_it + (uint64_t)((uint32_t)(dhi * 3 * p.cpt) * bsub_units)
+                                       : b_it + (uint64_t)(dhi * bsub_units);
 #pragma unroll
               for (int k = 0; k < KSTEPS; ++k) {
-                umma_bf16_ss(tacc, mk(a0 + 2 * k), mk(b0 + 2 * k), idesc, acc_flag);
-                acc_flag = 1;
+                umma_bf16_ss(tacc0 + (mi & ksmask) * (uint32_t)n_tile, ad + 2 * k, bd + 2 * k, idesc, mi >= (uint32_t)ksplit);
+                ++mi;
               }
             }
             if (++dwi == 3) {
@@ -601,13 +605,14 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
             }
           } else {
             const int nsub = min(SUB, nkb - it * SUB);
+            const uint64_t bw_it = dbase + (uint64_t)(wres_units + (uint32_t)(it * SUB) * bsub_units);
             for (int j = 0; j < nsub; ++j) {
-              const uint32_t a0 = sa + (uint32_t)j * (A_SUB_BYTES >> 4);
-              const uint32_t b0 = wres ? (wres_addr >> 4) + (uint32_t)(it * SUB + j) * bsub_units : sb + j * bsub_units;
+              const uint64_t ad = a_it + (uint64_t)((uint32_t)j * (A_SUB_BYTES >> 4));
+              const uint64_t bd = (wres ? bw_it : b_it) + (uint64_t)((uint32_t)j * bsub_units);
 #pragma unroll
               for (int k = 0; k < KSTEPS; ++k) {
-                umma_bf16_ss(tacc, mk(a0 + 2 * k), mk(b0 + 2 * k), idesc, acc_flag);
-                acc_flag = 1;
+                umma_bf16_ss(tacc0 + (mi & ksmask) * (uint32_t)n_tile, ad + 2 * k, bd + 2 * k, idesc, mi >= (uint32_t)ksplit);
+                ++mi;
               }
             }
           }
@@ -693,7 +698,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
       const bool relu_in_cvt = p.relu && !(EPI == EPI_FULL && (postp != nullptr || pool));
       const bool relu_explicit = p.relu && !relu_in_cvt;
       uint8_t* const stage_row = stag_base + (size_t)sbuf * stag_bytes + (size_t)row * (cko * 2);
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * n_tile);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * ksplit * n_tile);
       const int c_lim = min(n_tile, p.Cout - c_base);
       const float* sc = sb_smem + c_base;
       const float* sh_ = sb_smem + p.cout_pad + c_base;
@@ -713,6 +718,13 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
         uint32_t acc[32];
         tmem_ld32(taddr + (uint32_t)c0, acc);
         tmem_ld_wait();
+        for (int ks = 1; ks < ksplit; ++ks) {  // partial sums of the K-split accumulators
+          uint32_t part[32];
+          tmem_ld32(taddr + (uint32_t)(ks * n_tile + c0), part);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __uint_as_float(part[i]));
+        }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const int cg = c0 + g * 8;
@@ -1191,8 +1203,14 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed) {
     c.th_shift = 0;
     while ((1 << c.th_shift) < p.tiles_h) ++c.th_shift;
     HRP_REQUIRE((1 << c.tw_shift) == p.tiles_w && (1 << c.th_shift) == p.tiles_h, "tile counts must be powers of two");
+    const char* e3 = getenv("HRP_CONV_KSPLIT");
+    int ks = (p.n_tile <= 64) ? 4 : (p.n_tile <= 128) ? 2 : 1;
+    if (e3 != nullptr && (e3[0] == '1' || e3[0] == '2' || e3[0] == '4')) ks = std::min(ks, e3[0] - '0');
+    const int n_mma = p.ntaps * p.cpt * (p.ck / 16);
+    while (ks > 1 && n_mma < 2 * ks) ks >>= 1;  // every accumulator must receive at least one MMA (no stale TMEM)
+    c.ksplit = ks;
     int cols = 32;
-    while (cols < 2 * p.n_tile) cols <<= 1;
+    while (cols < 2 * ks * p.n_tile) cols <<= 1;
     c.tmem_cols = cols;
     plan->psmem = c.bar_offset + tail;
     plan->pgrid = (unsigned)std::min(c.total_tiles, num_sms);
