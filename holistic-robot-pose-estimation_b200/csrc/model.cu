@@ -123,6 +123,8 @@ struct hrp_model {
   bool finalized = false;
   std::map<std::string, HostTensor> host;
   std::map<std::string, ConvWeights> wcache;
+  std::map<std::string, int> tune_cache;  // conv shape signature -> 1 persistent kernel, 0 one-tile-per-CTA kernel
+  bool autotune = true;
   std::vector<void*> owned;
   const hrp_robot* robot = nullptr;
   RegressorTable* reg_pose = nullptr;
@@ -588,6 +590,53 @@ int launch_op(const hrp_model* m, const Op& op, cudaStream_t s) {
   return HRP_ERR_STATE;
 }
 
+// Pick, per conv shape, the faster of the two tcgen05 kernels (persistent vs one-tile-per-CTA) by timing both on
+// the plan's own buffers (3 launches each, CUDA events).  Decisions are cached by shape signature.
+int autotune_plan(hrp_model* m, Plan* pl) {
+  if (!m->autotune || m->use_simt) return HRP_OK;
+  cudaStream_t s = nullptr;
+  HRP_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  cudaEvent_t e0, e1;
+  HRP_CUDA_CHECK(cudaEventCreate(&e0));
+  HRP_CUDA_CHECK(cudaEventCreate(&e1));
+  char key[256];
+  int rc = HRP_OK;
+  for (auto& op : pl->ops) {
+    if (op.kind != OP_CONV) continue;
+    const ConvParams& q = op.conv.p;
+    snprintf(key, sizeof(key), "%d:%d:%d:%d:%d:%d:%d:%d:%d:%d:%d:%d:%d", q.B, q.Hin, q.Win, q.Cin, q.Cout, q.Hout, q.ntaps,
+             q.nphase, q.src_sh, op.conv.epi, q.pre[0] != nullptr, q.pool_out != nullptr, q.out != nullptr);
+    auto it = m->tune_cache.find(key);
+    if (it != m->tune_cache.end()) {
+      op.conv.persistent = (it->second != 0);
+      continue;
+    }
+    float best[2] = {0.f, 0.f};
+    for (int variant = 0; variant < 2 && rc == HRP_OK; ++variant) {
+      op.conv.persistent = (variant == 1);
+      rc = conv_plan_launch(op.conv, s);  // warm-up (also faults in code / descriptors)
+      if (rc != HRP_OK) break;
+      cudaEventRecord(e0, s);
+      for (int i = 0; i < 3 && rc == HRP_OK; ++i) rc = conv_plan_launch(op.conv, s);
+      cudaEventRecord(e1, s);
+      if (cudaEventSynchronize(e1) != cudaSuccess) {
+        set_error(std::string("autotune launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+        rc = HRP_ERR_CUDA;
+        break;
+      }
+      cudaEventElapsedTime(&best[variant], e0, e1);
+    }
+    if (rc != HRP_OK) break;
+    const int pick = (best[1] < best[0]) ? 1 : 0;
+    op.conv.persistent = (pick == 1);
+    m->tune_cache[key] = pick;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaStreamDestroy(s);
+  return rc;
+}
+
 int capture_plan(hrp_model* m, Plan* pl) {
   // cross-lane dependencies -> events
   for (size_t i = 0; i < pl->ops.size(); ++i)
@@ -687,6 +736,14 @@ int build_plan(hrp_model* m, int B, Plan** out_plan, int replica) {
     }
   }
   if (b.rc != HRP_OK) return b.rc;
+  {
+    const int64_t launches_before = g_launch_count.load();
+    rc = autotune_plan(m, pl.get());
+    g_launch_count.store(launches_before);
+    if (rc != HRP_OK) return rc;
+    if (pl->feat) HRP_CUDA_CHECK(cudaMemset(pl->feat, 0, (size_t)B * 2048 * 4));
+    if (pl->xf) HRP_CUDA_CHECK(cudaMemset(pl->xf, 0, (size_t)B * 2048 * 4));
+  }
   rc = capture_plan(m, pl.get());
   if (rc != HRP_OK) return rc;
   *out_plan = pl.get();
@@ -742,6 +799,8 @@ int hrp_model_create(const hrp_model_desc* desc, hrp_model** out) {
   m->use_graph = !(e != nullptr && e[0] == '1');
   e = getenv("HRP_CONV_IMPL");
   m->use_simt = (e != nullptr && std::string(e) == "simt");
+  e = getenv("HRP_AUTOTUNE");
+  m->autotune = !(e != nullptr && e[0] == '0') && getenv("HRP_CONV_PERSISTENT") == nullptr;
   *out = m;
   return HRP_OK;
 }
@@ -1003,9 +1062,10 @@ int hrp_model_profile(hrp_model* m, int32_t batch, int32_t iters, char* buf, int
     if (op.kind == OP_CONV) {
       const ConvParams& q = op.conv.p;
       const double in_b = (double)q.B * q.Hin * q.Win * q.Cin * 2.0, out_b = (double)q.B * q.Hout * q.Wout * q.Cout * 2.0;
-      snprintf(line, sizeof(line), "%s\tconv\t%d\t%dx%d\t%d\t%d\t%dx%d\t%d\t%d\t%d\t%u\t%d\t%.2f\t%.1f\t%.1f\n",
+      snprintf(line, sizeof(line), "%s\tconv\t%d\t%dx%d\t%d\t%d\t%dx%d\t%d\t%d\t%d\t%s\t%d\t%.2f\t%.1f\t%.1f\n",
                op.name.c_str(), op.lane, q.Hin, q.Win, q.Cin, q.Cout, q.Hout, q.Wout, q.ntaps, q.n_tile, op.conv.epi,
-               op.conv.grid.x * op.conv.grid.z, op.conv.stages, us, op.conv.flops / us * 1e-6, (in_b + out_b) / us * 1e-3);
+               op.conv.persistent ? "persist" : "tile", op.conv.persistent ? op.conv.pcfg.stages : op.conv.stages, us,
+               op.conv.flops / us * 1e-6, (in_b + out_b) / us * 1e-3);
     } else {
       snprintf(line, sizeof(line), "%s\tmisc\t%d\t-\t-\t-\t-\t-\t-\t-\t-\t-\t%.2f\t0\t0\n", op.name.c_str(), op.lane, us);
     }

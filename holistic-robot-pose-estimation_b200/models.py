@@ -54,7 +54,7 @@ class _EngineModule(nn.Module):
         self._sd = None
         self._handle = None
         self._device = None
-        self.chunk = int(os.environ.get("HRP_CHUNK", "32"))
+        self.chunk = int(os.environ.get("HRP_CHUNK", "128"))
         self.inflight = int(os.environ.get("HRP_INFLIGHT", "2"))
 
     # -- nn.Module surface the reference callers use -----------------------------------------------------

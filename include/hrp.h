@@ -220,6 +220,9 @@ int hrp_model_depthnet_forward(hrp_model* model, const float* x, const float* k_
  * pointer; C < 0 means an fp32 (B,|C|) vector), and per-plan statistics */
 int hrp_model_activation(hrp_model* model, const char* name, const void** ptr, int32_t* B, int32_t* H, int32_t* W,
                          int32_t* C);
+/* hardware probe (profiling aid): cycles to issue / complete `reps` back-to-back tcgen05.mma (SS mode, bf16, K=16)
+ * of shape M x N on `ctas` CTAs; dev_out2 = {issue cycles, completion cycles} of CTA 0 */
+int hrp_probe_mma_rate(int32_t M, int32_t N, int32_t reps, int32_t kdistinct, long long* dev_out2, int32_t ctas);
 /* asynchronous device-to-device copy on `stream` (used by the shims to snapshot activations) */
 int hrp_copy_device(void* dst, const void* src, int64_t bytes, void* stream);
 /* per-operation timing of one plan (eager, CUDA events, `iters` back-to-back launches per op): tab-separated text
