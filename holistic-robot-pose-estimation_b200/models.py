@@ -54,8 +54,8 @@ class _EngineModule(nn.Module):
         self._sd = None
         self._handle = None
         self._device = None
-        self.chunk = int(os.environ.get("HRP_CHUNK", "128"))
-        self.inflight = int(os.environ.get("HRP_INFLIGHT", "2"))
+        self.chunk = int(os.environ.get("HRP_CHUNK", "256"))
+        self.inflight = int(os.environ.get("HRP_INFLIGHT", "1"))
 
     # -- nn.Module surface the reference callers use -----------------------------------------------------
     def load_state_dict(self, state_dict, strict=True):

@@ -136,6 +136,16 @@ def test_chunking_ragged_batches_and_graph_replay(hrp_lib):
     """B=5 with chunk=2, 2 replicas in flight: multi-chunk + ragged tail must equal per-image runs; replays must be
     bit-identical (graph state, pooled-feature zeroing, head counters)."""
     from horopose_b200 import synth
+    # autotune may pick different (equally valid) kernels for different batch sizes, whose fp32 accumulation orders
+    # differ; pin the shape-based choice so that per-image results are independent of how the batch is chunked
+    os.environ["HRP_AUTOTUNE"] = "0"
+    try:
+        _check_chunking(synth)
+    finally:
+        del os.environ["HRP_AUTOTUNE"]
+
+
+def _check_chunking(synth):
     x_reg, x_root, k, K = (t.cuda() for t in synth.inputs(5, seed=23))
     m = _model("panda", chunk=2, inflight=2)
     a = [t.clone() for t in m(x_reg, x_root, k, K)]
