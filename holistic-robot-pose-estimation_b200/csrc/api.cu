@@ -91,7 +91,7 @@ int hrp_conv_create(const hrp_conv_desc* desc, const void* in_dev, const void* w
     p.out = reinterpret_cast<bf16*>(epi->out);
     p.pool_out = epi->pool_out;
     rc = conv_plan_finalize(&c->plan, reinterpret_cast<const bf16*>(in_dev),
-                            reinterpret_cast<const bf16*>(w_packed_dev));
+                            reinterpret_cast<const bf16*>(w_packed_dev), &c->desc);
   }
   if (rc != HRP_OK) {
     delete c;
@@ -118,6 +118,23 @@ int hrp_conv_run(hrp_conv* conv, int32_t impl, void* stream) {
 }
 
 void hrp_conv_destroy(hrp_conv* conv) { delete conv; }
+
+int hrp_conv_set_variant(hrp_conv* conv, int32_t variant) {
+  HRP_REQUIRE(conv != nullptr, "null conv handle");
+  HRP_REQUIRE(variant >= 0 && variant <= 2, "variant must be 0 (tile), 1 (persistent) or 2 (halo)");
+  if (variant == 2 && !conv->plan.halo_ok) {
+    set_error("the halo-tile kernel cannot run this layer");
+    return HRP_ERR_UNSUPPORTED;
+  }
+  conv->plan.halo = (variant == 2);
+  if (variant < 2) conv->plan.persistent = (variant == 1);
+  return HRP_OK;
+}
+
+int hrp_conv_variant(const hrp_conv* conv) {
+  if (conv == nullptr) return -1;
+  return conv->plan.halo ? 2 : (conv->plan.persistent ? 1 : 0);
+}
 
 int hrp_conv_set_timeline(hrp_conv* conv, long long* dev_buf) {
   HRP_REQUIRE(conv != nullptr, "null conv handle");

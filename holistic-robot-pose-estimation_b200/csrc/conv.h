@@ -75,6 +75,22 @@ struct PersistCfg {
   int ksplit;        // accumulators per tile: K steps round-robin over them to hide the dependent-MMA latency
 };
 
+// Halo-tile 3x3 kernel (conv_halo.cu): a unit = T consecutive 128-position tiles of one zero-padded image
+struct HaloParams {
+  int B, H, W, Cout, relu;
+  int Wp;                // W + 2: padded row pitch in positions
+  int NR;                // input rows per TMA box (band + halo)
+  int T;                 // 128-position tiles per unit
+  int tiles_per_img, units_per_img, total_units;
+  int n_abuf;            // band buffers in flight
+  int a_buf_bytes, a_offset, stag_offset, bar_offset;
+  uint32_t div_magic;    // P / Wp == (P * div_magic) >> 20
+  const float* scale;
+  const float* bias;
+  const bf16* res;       // residual addend (pre[0]) or null
+  bf16* out;
+};
+
 struct ConvPlan {
   ConvParams p;
   ConvMaps maps;
@@ -84,6 +100,12 @@ struct ConvPlan {
   int stages;
   int epi;         // epilogue flavour (EPI_PLAIN / EPI_PRE / EPI_FULL)
   bool persistent; // persistent kernel (default) vs one-tile-per-CTA kernel (HRP_CONV_V1=1)
+  bool halo_ok;    // the halo-tile kernel can run this layer
+  bool halo;       // ... and has been selected (heuristic / autotune / HRP_CONV_VARIANT)
+  HaloParams hp;
+  CUtensorMap halo_map_a;
+  unsigned halo_grid;
+  int halo_smem;
   PersistCfg pcfg;
   unsigned pgrid;
   int psmem;
@@ -113,7 +135,12 @@ int conv_pack_weights(const ConvLayerDesc& d, const ConvParams& p, int cin_ref, 
 
 // Build tensor maps + launch config.  `in`/`w_packed` are device pointers; epilogue pointers are taken from p.
 void conv_init();  // one-time kernel attribute setup (call outside stream capture)
-int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed);
+void conv_halo_init();
+int conv_encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, int ck);  // bf16 tiled map, swizzle = ck*2 bytes
+int conv_halo_plan(ConvPlan* plan, const ConvLayerDesc& d, const bf16* in);  // eligibility + tiling of the halo kernel
+int conv_halo_launch(const ConvPlan& plan, cudaStream_t stream);
+int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed, const ConvLayerDesc* desc = nullptr);
 int conv_plan_launch(const ConvPlan& plan, cudaStream_t stream);       // tcgen05 path
 int conv_plan_launch_simt(const ConvPlan& plan, cudaStream_t stream);  // cross-check path (tests only)
 

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
   constexpr uint32_t SBO = 8 * CK * 2;         // 8 rows of CK bf16
 
   extern __shared__ uint8_t smem_dyn[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_dyn);
   const int n_tile = p.n_tile;
   const int b_sub_bytes = n_tile * CK * 2;
   const int stage_bytes = p.vsh ? p.vsh_stage_bytes : kStageABytes + n_tile * 128;
@@ -394,10 +394,6 @@ struct __align__(16) PersistBarriers {
   uint32_t pad;
 };
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
 template <int CK, int EPI>
 __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __grid_constant__ ConvMaps maps,
                                                                      const __grid_constant__ ConvParams p,
@@ -409,7 +405,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
   constexpr uint32_t SBO = 8 * CK * 2;
 
   extern __shared__ uint8_t smem_dyn[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_dyn);
   const int n_tile = p.n_tile;
   const int b_sub_bytes = n_tile * CK * 2;
   const int stage_bytes = cfg.stage_bytes;      // A region (+ B region unless the weights are resident)
@@ -1020,8 +1016,8 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                      const uint32_t* box, int ck) {
+int conv_encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, int ck) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
@@ -1060,9 +1056,12 @@ static void set_smem_attr_once() {
   });
 }
 
-void conv_init() { set_smem_attr_once(); }
+void conv_init() {
+  set_smem_attr_once();
+  conv_halo_init();
+}
 
-int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed) {
+int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed, const ConvLayerDesc* desc) {
   ConvParams& p = plan->p;
   HRP_REQUIRE(in != nullptr && w_packed != nullptr, "null tensor");
   HRP_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0,
@@ -1078,7 +1077,7 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed) {
     uint64_t strides[3] = {(uint64_t)p.src_sw * p.Cin * 2, (uint64_t)p.src_sh * p.Win * p.Cin * 2,
                            (uint64_t)p.Hin * p.Win * p.Cin * 2};
     uint32_t box[4] = {(uint32_t)p.ck, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
-    int rc = encode_map(&plan->maps.a[m], base, 4, dims, strides, box, p.ck);
+    int rc = conv_encode_map(&plan->maps.a[m], base, 4, dims, strides, box, p.ck);
     if (rc != HRP_OK) return rc;
   }
   for (int m = nmaps; m < 4; ++m) plan->maps.a[m] = plan->maps.a[0];
@@ -1087,14 +1086,14 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed) {
     uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.Ws, (uint64_t)p.Hs, (uint64_t)p.B};
     uint64_t strides[3] = {(uint64_t)p.Cin * 2, (uint64_t)p.Win * p.Cin * 2, (uint64_t)p.Hin * p.Win * p.Cin * 2};
     uint32_t box[4] = {(uint32_t)p.ck, (uint32_t)p.bw, (uint32_t)(p.bh + 2), 1u};
-    int rc = encode_map(&plan->maps.av, in, 4, dims, strides, box, p.ck);
+    int rc = conv_encode_map(&plan->maps.av, in, 4, dims, strides, box, p.ck);
     if (rc != HRP_OK) return rc;
   }
   {
     uint64_t dims[2] = {(uint64_t)p.ktot, (uint64_t)p.nphase * p.cout_pad};
     uint64_t strides[1] = {(uint64_t)p.ktot * 2};
     uint32_t box[2] = {(uint32_t)p.ck, (uint32_t)p.n_tile};
-    int rc = encode_map(&plan->maps.b, w_packed, 2, dims, strides, box, p.ck);
+    int rc = conv_encode_map(&plan->maps.b, w_packed, 2, dims, strides, box, p.ck);
     if (rc != HRP_OK) return rc;
   }
   if (p.pool_out != nullptr)
@@ -1109,7 +1108,7 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed) {
       uint64_t strides[3] = {(uint64_t)p.os * p.Cout * 2, (uint64_t)p.os * p.Wout * p.Cout * 2,
                              (uint64_t)p.Hout * p.Wout * p.Cout * 2};
       uint32_t box[4] = {(uint32_t)p.cko, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
-      int rc = encode_map(&plan->maps.o[ph], base, 4, dims, strides, box, p.cko);
+      int rc = conv_encode_map(&plan->maps.o[ph], base, 4, dims, strides, box, p.cko);
       if (rc != HRP_OK) return rc;
     }
     for (int ph = p.nphase; ph < 4; ++ph) plan->maps.o[ph] = plan->maps.o[0];
@@ -1155,7 +1154,7 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed) {
       uint64_t dims[4] = {(uint64_t)p.Cout, (uint64_t)p.Wout, (uint64_t)p.Hout, (uint64_t)p.B};
       uint64_t strides[3] = {(uint64_t)p.Cout * 2, (uint64_t)p.Wout * p.Cout * 2, (uint64_t)p.Hout * p.Wout * p.Cout * 2};
       uint32_t box[4] = {(uint32_t)p.cko, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
-      int rc = encode_map(&plan->maps.r, p.pre[0], 4, dims, strides, box, p.cko);
+      int rc = conv_encode_map(&plan->maps.r, p.pre[0], 4, dims, strides, box, p.cko);
       if (rc != HRP_OK) return rc;
     } else {
       plan->maps.r = plan->maps.a[0];
@@ -1182,7 +1181,7 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed) {
       uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.Ws, (uint64_t)p.Hs, (uint64_t)p.B};
       uint64_t strides[3] = {(uint64_t)p.Cin * 2, (uint64_t)p.Win * p.Cin * 2, (uint64_t)p.Hin * p.Win * p.Cin * 2};
       uint32_t box[4] = {(uint32_t)p.ck, (uint32_t)p.bw, (uint32_t)(p.bh + 2), 1u};
-      int rc = encode_map(&plan->maps.av, in, 4, dims, strides, box, p.ck);
+      int rc = conv_encode_map(&plan->maps.av, in, 4, dims, strides, box, p.ck);
       if (rc != HRP_OK) return rc;
     }
     const int pipe_avail = avail - c.pipe_offset;
@@ -1215,12 +1214,27 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed) {
     plan->psmem = c.bar_offset + tail;
     plan->pgrid = (unsigned)std::min(c.total_tiles, num_sms);
   }
+  // ---- halo-tile variant for narrow 3x3 stride-1 layers (conv_halo.cu) ----
+  plan->halo_ok = plan->halo = false;
+  if (desc != nullptr && p.n_tiles == 1 && p.n_tile == p.Cout) {
+    int rc = conv_halo_plan(plan, *desc, in);
+    if (rc != HRP_OK) return rc;
+    plan->halo = plan->halo_ok;
+  }
+  // HRP_CONV_VARIANT=tile|persist|halo pins the kernel (tests, profiling); halo falls back where it is not eligible
+  if (const char* v = getenv("HRP_CONV_VARIANT")) {
+    const std::string vs(v);
+    if (vs == "tile") { plan->persistent = false; plan->halo = false; }
+    else if (vs == "persist") { plan->persistent = true; plan->halo = false; }
+    else if (vs == "halo") { plan->halo = plan->halo_ok; }
+  }
   return HRP_OK;
 }
 
 int conv_plan_launch(const ConvPlan& plan, cudaStream_t stream) {
   set_smem_attr_once();
   const ConvParams& p = plan.p;
+  if (plan.halo) return conv_halo_launch(plan, stream);
   if (plan.persistent) {
 #define HRP_LAUNCH_P(CKV, EPIV) \
   conv_gemm_persistent<CKV, EPIV><<<plan.pgrid, kThreadsP, plan.psmem, stream>>>(plan.maps, p, plan.pcfg)

@@ -67,6 +67,12 @@ static inline float bf16_bits_to_f32(uint16_t h) {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
+// 1024-byte aligned start of the dynamic shared-memory window.  Pointer arithmetic on the __shared__ array (not a
+// round trip through uintptr_t) keeps the address space known to the compiler: LDS/STS instead of generic LD/ST.
+__device__ __forceinline__ uint8_t* smem_align1024(uint8_t* dyn) {
+  const uint32_t a = smem_u32(dyn);
+  return dyn + ((1024u - (a & 1023u)) & 1023u);
+}
 __device__ __forceinline__ float bf16lo_to_f32(uint32_t packed) { return __uint_as_float(packed << 16); }
 __device__ __forceinline__ float bf16hi_to_f32(uint32_t packed) { return __uint_as_float(packed & 0xffff0000u); }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -94,6 +100,9 @@ __device__ __forceinline__ void fence_mbar_init() {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // Spin on try_wait (HW-suspending) with a bounded retry count: a pipeline bug traps instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {

@@ -380,7 +380,7 @@ struct Builder {
       p.post = pl->acts[epi.post].ptr;
       op.reads.push_back(epi.post);
     }
-    rc = conv_plan_finalize(&op.conv, raw_in != nullptr ? raw_in : pl->acts[in].ptr, cw.w);
+    rc = conv_plan_finalize(&op.conv, raw_in != nullptr ? raw_in : pl->acts[in].ptr, cw.w, &d);
     if (rc != HRP_OK) return -1;
     // algorithmic FLOPs of the reference layer (2*MACs, unpadded)
     {

@@ -78,6 +78,10 @@ int hrp_conv_out_shape(const hrp_conv* conv, int32_t* Hout, int32_t* Wout);
 int hrp_conv_run(hrp_conv* conv, int32_t impl, void* stream);
 void hrp_conv_destroy(hrp_conv* conv);
 /* debug: device buffer of 8 CTAs x 8 tiles x 16 int64 clock64() stamps per pipeline role, or NULL to disable */
+/* kernel variant of a planned conv: 0 = one tile per CTA, 1 = persistent, 2 = halo-tile (3x3 s1, Cin=Cout in {32,64});
+ * set_variant(2) returns HRP_ERR_UNSUPPORTED where the halo kernel is not eligible */
+int hrp_conv_set_variant(hrp_conv* conv, int32_t variant);
+int hrp_conv_variant(const hrp_conv* conv);
 int hrp_conv_set_timeline(hrp_conv* conv, long long* dev_buf);
 
 /* ------------------------------------------------------------------------------------------------
@@ -223,6 +227,10 @@ int hrp_model_activation(hrp_model* model, const char* name, const void** ptr, i
 /* hardware probe (profiling aid): cycles to issue / complete `reps` back-to-back tcgen05.mma (SS mode, bf16, K=16)
  * of shape M x N on `ctas` CTAs; dev_out2 = {issue cycles, completion cycles} of CTA 0 */
 int hrp_probe_mma_rate(int32_t M, int32_t N, int32_t reps, int32_t kdistinct, long long* dev_out2, int32_t ctas);
+/* hardware probe: one 128x32xCK product whose swizzled K-major A operand starts `shift` rows into a [rows x ck] bf16
+ * shared-memory tile (bo_mode 1 sets the descriptor base_offset field); D (128x32 fp32) is written to out_dev */
+int hrp_probe_desc_shift(int32_t ck, int32_t rows, int32_t shift, int32_t bo_mode, const void* A_dev, const void* B_dev,
+                         float* out_dev);
 /* asynchronous device-to-device copy on `stream` (used by the shims to snapshot activations) */
 int hrp_copy_device(void* dst, const void* src, int64_t bytes, void* stream);
 /* per-operation timing of one plan (eager, CUDA events, `iters` back-to-back launches per op): tab-separated text

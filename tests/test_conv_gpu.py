@@ -196,3 +196,65 @@ def test_maxpool_and_bridges(hrp_lib):
     mp = ops.maxpool3x3s2(xn)
     ref = F.max_pool2d(x, 3, 2, 1).permute(0, 2, 3, 1)
     assert torch.equal(mp.float(), ref)
+
+
+# ---- halo-tile kernel (conv_halo.cu): 3x3 stride-1 convs with Cin = Cout in {32, 64} ----
+HALO_CASES = [
+    # name, B, C, H, W, residual, relu
+    ("halo_32_64x64", 3, 32, 64, 64, False, True),
+    ("halo_32_64x64_res", 2, 32, 64, 64, True, True),
+    ("halo_64_32x32_res", 5, 64, 32, 32, True, True),
+    ("halo_64_64x64", 2, 64, 64, 64, False, True),
+    ("halo_64_16x16_norelu", 7, 64, 16, 16, True, False),
+    ("halo_32_ragged_32x16", 3, 32, 32, 16, True, True),   # non-square; 32*18 = 576 positions = 4.5 tiles
+    ("halo_32_8x8", 9, 32, 8, 8, False, True),
+    ("halo_64_many_units", 150, 64, 32, 32, True, True),    # more units than SMs: band buffers and accumulators wrap
+]
+
+
+@pytest.mark.parametrize("case", HALO_CASES, ids=[c[0] for c in HALO_CASES])
+def test_halo_conv_vs_torch(case, hrp_lib):
+    import ctypes as C
+    import zlib
+    from horopose_b200 import _lib, ops
+    name, B, Cc, H, W, residual, relu = case
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator().manual_seed(zlib.crc32(name.encode()) % 1000)
+    x = _bf16_round(torch.randn(B, Cc, H, W, generator=g)).cuda()
+    w = _bf16_round(torch.randn(Cc, Cc, 3, 3, generator=g) / (Cc * 9) ** 0.5)
+    scale = (torch.rand(Cc, generator=g) + 0.5)
+    bias = torch.randn(Cc, generator=g) * 0.1
+    res = _bf16_round(torch.randn(B, Cc, H, W, generator=g)).cuda() if residual else None
+    pre = (_nhwc(res),) if residual else ()
+    op = ops.ConvOp(_nhwc(x), w, stride=1, pad=1, relu=relu, scale=scale, bias=bias, pre=pre)
+    L = _lib.lib()
+    _lib.check(L.hrp_conv_set_variant(op.handle, C.c_int32(2)))  # raises if the halo kernel is not eligible
+    assert L.hrp_conv_variant(op.handle) == 2
+    ref = F.conv2d(x, w.cuda(), padding=1) * scale.cuda()[None, :, None, None] + bias.cuda()[None, :, None, None]
+    if residual:
+        ref = ref + res
+    if relu:
+        ref = torch.relu(ref)
+    ref = ref.permute(0, 2, 3, 1).contiguous()
+    op.out.fill_(float("nan"))  # every valid pixel must be written, junk positions must not spill anywhere
+    got = op.run(ops.IMPL_TCGEN05)
+    torch.cuda.synchronize()
+    assert torch.isfinite(got.float()).all(), f"{name}: unwritten output pixels"
+    _report(name + "[halo]", got, ref)
+    # bit-exact against the one-tile-per-CTA tcgen05 kernel (same operands, same fp32 accumulation order per tap)
+    _lib.check(L.hrp_conv_set_variant(op.handle, C.c_int32(0)))
+    got_tile = op.run(ops.IMPL_TCGEN05).clone()
+    _lib.check(L.hrp_conv_set_variant(op.handle, C.c_int32(2)))
+    got2 = op.run(ops.IMPL_TCGEN05)
+    torch.cuda.synchronize()
+    diff = (got2.float() - got_tile.float()).abs().max().item()
+    assert diff <= 2.0 ** -6 * max(1.0, ref.abs().max().item()), f"{name}: halo vs tile kernel differ by {diff}"
+
+
+def test_halo_not_eligible_raises(hrp_lib):
+    import ctypes as C
+    from horopose_b200 import _lib, ops
+    x = torch.randn(1, 16, 16, 128, device="cuda").to(torch.bfloat16)
+    op = ops.ConvOp(x, torch.randn(128, 128, 3, 3) * 0.03, stride=1, pad=1, relu=True)
+    with pytest.raises(_lib.HrpError):
+        _lib.check(_lib.lib().hrp_conv_set_variant(op.handle, C.c_int32(2)))

@@ -7,7 +7,11 @@ import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import horopose_b200  # noqa
-from horopose_b200 import ops
+from horopose_b200 import _lib, ops
+import ctypes as C
+
+VARIANTS = {0: 'tile', 1: 'persist', 2: 'halo'}
+RES = len(sys.argv) > 2 and sys.argv[2] == 'res'
 
 SHAPES = [
     # name, Cin, H, Cout, k, stride, pad, kind
@@ -43,22 +47,32 @@ def main():
             w = torch.randn(cout, cin, k, k) * 0.02
             ho = (h + 2 * pad - k) // stride + 1
             macs = B * ho * ho * k * k * cin * cout
-        op = ops.ConvOp(x, w, kind=kind, stride=stride, pad=pad, relu=True)
-        for _ in range(3):
-            op.run()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n = 20
-        e0.record()
-        for _ in range(n):
-            op.run()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / n
+        res = ()
+        if RES and kind == ops.CONV and stride == 1:
+            ho = (h + 2 * pad - k) // stride + 1
+            res = (torch.randn(B, ho, ho, cout, device="cuda").to(torch.bfloat16),)
+        op = ops.ConvOp(x, w, kind=kind, stride=stride, pad=pad, relu=True, pre=res)
+        L = _lib.lib()
+        line = f"{name:26s}"
+        for variant in (0, 1, 2):
+            if L.hrp_conv_set_variant(op.handle, C.c_int32(variant)) != 0:
+                line += f"  {VARIANTS[variant]:8s}      n/a        "
+                continue
+            for _ in range(3):
+                op.run()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = 20
+            e0.record()
+            for _ in range(n):
+                op.run()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / n
+            line += f"  {VARIANTS[variant]:8s}{ms*1e3:8.1f} us {2*macs/ms/1e9:7.1f} TF"
         in_b = x.numel() * 2
-        out_b = op.out.numel() * 2
-        print(f"{name:26s} {ms*1e3:9.1f} us  {2*macs/ms/1e9:8.1f} TFLOP/s  io {(in_b+out_b)/ms/1e6:7.1f} GB/s  "
-              f"grid={op_grid(op)}")
+        out_b = op.out.numel() * 2 * (2 if res else 1)
+        print(line + f"   io {(in_b + out_b) / 1e6:7.1f} MB")
 
 
 def op_grid(op):
