@@ -177,40 +177,47 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // Warp-uniform control flow: descriptor words are computed by the whole warp (uniform datapath), only the
+    // tcgen05 instructions are issued by one elected lane -- a divergent single-thread loop costs ~10 SASS
+    // instructions (R2UR waterfalls) per MMA, more than a narrow MMA (N <= 64: 40-48 cycles) lasts.
     const uint32_t idesc = make_idesc_bf16(kTileM, (uint32_t)n_tile);
+    const uint64_t dhi = make_kmajor_desc(0, SBO, LAYOUT) & 0xffffffff00000000ull;
+    const uint32_t dlo = (uint32_t)make_kmajor_desc(0, SBO, LAYOUT);
+    const uint32_t smem_units = dlo + (smem_u32(smem) >> 4);
+    const uint32_t stage_units = (uint32_t)stage_bytes >> 4;
+    const uint32_t bsub_units = (uint32_t)b_sub_bytes >> 4;
     int s = 0;
     uint32_t par = 0;
     for (int it = 0; it < n_iters; ++it) {
       mbar_wait(&bars->full[s], par);
       tc_fence_after();
-      if (elect_one()) {
-        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-        if (p.vsh) {
-          const uint32_t sbv = sa + (uint32_t)p.vsh_a_pad;
-          const uint32_t row_bytes = (uint32_t)(p.bw * CK * 2);  // one image row of the tile
-          for (int dhi = 0; dhi < 3; ++dhi) {
+      const uint32_t sa = smem_units + (uint32_t)s * stage_units;
+      if (p.vsh) {
+        const uint32_t sbv = sa + ((uint32_t)p.vsh_a_pad >> 4);
+        const uint32_t row_units = (uint32_t)(p.bw * CK * 2) >> 4;  // one image row of the tile
+        if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < KSTEPS; ++k) {
-              const uint64_t adesc = make_kmajor_desc(sa + dhi * row_bytes + k * 32, SBO, LAYOUT);
-              const uint64_t bdesc = make_kmajor_desc(sbv + dhi * b_sub_bytes + k * 32, SBO, LAYOUT);
-              umma_bf16_ss(tmem_base, adesc, bdesc, idesc, (it | dhi | k) != 0 ? 1u : 0u);
-            }
+          for (int dhi_ = 0; dhi_ < 3; ++dhi_) {
+#pragma unroll
+            for (int k = 0; k < KSTEPS; ++k)
+              umma_bf16_ss(tmem_base, dhi | (sa + dhi_ * row_units + 2 * k), dhi | (sbv + dhi_ * bsub_units + 2 * k), idesc,
+                           (it | dhi_ | k) != 0 ? 1u : 0u);
           }
           umma_commit(&bars->empty[s]);
           if (it == n_iters - 1) umma_commit(&bars->tmem_full);
-        } else {
-        const int nsub = min(SUB, nkb - it * SUB);
-        const uint32_t sb = sa + kStageABytes;
-        for (int j = 0; j < nsub; ++j) {
-#pragma unroll
-          for (int k = 0; k < KSTEPS; ++k) {
-            const uint64_t adesc = make_kmajor_desc(sa + j * A_SUB_BYTES + k * 32, SBO, LAYOUT);
-            const uint64_t bdesc = make_kmajor_desc(sb + j * b_sub_bytes + k * 32, SBO, LAYOUT);
-            umma_bf16_ss(tmem_base, adesc, bdesc, idesc, (it | j | k) != 0 ? 1u : 0u);
-          }
         }
-        umma_commit(&bars->empty[s]);                          // frees the smem stage when the MMAs retire
-        if (it == n_iters - 1) umma_commit(&bars->tmem_full);  // accumulator complete
+      } else {
+        const int nsub = min(SUB, nkb - it * SUB);
+        const uint32_t sb = sa + (kStageABytes >> 4);
+        if (elect_one()) {
+          for (int j = 0; j < nsub; ++j) {
+#pragma unroll
+            for (int k = 0; k < KSTEPS; ++k)
+              umma_bf16_ss(tmem_base, dhi | (sa + j * (A_SUB_BYTES >> 4) + 2 * k), dhi | (sb + j * bsub_units + 2 * k), idesc,
+                           (it | j | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&bars->empty[s]);                          // frees the smem stage when the MMAs retire
+          if (it == n_iters - 1) umma_commit(&bars->tmem_full);  // accumulator complete
         }
       }
       __syncwarp();
@@ -550,14 +557,15 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer: ONE thread runs the whole loop (scalar latency = issue rate) ==========
-    if (lane == 0) {
+    // ===================== MMA issuer: warp-uniform loop, one elected lane issues the tcgen05 instructions ==========
+    {
       const uint32_t idesc = make_idesc_bf16(kTileM, (uint32_t)n_tile);
-      // descriptor = constant 64-bit base + (smem byte address >> 4): one 64-bit add per operand, no masking needed
-      // because shared-memory addresses stay below 2^18
-      const uint64_t dbase = make_kmajor_desc(0, SBO, LAYOUT);
-      const uint32_t pipe_units = smem_u32(pipe_base) >> 4;
-      const uint32_t wres_units = smem_u32(smem) >> 4;
+      // descriptor = constant high word | (constant low word + smem byte address >> 4): one 32-bit add per operand
+      // on the uniform datapath (shared-memory addresses stay below 2^18, so the 14-bit field never carries)
+      const uint64_t dhi = make_kmajor_desc(0, SBO, LAYOUT) & 0xffffffff00000000ull;
+      const uint32_t dlo = (uint32_t)make_kmajor_desc(0, SBO, LAYOUT);
+      const uint32_t pipe_units = dlo + (smem_u32(pipe_base) >> 4);
+      const uint32_t wres_units = dlo + (smem_u32(smem) >> 4);
       const uint32_t stage_units = (uint32_t)stage_bytes >> 4;
       const uint32_t aregion_units = (uint32_t)a_region >> 4;
       const uint32_t row_units = (uint32_t)(p.bw * CK * 2) >> 4;   // one image row of the tile, in 16-byte units
@@ -570,53 +578,62 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
         const int abuf = li & 1;
         mbar_wait(&bars->tmem_empty[abuf], (uint32_t)(((li >> 1) & 1) ^ 1));  // epilogue drained this accumulator
         tc_fence_after();
-        tl_stamp(p.timeline, li, 3);
-        // dependent tcgen05.mma into ONE accumulator are latency-bound (~130 cycles each) when N is small: round-robin
-        // the K steps over `ksplit` accumulators (summed by the epilogue) so independent chains overlap
+        if (lane == 0) tl_stamp(p.timeline, li, 3);
+        // K steps round-robin over `ksplit` accumulators (summed by the epilogue)
         const uint32_t tacc0 = tmem_base + (uint32_t)(abuf * ksplit * n_tile);
         int cc = 0, dwi = 0;
         uint32_t mi = 0;
         for (int it = 0; it < n_iters; ++it) {
           mbar_wait(&bars->full[s], par);
           tc_fence_after();
-          if (it == 0) tl_stamp(p.timeline, li, 4);
-          const uint64_t a_it = dbase + (uint64_t)(pipe_units + (uint32_t)s * stage_units);
-          const uint64_t b_it = a_it + aregion_units;
+          if (it == 0 && lane == 0) tl_stamp(p.timeline, li, 4);
+          const uint32_t a_it = pipe_units + (uint32_t)s * stage_units;
+          const uint32_t b_it = a_it + aregion_units;
           if (vsh) {
-            const uint64_t bw_it = dbase + (uint64_t)(wres_units + (uint32_t)(dwi * p.cpt + cc) * bsub_units);
+            const uint32_t bw_it = wres_units + (uint32_t)(dwi * p.cpt + cc) * bsub_units;
+            const uint32_t bw_step = (uint32_t)(3 * p.cpt) * bsub_units;
+            if (elect_one()) {
 #pragma unroll
-            for (int dhi = 0; dhi < 3; ++dhi) {
-              const uint64_t ad = a_it + (uint64_t)(dhi * row_units);
-              const uint64_t bd = wres ? bw_it + (uint64_t)((uint32_t)(dhi * 3 * p.cpt) * bsub_units)
-                                       : b_it + (uint64_t)(dhi * bsub_units);
+              for (int dhi_ = 0; dhi_ < 3; ++dhi_) {
+                const uint32_t ad = a_it + dhi_ * row_units;
+                const uint32_t bd = wres ? bw_it + dhi_ * bw_step : b_it + dhi_ * bsub_units;
 #pragma unroll
-              for (int k = 0; k < KSTEPS; ++k) {
-                umma_bf16_ss(tacc0 + (mi & ksmask) * (uint32_t)n_tile, ad + 2 * k, bd + 2 * k, idesc, mi >= (uint32_t)ksplit);
-                ++mi;
+                for (int k = 0; k < KSTEPS; ++k) {
+                  umma_bf16_ss(tacc0 + (mi & ksmask) * (uint32_t)n_tile, dhi | (ad + 2 * k), dhi | (bd + 2 * k), idesc,
+                               mi >= (uint32_t)ksplit);
+                  ++mi;
+                }
               }
+              umma_commit(&bars->empty[s]);
+              if (it == n_iters - 1) umma_commit(&bars->tmem_full[abuf]);
             }
+            mi = (uint32_t)((it + 1) * 3 * KSTEPS);
             if (++dwi == 3) {
               dwi = 0;
               ++cc;
             }
           } else {
             const int nsub = min(SUB, nkb - it * SUB);
-            const uint64_t bw_it = dbase + (uint64_t)(wres_units + (uint32_t)(it * SUB) * bsub_units);
-            for (int j = 0; j < nsub; ++j) {
-              const uint64_t ad = a_it + (uint64_t)((uint32_t)j * (A_SUB_BYTES >> 4));
-              const uint64_t bd = (wres ? bw_it : b_it) + (uint64_t)((uint32_t)j * bsub_units);
+            const uint32_t bw_it = wres_units + (uint32_t)(it * SUB) * bsub_units;
+            const uint32_t b0 = wres ? bw_it : b_it;
+            if (elect_one()) {
+              for (int j = 0; j < nsub; ++j) {
+                const uint32_t ad = a_it + (uint32_t)j * (A_SUB_BYTES >> 4);
+                const uint32_t bd = b0 + (uint32_t)j * bsub_units;
 #pragma unroll
-              for (int k = 0; k < KSTEPS; ++k) {
-                umma_bf16_ss(tacc0 + (mi & ksmask) * (uint32_t)n_tile, ad + 2 * k, bd + 2 * k, idesc, mi >= (uint32_t)ksplit);
-                ++mi;
+                for (int k = 0; k < KSTEPS; ++k) {
+                  umma_bf16_ss(tacc0 + (mi & ksmask) * (uint32_t)n_tile, dhi | (ad + 2 * k), dhi | (bd + 2 * k), idesc,
+                               mi >= (uint32_t)ksplit);
+                  ++mi;
+                }
               }
+              umma_commit(&bars->empty[s]);
+              if (it == n_iters - 1) umma_commit(&bars->tmem_full[abuf]);
             }
+            mi = (uint32_t)(min((it + 1) * SUB, nkb) * KSTEPS);
           }
-          umma_commit(&bars->empty[s]);
-          if (it == n_iters - 1) {
-            umma_commit(&bars->tmem_full[abuf]);
-            tl_stamp(p.timeline, li, 5);
-          }
+          __syncwarp();
+          if (it == n_iters - 1 && lane == 0) tl_stamp(p.timeline, li, 5);
           if (++s == stages) {
             s = 0;
             par ^= 1;

@@ -608,11 +608,14 @@ int autotune_plan(hrp_model* m, Plan* pl) {
              q.nphase, q.src_sh, op.conv.epi, q.pre[0] != nullptr, q.pool_out != nullptr, q.out != nullptr);
     auto it = m->tune_cache.find(key);
     if (it != m->tune_cache.end()) {
-      op.conv.persistent = (it->second != 0);
+      op.conv.halo = (it->second == 2) && op.conv.halo_ok;
+      if (it->second < 2) op.conv.persistent = (it->second == 1);
       continue;
     }
-    float best[2] = {0.f, 0.f};
-    for (int variant = 0; variant < 2 && rc == HRP_OK; ++variant) {
+    float best[3] = {0.f, 0.f, 0.f};
+    const int nvar = op.conv.halo_ok ? 3 : 2;
+    for (int variant = 0; variant < nvar && rc == HRP_OK; ++variant) {
+      op.conv.halo = (variant == 2);
       op.conv.persistent = (variant == 1);
       rc = conv_plan_launch(op.conv, s);  // warm-up (also faults in code / descriptors)
       if (rc != HRP_OK) break;
@@ -627,7 +630,9 @@ int autotune_plan(hrp_model* m, Plan* pl) {
       cudaEventElapsedTime(&best[variant], e0, e1);
     }
     if (rc != HRP_OK) break;
-    const int pick = (best[1] < best[0]) ? 1 : 0;
+    int pick = (best[1] < best[0]) ? 1 : 0;
+    if (nvar == 3 && best[2] < best[pick]) pick = 2;
+    op.conv.halo = (pick == 2);
     op.conv.persistent = (pick == 1);
     m->tune_cache[key] = pick;
   }
@@ -800,7 +805,8 @@ int hrp_model_create(const hrp_model_desc* desc, hrp_model** out) {
   e = getenv("HRP_CONV_IMPL");
   m->use_simt = (e != nullptr && std::string(e) == "simt");
   e = getenv("HRP_AUTOTUNE");
-  m->autotune = !(e != nullptr && e[0] == '0') && getenv("HRP_CONV_PERSISTENT") == nullptr;
+  m->autotune = !(e != nullptr && e[0] == '0') && getenv("HRP_CONV_PERSISTENT") == nullptr &&
+                getenv("HRP_CONV_VARIANT") == nullptr;
   *out = m;
   return HRP_OK;
 }
@@ -1064,7 +1070,8 @@ int hrp_model_profile(hrp_model* m, int32_t batch, int32_t iters, char* buf, int
       const double in_b = (double)q.B * q.Hin * q.Win * q.Cin * 2.0, out_b = (double)q.B * q.Hout * q.Wout * q.Cout * 2.0;
       snprintf(line, sizeof(line), "%s\tconv\t%d\t%dx%d\t%d\t%d\t%dx%d\t%d\t%d\t%d\t%s\t%d\t%.2f\t%.1f\t%.1f\n",
                op.name.c_str(), op.lane, q.Hin, q.Win, q.Cin, q.Cout, q.Hout, q.Wout, q.ntaps, q.n_tile, op.conv.epi,
-               op.conv.persistent ? "persist" : "tile", op.conv.persistent ? op.conv.pcfg.stages : op.conv.stages, us,
+               op.conv.halo ? "halo" : (op.conv.persistent ? "persist" : "tile"),
+               op.conv.halo ? op.conv.hp.T : (op.conv.persistent ? op.conv.pcfg.stages : op.conv.stages), us,
                op.conv.flops / us * 1e-6, (in_b + out_b) / us * 1e-3);
     } else {
       snprintf(line, sizeof(line), "%s\tmisc\t%d\t-\t-\t-\t-\t-\t-\t-\t-\t-\t%.2f\t0\t0\n", op.name.c_str(), op.lane, us);
