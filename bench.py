@@ -158,6 +158,8 @@ def main():
     ap.add_argument("--robot", default=ROBOT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--profile-range", action="store_true",
+                    help="wrap the timed device-resident steps in cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -222,11 +224,15 @@ def main():
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if args.profile_range:
+        torch.cuda.profiler.start()
     e0.record()
     for _ in range(args.steps):
         outs = model(x_reg_d, x_root_d, k_d, K_d)
     e1.record()
     barrier()
+    if args.profile_range:
+        torch.cuda.profiler.stop()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = _lib.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None

@@ -1068,13 +1068,22 @@ int hrp_model_profile(hrp_model* m, int32_t batch, int32_t iters, char* buf, int
     if (op.kind == OP_CONV) {
       const ConvParams& q = op.conv.p;
       const double in_b = (double)q.B * q.Hin * q.Win * q.Cin * 2.0, out_b = (double)q.B * q.Hout * q.Wout * q.Cout * 2.0;
-      snprintf(line, sizeof(line), "%s\tconv\t%d\t%dx%d\t%d\t%d\t%dx%d\t%d\t%d\t%d\t%s\t%d\t%.2f\t%.1f\t%.1f\n",
+      // algorithmic bytes of the layer: input + output + every addend read by the epilogue + packed weights
+      double add_b = 0.0;
+      for (int a = 0; a < 3; ++a) {
+        if (q.pre[a] != nullptr) add_b += out_b;
+        if (q.up[a] != nullptr) add_b += out_b / (double)(1 << (2 * q.up_shift[a]));
+      }
+      if (q.post != nullptr) add_b += out_b;
+      const double w_b = (double)q.nphase * q.cout_pad * q.ktot * 2.0;
+      const double all_b = in_b + (q.out != nullptr ? out_b : 0.0) + add_b + w_b;
+      snprintf(line, sizeof(line), "%s\tconv\t%d\t%dx%d\t%d\t%d\t%dx%d\t%d\t%d\t%d\t%s\t%d\t%.2f\t%.1f\t%.1f\t%.0f\t%.0f\n",
                op.name.c_str(), op.lane, q.Hin, q.Win, q.Cin, q.Cout, q.Hout, q.Wout, q.ntaps, q.n_tile, op.conv.epi,
                op.conv.halo ? "halo" : (op.conv.persistent ? "persist" : "tile"),
                op.conv.halo ? op.conv.hp.T : (op.conv.persistent ? op.conv.pcfg.stages : op.conv.stages), us,
-               op.conv.flops / us * 1e-6, (in_b + out_b) / us * 1e-3);
+               op.conv.flops / us * 1e-6, all_b / us * 1e-3, op.conv.flops, all_b);
     } else {
-      snprintf(line, sizeof(line), "%s\tmisc\t%d\t-\t-\t-\t-\t-\t-\t-\t-\t-\t%.2f\t0\t0\n", op.name.c_str(), op.lane, us);
+      snprintf(line, sizeof(line), "%s\tmisc\t%d\t-\t-\t-\t-\t-\t-\t-\t-\t-\t%.2f\t0\t0\t0\t0\n", op.name.c_str(), op.lane, us);
     }
     out += line;
   }

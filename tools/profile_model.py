@@ -71,6 +71,26 @@ def profile(robot="kuka", B=32):
     print(f"== per-op profile {robot} B={B}: {len(rows)} ops, sum {tot:.0f} us -> {B / tot * 1e6:.0f} img/s if serial")
     for name, (us, fl, n) in sorted(cat.items(), key=lambda kv: -kv[1][0]):
         print(f"  {name:30s} {n:4d} ops {us:9.1f} us {us / tot * 100:5.1f}%  {fl / us * 1e-6 if us else 0:7.1f} TFLOP/s")
+    # per-layer roofline: ideal time = max(flops / tensor peak, bytes / HBM peak) with the measured peaks
+    import json
+    pk = json.loads((Path(__file__).resolve().parent.parent / "MEASURED_PEAKS.json").read_text()) \
+        if (Path(__file__).resolve().parent.parent / "MEASURED_PEAKS.json").exists() else {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0}
+    ideal = t_mem = t_mma = 0.0
+    for r in rows:
+        if r[1] != "conv":
+            continue
+        tm, tb = float(r[15]) / (pk["bf16_tflops_sustained"] * 1e6), float(r[16]) / (pk["hbm_gbs"] * 1e3)
+        ideal += max(tm, tb)
+        t_mma += tm
+        t_mem += tb
+    print(f"  roofline sums over conv ops: tensor-only {t_mma:.0f} us, hbm-only {t_mem:.0f} us, per-layer max {ideal:.0f} us "
+          f"-> measured/ideal = {tot / ideal:.2f}")
+    out = Path(__file__).resolve().parent.parent / "gpurun_out"
+    out.mkdir(exist_ok=True)
+    with open(out / f"per_op_{robot}_{B}.tsv", "w") as f:
+        f.write("name\tkind\tlane\tin\tCin\tCout\tout\ttaps\tn_tile\tepi\tvariant\tstages\tus\tTFLOPs\tGBs\tflops\tbytes\n")
+        for r in rows:
+            f.write("\t".join(r) + "\n")
     print("  top ops:")
     for r in sorted(rows, key=lambda r: -float(r[12]))[:25]:
         print("   ", "  ".join(r))
@@ -82,7 +102,7 @@ def sweep(robot="kuka", B=512):
     to_u8 = lambda t: (t * 255).round().to(torch.uint8).repeat(B // 32, 1, 1, 1).cuda()
     xr, xo = to_u8(x_reg), to_u8(x_root)
     kk, KK = k.repeat(B // 32).cuda(), K.repeat(B // 32, 1, 1).cuda()
-    for chunk, inflight in [(64, 2), (128, 1), (128, 2), (256, 1), (256, 2)]:
+    for chunk, inflight in [(128, 2), (256, 1), (256, 2), (512, 1)]:
         m = make(robot, chunk, inflight)
         for _ in range(2):
             m(xr, xo, kk, KK)
