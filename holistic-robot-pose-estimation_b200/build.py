@@ -51,7 +51,7 @@ def build(verbose: bool = False, force: bool = False) -> Path:
         obj = BUILD_DIR / (src.stem + ".o")
         objs.append(obj)
         if force or not obj.exists() or obj.stat().st_mtime < max(src.stat().st_mtime, hdr_m):
-            cmd = [_nvcc(), *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+            cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("HRP_NVCC_EXTRA", "").split(), "-c", str(src), "-o", str(obj)]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             jobs.append(cmd)

@@ -34,6 +34,7 @@ struct ConvParams {
   int ktot;               // ntaps*Cin
   int vsh;                // vertical tap sharing (3x3 s1 p1, tile inside one image): A buffer = bh+2 image rows per dw
   int vsh_a_bytes, vsh_a_pad, vsh_stage_bytes;
+  int pair_off;           // > 0: element offset of the pixel-pair weight matrix behind the regular packing (conv_halo.cu)
   int8_t tap_dh[kMaxTaps], tap_dw[kMaxTaps], tap_map[kMaxTaps];
   // epilogue
   const float* scale;     // [Cout] folded BN scale (1 if none)
@@ -78,17 +79,20 @@ struct PersistCfg {
 // Halo-tile 3x3 kernel (conv_halo.cu): a unit = T consecutive 128-position tiles of one zero-padded image
 struct HaloParams {
   int B, H, W, Cout, relu;
+  int pair;              // pixel-pair view of a 32-channel layer: W, Wp, Cout describe the (W/2, 64-channel) problem
   int Wp;                // W + 2: padded row pitch in positions
   int NR;                // input rows per TMA box (band + halo)
   int T;                 // 128-position tiles per unit
   int tiles_per_img, units_per_img, total_units;
   int n_abuf;            // band buffers in flight
-  int a_buf_bytes, a_offset, stag_offset, bar_offset;
+  int nacc, nacc_shift;  // accumulators in the TMEM ring (power of two)
+  int a_buf_bytes, a_offset, stag_offset, res_offset, bar_offset;
   uint32_t div_magic;    // P / Wp == (P * div_magic) >> 20
   const float* scale;
   const float* bias;
   const bf16* res;       // residual addend (pre[0]) or null
   bf16* out;
+  long long* tl;         // debug timeline (globaltimer stamps of the first 8 CTAs), null in production
 };
 
 struct ConvPlan {
@@ -104,6 +108,8 @@ struct ConvPlan {
   bool halo;       // ... and has been selected (heuristic / autotune / HRP_CONV_VARIANT)
   HaloParams hp;
   CUtensorMap halo_map_a;
+  CUtensorMap halo_map_r;  // residual as a 2-D (pixels, C) tensor, swizzled 128-row boxes
+  CUtensorMap halo_map_b;  // pixel-pair weight matrix (pair mode only)
   unsigned halo_grid;
   int halo_smem;
   PersistCfg pcfg;

@@ -970,10 +970,17 @@ int conv_geometry(const ConvLayerDesc& d, ConvParams* pp) {
     p.vsh_a_pad = (p.vsh_a_bytes + 1023) / 1024 * 1024;
     p.vsh_stage_bytes = p.vsh_a_pad + 3 * p.n_tile * p.ck * 2;
   }
+  // pixel-pair weights for the halo kernel (conv_halo.cu): 32 -> 32 channel 3x3 stride-1 layers with an even width
+  p.pair_off = 0;
+  if (d.kind == kConv && d.stride == 1 && d.kh == 3 && d.kw == 3 && d.pad == 1 && d.Cin == 32 && d.Cout == 32 &&
+      d.Win % 2 == 0 && p.n_tile == 32 && p.cout_pad == 32)
+    p.pair_off = p.nphase * p.cout_pad * p.ktot;
   return HRP_OK;
 }
 
-size_t conv_packed_weight_elems(const ConvParams& p) { return (size_t)p.nphase * p.cout_pad * p.ktot; }
+size_t conv_packed_weight_elems(const ConvParams& p) {
+  return (size_t)p.nphase * p.cout_pad * p.ktot + (p.pair_off > 0 ? (size_t)64 * 9 * 64 : 0);
+}
 
 int conv_pack_weights(const ConvLayerDesc& d, const ConvParams& p, int cin_ref, const float* w, uint16_t* out) {
   const size_t total = conv_packed_weight_elems(p);
@@ -987,6 +994,23 @@ int conv_pack_weights(const ConvLayerDesc& d, const ConvParams& p, int cin_ref, 
             const float v = w[(((size_t)co * cin_ref + ci) * d.kh + i) * d.kw + j];
             out[(size_t)co * p.ktot + (size_t)(i * d.kw + j) * p.Cin + ci] = f32_to_bf16_bits(v);
           }
+    if (p.pair_off > 0) {
+      // Pixel-pair view (conv_halo.cu): two horizontally adjacent pixels form one 64-channel position, so the layer
+      // becomes a 64 -> 64 channel 3x3 conv over (H, W/2) whose matrix has structured zero blocks:
+      //   Wpair[dh][dj][po*32+co][pi*32+ci] = W[co][ci][dh][dw],  dw = 2*dj + pi - po  (zero when |dw| > 1)
+      uint16_t* pw = out + p.pair_off;
+      for (int i = 0; i < 3; ++i)
+        for (int dj = -1; dj <= 1; ++dj)
+          for (int po = 0; po < 2; ++po)
+            for (int pi = 0; pi < 2; ++pi) {
+              const int dw = 2 * dj + pi - po;
+              if (dw < -1 || dw > 1) continue;
+              for (int co = 0; co < 32; ++co)
+                for (int ci = 0; ci < cin_ref; ++ci)
+                  pw[(size_t)(po * 32 + co) * 576 + (size_t)(i * 3 + dj + 1) * 64 + pi * 32 + ci] =
+                      f32_to_bf16_bits(w[(((size_t)co * cin_ref + ci) * 3 + i) * 3 + (dw + 1)]);
+            }
+    }
   } else if (d.kind == kDeconvK4S2P1) {
     HRP_REQUIRE(cin_ref <= p.Cin, "reference Cin exceeds stored Cin");
     for (int ph = 0; ph < 2; ++ph)

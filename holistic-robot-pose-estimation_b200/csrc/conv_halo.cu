@@ -32,14 +32,23 @@ struct __align__(16) HaloBars {
   uint64_t w_full;
   uint64_t a_full[4];
   uint64_t a_empty[4];
-  uint64_t acc_full[4];
-  uint64_t acc_empty[4];
+  uint64_t acc_full[8];
+  uint64_t acc_empty[8];
+  uint64_t res_full[2];
   uint32_t tmem_base;
   uint32_t pad;
 };
 
-constexpr int kHaloThreads = 320;  // producer, MMA issuer, 2 x 4 epilogue warps
-constexpr int kHaloAcc = 4;  // accumulators in the TMEM ring
+// debug timeline: slot (cta * 16 + event) <- %globaltimer (ns) for the first 8 CTAs
+__device__ __forceinline__ void halo_stamp(long long* tl, int ev) {
+  if (tl != nullptr && blockIdx.x < 8) {
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    tl[blockIdx.x * 16 + ev] = (long long)g;
+  }
+}
+
+constexpr int kHaloThreads = 352;  // producer, MMA issuer A, 2 x 4 epilogue warps, MMA issuer B
 
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   uint4 r;
@@ -47,9 +56,12 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   return r;
 }
 
-template <int CK, int NOUT, bool RES>
+// PAIR: the 64-channel positions are pixel pairs of a 32-channel layer; the weight matrix then has zero blocks
+// (tap column dj = -1 only sees the right pixel of its pair, dj = +1 only the left one), whose K steps are skipped.
+template <int CK, int NOUT, bool RES, bool PAIR>
 __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                     const __grid_constant__ CUtensorMap map_b,
+                                                                    const __grid_constant__ CUtensorMap map_r,
                                                                     const __grid_constant__ HaloParams hp) {
   constexpr int KSTEPS = CK / 16;
   constexpr int ROWB = CK * 2;                    // bytes per position (one swizzle span)
@@ -64,6 +76,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   uint8_t* const sW = smem;
   uint8_t* const sA = smem + hp.a_offset;
   uint8_t* const sStag = smem + hp.stag_offset;
+  uint8_t* const sRes = smem + hp.res_offset;  // per epilogue group: residual tile, TMA-swizzled (RES only)
   HaloBars* bars = reinterpret_cast<HaloBars*>(smem + hp.bar_offset);
   float* sb_smem = reinterpret_cast<float*>(bars + 1);  // [2][NOUT] folded-BN scale / shift
 
@@ -72,31 +85,39 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   const int Wp = hp.Wp, T = hp.T, upi = hp.units_per_img;
 
   if (threadIdx.x == 0) {
+    halo_stamp(hp.tl, 0);
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    if (RES) tma_prefetch_desc(&map_r);
     mbar_init(&bars->w_full, 1);
     for (int i = 0; i < 4; ++i) {
       mbar_init(&bars->a_full[i], 1);
-      mbar_init(&bars->a_empty[i], 1);
+      mbar_init(&bars->a_empty[i], 2);  // both MMA issuers release a band
+    }
+    mbar_init(&bars->res_full[0], 1);
+    mbar_init(&bars->res_full[1], 1);
+    for (int i = 0; i < 8; ++i) {
       mbar_init(&bars->acc_full[i], 1);
-      mbar_init(&bars->acc_empty[i], 128);
+      mbar_init(&bars->acc_empty[i], 4);  // one arrival per epilogue warp of the owning group
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(&bars->tmem_base, (uint32_t)(kHaloAcc * NOUT));
+    tmem_alloc(&bars->tmem_base, (uint32_t)(hp.nacc * NOUT));
     tmem_relinquish();
   }
-  if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < NOUT; i += kHaloThreads - 64) {
-      sb_smem[i] = __ldg(hp.scale + i);
-      sb_smem[NOUT + i] = __ldg(hp.bias + i);
+  if (warp >= 2 && warp < 10) {
+    for (int i = threadIdx.x - 64; i < NOUT; i += 256) {
+      const int c = PAIR ? (i & 31) : i;
+      sb_smem[i] = __ldg(hp.scale + c);
+      sb_smem[NOUT + i] = __ldg(hp.bias + c);
     }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  if (threadIdx.x == 0) halo_stamp(hp.tl, 1);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -118,8 +139,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 || warp == 10) {
+    // ===================== MMA issuers: warp 1 takes the even tiles (epilogue group 0), warp 10 the odd ones ==========
+    // Two issuers hide each other's per-tile bookkeeping (barrier waits, fences): with one issuer the tensor pipe
+    // drained its queue between tiles and idled ~40 % of the time (measured with the debug timeline).
     // The whole warp runs the (warp-uniform) control flow so that descriptors live in uniform registers; only the
     // tcgen05 instructions themselves are issued by one elected lane.  A dense back-to-back MMA stream matters here:
     // at N = 32..64 one MMA occupies the tensor pipe for only 40-48 cycles.
@@ -131,22 +154,37 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       const uint32_t a_lo = dlo + (smem_u32(sA) >> 4);
       const uint32_t abuf_stride = (uint32_t)hp.a_buf_bytes >> 4;
       const int wp_units = Wp * (ROWB >> 4);
+      const uint32_t mw = (warp == 1) ? 0u : 1u;
       mbar_wait(&bars->w_full, 0);
+      if (lane == 0 && mw == 0) halo_stamp(hp.tl, 2);
       int abuf = 0;
       uint32_t par = 0;
       uint32_t tc = 0;
+      const bool timing = (hp.tl != nullptr);  // debug only: cycles spent in each wait / in the issue loop
+      long long t_afull = 0, t_acc = 0, t_issue = 0;
+      const long long t_loop0 = timing ? clock64() : 0;
       for (int u = blockIdx.x; u < hp.total_units; u += gridDim.x) {
         const int n = u / upi, uu = u - n * upi;
         const int P0 = uu * T * kTileM;
         const int r_lo = (int)(((uint32_t)P0 * hp.div_magic) >> 20) - 1;
         const int base_row = P0 - r_lo * Wp + 1;  // tile-local row of output position P0 for tap (0, 0)
+        const long long ta0 = timing ? clock64() : 0;
         mbar_wait(&bars->a_full[abuf], par);
+        if (timing) t_afull += clock64() - ta0;
         tc_fence_after();
+        if (tc == 0 && lane == 0 && mw == 0) halo_stamp(hp.tl, 3);
         const uint32_t a_unit0 = a_lo + (uint32_t)abuf * abuf_stride + (uint32_t)(base_row * (ROWB >> 4));
         for (int m = 0; m < T; ++m) {
           if (uu * T + m >= hp.tiles_per_img) break;
-          const uint32_t acc = tc & (kHaloAcc - 1);
-          mbar_wait(&bars->acc_empty[acc], ((tc / kHaloAcc) & 1) ^ 1);
+          if ((tc & 1u) != mw) {
+            ++tc;
+            continue;
+          }
+          const uint32_t acc = tc & (uint32_t)(hp.nacc - 1);
+          const long long tb0 = timing ? clock64() : 0;
+          mbar_wait(&bars->acc_empty[acc], ((tc >> hp.nacc_shift) & 1) ^ 1);
+          const long long tb1 = timing ? clock64() : 0;
+          t_acc += tb1 - tb0;
           tc_fence_after();
           const uint32_t taddr = tmem_base + acc * NOUT;
           const uint32_t a_tile = a_unit0 + (uint32_t)(m * kTileM * (ROWB >> 4));
@@ -156,14 +194,17 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
               const int dh = tap / 3 - 1, dw = tap % 3 - 1;
               const uint32_t al = a_tile + (uint32_t)(dh * wp_units + dw * (ROWB >> 4));
               const uint32_t bl = w_lo + (uint32_t)(tap * (B_SUB >> 4));
+              const int k_lo = (PAIR && tap % 3 == 0) ? KSTEPS / 2 : 0;
+              const int k_hi = (PAIR && tap % 3 == 2) ? KSTEPS / 2 : KSTEPS;
 #pragma unroll
-              for (int k = 0; k < KSTEPS; ++k)
+              for (int k = k_lo; k < k_hi; ++k)
                 umma_bf16_ss(taddr, ((uint64_t)dhi << 32) | (al + 2 * k), ((uint64_t)dhi << 32) | (bl + 2 * k), idesc,
-                             (tap | k) != 0 ? 1u : 0u);
+                             (tap != 0 || k != k_lo) ? 1u : 0u);
             }
             umma_commit(&bars->acc_full[acc]);
           }
           __syncwarp();
+          if (timing) t_issue += clock64() - tb1;
           ++tc;
         }
         if (elect_one()) umma_commit(&bars->a_empty[abuf]);  // the band can be overwritten once these MMAs have read it
@@ -172,6 +213,15 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           abuf = 0;
           par ^= 1;
         }
+      }
+      if (lane == 0 && mw == 0) halo_stamp(hp.tl, 4);
+      if (timing && lane == 0 && blockIdx.x < 8 && mw == 0) {
+        long long* o = hp.tl + blockIdx.x * 16;
+        o[10] = t_afull;
+        o[11] = t_acc;
+        o[12] = t_issue;
+        o[13] = clock64() - t_loop0;
+        o[14] = (long long)tc;
       }
     }
   } else {
@@ -182,115 +232,186 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     const int HW = hp.H * hp.W;
     const bool leader = (threadIdx.x == 64 + grp * 128);
     uint8_t* const stag = sStag + (size_t)grp * STAG;
+    // CTA-order tile iterator; this group takes every other tile
+    int u = blockIdx.x, m = 0;
     uint32_t tc = 0;
-    for (int u = blockIdx.x; u < hp.total_units; u += gridDim.x) {
-      const int n = u / upi, uu = u - n * upi;
-      const int P0 = uu * T * kTileM;
-      for (int m = 0; m < T; ++m) {
-        if (uu * T + m >= hp.tiles_per_img) break;
-        if ((int)(tc & 1) != grp) {  // the other group's tile
-          ++tc;
-          continue;
-        }
-        const int Pt = P0 + m * kTileM;
-        // this thread's output position and the tile's contiguous pixel range [pix_lo, pix_hi)
-        const int P = Pt + row;
-        const int r = (int)(((uint32_t)P * hp.div_magic) >> 20), w = P - r * Wp;
-        const bool valid = (w < hp.W) && (r < hp.H);
-        const int rf = (int)(((uint32_t)Pt * hp.div_magic) >> 20), wf = Pt - rf * Wp;
-        const int Pe = Pt + kTileM;
-        const int re = (int)(((uint32_t)Pe * hp.div_magic) >> 20), we = Pe - re * Wp;
-        const int pix_lo = min(rf * hp.W + min(wf, hp.W), HW);
-        const int pix_hi = min(re * hp.W + min(we, hp.W), HW);
-        const int pix = r * hp.W + w;
-        const size_t img_base = (size_t)n * HW;
-        uint4 rv[CH16];
-        if (RES) {
-          if (valid) {
-            const uint4* rp = reinterpret_cast<const uint4*>(hp.res + (img_base + pix) * NOUT);
-#pragma unroll
-            for (int c = 0; c < CH16; ++c) rv[c] = ldg_nc_v4(rp + c);
-          } else {
-#pragma unroll
-            for (int c = 0; c < CH16; ++c) rv[c] = make_uint4(0u, 0u, 0u, 0u);
-          }
-        }
-        const uint32_t acc = tc & (kHaloAcc - 1);
-        // the bulk store that last read this group's staging buffer must have drained
-        if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-        mbar_wait(&bars->acc_full[acc], (tc / kHaloAcc) & 1);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * NOUT;
-        uint8_t* const srow = stag + (size_t)(pix - pix_lo) * (NOUT * 2);
-#pragma unroll
-        for (int c0 = 0; c0 < NOUT; c0 += 32) {
-          uint32_t a[32];
-          tmem_ld32(taddr + (uint32_t)c0, a);
-          tmem_ld_wait();
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int cg = c0 + g * 8;
-            float v[8];
-            const float4 s0 = *reinterpret_cast<const float4*>(sb_smem + cg);
-            const float4 s1 = *reinterpret_cast<const float4*>(sb_smem + cg + 4);
-            const float4 b0 = *reinterpret_cast<const float4*>(sb_smem + NOUT + cg);
-            const float4 b1 = *reinterpret_cast<const float4*>(sb_smem + NOUT + cg + 4);
-            v[0] = fmaf(__uint_as_float(a[g * 8 + 0]), s0.x, b0.x);
-            v[1] = fmaf(__uint_as_float(a[g * 8 + 1]), s0.y, b0.y);
-            v[2] = fmaf(__uint_as_float(a[g * 8 + 2]), s0.z, b0.z);
-            v[3] = fmaf(__uint_as_float(a[g * 8 + 3]), s0.w, b0.w);
-            v[4] = fmaf(__uint_as_float(a[g * 8 + 4]), s1.x, b1.x);
-            v[5] = fmaf(__uint_as_float(a[g * 8 + 5]), s1.y, b1.y);
-            v[6] = fmaf(__uint_as_float(a[g * 8 + 6]), s1.z, b1.z);
-            v[7] = fmaf(__uint_as_float(a[g * 8 + 7]), s1.w, b1.w);
-            if (RES) {
-              const uint4 x = rv[cg >> 3];
-              v[0] += bf16lo_to_f32(x.x); v[1] += bf16hi_to_f32(x.x);
-              v[2] += bf16lo_to_f32(x.y); v[3] += bf16hi_to_f32(x.y);
-              v[4] += bf16lo_to_f32(x.z); v[5] += bf16hi_to_f32(x.z);
-              v[6] += bf16lo_to_f32(x.w); v[7] += bf16hi_to_f32(x.w);
-            }
-            uint4 o;
-            if (hp.relu) {
-              asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(o.x) : "f"(v[1]), "f"(v[0]));
-              asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(o.y) : "f"(v[3]), "f"(v[2]));
-              asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(o.z) : "f"(v[5]), "f"(v[4]));
-              asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(o.w) : "f"(v[7]), "f"(v[6]));
-            } else {
-              o.x = pack_bf16x2(v[0], v[1]);
-              o.y = pack_bf16x2(v[2], v[3]);
-              o.z = pack_bf16x2(v[4], v[5]);
-              o.w = pack_bf16x2(v[6], v[7]);
-            }
-            if (valid) *reinterpret_cast<uint4*>(srow + ((cg >> 3) << 4)) = o;
-          }
-        }
-        tc_fence_before();
-        mbar_arrive(&bars->acc_empty[acc]);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-        if (leader) {
-          const int npix = pix_hi - pix_lo;
-          if (npix > 0) {
-            bf16* dst = hp.out + (img_base + pix_lo) * NOUT;
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(stag)),
-                         "r"((uint32_t)(npix * NOUT * 2))
-                         : "memory");
-          }
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-        ++tc;
+    auto step = [&]() {
+      ++m;
+      ++tc;
+      const int uu = u % upi;
+      if (m >= T || uu * T + m >= hp.tiles_per_img) {
+        m = 0;
+        u += gridDim.x;
       }
+    };
+    // this thread's output position in tile (u_, m_): pixel index inside the image (-1 = junk) and the image base
+    auto my_pixel = [&](int u_, int m_, size_t* img_base) -> int {
+      const int n = u_ / upi, uu = u_ - n * upi;
+      const int P = (uu * T + m_) * kTileM + row;
+      const int r = (int)(((uint32_t)P * hp.div_magic) >> 20), w = P - r * Wp;
+      *img_base = (size_t)n * HW;
+      return ((w < hp.W) && (r < hp.H)) ? r * hp.W + w : -1;
+    };
+    // first pixel of tile (u_, m_) and its image: the tile's valid outputs are the contiguous pixels [pix_lo, pix_hi)
+    auto tile_pix_lo = [&](int u_, int m_, size_t* img_base) -> int {
+      const int n = u_ / upi, uu = u_ - n * upi;
+      const int Pt = (uu * T + m_) * kTileM;
+      const int rf = (int)(((uint32_t)Pt * hp.div_magic) >> 20), wf = Pt - rf * Wp;
+      *img_base = (size_t)n * HW;
+      return min(rf * hp.W + min(wf, hp.W), HW);
+    };
+    // Residual tile = 128 pixel rows starting at the tile's first pixel, fetched by TMA into this group's buffer with
+    // the 64-/128-byte swizzle (row-per-lane reads are then bank-conflict free); rows past the tile are never used.
+    uint8_t* const rbuf = sRes + (size_t)grp * STAG;
+    auto load_residual = [&](int u_, int m_) {
+      if (u_ >= hp.total_units) return;
+      size_t ib;
+      const int lo = tile_pix_lo(u_, m_, &ib);
+      mbar_expect_tx(&bars->res_full[grp], (uint32_t)STAG);
+      tma_load_2d(rbuf, &map_r, &bars->res_full[grp], 0, (int)(ib + (size_t)lo));
+    };
+    uint32_t rpar = 0;
+    if (grp == 1 && u < hp.total_units) step();
+    if (RES && leader) load_residual(u, m);
+    while (u < hp.total_units) {
+      const int n = u / upi, uu = u - n * upi;
+      const int Pt = (uu * T + m) * kTileM;
+      // this thread's output position and the tile's contiguous pixel range [pix_lo, pix_hi)
+      size_t img_base;
+      const int pix = my_pixel(u, m, &img_base);
+      const bool valid = pix >= 0;
+      const int rf = (int)(((uint32_t)Pt * hp.div_magic) >> 20), wf = Pt - rf * Wp;
+      const int Pe = Pt + kTileM;
+      const int re = (int)(((uint32_t)Pe * hp.div_magic) >> 20), we = Pe - re * Wp;
+      const int pix_lo = min(rf * hp.W + min(wf, hp.W), HW);
+      const int pix_hi = min(re * hp.W + min(we, hp.W), HW);
+      const uint32_t acc = tc & (uint32_t)(hp.nacc - 1);
+      // the bulk store that last read this group's staging buffer must have drained
+      if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+      mbar_wait(&bars->acc_full[acc], (tc >> hp.nacc_shift) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * NOUT;
+      const int sr = pix - pix_lo;  // this thread's row in the staging / residual tile (valid lanes only)
+      if (RES) {
+        mbar_wait(&bars->res_full[grp], rpar);
+        rpar ^= 1;
+      }
+      const uint8_t* const rrow = rbuf + (size_t)sr * (NOUT * 2);
+      const int rsw = (CH16 == 8) ? (sr & 7) : ((sr >> 1) & 3);
+      uint4 o[CH16];
+#pragma unroll
+      for (int c0 = 0; c0 < NOUT; c0 += 32) {
+        uint32_t a[32];
+        tmem_ld32(taddr + (uint32_t)c0, a);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int cg = c0 + g * 8;
+          float v[8];
+          const float4 s0 = *reinterpret_cast<const float4*>(sb_smem + cg);
+          const float4 s1 = *reinterpret_cast<const float4*>(sb_smem + cg + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(sb_smem + NOUT + cg);
+          const float4 b1 = *reinterpret_cast<const float4*>(sb_smem + NOUT + cg + 4);
+          v[0] = fmaf(__uint_as_float(a[g * 8 + 0]), s0.x, b0.x);
+          v[1] = fmaf(__uint_as_float(a[g * 8 + 1]), s0.y, b0.y);
+          v[2] = fmaf(__uint_as_float(a[g * 8 + 2]), s0.z, b0.z);
+          v[3] = fmaf(__uint_as_float(a[g * 8 + 3]), s0.w, b0.w);
+          v[4] = fmaf(__uint_as_float(a[g * 8 + 4]), s1.x, b1.x);
+          v[5] = fmaf(__uint_as_float(a[g * 8 + 5]), s1.y, b1.y);
+          v[6] = fmaf(__uint_as_float(a[g * 8 + 6]), s1.z, b1.z);
+          v[7] = fmaf(__uint_as_float(a[g * 8 + 7]), s1.w, b1.w);
+          if (RES && valid) {
+            const uint4 x = *reinterpret_cast<const uint4*>(rrow + ((((cg >> 3)) ^ rsw) << 4));
+            v[0] += bf16lo_to_f32(x.x); v[1] += bf16hi_to_f32(x.x);
+            v[2] += bf16lo_to_f32(x.y); v[3] += bf16hi_to_f32(x.y);
+            v[4] += bf16lo_to_f32(x.z); v[5] += bf16hi_to_f32(x.z);
+            v[6] += bf16lo_to_f32(x.w); v[7] += bf16hi_to_f32(x.w);
+          }
+          uint4& oo = o[cg >> 3];
+          if (hp.relu) {
+            asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(oo.x) : "f"(v[1]), "f"(v[0]));
+            asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(oo.y) : "f"(v[3]), "f"(v[2]));
+            asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(oo.z) : "f"(v[5]), "f"(v[4]));
+            asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(oo.w) : "f"(v[7]), "f"(v[6]));
+          } else {
+            oo.x = pack_bf16x2(v[0], v[1]);
+            oo.y = pack_bf16x2(v[2], v[3]);
+            oo.z = pack_bf16x2(v[4], v[5]);
+            oo.w = pack_bf16x2(v[6], v[7]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
+      // residual of this group's NEXT tile: in flight while this tile is stored and the next accumulator completes
+      int u2 = u, m2 = m;
+      {
+        const int u0 = u, m0 = m;
+        const uint32_t tc0 = tc;
+        step();
+        if (u < hp.total_units) step();
+        u2 = u;
+        m2 = m;
+        u = u0;
+        m = m0;
+        tc = tc0;
+      }
+      // Staging rows are dense pixels (64 or 128 bytes apart): written chunk-by-chunk in lane order every 16-byte
+      // store would hit the same 4 banks (8- / 16-way conflict).  Row sr therefore writes its chunks in the
+      // rotated order (c + rot(sr)) % CH16, which spreads every quarter-warp over all 32 banks.
+      if (valid) {
+        const int rot = (CH16 == 8) ? (sr & 7) : ((sr >> 1) & 3);
+#pragma unroll
+        for (int b = 1; b < CH16; b <<= 1) {  // rotate o[] left by rot (log steps, register selects only)
+          const bool on = (rot & b) != 0;
+          uint4 t[CH16];
+#pragma unroll
+          for (int i = 0; i < CH16; ++i) {
+            const uint4 x = o[(i + b) % CH16], y = o[i];
+            t[i].x = on ? x.x : y.x;
+            t[i].y = on ? x.y : y.y;
+            t[i].z = on ? x.z : y.z;
+            t[i].w = on ? x.w : y.w;
+          }
+#pragma unroll
+          for (int i = 0; i < CH16; ++i) o[i] = t[i];
+        }
+        uint8_t* const srow = stag + (size_t)sr * (NOUT * 2);
+#pragma unroll
+        for (int c = 0; c < CH16; ++c) *reinterpret_cast<uint4*>(srow + (((c + rot) & (CH16 - 1)) << 4)) = o[c];
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+      if (leader) {
+        const int npix = pix_hi - pix_lo;
+        if (npix > 0) {
+          bf16* dst = hp.out + (img_base + pix_lo) * NOUT;
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(stag)),
+                       "r"((uint32_t)(npix * NOUT * 2))
+                       : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        // every thread of the group has consumed the residual tile (it is read before the staging stores and the
+        // barrier above): fetch the one of this group's next tile
+        if (RES) load_residual(u2, m2);
+      }
+      u = u2;
+      m = m2;
+      tc += 2;
     }
+    if (leader) halo_stamp(hp.tl, 5 + grp);
     if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (leader) halo_stamp(hp.tl, 7 + grp);
   }
 
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)(kHaloAcc * NOUT));
+    tmem_dealloc(tmem_base, (uint32_t)(hp.nacc * NOUT));
   }
+  if (threadIdx.x == 0) halo_stamp(hp.tl, 9);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -299,12 +420,14 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
 static void halo_attr_once() {
   static std::once_flag once;
   std::call_once(once, [] {
-#define HRP_HALO_ATTR(CKV, NV, RV) \
-  cudaFuncSetAttribute(conv_halo_kernel<CKV, NV, RV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
-    HRP_HALO_ATTR(32, 32, false);
-    HRP_HALO_ATTR(32, 32, true);
-    HRP_HALO_ATTR(64, 64, false);
-    HRP_HALO_ATTR(64, 64, true);
+#define HRP_HALO_ATTR(CKV, NV, RV, PV) \
+  cudaFuncSetAttribute(conv_halo_kernel<CKV, NV, RV, PV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+    HRP_HALO_ATTR(32, 32, false, false);
+    HRP_HALO_ATTR(32, 32, true, false);
+    HRP_HALO_ATTR(64, 64, false, false);
+    HRP_HALO_ATTR(64, 64, true, false);
+    HRP_HALO_ATTR(64, 64, false, true);
+    HRP_HALO_ATTR(64, 64, true, true);
 #undef HRP_HALO_ATTR
   });
 }
@@ -323,14 +446,19 @@ int conv_halo_plan(ConvPlan* plan, const ConvLayerDesc& d, const bf16* in) {
   if (p.pre[1] != nullptr || p.pre[2] != nullptr || p.up[0] != nullptr || p.up[1] != nullptr || p.up[2] != nullptr)
     return HRP_OK;
   if (p.n_tiles != 1 || p.n_tile != d.Cout || p.ck != d.Cin) return HRP_OK;
-  const int H = d.Hin, W = d.Win, Wp = W + 2;
+  // pixel-pair view of a 32-channel layer (weights packed behind the regular matrix by conv_pack_weights)
+  const char* penv = getenv("HRP_HALO_PAIR");
+  const bool pair = (p.pair_off > 0) && !(penv != nullptr && penv[0] == '0');
+  const int C = pair ? 64 : d.Cin;  // channels per position (= Cin = Cout of the problem the kernel sees)
+  const int H = d.Hin, W = pair ? d.Win / 2 : d.Win, Wp = W + 2;
   if (Wp > 256 || H * Wp > 60000) return HRP_OK;
   HaloParams& h = plan->hp;
   memset(&h, 0, sizeof(h));
   h.B = d.B;
   h.H = H;
   h.W = W;
-  h.Cout = d.Cout;
+  h.Cout = C;
+  h.pair = pair ? 1 : 0;
   h.relu = d.relu;
   h.Wp = Wp;
   h.tiles_per_img = (H * Wp + kTileM - 1) / kTileM;
@@ -340,11 +468,12 @@ int conv_halo_plan(ConvPlan* plan, const ConvLayerDesc& d, const bf16* in) {
   for (int P = 0; P <= p_max; ++P)
     if ((int)(((uint64_t)(uint32_t)P * h.div_magic) >> 20) != P / Wp || (uint64_t)P * h.div_magic >= (1ull << 32))
       return HRP_OK;  // (never happens for the shapes on the path; stay on the generic kernels if it does)
-  const int rowb = d.Cin * 2;
-  const int w_bytes = 9 * d.Cout * rowb;
-  const int stag_bytes = 2 * kTileM * d.Cout * 2;
-  const int tail = (int)sizeof(HaloBars) + 2 * d.Cout * 4 + 1024;
-  const int avail = 227 * 1024 - tail - stag_bytes - (w_bytes + 1023) / 1024 * 1024;
+  const int rowb = C * 2;
+  const int w_bytes = 9 * C * rowb;
+  const int stag_bytes = 2 * kTileM * C * 2;
+  const int res_bytes = (p.pre[0] != nullptr) ? stag_bytes : 0;  // residual tiles (one per epilogue group)
+  const int tail = (int)sizeof(HaloBars) + 2 * C * 4 + 1024;
+  const int avail = 227 * 1024 - tail - stag_bytes - res_bytes - (w_bytes + 1023) / 1024 * 1024;
   int best_T = 0, best_NR = 0, best_nbuf = 0;
   for (int T = 4; T >= 1 && best_T == 0; --T) {
     const int upi = (h.tiles_per_img + T - 1) / T;
@@ -372,17 +501,36 @@ int conv_halo_plan(ConvPlan* plan, const ConvLayerDesc& d, const bf16* in) {
   h.a_buf_bytes = (h.NR * Wp * rowb + 1023) / 1024 * 1024;
   h.a_offset = (w_bytes + 1023) / 1024 * 1024;
   h.stag_offset = h.a_offset + h.n_abuf * h.a_buf_bytes;
-  h.bar_offset = h.stag_offset + stag_bytes;
+  h.res_offset = h.stag_offset + stag_bytes;
+  h.bar_offset = h.res_offset + res_bytes;
   h.scale = p.scale;
   h.bias = p.bias;
   h.res = p.pre[0];
   h.out = p.out;
+  // accumulator ring in TMEM: a power of two, at most 8 and at most 512 columns
+  h.nacc = (8 * C <= 512) ? 8 : 4;
+  h.nacc_shift = (h.nacc == 8) ? 3 : 2;
   plan->halo_smem = h.bar_offset + tail;
   {
-    uint64_t dims[4] = {(uint64_t)d.Cin, (uint64_t)W, (uint64_t)H, (uint64_t)d.B};
-    uint64_t strides[3] = {(uint64_t)d.Cin * 2, (uint64_t)W * d.Cin * 2, (uint64_t)H * W * d.Cin * 2};
-    uint32_t box[4] = {(uint32_t)d.Cin, (uint32_t)Wp, (uint32_t)h.NR, 1u};
-    int rc = conv_encode_map(&plan->halo_map_a, in, 4, dims, strides, box, d.Cin);
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)d.B};
+    uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+    uint32_t box[4] = {(uint32_t)C, (uint32_t)Wp, (uint32_t)h.NR, 1u};
+    int rc = conv_encode_map(&plan->halo_map_a, in, 4, dims, strides, box, C);
+    if (rc != HRP_OK) return rc;
+  }
+  plan->halo_map_r = plan->halo_map_a;
+  if (p.pre[0] != nullptr) {
+    uint64_t dims[2] = {(uint64_t)C, (uint64_t)d.B * H * W};
+    uint64_t strides[1] = {(uint64_t)C * 2};
+    uint32_t box[2] = {(uint32_t)C, (uint32_t)kTileM};
+    int rc = conv_encode_map(&plan->halo_map_r, p.pre[0], 2, dims, strides, box, C);
+    if (rc != HRP_OK) return rc;
+  }
+  if (pair) {
+    uint64_t dims[2] = {(uint64_t)9 * 64, 64};
+    uint64_t strides[1] = {(uint64_t)9 * 64 * 2};
+    uint32_t box[2] = {64u, 64u};
+    int rc = conv_encode_map(&plan->halo_map_b, p.w + p.pair_off, 2, dims, strides, box, 64);
     if (rc != HRP_OK) return rc;
   }
   int num_sms = 0, dev = 0;
@@ -396,16 +544,20 @@ int conv_halo_plan(ConvPlan* plan, const ConvLayerDesc& d, const bf16* in) {
 
 int conv_halo_launch(const ConvPlan& plan, cudaStream_t stream) {
   halo_attr_once();
-  const HaloParams& h = plan.hp;
+  HaloParams h = plan.hp;
+  h.tl = plan.p.timeline;
   const bool res = (h.res != nullptr);
-#define HRP_HALO_LAUNCH(CKV, NV, RV) \
-  conv_halo_kernel<CKV, NV, RV><<<plan.halo_grid, kHaloThreads, plan.halo_smem, stream>>>(plan.halo_map_a, plan.maps.b, h)
-  if (h.Cout == 32) {
-    if (res) HRP_HALO_LAUNCH(32, 32, true);
-    else HRP_HALO_LAUNCH(32, 32, false);
+#define HRP_HALO_LAUNCH(CKV, NV, RV, PV, MAPB) \
+  conv_halo_kernel<CKV, NV, RV, PV><<<plan.halo_grid, kHaloThreads, plan.halo_smem, stream>>>(plan.halo_map_a, MAPB, plan.halo_map_r, h)
+  if (h.pair) {
+    if (res) HRP_HALO_LAUNCH(64, 64, true, true, plan.halo_map_b);
+    else HRP_HALO_LAUNCH(64, 64, false, true, plan.halo_map_b);
+  } else if (h.Cout == 32) {
+    if (res) HRP_HALO_LAUNCH(32, 32, true, false, plan.maps.b);
+    else HRP_HALO_LAUNCH(32, 32, false, false, plan.maps.b);
   } else {
-    if (res) HRP_HALO_LAUNCH(64, 64, true);
-    else HRP_HALO_LAUNCH(64, 64, false);
+    if (res) HRP_HALO_LAUNCH(64, 64, true, false, plan.maps.b);
+    else HRP_HALO_LAUNCH(64, 64, false, false, plan.maps.b);
   }
 #undef HRP_HALO_LAUNCH
   count_launch();

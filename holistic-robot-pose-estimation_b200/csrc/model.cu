@@ -643,6 +643,13 @@ int autotune_plan(hrp_model* m, Plan* pl) {
 }
 
 int capture_plan(hrp_model* m, Plan* pl) {
+  // Lanes pay off only when a kernel cannot fill the GPU by itself (small batches: batch-1 latency).  From ~64 images
+  // on, every conv launch is a full persistent grid and concurrent lanes only contend for SMs, shared memory and L2
+  // (measured on B200, chunk 512: 12.9k img/s on one stream vs 12.6k on five).  HRP_SINGLE_LANE=0/1 overrides.
+  bool single_lane = pl->B >= 64;
+  if (const char* sl = getenv("HRP_SINGLE_LANE")) single_lane = (sl[0] == '1');
+  if (single_lane)
+    for (auto& op : pl->ops) op.lane = 0;
   // cross-lane dependencies -> events
   for (size_t i = 0; i < pl->ops.size(); ++i)
     for (int a : pl->ops[i].reads) {

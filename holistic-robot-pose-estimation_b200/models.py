@@ -54,7 +54,7 @@ class _EngineModule(nn.Module):
         self._sd = None
         self._handle = None
         self._device = None
-        self.chunk = int(os.environ.get("HRP_CHUNK", "256"))
+        self.chunk = int(os.environ.get("HRP_CHUNK", "512"))
         self.inflight = int(os.environ.get("HRP_INFLIGHT", "1"))
 
     # -- nn.Module surface the reference callers use -----------------------------------------------------

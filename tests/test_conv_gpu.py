@@ -251,6 +251,32 @@ def test_halo_conv_vs_torch(case, hrp_lib):
     assert diff <= 2.0 ** -6 * max(1.0, ref.abs().max().item()), f"{name}: halo vs tile kernel differ by {diff}"
 
 
+@pytest.mark.parametrize("shape", [(3, 64, 64, True), (2, 32, 16, False), (5, 8, 8, True)])
+def test_halo_pixel_pair_vs_plain(shape, hrp_lib, monkeypatch):
+    """32-channel layers run as 64-channel pixel pairs with zero weight blocks (HaloParams.pair); the plain
+    32-channel instantiation of the same kernel (HRP_HALO_PAIR=0) must agree up to fp32 summation order."""
+    import ctypes as C
+    from horopose_b200 import _lib, ops
+    B, H, W, residual = shape
+    g = torch.Generator().manual_seed(H * 131 + W)
+    x = _bf16_round(torch.randn(B, 32, H, W, generator=g)).cuda()
+    w = _bf16_round(torch.randn(32, 32, 3, 3, generator=g) / (32 * 9) ** 0.5)
+    scale, bias = torch.rand(32, generator=g) + 0.5, torch.randn(32, generator=g) * 0.1
+    res = _bf16_round(torch.randn(B, 32, H, W, generator=g)).cuda() if residual else None
+    pre = (_nhwc(res),) if residual else ()
+    outs = []
+    for pair in ("1", "0"):
+        monkeypatch.setenv("HRP_HALO_PAIR", pair)
+        op = ops.ConvOp(_nhwc(x), w, stride=1, pad=1, relu=True, scale=scale, bias=bias, pre=pre)
+        _lib.check(_lib.lib().hrp_conv_set_variant(op.handle, C.c_int32(2)))
+        op.out.fill_(float("nan"))
+        outs.append(op.run(ops.IMPL_TCGEN05).clone())
+    torch.cuda.synchronize()
+    assert torch.isfinite(outs[0].float()).all() and torch.isfinite(outs[1].float()).all()
+    diff = (outs[0].float() - outs[1].float()).abs().max().item()
+    assert diff <= 2.0 ** -6 * max(1.0, outs[1].float().abs().max().item()), f"pair vs plain halo differ by {diff}"
+
+
 def test_halo_not_eligible_raises(hrp_lib):
     import ctypes as C
     from horopose_b200 import _lib, ops

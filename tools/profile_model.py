@@ -102,7 +102,9 @@ def sweep(robot="kuka", B=512):
     to_u8 = lambda t: (t * 255).round().to(torch.uint8).repeat(B // 32, 1, 1, 1).cuda()
     xr, xo = to_u8(x_reg), to_u8(x_root)
     kk, KK = k.repeat(B // 32).cuda(), K.repeat(B // 32, 1, 1).cuda()
-    for chunk, inflight in [(128, 2), (256, 1), (256, 2), (512, 1)]:
+    import os
+    cfgs = [tuple(int(v) for v in c.split(":")) for c in os.environ.get("HRP_SWEEP", "256:1,512:1").split(",")]
+    for chunk, inflight in cfgs:
         m = make(robot, chunk, inflight)
         for _ in range(2):
             m(xr, xo, kk, KK)
