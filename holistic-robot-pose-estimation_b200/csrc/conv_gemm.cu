@@ -265,6 +265,7 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
     const bool relu_in_cvt = p.relu && !(EPI == EPI_FULL && (postp != nullptr || pool));
     const bool relu_explicit = p.relu && !relu_in_cvt;
     const int cko = p.cko;
+    const int cko_shift = (cko == 64) ? 6 : 5;
     const int sw = (cko == 64) ? (row & 7) : ((row >> 1) & 3);
     uint8_t* const stage_row = stag_base + (size_t)row * (cko * 2);
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -295,8 +296,8 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
         v[5] = fmaf(__uint_as_float(acc[g * 8 + 5]), s1.y, b1.y);
         v[6] = fmaf(__uint_as_float(acc[g * 8 + 6]), s1.z, b1.z);
         v[7] = fmaf(__uint_as_float(acc[g * 8 + 7]), s1.w, b1.w);
-        const int blk = cg / cko;
-        const int ch = (cg - blk * cko) >> 3;
+        const int blk = cg >> cko_shift;  // cko is 32 or 64: no integer division in the epilogue
+        const int ch = (cg & (cko - 1)) >> 3;
         uint4* const sptr = reinterpret_cast<uint4*>(stage_row + (size_t)blk * (kTileM * cko * 2) + ((ch ^ sw) << 4));
         if (EPI != EPI_PLAIN && has_res) add_bf16x8(v, *sptr);  // TMA-prefetched residual (zero outside the tensor)
         if (EPI != EPI_PLAIN && valid) {
@@ -445,10 +446,10 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->tmem_full[i], 1);
-      mbar_init(&bars->tmem_empty[i], kEpiThreadsP);
+      mbar_init(&bars->tmem_empty[i], kEpiThreadsP / 32);  // one arrival per epilogue warp
       mbar_init(&bars->res_full[i], 1);
       mbar_init(&bars->stag_free[i], 1);
-      mbar_init(&bars->stag_ready[i], kEpiThreadsP);
+      mbar_init(&bars->stag_ready[i], kEpiThreadsP / 32);
     }
     mbar_init(&bars->w_full, 1);
     fence_mbar_init();
@@ -669,6 +670,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
+    const int cko_shift = (cko == 64) ? 6 : 5;
     const int sw = (cko == 64) ? (row & 7) : ((row >> 1) & 3);
     const bool do_store = (p.out != nullptr);
     const bool pool = (EPI == EPI_FULL) && (p.pool_out != nullptr);
@@ -754,8 +756,8 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
           v[5] = fmaf(__uint_as_float(acc[g * 8 + 5]), s1.y, b1.y);
           v[6] = fmaf(__uint_as_float(acc[g * 8 + 6]), s1.z, b1.z);
           v[7] = fmaf(__uint_as_float(acc[g * 8 + 7]), s1.w, b1.w);
-          const int blk = cg / cko;
-          const int ch = (cg - blk * cko) >> 3;
+          const int blk = cg >> cko_shift;
+          const int ch = (cg & (cko - 1)) >> 3;
           uint4* const sptr = reinterpret_cast<uint4*>(stage_row + (size_t)blk * (kTileM * cko * 2) + ((ch ^ sw) << 4));
           if (EPI != EPI_PLAIN) {
             if (has_res) add_bf16x8(v, *sptr);  // residual prefetched by TMA (zero-filled outside the tensor)
@@ -811,15 +813,16 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
           }
         }
       }
-      // accumulator drained: hand it back to the MMA warp
+      // accumulator drained: hand it back to the MMA warp (one mbarrier arrival per warp: 256 per-thread arrivals
+      // on one shared-memory word serialise and cost more than the epilogue arithmetic)
       tc_fence_before();
-      mbar_arrive(&bars->tmem_empty[abuf]);
-      if (warp == 2 && lane == 0) tl_stamp(p.timeline, li, 9);
-      if (do_store) {
-        // generic-proxy staging writes -> async proxy, then hand the buffer to the store warp
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(&bars->stag_ready[sbuf]);
+      if (do_store) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // staging writes -> async proxy
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&bars->tmem_empty[abuf]);
+        if (do_store) mbar_arrive(&bars->stag_ready[sbuf]);  // hand the staging buffer to the store warp
       }
+      if (warp == 2 && lane == 0) tl_stamp(p.timeline, li, 9);
     }
   }
 #undef HRP_DECODE_TILE
@@ -1244,8 +1247,11 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed, con
     while ((1 << c.th_shift) < p.tiles_h) ++c.th_shift;
     HRP_REQUIRE((1 << c.tw_shift) == p.tiles_w && (1 << c.th_shift) == p.tiles_h, "tile counts must be powers of two");
     const char* e3 = getenv("HRP_CONV_KSPLIT");
-    int ks = (p.n_tile <= 64) ? 4 : (p.n_tile <= 128) ? 2 : 1;
-    if (e3 != nullptr && (e3[0] == '1' || e3[0] == '2' || e3[0] == '4')) ks = std::min(ks, e3[0] - '0');
+    // K-split accumulators are off by default: back-to-back MMAs into ONE accumulator already run at the operand
+    // fetch rate (tools/probe_mma.py: 40.3 / 48.3 / 64.3 cycles at N = 32 / 64 / 128 with 1 or 4 accumulators), and
+    // every extra accumulator costs the epilogue another TMEM read.  HRP_CONV_KSPLIT=2|4 re-enables it for probing.
+    int ks = 1;
+    if (e3 != nullptr && (e3[0] == '2' || e3[0] == '4')) ks = std::min((p.n_tile <= 64) ? 4 : (p.n_tile <= 128) ? 2 : 1, e3[0] - '0');
     const int n_mma = p.ntaps * p.cpt * (p.ck / 16);
     while (ks > 1 && n_mma < 2 * ks) ks >>= 1;  // every accumulator must receive at least one MMA (no stale TMEM)
     c.ksplit = ks;

@@ -171,3 +171,61 @@ extern "C" int hrp_probe_desc_shift(int32_t ck, int32_t rows, int32_t shift, int
   HRP_CUDA_CHECK(cudaDeviceSynchronize());
   return HRP_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------
+// Probe 3: tcgen05.ld throughput.  W warps (4 or 8; warp w reads TMEM lane quarter w % 4) each issue `reps`
+// 32x32b.x32 loads (32 lanes x 32 fp32 columns = 4 KiB per instruction), optionally waiting after each one.
+// The epilogue of every conv kernel is bounded below by this rate (accumulator bytes / TMEM read bandwidth).
+// ------------------------------------------------------------------------------------------------------
+namespace hrp {
+
+__global__ void __launch_bounds__(256) tmem_ld_rate_kernel(int reps, int wait_each, long long* out) {
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t taddr = tmem_base_s + ((uint32_t)((warp & 3) * 32) << 16);
+  uint32_t acc[32];
+  uint32_t sink = 0;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int r = 0; r < reps; ++r) {
+    tmem_ld32(taddr + (uint32_t)((r * 32) & 511), acc);
+    if (wait_each) {
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) sink ^= acc[i];
+    }
+  }
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) sink ^= acc[i];
+  const long long t1 = clock64();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    out[0] = t1 - t0;
+    out[1] = (long long)sink;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base_s, 512);
+  }
+}
+
+}  // namespace hrp
+
+extern "C" int hrp_probe_tmem_ld_rate(int32_t warps, int32_t reps, int32_t wait_each, long long* dev_out2) {
+  using namespace hrp;
+  HRP_REQUIRE((warps == 1 || warps == 4 || warps == 8) && reps > 0 && dev_out2 != nullptr, "bad args");
+  tmem_ld_rate_kernel<<<1, warps * 32, 0>>>(reps, wait_each, dev_out2);
+  HRP_CUDA_CHECK(cudaGetLastError());
+  HRP_CUDA_CHECK(cudaDeviceSynchronize());
+  return HRP_OK;
+}

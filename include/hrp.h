@@ -231,6 +231,9 @@ int hrp_probe_mma_rate(int32_t M, int32_t N, int32_t reps, int32_t kdistinct, lo
  * shared-memory tile (bo_mode 1 sets the descriptor base_offset field); D (128x32 fp32) is written to out_dev */
 int hrp_probe_desc_shift(int32_t ck, int32_t rows, int32_t shift, int32_t bo_mode, const void* A_dev, const void* B_dev,
                          float* out_dev);
+/* hardware probe: cycles for `warps` (1, 4 or 8) warps of one CTA to issue `reps` tcgen05.ld.32x32b.x32 each (4 KiB per
+ * instruction), waiting after every load (wait_each = 1) or only at the end; dev_out2[0] = cycles */
+int hrp_probe_tmem_ld_rate(int32_t warps, int32_t reps, int32_t wait_each, long long* dev_out2);
 /* asynchronous device-to-device copy on `stream` (used by the shims to snapshot activations) */
 int hrp_copy_device(void* dst, const void* src, int64_t bytes, void* stream);
 /* per-operation timing of one plan (eager, CUDA events, `iters` back-to-back launches per op): tab-separated text
