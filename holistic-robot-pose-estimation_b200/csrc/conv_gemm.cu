@@ -42,6 +42,8 @@ __device__ __forceinline__ void tl_stamp(long long* tl, int tile_local, int ev) 
 constexpr int EPI_PLAIN = 0;  // y = [relu](acc*scale + bias)
 constexpr int EPI_PRE = 1;    // + up to three same-resolution addends before the ReLU (residual / fuse partials)
 constexpr int EPI_FULL = 2;   // + nearest-upsampled addends, post-ReLU addend, pooled output
+constexpr int EPI_RES = 3;    // + exactly one residual, TMA-prefetched into the staging tile (no per-row predicates or
+                              //   global loads: the generic flavours spend ~60 issue slots per 8 channels on them)
 
 __device__ __forceinline__ void add_bf16x8(float* v, const uint4& x) {
   v[0] += bf16lo_to_f32(x.x); v[1] += bf16hi_to_f32(x.x);
@@ -95,7 +97,8 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
 
   // residual (pre[0]) prefetched by TMA into a dedicated staging buffer behind the pipeline stages; without a
   // residual the staging buffer aliases the (by then idle) stages
-  const bool has_res = (EPI != EPI_PLAIN) && (p.pre[0] != nullptr) && (p.out != nullptr);
+  constexpr bool GENERIC = (EPI == EPI_PRE || EPI == EPI_FULL);
+  const bool has_res = (EPI == EPI_RES) || (GENERIC && (p.pre[0] != nullptr) && (p.out != nullptr));
   uint8_t* const stag_base = has_res ? smem + (size_t)stages * stage_bytes : smem;
   const int nkb = p.ntaps * p.cpt;
   // vertical tap sharing (3x3 stride-1 convs): one iteration = (channel chunk, dw); its A buffer holds bh+2 image
@@ -234,7 +237,7 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
     bool valid = true;
     size_t opix = 0;
     int n = 0, oh = 0, ow = 0;
-    if (EPI != EPI_PLAIN) {
+    if (GENERIC) {
       const int wi = row & (p.bw - 1);
       const int hi = (row >> p.bw_shift) & (p.bh - 1);
       const int ni = row >> (p.bw_shift + p.bh_shift);
@@ -245,9 +248,9 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
       ow = w * p.os + p.ow0 + pw;
       opix = ((size_t)n * p.Hout + oh) * p.Wout + ow;
     }
-    const bf16* pre0 = (EPI != EPI_PLAIN && !has_res && p.pre[0] != nullptr) ? p.pre[0] + opix * p.Cout + c_base : nullptr;
-    const bf16* pre1 = (EPI != EPI_PLAIN && p.pre[1] != nullptr) ? p.pre[1] + opix * p.Cout + c_base : nullptr;
-    const bf16* pre2 = (EPI != EPI_PLAIN && p.pre[2] != nullptr) ? p.pre[2] + opix * p.Cout + c_base : nullptr;
+    const bf16* pre0 = (GENERIC && !has_res && p.pre[0] != nullptr) ? p.pre[0] + opix * p.Cout + c_base : nullptr;
+    const bf16* pre1 = (GENERIC && p.pre[1] != nullptr) ? p.pre[1] + opix * p.Cout + c_base : nullptr;
+    const bf16* pre2 = (GENERIC && p.pre[2] != nullptr) ? p.pre[2] + opix * p.Cout + c_base : nullptr;
     const bf16* upp[3] = {nullptr, nullptr, nullptr};
     const bf16* postp = nullptr;
     if (EPI == EPI_FULL) {
@@ -260,14 +263,18 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
         }
       if (p.post != nullptr) postp = p.post + opix * p.Cout + c_base;
     }
-    const bool do_store = (p.out != nullptr);
+    const bool do_store = (EPI == EPI_RES || EPI == EPI_PLAIN) || (p.out != nullptr);
     const bool pool = (EPI == EPI_FULL) && (p.pool_out != nullptr);
     const bool relu_in_cvt = p.relu && !(EPI == EPI_FULL && (postp != nullptr || pool));
-    const bool relu_explicit = p.relu && !relu_in_cvt;
+    const bool relu_explicit = (EPI == EPI_FULL) && p.relu && !relu_in_cvt;
     const int cko = p.cko;
     const int cko_shift = (cko == 64) ? 6 : 5;
     const int sw = (cko == 64) ? (row & 7) : ((row >> 1) & 3);
     uint8_t* const stage_row = stag_base + (size_t)row * (cko * 2);
+    // swizzled 16-byte chunk offsets of the four channel groups of a 32-column step (see chunk_base below)
+    const uint32_t goff[4] = {(uint32_t)((0 ^ (sw & 3)) << 4), (uint32_t)((1 ^ (sw & 3)) << 4),
+                              (uint32_t)((2 ^ (sw & 3)) << 4), (uint32_t)((3 ^ (sw & 3)) << 4)};
+    const uint32_t blk_bytes = (uint32_t)(kTileM * cko * 2);
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     const int c_lim = min(n_tile, p.Cout - c_base);  // channels of this N tile that exist (multiple of 32)
 
@@ -280,6 +287,10 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
       uint32_t acc[32];
       tmem_ld32(taddr + (uint32_t)c0, acc);
       tmem_ld_wait();
+      // staging address of this 32-column step: column block (cko channels x 128 rows), then the 16-byte chunk
+      // (c0 % cko) / 8 + g XOR-swizzled by the row: the high chunk bit is folded in here, the low two in goff[g]
+      uint8_t* const chunk_base =
+          stage_row + (size_t)(c0 >> cko_shift) * blk_bytes + (((uint32_t)((c0 & (cko - 1)) >> 3) ^ (uint32_t)(sw & 4)) << 4);
 #pragma unroll
       for (int g = 0; g < 4; ++g) {  // 8 channels at a time
         const int cg = c0 + g * 8;
@@ -296,11 +307,9 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
         v[5] = fmaf(__uint_as_float(acc[g * 8 + 5]), s1.y, b1.y);
         v[6] = fmaf(__uint_as_float(acc[g * 8 + 6]), s1.z, b1.z);
         v[7] = fmaf(__uint_as_float(acc[g * 8 + 7]), s1.w, b1.w);
-        const int blk = cg >> cko_shift;  // cko is 32 or 64: no integer division in the epilogue
-        const int ch = (cg & (cko - 1)) >> 3;
-        uint4* const sptr = reinterpret_cast<uint4*>(stage_row + (size_t)blk * (kTileM * cko * 2) + ((ch ^ sw) << 4));
+        uint4* const sptr = reinterpret_cast<uint4*>(chunk_base + goff[g]);
         if (EPI != EPI_PLAIN && has_res) add_bf16x8(v, *sptr);  // TMA-prefetched residual (zero outside the tensor)
-        if (EPI != EPI_PLAIN && valid) {
+        if (GENERIC && valid) {
           if (pre0 != nullptr) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(pre0 + cg)));
           if (pre1 != nullptr) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(pre1 + cg)));
           if (pre2 != nullptr) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(pre2 + cg)));
@@ -394,9 +403,9 @@ struct __align__(16) PersistBarriers {
   uint64_t empty[8];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
-  uint64_t res_full[2];
-  uint64_t stag_free[2];
-  uint64_t stag_ready[2];
+  uint64_t res_full[4];
+  uint64_t stag_free[4];
+  uint64_t stag_ready[4];
   uint64_t w_full;
   uint32_t tmem_base;
   uint32_t pad;
@@ -419,7 +428,8 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
   const int stage_bytes = cfg.stage_bytes;      // A region (+ B region unless the weights are resident)
   const int a_region = cfg.a_region;
   const int stag_bytes = kTileM * n_tile * 2;
-  const int stages = cfg.stages, nstag = cfg.nstag;
+  const int stages = cfg.stages, nstag = cfg.nstag;  // nstag: 1, 2 or 4 output staging buffers (ring)
+  const int nstag_shift = (nstag == 4) ? 2 : (nstag == 2) ? 1 : 0;
   const bool vsh = cfg.vsh != 0, wres = cfg.wres != 0;
   const int ksplit = cfg.ksplit;               // accumulators per tile (1, 2 or 4)
   const uint32_t ksmask = (uint32_t)ksplit - 1u;
@@ -434,7 +444,8 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
   const int n_iters = vsh ? 3 * p.cpt : (nkb + SUB - 1) / SUB;
   const int cko = p.cko;
   const int nblk_full = n_tile / cko;
-  const bool has_res = (EPI != EPI_PLAIN) && (p.pre[0] != nullptr) && (p.out != nullptr);
+  constexpr bool GENERIC = (EPI == EPI_PRE || EPI == EPI_FULL);
+  const bool has_res = (EPI == EPI_RES) || (GENERIC && (p.pre[0] != nullptr) && (p.out != nullptr));
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
 
   if (warp == 0 && lane == 0) {
@@ -447,6 +458,8 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->tmem_full[i], 1);
       mbar_init(&bars->tmem_empty[i], kEpiThreadsP / 32);  // one arrival per epilogue warp
+    }
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&bars->res_full[i], 1);
       mbar_init(&bars->stag_free[i], 1);
       mbar_init(&bars->stag_ready[i], kEpiThreadsP / 32);
@@ -504,8 +517,8 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
       for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x, ++li) {
         HRP_DECODE_TILE(tile)
         (void)th; (void)tw; (void)tn;
-        const int sbuf = (nstag == 2) ? (li & 1) : 0;
-        const uint32_t spar = (uint32_t)(((nstag == 2) ? (li >> 1) : li) & 1);
+        const int sbuf = li & (nstag - 1);
+        const uint32_t spar = (uint32_t)((li >> nstag_shift) & 1);
         const int brow = phase * p.cout_pad + c_base;
         int tap = 0, cc = 0, dwi = 0;
         auto load_residual = [&]() {
@@ -517,7 +530,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
             tma_load_4d(stag_base + (size_t)sbuf * stag_bytes + (size_t)j * (kTileM * cko * 2), &maps.r,
                         &bars->res_full[sbuf], c_base + j * cko, w0, h0, n0);
         };
-        if (has_res && nstag == 2) load_residual();
+        if (has_res && nstag >= 2) load_residual();
         tl_stamp(p.timeline, li, 0);
         for (int it = 0; it < n_iters; ++it) {
           mbar_wait(&bars->empty[s], par ^ 1);
@@ -649,8 +662,8 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
       for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x, ++li) {
         HRP_DECODE_TILE(tile)
         (void)th; (void)tw; (void)tn; (void)ph; (void)pw;
-        const int sbuf = (nstag == 2) ? (li & 1) : 0;
-        mbar_wait(&bars->stag_ready[sbuf], (uint32_t)(((nstag == 2) ? (li >> 1) : li) & 1));
+        const int sbuf = li & (nstag - 1);
+        mbar_wait(&bars->stag_ready[sbuf], (uint32_t)((li >> nstag_shift) & 1));
         tl_stamp(p.timeline, li, 10);
         for (int j = 0; j < nblk_full; ++j) {
           const int cj = c_base + j * cko;
@@ -672,19 +685,22 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
     const int row = q * 32 + lane;
     const int cko_shift = (cko == 64) ? 6 : 5;
     const int sw = (cko == 64) ? (row & 7) : ((row >> 1) & 3);
-    const bool do_store = (p.out != nullptr);
+    const uint32_t goff[4] = {(uint32_t)((0 ^ (sw & 3)) << 4), (uint32_t)((1 ^ (sw & 3)) << 4),
+                              (uint32_t)((2 ^ (sw & 3)) << 4), (uint32_t)((3 ^ (sw & 3)) << 4)};
+    const uint32_t blk_bytes = (uint32_t)(kTileM * cko * 2);
+    const bool do_store = (EPI == EPI_RES || EPI == EPI_PLAIN) || (p.out != nullptr);
     const bool pool = (EPI == EPI_FULL) && (p.pool_out != nullptr);
     int li = 0;
     for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x, ++li) {
       HRP_DECODE_TILE(tile)
       (void)th; (void)tw; (void)tn;
       const int abuf = li & 1;
-      const int sbuf = (nstag == 2) ? (li & 1) : 0;
-      const uint32_t spar = (uint32_t)(((nstag == 2) ? (li >> 1) : li) & 1);
+      const int sbuf = li & (nstag - 1);
+      const uint32_t spar = (uint32_t)((li >> nstag_shift) & 1);
       bool valid = true;
       size_t opix = 0;
       int n = 0, oh = 0, ow = 0;
-      if (EPI != EPI_PLAIN) {
+      if (GENERIC) {
         const int wi = row & (p.bw - 1);
         const int hi = (row >> p.bw_shift) & (p.bh - 1);
         const int ni = row >> (p.bw_shift + p.bh_shift);
@@ -695,9 +711,9 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
         ow = w * p.os + p.ow0 + pw;
         opix = ((size_t)n * p.Hout + oh) * p.Wout + ow;
       }
-      const bf16* pre0 = (EPI != EPI_PLAIN && !has_res && p.pre[0] != nullptr) ? p.pre[0] + opix * p.Cout + c_base : nullptr;
-      const bf16* pre1 = (EPI != EPI_PLAIN && p.pre[1] != nullptr) ? p.pre[1] + opix * p.Cout + c_base : nullptr;
-      const bf16* pre2 = (EPI != EPI_PLAIN && p.pre[2] != nullptr) ? p.pre[2] + opix * p.Cout + c_base : nullptr;
+      const bf16* pre0 = (GENERIC && !has_res && p.pre[0] != nullptr) ? p.pre[0] + opix * p.Cout + c_base : nullptr;
+      const bf16* pre1 = (GENERIC && p.pre[1] != nullptr) ? p.pre[1] + opix * p.Cout + c_base : nullptr;
+      const bf16* pre2 = (GENERIC && p.pre[2] != nullptr) ? p.pre[2] + opix * p.Cout + c_base : nullptr;
       const bf16* upp[3] = {nullptr, nullptr, nullptr};
       const bf16* postp = nullptr;
       if (EPI == EPI_FULL) {
@@ -711,7 +727,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
         if (p.post != nullptr) postp = p.post + opix * p.Cout + c_base;
       }
       const bool relu_in_cvt = p.relu && !(EPI == EPI_FULL && (postp != nullptr || pool));
-      const bool relu_explicit = p.relu && !relu_in_cvt;
+      const bool relu_explicit = (EPI == EPI_FULL) && p.relu && !relu_in_cvt;
       uint8_t* const stage_row = stag_base + (size_t)sbuf * stag_bytes + (size_t)row * (cko * 2);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * ksplit * n_tile);
       const int c_lim = min(n_tile, p.Cout - c_base);
@@ -740,6 +756,8 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
 #pragma unroll
           for (int i = 0; i < 32; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __uint_as_float(part[i]));
         }
+        uint8_t* const chunk_base = stage_row + (size_t)(c0 >> cko_shift) * blk_bytes +
+                                    (((uint32_t)((c0 & (cko - 1)) >> 3) ^ (uint32_t)(sw & 4)) << 4);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const int cg = c0 + g * 8;
@@ -756,12 +774,10 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
           v[5] = fmaf(__uint_as_float(acc[g * 8 + 5]), s1.y, b1.y);
           v[6] = fmaf(__uint_as_float(acc[g * 8 + 6]), s1.z, b1.z);
           v[7] = fmaf(__uint_as_float(acc[g * 8 + 7]), s1.w, b1.w);
-          const int blk = cg >> cko_shift;
-          const int ch = (cg & (cko - 1)) >> 3;
-          uint4* const sptr = reinterpret_cast<uint4*>(stage_row + (size_t)blk * (kTileM * cko * 2) + ((ch ^ sw) << 4));
+          uint4* const sptr = reinterpret_cast<uint4*>(chunk_base + goff[g]);
           if (EPI != EPI_PLAIN) {
             if (has_res) add_bf16x8(v, *sptr);  // residual prefetched by TMA (zero-filled outside the tensor)
-            if (valid) {
+            if (GENERIC && valid) {
               if (pre0 != nullptr) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(pre0 + cg)));
               if (pre1 != nullptr) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(pre1 + cg)));
               if (pre2 != nullptr) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(pre2 + cg)));
@@ -1087,15 +1103,15 @@ static void set_smem_attr_once() {
   std::call_once(once, [] {
   #define HRP_SET_ATTR(CKV, EPIV) \
   cudaFuncSetAttribute(conv_gemm_kernel<CKV, EPIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
-    HRP_SET_ATTR(16, EPI_PLAIN); HRP_SET_ATTR(16, EPI_PRE); HRP_SET_ATTR(16, EPI_FULL);
-    HRP_SET_ATTR(32, EPI_PLAIN); HRP_SET_ATTR(32, EPI_PRE); HRP_SET_ATTR(32, EPI_FULL);
-    HRP_SET_ATTR(64, EPI_PLAIN); HRP_SET_ATTR(64, EPI_PRE); HRP_SET_ATTR(64, EPI_FULL);
+    HRP_SET_ATTR(16, EPI_PLAIN); HRP_SET_ATTR(16, EPI_PRE); HRP_SET_ATTR(16, EPI_FULL); HRP_SET_ATTR(16, EPI_RES);
+    HRP_SET_ATTR(32, EPI_PLAIN); HRP_SET_ATTR(32, EPI_PRE); HRP_SET_ATTR(32, EPI_FULL); HRP_SET_ATTR(32, EPI_RES);
+    HRP_SET_ATTR(64, EPI_PLAIN); HRP_SET_ATTR(64, EPI_PRE); HRP_SET_ATTR(64, EPI_FULL); HRP_SET_ATTR(64, EPI_RES);
 #undef HRP_SET_ATTR
 #define HRP_SET_ATTR_P(CKV, EPIV) \
   cudaFuncSetAttribute(conv_gemm_persistent<CKV, EPIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
-    HRP_SET_ATTR_P(16, EPI_PLAIN); HRP_SET_ATTR_P(16, EPI_PRE); HRP_SET_ATTR_P(16, EPI_FULL);
-    HRP_SET_ATTR_P(32, EPI_PLAIN); HRP_SET_ATTR_P(32, EPI_PRE); HRP_SET_ATTR_P(32, EPI_FULL);
-    HRP_SET_ATTR_P(64, EPI_PLAIN); HRP_SET_ATTR_P(64, EPI_PRE); HRP_SET_ATTR_P(64, EPI_FULL);
+    HRP_SET_ATTR_P(16, EPI_PLAIN); HRP_SET_ATTR_P(16, EPI_PRE); HRP_SET_ATTR_P(16, EPI_FULL); HRP_SET_ATTR_P(16, EPI_RES);
+    HRP_SET_ATTR_P(32, EPI_PLAIN); HRP_SET_ATTR_P(32, EPI_PRE); HRP_SET_ATTR_P(32, EPI_FULL); HRP_SET_ATTR_P(32, EPI_RES);
+    HRP_SET_ATTR_P(64, EPI_PLAIN); HRP_SET_ATTR_P(64, EPI_PRE); HRP_SET_ATTR_P(64, EPI_FULL); HRP_SET_ATTR_P(64, EPI_RES);
 #undef HRP_SET_ATTR_P
   });
 }
@@ -1174,7 +1190,9 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed, con
   plan->grid = dim3((unsigned)(p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles), 1u, (unsigned)p.nphase);
   const bool full = p.up[0] || p.up[1] || p.up[2] || p.post || p.pool_out;
   const bool pre = p.pre[0] || p.pre[1] || p.pre[2];
-  plan->epi = full ? EPI_FULL : (pre ? EPI_PRE : EPI_PLAIN);
+  const bool res_only = !full && p.pre[0] != nullptr && p.pre[1] == nullptr && p.pre[2] == nullptr && p.out != nullptr &&
+                        p.nphase == 1 && p.os == 1;
+  plan->epi = full ? EPI_FULL : (res_only ? EPI_RES : (pre ? EPI_PRE : EPI_PLAIN));
 
   // ---- persistent variant (default) ----
   {
@@ -1204,7 +1222,7 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed, con
       plan->maps.r = plan->maps.a[0];
     }
     const int stag_bytes = (p.out != nullptr) ? kTileM * p.n_tile * 2 : 0;
-    const int tail = 256 + 2 * p.cout_pad * (int)sizeof(float) + 1024;  // barriers + scale/shift + alignment slack
+    const int tail = 512 + 2 * p.cout_pad * (int)sizeof(float) + 1024;  // barriers + scale/shift + alignment slack
     const int avail = 227 * 1024 - tail;
     const int b_sub = p.n_tile * p.ck * 2;
     // vertical tap sharing + resident weights: in the persistent kernel the producer thread's issue rate is the
@@ -1229,11 +1247,15 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed, con
       if (rc != HRP_OK) return rc;
     }
     const int pipe_avail = avail - c.pipe_offset;
-    int nstag = (stag_bytes > 0 && p.n_tile <= 128) ? 2 : 1;
+    // Staging ring: the residual tile of tile i + nstag - 1 is fetched (by TMA, into the staging buffer it will be
+    // updated in) while tile i is in the epilogue, so with a residual the ring depth is the prefetch distance and
+    // must cover a DRAM round trip (~2 tile periods on short-K layers): 4 buffers when they fit, else 2, else 1.
+    const char* e4 = getenv("HRP_CONV_NSTAG");
+    int nstag = (stag_bytes > 0 && p.n_tile <= 128) ? ((has_res && !(e4 != nullptr && e4[0] == '2')) ? 4 : 2) : 1;
     int st = (pipe_avail - nstag * stag_bytes) / c.stage_bytes;
-    if (st < 3 && nstag == 2) {
-      nstag = 1;
-      st = (pipe_avail - stag_bytes) / c.stage_bytes;
+    while (st < 3 && nstag > 1) {
+      nstag >>= 1;
+      st = (pipe_avail - nstag * stag_bytes) / c.stage_bytes;
     }
     HRP_REQUIRE(st >= 1, "layer does not fit in shared memory");
     c.stages = std::min(8, st);
@@ -1288,6 +1310,7 @@ int conv_plan_launch(const ConvPlan& plan, cudaStream_t stream) {
 #define HRP_LAUNCH_P_CK(CKV)                                  \
   do {                                                        \
     if (plan.epi == EPI_PLAIN) HRP_LAUNCH_P(CKV, EPI_PLAIN);   \
+    else if (plan.epi == EPI_RES) HRP_LAUNCH_P(CKV, EPI_RES);  \
     else if (plan.epi == EPI_PRE) HRP_LAUNCH_P(CKV, EPI_PRE);  \
     else HRP_LAUNCH_P(CKV, EPI_FULL);                         \
   } while (0)
@@ -1306,6 +1329,7 @@ int conv_plan_launch(const ConvPlan& plan, cudaStream_t stream) {
 #define HRP_LAUNCH_CK(CKV)                                \
   do {                                                    \
     if (plan.epi == EPI_PLAIN) HRP_LAUNCH(CKV, EPI_PLAIN); \
+    else if (plan.epi == EPI_RES) HRP_LAUNCH(CKV, EPI_RES); \
     else if (plan.epi == EPI_PRE) HRP_LAUNCH(CKV, EPI_PRE); \
     else HRP_LAUNCH(CKV, EPI_FULL);                       \
   } while (0)

@@ -16,7 +16,11 @@ B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 name, cin, h, cout, k, stride, pad, kind = SHAPES[idx]
 x = torch.randn(B, h, h, cin, device="cuda").to(torch.bfloat16)
 w = torch.randn(cin, cout, 4, 4) * 0.02 if kind == ops.DECONV_K4S2P1 else torch.randn(cout, cin, k, k) * 0.02
-op = ops.ConvOp(x, w, kind=kind, stride=stride, pad=pad, relu=True)
+res = ()
+if len(sys.argv) > 3 and sys.argv[3] == "res":
+    ho = (h + 2 * pad - k) // stride + 1
+    res = (torch.randn(B, ho, ho, cout, device="cuda").to(torch.bfloat16),)
+op = ops.ConvOp(x, w, kind=kind, stride=stride, pad=pad, relu=True, pre=res)
 tl = torch.zeros(8 * 8 * 16, dtype=torch.int64, device="cuda")
 for _ in range(3):
     op.run()
@@ -27,7 +31,7 @@ t = tl.cpu().view(8, 8, 16)
 names = ["P.start", "P.empty0", "P.issued", "M.tmemfree", "M.full0", "M.lastcommit", "E.top", "E.tmemfull", "E.stagok",
          "E.done", "S.ready", "S.issued", "S.drained"]
 print(name, "B", B)
-for cta in (0, 5):
+for cta in (0,):
     t0 = int(t[cta, 0][t[cta, 0] > 0].min())
     print(f"CTA {cta}: cycles relative to first stamp")
     print("tile " + " ".join(f"{n:>11s}" for n in names))
