@@ -13,6 +13,7 @@ static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
 const char* last_error() { return g_err.c_str(); }
 std::atomic<int64_t> g_launch_count{0};
+thread_local bool g_pdl_launch = false;
 }  // namespace hrp
 
 using namespace hrp;

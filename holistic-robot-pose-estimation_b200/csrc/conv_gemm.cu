@@ -133,6 +133,8 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  pdl_launch_dependents();
+  pdl_wait();  // everything above (barriers, TMEM, scale/shift) overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -481,6 +483,8 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  pdl_launch_dependents();
+  if (!(warp == 0 && wres)) pdl_wait();  // (the producer first fetches the resident weights: not produced by a kernel)
 
   // tile -> (n tile, phase, w/h/n tile) with shifts: tiles_w and tiles_h are powers of two by construction
 #define HRP_DECODE_TILE(tile)                                          \
@@ -510,6 +514,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
       if (wres) {  // the whole (single) N tile of packed weights stays in shared memory for the CTA's lifetime
         mbar_expect_tx(&bars->w_full, (uint32_t)(nkb * b_sub_bytes));
         for (int kb = 0; kb < nkb; ++kb) tma_load_2d(smem + (size_t)kb * b_sub_bytes, &maps.b, &bars->w_full, kb * CK, 0);
+        pdl_wait();
       }
       int s = 0;
       uint32_t par = 0;
@@ -1306,7 +1311,7 @@ int conv_plan_launch(const ConvPlan& plan, cudaStream_t stream) {
   if (plan.halo) return conv_halo_launch(plan, stream);
   if (plan.persistent) {
 #define HRP_LAUNCH_P(CKV, EPIV) \
-  conv_gemm_persistent<CKV, EPIV><<<plan.pgrid, kThreadsP, plan.psmem, stream>>>(plan.maps, p, plan.pcfg)
+  launch_ex(conv_gemm_persistent<CKV, EPIV>, dim3(plan.pgrid), dim3(kThreadsP), (size_t)plan.psmem, stream, plan.maps, p, plan.pcfg)
 #define HRP_LAUNCH_P_CK(CKV)                                  \
   do {                                                        \
     if (plan.epi == EPI_PLAIN) HRP_LAUNCH_P(CKV, EPI_PLAIN);   \
@@ -1324,8 +1329,8 @@ int conv_plan_launch(const ConvPlan& plan, cudaStream_t stream) {
     return HRP_OK;
   }
 #define HRP_LAUNCH(CKV, EPIV)                                                                              \
-  conv_gemm_kernel<CKV, EPIV><<<plan.grid, kNumThreads, plan.smem_bytes, stream>>>(plan.maps, p, plan.stages, \
-                                                                                     plan.bar_offset)
+  launch_ex(conv_gemm_kernel<CKV, EPIV>, plan.grid, dim3(kNumThreads), (size_t)plan.smem_bytes, stream, plan.maps, p, \
+            plan.stages, plan.bar_offset)
 #define HRP_LAUNCH_CK(CKV)                                \
   do {                                                    \
     if (plan.epi == EPI_PLAIN) HRP_LAUNCH(CKV, EPI_PLAIN); \

@@ -118,12 +118,15 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
   if (threadIdx.x == 0) halo_stamp(hp.tl, 1);
+  pdl_launch_dependents();
+  if (warp != 0) pdl_wait();  // (the producer fetches the weights first: they are not produced by a kernel)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
       mbar_expect_tx(&bars->w_full, (uint32_t)(9 * B_SUB));
       for (int t = 0; t < 9; ++t) tma_load_2d(sW + t * B_SUB, &map_b, &bars->w_full, t * CK, 0);
+      pdl_wait();
       int abuf = 0;
       uint32_t par = 0;
       for (int u = blockIdx.x; u < hp.total_units; u += gridDim.x) {
@@ -548,7 +551,8 @@ int conv_halo_launch(const ConvPlan& plan, cudaStream_t stream) {
   h.tl = plan.p.timeline;
   const bool res = (h.res != nullptr);
 #define HRP_HALO_LAUNCH(CKV, NV, RV, PV, MAPB) \
-  conv_halo_kernel<CKV, NV, RV, PV><<<plan.halo_grid, kHaloThreads, plan.halo_smem, stream>>>(plan.halo_map_a, MAPB, plan.halo_map_r, h)
+  launch_ex(conv_halo_kernel<CKV, NV, RV, PV>, dim3(plan.halo_grid), dim3(kHaloThreads), (size_t)plan.halo_smem, stream, \
+            plan.halo_map_a, MAPB, plan.halo_map_r, h)
   if (h.pair) {
     if (res) HRP_HALO_LAUNCH(64, 64, true, true, plan.halo_map_b);
     else HRP_HALO_LAUNCH(64, 64, false, true, plan.halo_map_b);

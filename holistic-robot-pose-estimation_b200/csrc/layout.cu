@@ -82,6 +82,8 @@ __global__ void pack_input_s2d_u8_kernel(const uint8_t* __restrict__ x, uint4* _
 // MaxPool2d(kernel 3, stride 2, pad 1) on bf16 NHWC; thread = (output pixel, 8-channel group)
 __global__ void maxpool3x3s2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W,
                                     int C8) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int Ho = H >> 1, Wo = W >> 1;
   const size_t total = (size_t)B * Ho * Wo * C8;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -156,6 +158,8 @@ __global__ void nhwc_bf16_to_nchw_f32_kernel(const bf16* __restrict__ in, float*
 // HRNet fuse for the highest-resolution branch (no conv lands on it): out = relu(pre + sum_i upsample(up_i))
 // (HRnet.py:254-263 with i == 0); thread = (pixel, 8-channel group)
 __global__ void fuse_add_kernel(const FuseAddParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int C8 = p.C >> 3;
   const size_t total = (size_t)p.B * p.H * p.W * C8;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -227,8 +231,8 @@ int launch_maxpool3x3s2(const void* in, void* out, int B, int H, int W, int C, c
   const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 8);
   const int threads = 256;
   const int blocks = (int)std::min<size_t>((total + threads - 1) / threads, 148 * 16);
-  maxpool3x3s2_kernel<<<blocks, threads, 0, s>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), B,
-                                                 H, W, C / 8);
+  launch_ex(maxpool3x3s2_kernel, dim3(blocks), dim3(threads), 0, s, reinterpret_cast<const uint4*>(in),
+            reinterpret_cast<uint4*>(out), B, H, W, C / 8);
   count_launch();
   HRP_CUDA_CHECK(cudaGetLastError());
   return HRP_OK;
@@ -255,7 +259,7 @@ int launch_fuse_add(const FuseAddParams& p, cudaStream_t s) {
   const size_t total = (size_t)p.B * p.H * p.W * (p.C / 8);
   const int threads = 256;
   const int blocks = (int)std::min<size_t>((total + threads - 1) / threads, 148 * 16);
-  fuse_add_kernel<<<blocks, threads, 0, s>>>(p);
+  launch_ex(fuse_add_kernel, dim3(blocks), dim3(threads), 0, s, p);
   count_launch();
   HRP_CUDA_CHECK(cudaGetLastError());
   return HRP_OK;

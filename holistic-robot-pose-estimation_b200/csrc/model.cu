@@ -677,15 +677,28 @@ int capture_plan(hrp_model* m, Plan* pl) {
     if (cudaEventRecord(pl->fork_ev, pl->cap[0]) != cudaSuccess) { rc = HRP_ERR_CUDA; break; }
     for (int l = 1; l < kNumLanes && rc == HRP_OK; ++l)
       if (cudaStreamWaitEvent(pl->cap[l], pl->fork_ev, 0) != cudaSuccess) rc = HRP_ERR_CUDA;
+    // Programmatic dependent launch between consecutive kernels of a lane (HRP_PDL=1 enables): the successor's
+    // prologue overlaps the predecessor's tail and the ~5 us launch gap disappears.  Not used behind a memset
+    // node or a cross-lane event wait.
+    const char* pdl_env = getenv("HRP_PDL");
+    const bool pdl_on = (pdl_env != nullptr && pdl_env[0] == '1') && !m->use_simt;  // opt-in: measured no gain
+    bool prev_kernel[kNumLanes] = {};
     for (size_t i = 0; i < pl->ops.size() && rc == HRP_OK; ++i) {
       Op& op = pl->ops[i];
+      bool waited = false;
       for (int a : op.reads) {
         const int prod = pl->acts[a].producer;
-        if (prod >= 0 && pl->ops[prod].lane != op.lane)
+        if (prod >= 0 && pl->ops[prod].lane != op.lane) {
+          waited = true;
           if (cudaStreamWaitEvent(pl->cap[op.lane], pl->ops[prod].done, 0) != cudaSuccess) rc = HRP_ERR_CUDA;
+        }
       }
       if (rc != HRP_OK) break;
-      rc = launch_op(m, op, pl->cap[op.lane]);
+      {
+        PdlScope pdl(pdl_on && op.kind != OP_MEMSET && prev_kernel[op.lane] && !waited);
+        rc = launch_op(m, op, pl->cap[op.lane]);
+      }
+      prev_kernel[op.lane] = (op.kind != OP_MEMSET);
       if (rc == HRP_OK && op.cross_lane_consumer)
         if (cudaEventRecord(op.done, pl->cap[op.lane]) != cudaSuccess) rc = HRP_ERR_CUDA;
     }
@@ -778,9 +791,15 @@ int run_plan_body(hrp_model* m, Plan* pl, cudaStream_t s) {
     count_launch(pl->n_kernels);
     return HRP_OK;
   }
+  // eager path (HRP_NO_GRAPH=1): one stream, optional programmatic dependent launches between kernels
+  const char* pdl_env = getenv("HRP_PDL");
+  const bool pdl_on = (pdl_env != nullptr && pdl_env[0] == '1') && !m->use_simt;
+  bool prev_kernel = false;
   for (auto& op : pl->ops) {
+    PdlScope pdl(pdl_on && op.kind != OP_MEMSET && prev_kernel);
     int rc = launch_op(m, op, s);
     if (rc != HRP_OK) return rc;
+    prev_kernel = (op.kind != OP_MEMSET);
   }
   return HRP_OK;
 }

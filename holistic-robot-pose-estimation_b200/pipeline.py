@@ -65,3 +65,53 @@ class HostPipeline:
                 h[c:c + n].copy_(o, non_blocking=True)
         main.synchronize()
         return host_out
+
+    # ---- stream of batches: the upload of batch i+1 overlaps the forward of batch i (a DataLoader-style eval loop) ----
+    def run_stream(self, batches):
+        """Iterate over host batches `(x_reg_h, x_root_h, k_h, K_h)` (pinned) and yield the host outputs of each, in
+        order.  Every batch is copied host->device on the copy stream into one of two full-batch device buffer sets
+        while the previous batch is being computed; its eight outputs are copied back before it is yielded."""
+        dev = torch.device("cuda", torch.cuda.current_device())
+        main = torch.cuda.current_stream()
+        if self.copy_stream is None:
+            self.copy_stream = torch.cuda.Stream(device=dev)
+        bufs = [None, None]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        free = [None, None]
+
+        def upload(batch, slot):
+            if bufs[slot] is None or any(b.shape != h.shape or b.dtype != h.dtype for b, h in zip(bufs[slot], batch)):
+                bufs[slot] = tuple(torch.empty(h.shape, dtype=h.dtype, device=dev) for h in batch)
+            with torch.cuda.stream(self.copy_stream):
+                if free[slot] is not None:
+                    self.copy_stream.wait_event(free[slot])  # the forward that last read this buffer set is done
+                for b, h in zip(bufs[slot], batch):
+                    assert h.is_pinned(), "HostPipeline expects pinned host tensors"
+                    b.copy_(h, non_blocking=True)
+                ready[slot].record(self.copy_stream)
+
+        it = iter(batches)
+        nxt = next(it, None)
+        slot = 0
+        if nxt is not None:
+            upload(nxt, slot)
+        while nxt is not None:
+            cur_slot = slot
+            B = nxt[0].shape[0]
+            nxt = next(it, None)
+            main.wait_event(ready[cur_slot])
+            outs = self.model(*bufs[cur_slot])
+            free[cur_slot] = torch.cuda.Event()
+            free[cur_slot].record(main)
+            if nxt is not None:
+                slot ^= 1
+                upload(nxt, slot)
+            key = ("stream", B, tuple(tuple(o.shape[1:]) for o in outs))
+            host_out = self._host_out.get(key)
+            if host_out is None:
+                host_out = tuple(torch.empty((B,) + tuple(o.shape[1:]), dtype=torch.float32).pin_memory() for o in outs)
+                self._host_out[key] = host_out
+            for o, h in zip(outs, host_out):
+                h.copy_(o, non_blocking=True)
+            main.synchronize()
+            yield host_out

@@ -168,6 +168,35 @@ def _check_chunking(synth):
     assert len(r) == 9 and len(r[8]) == 3
 
 
+def test_host_pipeline_stream_matches_direct_forward(hrp_lib):
+    """HostPipeline (pinned host buffers in, host results out; bench.py's e2e call): both the sub-batch call and the
+    double-buffered stream of batches must return what a direct device forward returns."""
+    from horopose_b200 import synth
+    from horopose_b200.pipeline import HostPipeline
+    m = _model("panda", chunk=4, inflight=1)
+    batches = []
+    for seed in (3, 4, 5):
+        x_reg, x_root, k, K = synth.inputs(4, seed=seed)
+        u8 = lambda t: (t * 255.0).round().clamp(0, 255).to(torch.uint8).contiguous().pin_memory()
+        batches.append((u8(x_reg), u8(x_root), k.contiguous().pin_memory(), K.contiguous().pin_memory()))
+    pipe = HostPipeline(m, sub_batch=2)
+    direct = []
+    for b in batches:
+        outs = m(*(t.cuda() for t in b))
+        torch.cuda.synchronize()
+        direct.append([o.cpu().clone() for o in outs])
+    n = 0
+    for i, host_out in enumerate(pipe.run_stream(iter(batches))):
+        for name, h, d in zip(NAMES, host_out, direct[i]):
+            assert torch.allclose(h, d, rtol=0, atol=5e-5), (i, name, float((h - d).abs().max()))
+        n += 1
+    assert n == 3
+    # the sub-batch call may pick other kernels for its batch-2 plans (autotune): compare at the parity tolerances
+    host_out = pipe(*batches[1])
+    for name, h, d in zip(NAMES, host_out, direct[1]):
+        assert float((h - d).abs().max()) < TOL[name], name
+
+
 def test_simt_cross_check_matches_tcgen05(hrp_lib):
     """Whole network through the SIMT cross-check convolutions (HRP_CONV_IMPL=simt, eager) vs the tcgen05 graph."""
     from horopose_b200 import synth
