@@ -42,6 +42,7 @@ static ConvLayerDesc to_internal(const hrp_conv_desc* d) {
   o.pad = d->pad;
   o.relu = d->relu;
   o.has_residual = 0;
+  o.in_wpitch = o.in_wpad = 0;
   return o;
 }
 

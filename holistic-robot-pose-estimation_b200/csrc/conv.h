@@ -51,6 +51,10 @@ struct ConvParams {
   const bf16* in;         // (B,Hin,Win,Cin) source tensor base
   const bf16* w;          // (nphase*cout_pad, ktot) packed weights
   int Hin, Win, src_sh, src_sw;  // full input dims and source-grid stride (2 for parity maps)
+  // element strides of the source grid seen by the A tensor maps (and the SIMT cross-check): position (n, h, w) of
+  // map (hp, wp) starts at in + src_off + (hp*Win + wp)*Cin + n*src_img + h*src_row + w*src_pix
+  long long src_img;
+  int src_row, src_pix, src_off;
   long long* timeline;    // debug: per-role clock64 stamps of the first CTAs (null in production)
 };
 
@@ -129,6 +133,10 @@ struct ConvLayerDesc {
   int kh, kw, stride, pad;
   int relu;
   int has_residual;      // a same-resolution addend (pre[0]) will be attached: keeps the N tile <= 128
+  // kStemS2D only: the s2d input has padded rows (in_wpitch pixels per row, the image starts at column in_wpad, the
+  // padding is zero).  The horizontal taps of one kernel row are then ONE contiguous K block of nw*16 channels
+  // (overlapping TMA windows, pixel stride 32 B): 4x fewer, 4x longer TMA rows than one box per tap.  0 = dense.
+  int in_wpitch, in_wpad;
 };
 
 // Host-side weight packing: reference layouts -> (nphase*cout_pad, ktot) bf16 K-major.

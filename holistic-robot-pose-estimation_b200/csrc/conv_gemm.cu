@@ -250,6 +250,7 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
       ow = w * p.os + p.ow0 + pw;
       opix = ((size_t)n * p.Hout + oh) * p.Wout + ow;
     }
+    const bool use_pre0 = GENERIC && !has_res && p.pre[0] != nullptr;  // (uniform) pre[0] read with plain loads
     const bf16* pre0 = (GENERIC && !has_res && p.pre[0] != nullptr) ? p.pre[0] + opix * p.Cout + c_base : nullptr;
     const bf16* pre1 = (GENERIC && p.pre[1] != nullptr) ? p.pre[1] + opix * p.Cout + c_base : nullptr;
     const bf16* pre2 = (GENERIC && p.pre[2] != nullptr) ? p.pre[2] + opix * p.Cout + c_base : nullptr;
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
     }
     const bool do_store = (EPI == EPI_RES || EPI == EPI_PLAIN) || (p.out != nullptr);
     const bool pool = (EPI == EPI_FULL) && (p.pool_out != nullptr);
-    const bool relu_in_cvt = p.relu && !(EPI == EPI_FULL && (postp != nullptr || pool));
+    const bool relu_in_cvt = p.relu && !(EPI == EPI_FULL && (p.post != nullptr || pool));
     const bool relu_explicit = (EPI == EPI_FULL) && p.relu && !relu_in_cvt;
     const int cko = p.cko;
     const int cko_shift = (cko == 64) ? 6 : 5;
@@ -312,20 +313,22 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
         uint4* const sptr = reinterpret_cast<uint4*>(chunk_base + goff[g]);
         if (EPI != EPI_PLAIN && has_res) add_bf16x8(v, *sptr);  // TMA-prefetched residual (zero outside the tensor)
         if (GENERIC && valid) {
-          if (pre0 != nullptr) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(pre0 + cg)));
-          if (pre1 != nullptr) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(pre1 + cg)));
-          if (pre2 != nullptr) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(pre2 + cg)));
+          // the tests are on kernel parameters (uniform registers): absent addends cost a uniform branch, not a
+          // predicated copy of the load / unpack / add sequence
+          if (use_pre0) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(pre0 + cg)));
+          if (p.pre[1] != nullptr) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(pre1 + cg)));
+          if (p.pre[2] != nullptr) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(pre2 + cg)));
           if (EPI == EPI_FULL) {
 #pragma unroll
             for (int a = 0; a < 3; ++a)
-              if (upp[a] != nullptr) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(upp[a] + cg)));
+              if (p.up[a] != nullptr) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(upp[a] + cg)));
           }
         }
         if (relu_explicit) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
         }
-        if (EPI == EPI_FULL && postp != nullptr && valid) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(postp + cg)));
+        if (EPI == EPI_FULL && p.post != nullptr && valid) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(postp + cg)));
         if (do_store) {
           uint4 o;
           if (relu_in_cvt) {
@@ -716,6 +719,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
         ow = w * p.os + p.ow0 + pw;
         opix = ((size_t)n * p.Hout + oh) * p.Wout + ow;
       }
+      const bool use_pre0 = GENERIC && !has_res && p.pre[0] != nullptr;
       const bf16* pre0 = (GENERIC && !has_res && p.pre[0] != nullptr) ? p.pre[0] + opix * p.Cout + c_base : nullptr;
       const bf16* pre1 = (GENERIC && p.pre[1] != nullptr) ? p.pre[1] + opix * p.Cout + c_base : nullptr;
       const bf16* pre2 = (GENERIC && p.pre[2] != nullptr) ? p.pre[2] + opix * p.Cout + c_base : nullptr;
@@ -731,7 +735,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
           }
         if (p.post != nullptr) postp = p.post + opix * p.Cout + c_base;
       }
-      const bool relu_in_cvt = p.relu && !(EPI == EPI_FULL && (postp != nullptr || pool));
+      const bool relu_in_cvt = p.relu && !(EPI == EPI_FULL && (p.post != nullptr || pool));
       const bool relu_explicit = (EPI == EPI_FULL) && p.relu && !relu_in_cvt;
       uint8_t* const stage_row = stag_base + (size_t)sbuf * stag_bytes + (size_t)row * (cko * 2);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * ksplit * n_tile);
@@ -783,13 +787,13 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
           if (EPI != EPI_PLAIN) {
             if (has_res) add_bf16x8(v, *sptr);  // residual prefetched by TMA (zero-filled outside the tensor)
             if (GENERIC && valid) {
-              if (pre0 != nullptr) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(pre0 + cg)));
-              if (pre1 != nullptr) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(pre1 + cg)));
-              if (pre2 != nullptr) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(pre2 + cg)));
+              if (use_pre0) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(pre0 + cg)));
+              if (p.pre[1] != nullptr) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(pre1 + cg)));
+              if (p.pre[2] != nullptr) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(pre2 + cg)));
               if (EPI == EPI_FULL) {
 #pragma unroll
                 for (int a = 0; a < 3; ++a)
-                  if (upp[a] != nullptr) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(upp[a] + cg)));
+                  if (p.up[a] != nullptr) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(upp[a] + cg)));
               }
             }
           }
@@ -797,7 +801,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
           }
-          if (EPI == EPI_FULL && postp != nullptr && valid)
+          if (EPI == EPI_FULL && p.post != nullptr && valid)
             add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(postp + cg)));
           if (do_store) {
             uint4 o;
@@ -941,18 +945,46 @@ int conv_geometry(const ConvLayerDesc& d, ConvParams* pp) {
     const int dw_lo = floordiv(-d.pad, 2), dw_hi = floordiv(d.kw - 1 - d.pad, 2);
     const int nh = dh_hi - dh_lo + 1, nw = dw_hi - dw_lo + 1;
     HRP_REQUIRE(nh * nw <= kMaxTaps, "too many s2d taps");
-    p.ntaps = nh * nw;
-    for (int a = 0; a < nh; ++a)
-      for (int b = 0; b < nw; ++b) {
-        p.tap_dh[a * nw + b] = (int8_t)(dh_lo + a);
-        p.tap_dw[a * nw + b] = (int8_t)(dw_lo + b);
-        p.tap_map[a * nw + b] = 0;
+    const bool wide = d.in_wpitch > 0 && (nw * 16 == 32 || nw * 16 == 64) && d.in_wpad + dw_lo >= 0 &&
+                      d.in_wpad + d.Win + dw_hi <= d.in_wpitch;
+    if (wide) {
+      // one K block per kernel ROW: the nw horizontally adjacent s2d pixels are contiguous in the padded tensor, the
+      // zero padding columns stand in for the out-of-bounds taps (vertical taps still use the TMA zero fill).  The
+      // packed weight matrix is unchanged: its K order is already (row tap, column tap, 16 channels).
+      p.ntaps = nh;
+      p.Cin = nw * 16;
+      p.ck = p.Cin;
+      p.cpt = 1;
+      for (int a = 0; a < nh; ++a) {
+        p.tap_dh[a] = (int8_t)(dh_lo + a);
+        p.tap_dw[a] = 0;
+        p.tap_map[a] = 0;
       }
+      p.src_pix = 16;
+      p.src_row = d.in_wpitch * 16;
+      p.src_img = (long long)d.Hin * d.in_wpitch * 16;
+      p.src_off = (d.in_wpad + dw_lo) * 16;
+    } else {
+      HRP_REQUIRE(d.in_wpitch == 0, "padded s2d input does not fit this stem geometry");
+      p.ntaps = nh * nw;
+      for (int a = 0; a < nh; ++a)
+        for (int b = 0; b < nw; ++b) {
+          p.tap_dh[a * nw + b] = (int8_t)(dh_lo + a);
+          p.tap_dw[a * nw + b] = (int8_t)(dw_lo + b);
+          p.tap_map[a * nw + b] = 0;
+        }
+    }
   } else {
     set_error("unknown conv kind");
     return HRP_ERR_INVALID;
   }
   p.ktot = p.ntaps * p.Cin;
+  if (p.src_pix == 0) {  // dense NHWC source (everything but the padded stems)
+    p.src_pix = p.src_sw * p.Cin;
+    p.src_row = p.src_sh * p.Win * p.Cin;
+    p.src_img = (long long)p.Hin * p.Win * p.Cin;
+    p.src_off = 0;
+  }
   // M tile box
   p.bw = std::min(p.Wm, kTileM);
   // round bw down to a power of two so that bw*bh*bn == 128 exactly
@@ -1049,17 +1081,24 @@ int conv_pack_weights(const ConvLayerDesc& d, const ConvParams& p, int cin_ref, 
             }
   } else if (d.kind == kStemS2D) {
     HRP_REQUIRE(cin_ref == 3, "stem conv expects 3 input channels");
+    // K order = (row tap a, column tap b, 16 s2d channels), the same for the per-tap and the per-row (padded input)
+    // geometries of conv_geometry
+    const int dh_lo = floordiv(-d.pad, 2), dh_hi = floordiv(d.kh - 1 - d.pad, 2);
+    const int dw_lo = floordiv(-d.pad, 2), dw_hi = floordiv(d.kw - 1 - d.pad, 2);
+    const int nh = dh_hi - dh_lo + 1, nw = dw_hi - dw_lo + 1;
+    HRP_REQUIRE(nh * nw * 16 == p.ktot, "stem geometry / packing mismatch");
     for (int co = 0; co < p.Cout; ++co)
-      for (int t = 0; t < p.ntaps; ++t)
-        for (int hp = 0; hp < 2; ++hp)
-          for (int wp = 0; wp < 2; ++wp) {
-            const int i = 2 * p.tap_dh[t] + hp + d.pad, j = 2 * p.tap_dw[t] + wp + d.pad;
-            if (i < 0 || i >= d.kh || j < 0 || j >= d.kw) continue;
-            for (int ci = 0; ci < 3; ++ci) {
-              const float v = w[(((size_t)co * 3 + ci) * d.kh + i) * d.kw + j];
-              out[(size_t)co * p.ktot + (size_t)t * 16 + (hp * 2 + wp) * 3 + ci] = f32_to_bf16_bits(v);
+      for (int a = 0; a < nh; ++a)
+        for (int b = 0; b < nw; ++b)
+          for (int hp = 0; hp < 2; ++hp)
+            for (int wp = 0; wp < 2; ++wp) {
+              const int i = 2 * (dh_lo + a) + hp + d.pad, j = 2 * (dw_lo + b) + wp + d.pad;
+              if (i < 0 || i >= d.kh || j < 0 || j >= d.kw) continue;
+              for (int ci = 0; ci < 3; ++ci) {
+                const float v = w[(((size_t)co * 3 + ci) * d.kh + i) * d.kw + j];
+                out[(size_t)co * p.ktot + (size_t)(a * nw + b) * 16 + (hp * 2 + wp) * 3 + ci] = f32_to_bf16_bits(v);
+              }
             }
-          }
   }
   return HRP_OK;
 }
@@ -1137,10 +1176,9 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed, con
   const int nmaps = (p.src_sh == 2) ? 4 : 1;
   for (int m = 0; m < nmaps; ++m) {
     const int hp = m >> 1, wp = m & 1;
-    const bf16* base = in + ((size_t)hp * p.Win + wp) * p.Cin;
+    const bf16* base = in + p.src_off + ((size_t)hp * p.Win + wp) * p.Cin;
     uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.Ws, (uint64_t)p.Hs, (uint64_t)p.B};
-    uint64_t strides[3] = {(uint64_t)p.src_sw * p.Cin * 2, (uint64_t)p.src_sh * p.Win * p.Cin * 2,
-                           (uint64_t)p.Hin * p.Win * p.Cin * 2};
+    uint64_t strides[3] = {(uint64_t)p.src_pix * 2, (uint64_t)p.src_row * 2, (uint64_t)p.src_img * 2};
     uint32_t box[4] = {(uint32_t)p.ck, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
     int rc = conv_encode_map(&plan->maps.a[m], base, 4, dims, strides, box, p.ck);
     if (rc != HRP_OK) return rc;

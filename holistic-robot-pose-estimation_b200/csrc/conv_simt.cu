@@ -21,8 +21,8 @@ __global__ void conv_simt_kernel(const ConvParams p) {
     const int hs = h + p.tap_dh[t] + ph, ws = w + p.tap_dw[t] + pw;
     if (hs < 0 || hs >= p.Hs || ws < 0 || ws >= p.Ws) continue;
     const int hp = p.tap_map[t] >> 1, wp = p.tap_map[t] & 1;
-    const int hin = hs * p.src_sh + hp, win = ws * p.src_sw + wp;
-    const bf16* src = p.in + (((size_t)n * p.Hin + hin) * p.Win + win) * p.Cin;
+    const bf16* src = p.in + p.src_off + ((size_t)hp * p.Win + wp) * p.Cin + (size_t)n * p.src_img +
+                      (size_t)hs * p.src_row + (size_t)ws * p.src_pix;
     const bf16* wt = wrow + (size_t)t * p.Cin;
     for (int ci = 0; ci < p.Cin; ++ci) acc = fmaf(__bfloat162float(src[ci]), __bfloat162float(wt[ci]), acc);
   }

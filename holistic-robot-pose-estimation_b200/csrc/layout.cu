@@ -11,7 +11,8 @@ namespace hrp {
 // (B,3,H,W) fp32 -> (B,H/2,W/2,16) bf16; channel = (hp*2+wp)*3 + c; 12..15 = 0.
 // One thread per s2d pixel: reads 3 channels x 2 rows x 2 adjacent floats (float2, coalesced along W),
 // writes 32 contiguous bytes.
-__global__ void pack_input_s2d_kernel(const float* __restrict__ x, uint4* __restrict__ out, int B, int H, int W) {
+__global__ void pack_input_s2d_kernel(const float* __restrict__ x, uint4* __restrict__ out, int B, int H, int W,
+                                      int out_pitch, int out_off) {
   const int Ws = W >> 1, Hs = H >> 1;
   const size_t total = (size_t)B * Hs * Ws;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -39,14 +40,17 @@ __global__ void pack_input_s2d_kernel(const float* __restrict__ x, uint4* __rest
     o1.y = pack_bf16x2(v[10], v[11]);
     o1.z = pack_bf16x2(v[12], v[13]);
     o1.w = pack_bf16x2(v[14], v[15]);
-    out[2 * i] = o0;
-    out[2 * i + 1] = o1;
+    // output rows may be padded (out_pitch pixels per row, image at column out_off): see kStemS2D in conv.h
+    const size_t o = ((size_t)n * Hs + hs) * out_pitch + out_off + ws;
+    out[2 * o] = o0;
+    out[2 * o + 1] = o1;
   }
 }
 
 // uint8 variant: fuses the caller-side `images.float() / 255.` of scripts/test.py:83-86 into the packing pass.
 // One thread per s2d pixel; reads 2 bytes (uchar2) per channel-row.
-__global__ void pack_input_s2d_u8_kernel(const uint8_t* __restrict__ x, uint4* __restrict__ out, int B, int H, int W) {
+__global__ void pack_input_s2d_u8_kernel(const uint8_t* __restrict__ x, uint4* __restrict__ out, int B, int H, int W,
+                                         int out_pitch, int out_off) {
   const int Ws = W >> 1, Hs = H >> 1;
   const size_t total = (size_t)B * Hs * Ws;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -74,8 +78,10 @@ __global__ void pack_input_s2d_u8_kernel(const uint8_t* __restrict__ x, uint4* _
     o1.y = pack_bf16x2(v[10], v[11]);
     o1.z = pack_bf16x2(v[12], v[13]);
     o1.w = pack_bf16x2(v[14], v[15]);
-    out[2 * i] = o0;
-    out[2 * i + 1] = o1;
+    // output rows may be padded (out_pitch pixels per row, image at column out_off): see kStemS2D in conv.h
+    const size_t o = ((size_t)n * Hs + hs) * out_pitch + out_off + ws;
+    out[2 * o] = o0;
+    out[2 * o + 1] = o1;
   }
 }
 
@@ -204,23 +210,26 @@ __global__ void fuse_add_kernel(const FuseAddParams p) {
   }
 }
 
-int launch_pack_input_s2d(const float* x, void* out, int B, int H, int W, cudaStream_t s) {
+int launch_pack_input_s2d(const float* x, void* out, int B, int H, int W, cudaStream_t s, int out_pitch, int out_off) {
+  if (out_pitch <= 0) out_pitch = W / 2;
   HRP_REQUIRE(H % 2 == 0 && W % 2 == 0, "input size must be even");
   const size_t total = (size_t)B * (H / 2) * (W / 2);
   const int threads = 256;
   const int blocks = (int)std::min<size_t>((total + threads - 1) / threads, 148 * 16);
-  pack_input_s2d_kernel<<<blocks, threads, 0, s>>>(x, reinterpret_cast<uint4*>(out), B, H, W);
+  pack_input_s2d_kernel<<<blocks, threads, 0, s>>>(x, reinterpret_cast<uint4*>(out), B, H, W, out_pitch, out_off);
   count_launch();
   HRP_CUDA_CHECK(cudaGetLastError());
   return HRP_OK;
 }
 
-int launch_pack_input_s2d_u8(const uint8_t* x, void* out, int B, int H, int W, cudaStream_t s) {
+int launch_pack_input_s2d_u8(const uint8_t* x, void* out, int B, int H, int W, cudaStream_t s, int out_pitch,
+                             int out_off) {
+  if (out_pitch <= 0) out_pitch = W / 2;
   HRP_REQUIRE(H % 2 == 0 && W % 2 == 0, "input size must be even");
   const size_t total = (size_t)B * (H / 2) * (W / 2);
   const int threads = 256;
   const int blocks = (int)std::min<size_t>((total + threads - 1) / threads, 148 * 16);
-  pack_input_s2d_u8_kernel<<<blocks, threads, 0, s>>>(x, reinterpret_cast<uint4*>(out), B, H, W);
+  pack_input_s2d_u8_kernel<<<blocks, threads, 0, s>>>(x, reinterpret_cast<uint4*>(out), B, H, W, out_pitch, out_off);
   count_launch();
   HRP_CUDA_CHECK(cudaGetLastError());
   return HRP_OK;

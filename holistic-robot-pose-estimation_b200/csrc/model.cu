@@ -23,6 +23,9 @@ namespace hrp {
 
 namespace {
 
+// The s2d-packed inputs of the two stems carry zero columns on both sides of every row (see ConvLayerDesc::in_wpitch):
+constexpr int kS2dPad = 2;                        // left padding, pixels (7x7 stem: taps reach 2 s2d pixels left)
+constexpr int kS2dPitch = 256 / 2 + 2 * kS2dPad;  // pixels per padded row
 constexpr int kNumLanes = 5;  // lanes 0..3: HRNet branches (lane 0 also stem / layer1 / cls head); lane 4: ResNet path
 constexpr int kLaneRN = 4;
 constexpr int kImg = 256;
@@ -319,10 +322,15 @@ struct Builder {
     ConvLayerDesc d;
     d.kind = kind;
     d.B = pl->B;
+    d.in_wpitch = d.in_wpad = 0;
     if (raw_in != nullptr) {
       d.Hin = raw_H;
       d.Win = raw_W;
       d.Cin = raw_C;
+      if (kind == kStemS2D) {
+        d.in_wpitch = kS2dPitch;
+        d.in_wpad = kS2dPad;
+      }
     } else {
       d.Hin = pl->acts[in].H;
       d.Win = pl->acts[in].W;
@@ -727,9 +735,11 @@ int build_plan(hrp_model* m, int B, Plan** out_plan, int replica) {
     pl->owned.push_back(*p);
     return HRP_OK;
   };
-  const size_t s2d_bytes = (size_t)B * (kImg / 2) * (kImg / 2) * 16 * sizeof(bf16);
+  static_assert(kS2dPitch == kImg / 2 + 2 * kS2dPad, "s2d padding");
+  const size_t s2d_bytes = (size_t)B * (kImg / 2) * kS2dPitch * 16 * sizeof(bf16);
   int rc = dmalloc(s2d_bytes, reinterpret_cast<void**>(&pl->s2d_root));
   if (rc != HRP_OK) return rc;
+  HRP_CUDA_CHECK(cudaMemset(pl->s2d_root, 0, s2d_bytes));  // the padding columns stay zero: the pack kernel skips them
   rc = dmalloc((size_t)B * 2048 * 4, reinterpret_cast<void**>(&pl->feat));
   if (rc != HRP_OK) return rc;
   b.memset_op(0, pl->feat, (size_t)B * 2048 * 4);
@@ -737,6 +747,7 @@ int build_plan(hrp_model* m, int B, Plan** out_plan, int replica) {
   if (full) {
     rc = dmalloc(s2d_bytes, reinterpret_cast<void**>(&pl->s2d_reg));
     if (rc != HRP_OK) return rc;
+    HRP_CUDA_CHECK(cudaMemset(pl->s2d_reg, 0, s2d_bytes));
     rc = dmalloc((size_t)B * 2048 * 4, reinterpret_cast<void**>(&pl->xf));
     if (rc != HRP_OK) return rc;
     b.memset_op(kLaneRN, pl->xf, (size_t)B * 2048 * 4);
@@ -942,12 +953,12 @@ static int forward_impl(hrp_model* m, const void* x_reg_v, const void* x_root_v,
       HRP_CUDA_CHECK(cudaStreamWaitEvent(s, m->fork_ev, 0));
       used.push_back(pl);
     }
-    rc = in_u8 ? launch_pack_input_s2d_u8(x_root8 + b0 * img, pl->s2d_root, nb, kImg, kImg, s)
-               : launch_pack_input_s2d(x_root + b0 * img, pl->s2d_root, nb, kImg, kImg, s);
+    rc = in_u8 ? launch_pack_input_s2d_u8(x_root8 + b0 * img, pl->s2d_root, nb, kImg, kImg, s, kS2dPitch, kS2dPad)
+               : launch_pack_input_s2d(x_root + b0 * img, pl->s2d_root, nb, kImg, kImg, s, kS2dPitch, kS2dPad);
     if (rc != HRP_OK) return rc;
     if (full) {
-      rc = in_u8 ? launch_pack_input_s2d_u8(x_reg8 + b0 * img, pl->s2d_reg, nb, kImg, kImg, s)
-                 : launch_pack_input_s2d(x_reg + b0 * img, pl->s2d_reg, nb, kImg, kImg, s);
+      rc = in_u8 ? launch_pack_input_s2d_u8(x_reg8 + b0 * img, pl->s2d_reg, nb, kImg, kImg, s, kS2dPitch, kS2dPad)
+                 : launch_pack_input_s2d(x_reg + b0 * img, pl->s2d_reg, nb, kImg, kImg, s, kS2dPitch, kS2dPad);
       if (rc != HRP_OK) return rc;
     }
     rc = run_plan_body(m, pl, s);
@@ -1093,7 +1104,7 @@ int hrp_model_profile(hrp_model* m, int32_t batch, int32_t iters, char* buf, int
     const double us = 1e3 * ms / iters;
     if (op.kind == OP_CONV) {
       const ConvParams& q = op.conv.p;
-      const double in_b = (double)q.B * q.Hin * q.Win * q.Cin * 2.0, out_b = (double)q.B * q.Hout * q.Wout * q.Cout * 2.0;
+      const double in_b = (double)q.B * q.Hin * q.Win * std::min(q.Cin, q.src_pix) * 2.0, out_b = (double)q.B * q.Hout * q.Wout * q.Cout * 2.0;
       // algorithmic bytes of the layer: input + output + every addend read by the epilogue + packed weights
       double add_b = 0.0;
       for (int a = 0; a < 3; ++a) {

@@ -31,6 +31,10 @@ SHAPES = [
     ("deconv 2048->256 @8", 2048, 8, 256, 4, 2, 1, ops.DECONV_K4S2P1),
     ("deconv 256->256 @32", 256, 32, 256, 4, 2, 1, ops.DECONV_K4S2P1),
     ("final 256->512 k1 @64", 256, 64, 512, 1, 1, 0, ops.CONV),
+    ("hr 32->64 k3s2 @64", 32, 64, 64, 3, 2, 1, ops.CONV),
+    ("hr 32->32 k3s2 @64", 32, 64, 32, 3, 2, 1, ops.CONV),
+    ("hr 64->128 k3s2 @32", 64, 32, 128, 3, 2, 1, ops.CONV),
+    ("rn 128->128 k3s2 @64", 128, 64, 128, 3, 2, 1, ops.CONV),
 ]
 
 
