@@ -128,11 +128,11 @@ def cpu_forward_rate(robot, batch, runs, warmup=1):
 
 def run_reference(args):
     """--impl reference: the reference's own algorithm on the box's host cores (oracle port; the GPU box has no
-    /root/reference).  Each step is a bounded sample of the workload: one forward over 16 images."""
+    /root/reference).  Each step is a bounded sample of the workload: one forward over 64 images."""
     rank, world, _ = _dist()
     if rank != 0:
         return
-    sample = 16
+    sample = 64
     rate, cores, times = cpu_forward_rate(ROBOT, sample, runs=args.steps, warmup=max(1, min(args.warmup, 2)))
     ms = 1e3 * statistics.median(times)
     line = {
@@ -278,6 +278,37 @@ def main():
                 "note": f"algorithmic {gflop_img} GFLOP/image x {B} images / measured step time "
                         f"(whole step incl. packing, pooling and head kernels: a lower bound); peak = "
                         f"{peaks['src']} sustained bf16"}
+    # per-layer view, measured live: every op of the plan timed with CUDA events (3 back-to-back launches each, on the
+    # plan's stream) through hrp_model_profile; each conv is placed on ITS roofline (max of FLOPs / tensor peak and
+    # algorithmic bytes / HBM peak).  `traffic` of the dominant kernel comes from the committed ncu --set full capture.
+    layers = None
+    try:
+        import ctypes as C
+        buf = C.create_string_buffer(1 << 20)
+        _lib.check(_lib.lib().hrp_model_profile(model._handle, min(B, model.chunk), 3, buf, len(buf)))
+        rows = [r.split("\t") for r in buf.value.decode().strip().split("\n")]
+        convs = [r for r in rows if r[1] == "conv"]
+        t_meas = sum(float(r[12]) for r in rows)
+        t_ideal = sum(max(float(r[15]) / (peaks["tf_sust"] * 1e6), float(r[16]) / (peaks["hbm"] * 1e3)) for r in convs)
+        top = sorted(convs, key=lambda r: -float(r[12]))[:5]
+        layers = {"ops": len(rows), "sum_us": t_meas, "per_layer_roofline_us": t_ideal,
+                  "frac_of_per_layer_roofline": t_ideal / t_meas,
+                  "top": [{"layer": r[0], "kernel": r[10], "us": float(r[12]), "tflops": float(r[13]), "gbs": float(r[14]),
+                           "bound": "tensor" if float(r[15]) / (peaks["tf_sust"] * 1e6) > float(r[16]) / (peaks["hbm"] * 1e3) else "hbm",
+                           "frac": max(float(r[13]) / peaks["tf_sust"], float(r[14]) / peaks["hbm"])} for r in top]}
+    except Exception as e:  # the per-layer view is diagnostic: never fail the bench line on it
+        layers = {"error": str(e)}
+    tr = ROOT / "profiles" / "r01_ncu_traffic.json"
+    if tr.exists():
+        try:
+            t = json.loads(tr.read_text())
+            if t.get("robot") == robot and int(t.get("batch", 0)) > 0:
+                roofline["traffic"] = float(t["dram_bytes_per_step"]) * B / int(t["batch"])
+                roofline["traffic_note"] = (f"dram__bytes_read+write summed over the {t.get('kernels')} kernels of one "
+                                            f"{t['batch']}-image step (ncu, {t.get('source')}), scaled to {B} images; "
+                                            f"algorithmic bytes of the same step: {t.get('algorithmic_bytes_per_step')}")
+        except Exception:
+            pass
     # fused head alone (memory-bound): standalone launches of the same kernel on a > L2 heatmap, CUDA events
     hb = min(B, 512)
     hm = torch.randn(hb, 64, 64, nkpt * 64, device=dev).to(torch.bfloat16)
@@ -328,9 +359,9 @@ def main():
     # ---------------- reference algorithm on the host cores (bounded sample) ----------------
     cpu = None
     if not args.no_cpu_baseline:
-        rate, cores, times = cpu_forward_rate(robot, 16, runs=3, warmup=1)
+        rate, cores, times = cpu_forward_rate(robot, 64, runs=3, warmup=1)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"3 forwards of 16 images ({sum(times):.1f} s), fp32 PyTorch oracle port of the reference forward"}
+               "sample": f"3 forwards of 64 images ({sum(times):.1f} s), fp32 PyTorch oracle port of the reference forward"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -346,6 +377,7 @@ def main():
         "clocks": clocks,
         "roofline": roofline,
         "roofline_head": roofline_head,
+        "roofline_layers": layers,
         "cpu_baseline": cpu,
         "latency_b1": latency,
     }
