@@ -2,6 +2,7 @@
 #include "../../include/hrp.h"
 
 #include "conv.h"
+#include "eval.h"
 #include "head.h"
 #include "launch_count.h"
 #include "ops.h"
@@ -250,6 +251,92 @@ int hrp_fk(hrp_robot* robot, const float* q, const float* rot, int32_t rot_dim, 
   p.pts = out_xyz;
   p.rot_out = out_rot;
   return launch_fk(p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ---- input pipeline / metrics (eval.cu) ----------------------------------------------------------------
+int hrp_crop_resize(const hrp_crop_args* a, void* stream) {
+  HRP_REQUIRE(a != nullptr, "null argument");
+  HRP_REQUIRE(a->B > 0 && a->frame_h > 0 && a->frame_w > 0, "bad frame shape");
+  HRP_REQUIRE(a->out_size > 0 && a->out_size % 4 == 0, "out_size must be a positive multiple of 4");
+  HRP_REQUIRE(a->frames != nullptr && a->bbox != nullptr && a->K_in != nullptr, "frames / bbox / K_in are required");
+  HRP_REQUIRE(a->out_u8 != nullptr && a->K_out != nullptr, "out_u8 / K_out are required");
+  HRP_REQUIRE((a->k_value == nullptr) || (a->k_bbox != nullptr), "k_value needs k_bbox");
+  CropParams p;
+  p.B = a->B;
+  p.frame_h = a->frame_h;
+  p.frame_w = a->frame_w;
+  p.out_size = a->out_size;
+  p.frames = a->frames;
+  p.bbox = a->bbox;
+  p.K_in = a->K_in;
+  p.out_u8 = a->out_u8;
+  p.K_out = a->K_out;
+  p.k_bbox = a->k_bbox;
+  p.k_value = a->k_value;
+  p.k_use_crop_K = a->k_use_crop_K;
+  return launch_crop_resize(p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int hrp_metrics_workspace_bytes(int32_t B, int32_t nkpt, int32_t dof, int64_t* bytes) {
+  HRP_REQUIRE(bytes != nullptr && B > 0 && nkpt > 0 && dof >= 0, "bad argument");
+  *bytes = (int64_t)(3 * nkpt + dof) * B * (int64_t)sizeof(float);
+  return HRP_OK;
+}
+
+int hrp_metrics_batch(const hrp_metrics_args* a, void* stream) {
+  HRP_REQUIRE(a != nullptr, "null argument");
+  HRP_REQUIRE(a->B > 0 && a->nkpt > 0 && a->nkpt <= 32 && a->dof >= 0 && a->dof <= 32, "bad sizes (nkpt, dof <= 32)");
+  HRP_REQUIRE(a->ref_kpt >= 0 && a->ref_kpt < a->nkpt, "reference keypoint out of range");
+  HRP_REQUIRE(a->pred_kp3d && a->gt_kp3d && a->gt_kp2d && a->K_original, "keypoints / K are required");
+  HRP_REQUIRE(a->per_image && a->dis3d && a->dis2d, "outputs are required");
+  HRP_REQUIRE(a->pred_joint == nullptr || (a->gt_joint != nullptr && a->l1_jointerror != nullptr && a->dof > 0),
+              "pred_joint needs gt_joint, l1_jointerror and dof");
+  int64_t need = 0;
+  hrp_metrics_workspace_bytes(a->B, a->nkpt, a->dof, &need);
+  HRP_REQUIRE(a->workspace != nullptr && a->workspace_bytes >= need, "workspace too small");
+  MetricsParams p;
+  p.B = a->B;
+  p.nkpt = a->nkpt;
+  p.dof = a->dof;
+  p.ref_kpt = a->ref_kpt;
+  p.drop_last_joint = a->drop_last_joint;
+  p.frame_w = a->frame_w;
+  p.frame_h = a->frame_h;
+  p.pred_kp3d = a->pred_kp3d;
+  p.gt_kp3d = a->gt_kp3d;
+  p.gt_kp2d = a->gt_kp2d;
+  p.K = a->K_original;
+  p.pred_joint = a->pred_joint;
+  p.gt_joint = a->gt_joint;
+  float* ws = static_cast<float*>(a->workspace);
+  p.kp_err3d = ws;
+  p.kp_err2d = ws + (size_t)a->nkpt * a->B;
+  p.kp_valid = ws + (size_t)2 * a->nkpt * a->B;
+  p.joint_err = ws + (size_t)3 * a->nkpt * a->B;
+  p.per_image = a->per_image;
+  p.dis3d = a->dis3d;
+  p.dis2d = a->dis2d;
+  p.l1_jointerror = a->l1_jointerror;
+  return launch_metrics_batch(p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int hrp_metrics_summary(const float* dis3d, const float* dis2d, int64_t n, double* out, void* stream) {
+  HRP_REQUIRE(dis3d != nullptr && dis2d != nullptr && out != nullptr && n > 0, "bad argument");
+  SummaryParams p;
+  p.dis3d = dis3d;
+  p.dis2d = dis2d;
+  p.n = n;
+  // len(np.arange(0, limit, delta)) = ceil(limit / delta) in fp64 (metrics.py:131-134,144-147)
+  p.nthr_add = (int)ceil(0.1 / 0.00001);
+  p.nthr_pck = (int)ceil(20.0 / 0.01);
+  static const double add_mm[8] = {1, 5, 10, 20, 40, 60, 80, 100};
+  static const double pck_px[8] = {2.5, 5.0, 7.5, 10.0, 12.5, 15.0, 17.5, 20.0};
+  for (int i = 0; i < 8; ++i) {
+    p.table_thr[i] = (float)(add_mm[i] * 1e-3);  // `dis3d <= th_mm * 1e-3`: weak python scalar -> fp32 compare
+    p.table_thr[8 + i] = (float)pck_px[i];
+  }
+  p.out = out;
+  return launch_metrics_summary(p, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int hrp_project(const float* K, const float* pts, float* uv, int32_t B, int32_t N, void* stream) {

@@ -164,3 +164,63 @@ def fk_inputs(robot_type: str, batch: int, seed: int = 2):
     trans = torch.cat([sym_uniform("fk_txy_" + robot_type, (batch, 2), 0.3, seed),
                        range_uniform("fk_tz_" + robot_type, (batch, 1), 0.8, 2.5, seed)], dim=1)
     return q, rot, trans
+
+
+# fixed bounding boxes of the crop fixtures (wmin, hmin, wmax, hmax) in a 640 x 480 frame: wide / tall / exactly the
+# 256-pixel target (identity branch, augmentations.py:174-176) / small (up-sampling) / touching the frame edges /
+# odd sizes / the whole frame height
+CROP_BOXES = [(100, 50, 500, 300), (250, 10, 400, 470), (192, 112, 448, 368), (300, 200, 357, 243), (0, 0, 640, 480),
+              (5, 3, 262, 480), (383, 223, 640, 480), (10, 100, 266, 300), (200, 100, 300, 356), (17, 31, 600, 333)]
+
+
+def crop_inputs(batch: int, seed: int = 5, frame_hw=(480, 640)):
+    """Frames (B,H,W,3) uint8 (triangle-wave gradient + noise, so the bilinear resize is exercised on non-trivial data),
+    bboxes (B,4) int32 -- CROP_BOXES first, then seeded random boxes --, K (B,3,3) float64, k_bbox (B,4) float32."""
+    H, W = frame_hw
+    n = batch * H * W * 3
+    noise = uniform01("crop_frames", n, seed).reshape(batch, H, W, 3)
+    yy, xx = np.meshgrid(np.arange(H, dtype=np.int64), np.arange(W, dtype=np.int64), indexing="ij")
+    tri = np.abs(((xx * 5 + yy * 3) % 512) - 256).astype(np.float32)[None, :, :, None]  # integer triangle wave, 0..256
+    frames = np.clip(np.float32(0.6) * tri + np.float32(0.4 * 256.0) * noise, 0, 255).astype(np.uint8)
+    boxes = []
+    u = uniform01("crop_boxes", batch * 4, seed).reshape(batch, 4)
+    for i in range(batch):
+        if i < len(CROP_BOXES):
+            boxes.append(CROP_BOXES[i])
+            continue
+        w = 40 + int(u[i, 0] * (W - 40))
+        h = 40 + int(u[i, 1] * (H - 40))
+        x0 = int(u[i, 2] * (W - w + 1))
+        y0 = int(u[i, 3] * (H - h + 1))
+        boxes.append((x0, y0, x0 + w, y0 + h))
+    boxes = np.asarray(boxes, dtype=np.int32)
+    K = np.zeros((batch, 3, 3), dtype=np.float64)
+    f = uniform01("crop_f", batch, seed).astype(np.float64) * 100.0 + 560.0
+    K[:, 0, 0] = f
+    K[:, 1, 1] = f + 0.25
+    K[:, 0, 2] = 320.0 + uniform01("crop_cx", batch, seed).astype(np.float64) * 8.0
+    K[:, 1, 2] = 240.0 + uniform01("crop_cy", batch, seed).astype(np.float64) * 8.0
+    K[:, 2, 2] = 1.0
+    k_bbox = boxes.astype(np.float32) + uniform01("crop_kb", batch * 4, seed).reshape(batch, 4) * 3.0
+    return frames, boxes, K, k_bbox.astype(np.float32)
+
+
+def metric_inputs(robot_type: str, batch: int, seed: int = 6):
+    """Predictions and ground truth for the metric kernels: FK inputs (pred) and a perturbed copy (gt), the camera
+    matrix of the 640 x 480 frame, gt 2-D keypoints partly outside the frame (exercises the valid mask)."""
+    q, rot, trans = fk_inputs(robot_type, batch, seed)
+    from .tables import LINK_NAMES
+    nkpt = {"panda": 7, "kuka": 8, "baxter": 17}[robot_type]
+    assert robot_type == "baxter" or len(LINK_NAMES[robot_type]) == nkpt
+    gt_q = q + sym_uniform("m_dq_" + robot_type, tuple(q.shape), 0.05, seed)
+    gt3 = torch.cat([sym_uniform("m_xy_" + robot_type, (batch, nkpt, 2), 0.4, seed),
+                     range_uniform("m_z_" + robot_type, (batch, nkpt, 1), 0.8, 2.5, seed)], dim=2)
+    K = torch.zeros(batch, 3, 3)
+    K[:, 0, 0] = range_uniform("m_fx", (batch,), 560.0, 660.0, seed)
+    K[:, 1, 1] = range_uniform("m_fy", (batch,), 560.0, 660.0, seed)
+    K[:, 0, 2] = 320.0
+    K[:, 1, 2] = 240.0
+    K[:, 2, 2] = 1.0
+    gt2 = torch.stack([range_uniform("m_u_" + robot_type, (batch, nkpt), -60.0, 700.0, seed),
+                       range_uniform("m_v_" + robot_type, (batch, nkpt), -60.0, 540.0, seed)], dim=2)
+    return q, rot, trans, gt_q, gt3, gt2, K

@@ -164,6 +164,61 @@ int hrp_head_workspace_bytes(int32_t B, int32_t nkpt, int64_t* bytes);
 int hrp_head(const hrp_head_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Input pipeline: full camera frame + bounding box -> the 256x256 crop the network
+ * consumes, its intrinsics and the k_value scalar of the depth head.
+ * Replaces, per image, resize_image (lib/dataset/roboutils.py:128-157), CropResizeToAspectAugmentation
+ * (lib/dataset/augmentations.py:165-233: torch bilinear, align_corners=False, `(x*255).to(uint8)`),
+ * get_K_crop_resize (lib/utils/geometries.py:360-402) as chained by DreamDataset._get_rootnet_data /
+ * _get_other_data (lib/dataset/dream.py:281-388, no flip / padding), and the k_value formula of
+ * scripts/test.py:141-152.  The crop bytes are bit-exact with the reference's CPU path.
+ * bbox must lie inside the frame (the reference's numpy slice assignment raises otherwise).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct hrp_crop_args {
+  int32_t B, frame_h, frame_w;
+  int32_t out_size;         /* 256 (multiple of 4) */
+  const uint8_t* frames;    /* device uint8 (B, frame_h, frame_w, 3), HWC as decoded */
+  const int32_t* bbox;      /* device (B,4): wmin, hmin, wmax, hmax */
+  const double* K_in;       /* device fp64 (B,3,3): camera matrix of the full frame (state['camera']['K']) */
+  uint8_t* out_u8;          /* device uint8 (B,3,out,out): the dataset's "images" (feed hrp_model_forward_u8) */
+  float* K_out;             /* device fp32 (B,3,3): the dataset's "K" */
+  const float* k_bbox;      /* device fp32 (B,4) box for k_value (bbox_strict_bounded_original / extended), or NULL */
+  float* k_value;           /* device fp32 (B), or NULL */
+  int32_t k_use_crop_K;     /* 0: fx, fy of K_in (args.use_origin_bbox); 1: of K_out (root_K) */
+} hrp_crop_args;
+int hrp_crop_resize(const hrp_crop_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Evaluation metrics on the device.
+ * hrp_metrics_batch replaces compute_metrics_batch (lib/utils/metrics.py:8-119) given the predicted camera-frame
+ * keypoints (hrp_fk provides them, as URDFRobot.get_keypoints[_root] does at :27-33).
+ * per_image rows: 0 error3d, 1 error2d, 2 mean_jointerror, 3 error_depth, 4 batch_error_relative,
+ * 5 error3d_relative.  hrp_metrics_summary replaces summary_add_pck (:122-162); out[0..10] = ADD/mean, ADD/median,
+ * ADD/AUC, ADD_{1,5,10,20,40,60,80,100}_mm; out[11..21] = ADD_2D/mean, ADD_2D/median, PCK/AUC,
+ * PCK_{2.5,...,20}_pixel.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct hrp_metrics_args {
+  int32_t B, nkpt, dof, ref_kpt;
+  int32_t drop_last_joint;   /* 1 for Panda: the finger joint is excluded from mean_jointerror (:83-84) */
+  float frame_w, frame_h;    /* 640, 480 (:61) */
+  const float* pred_kp3d;    /* device fp32 (B,nkpt,3) */
+  const float* gt_kp3d;      /* (B,nkpt,3) */
+  const float* gt_kp2d;      /* (B,nkpt,2) original-frame pixels */
+  const float* K_original;   /* (B,3,3) */
+  const float* pred_joint;   /* (B,dof) or NULL */
+  const float* gt_joint;     /* (B,dof) or NULL */
+  void* workspace;           /* device, hrp_metrics_workspace_bytes() */
+  int64_t workspace_bytes;
+  float* per_image;          /* (6,B) */
+  float* dis3d;              /* (nkpt) batch mean per keypoint */
+  float* dis2d;              /* (nkpt) */
+  float* l1_jointerror;      /* (dof), or NULL when pred_joint is NULL */
+} hrp_metrics_args;
+int hrp_metrics_workspace_bytes(int32_t B, int32_t nkpt, int32_t dof, int64_t* bytes);
+int hrp_metrics_batch(const hrp_metrics_args* args, void* stream);
+/* dis3d / dis2d: device fp32 (n) per-image errors accumulated over the test set; out: device fp64 [22] */
+int hrp_metrics_summary(const float* dis3d, const float* dis2d, int64_t n, double* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Whole-network inference.
  * Replaces RootNetwithRegInt.forward (lib/models/full_net.py:239-397; construction :38-192 and
  * get_rootNetwithRegInt_model :401-435 incl. the backbone.* -> rootnet_backbone.* remap :423-427) and

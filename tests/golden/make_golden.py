@@ -19,6 +19,7 @@ sys.path.insert(0, str(ROOT))
 import horopose_b200  # noqa: E402,F401
 from horopose_b200 import arch, synth  # noqa: E402
 from oracle import horopose_oracle as O  # noqa: E402
+from oracle import eval_oracle as EO  # noqa: E402
 from oracle import ref_harness  # noqa: E402
 
 GOLDEN = Path(__file__).resolve().parent
@@ -167,14 +168,93 @@ def golden_geometry(ns):
              quat_to_rotmat=to_np(ns.geometries.quat_to_rotmat(quat)))
 
 
+CROP_BATCH = 16
+METRIC_BATCH = 48
+
+
+def golden_crop(ns):
+    """f1: the reference's own dataset chain (roboutils.resize_image -> CropResizeToAspectAugmentation) per image."""
+    import copy
+    import dataset.augmentations as aug
+    import dataset.roboutils as ru
+    frames, boxes, K, k_bbox = synth.crop_inputs(CROP_BATCH)
+    imgs, Ks = [], []
+    for b in range(CROP_BATCH):
+        state = {"camera": {"K": K[b].copy(), "resolution": (640, 480)},
+                 "objects": [{"keypoints_2d": [np.array([320.0, 240.0]), np.array([10.0, 20.0])],
+                              "TCO_keypoints_3d": np.array([[0.1, 0.0, 1.5], [0.0, 0.2, 1.2]])}]}
+        mask = np.zeros((480, 640), dtype=np.uint8)
+        rgb, mask, state = ru.resize_image(frames[b], tuple(int(v) for v in boxes[b]), mask, state)
+        crop = aug.CropResizeToAspectAugmentation(resize=(256, 256))
+        side = rgb.shape[0]
+        rgb, _, state = crop(rgb, np.zeros((side, side), dtype=np.uint8), state)
+        rgb = aug.to_torch_uint8(rgb).permute(2, 0, 1)
+        imgs.append(np.asarray(torch.FloatTensor(np.asarray(rgb))).astype(np.uint8))   # dream.py:309-310
+        Ks.append(torch.FloatTensor(np.asarray(state["camera"]["K"])).numpy())            # dream.py:311
+        o_img, o_K = EO.crop_resize(frames[b], boxes[b], K[b])
+        assert np.array_equal(o_img.numpy(), imgs[-1]), f"oracle crop {b} differs from the reference"
+        assert np.array_equal(o_K.numpy(), Ks[-1]), f"oracle K {b} differs from the reference"
+    # scripts/test.py:141-152 (the expression is inline in farward_loss; evaluated here verbatim on the same tensors)
+    Kt = torch.as_tensor(K).float()
+    bboxes = torch.as_tensor(k_bbox)
+    real_bbox = torch.tensor([1000.0, 1000.0]).to(torch.float32)
+    fx, fy = Kt[:, 0, 0], Kt[:, 1, 1]
+    area = torch.max(torch.abs(bboxes[:, 2] - bboxes[:, 0]), torch.abs(bboxes[:, 3] - bboxes[:, 1])) ** 2
+    kv = torch.tensor([torch.sqrt(fx[n] * fy[n] * real_bbox[0] * real_bbox[1] / area[n]) for n in range(CROP_BATCH)]).to(torch.float32)
+    assert torch.equal(kv, EO.k_value(fx, fy, bboxes))
+    np.savez_compressed(GOLDEN / "crop.npz", images=np.stack(imgs), K=np.stack(Ks), k_value=kv.numpy())
+
+
+def golden_metrics(ns, robot_type: str):
+    """f2: the reference's compute_metrics_batch / summary_add_pck on seeded predictions."""
+    import types
+    for name in ("matplotlib", "matplotlib.pyplot", "seaborn"):   # plotting imports of metrics.py:4-5 (unused here)
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    import utils.metrics as M
+    robot = ns.urdf_robot.URDFRobot(robot_type)
+    ref_id = arch.ROBOTS[robot_type][2]
+    q, rot, trans, gt_q, gt3, gt2, K = synth.metric_inputs(robot_type, METRIC_BATCH)
+    out = M.compute_metrics_batch(robot=robot, gt_keypoints3d=gt3, gt_keypoints2d=gt2, K_original=K, gt_joint=gt_q,
+                                  pred_joint=q, pred_rot=rot, pred_trans=trans, pred_depth=None, pred_xy=None,
+                                  pred_xyz_integral=None, reference_keypoint_id=ref_id)
+    names = ["error3d", "error2d", "dis3d", "dis2d", "l1_jointerror", "mean_jointerror", "error_depth",
+             "batch_error_relative", "error3d_relative"]
+    res = {n: np.asarray(v, dtype=np.float32) for n, v in zip(names, out)}
+    if ref_id == 0:
+        kp = robot.get_keypoints(q, rot, trans)
+    else:
+        kp = robot.get_keypoints_root(q, rot, trans, root=ref_id)
+    mine = EO.metrics_batch(to_np(kp), to_np(gt3), to_np(gt2), to_np(K), to_np(q), to_np(gt_q), ref_id, robot_type == "panda")
+    for n in names:
+        np.testing.assert_array_equal(np.asarray(mine[n], dtype=np.float32), res[n], err_msg=n)
+    # summary over per-image errors spread across the AUC range (scaled copies of the batch errors)
+    d3 = np.concatenate([res["error3d"] * s for s in (0.02, 0.05, 0.1, 0.2)]).astype(np.float32)
+    d2 = np.concatenate([res["error2d"] * s for s in (0.01, 0.02, 0.04, 0.08)]).astype(np.float32)
+    d2 = np.nan_to_num(d2, nan=25.0, posinf=25.0)
+    summ = M.summary_add_pck({"dis3d": list(d3), "dis2d": list(d2)})
+    mine_s = EO.summary_add_pck(d3, d2)
+    for k, v in summ.items():
+        assert float(mine_s[k]) == float(v), (k, mine_s[k], v)
+    np.savez(GOLDEN / f"metrics_{robot_type}.npz", pred_kp3d=to_np(kp), sum_dis3d=d3, sum_dis2d=d2,
+             sum_keys=np.array(list(summ.keys())), sum_vals=np.array([float(v) for v in summ.values()], dtype=np.float64),
+             **res)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--calibrate", action="store_true")
+    ap.add_argument("--only-eval", action="store_true", help="only the crop / metrics fixtures (rows f1, f2)")
     args = ap.parse_args()
     if args.calibrate:
         calibrate()
         return
     ns = ref_harness.setup({k: str(v) for k, v in synth.URDF_PATHS.items()})
+    golden_crop(ns)
+    for r in ("panda", "kuka", "baxter"):
+        golden_metrics(ns, r)
+    if args.only_eval:
+        return
     golden_geometry(ns)
     for r in ("panda", "kuka", "baxter"):
         golden_fk(ns, r)
