@@ -342,6 +342,15 @@ __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
   return r;
 }
 
+// 2^x for x <= 0 on the MUFU pipe alone: exp2f() brackets the same instruction with a range test and two predicated
+// multiplies to keep denormal results (4 issue slots per logit instead of 1 -- the streaming loop is issue-bound, not
+// HBM-bound, with them).  Results below 2^-126 flush to zero: < 1.2e-38 of a sum that is >= 1.
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ float block_sum(float v, float* red) {
   v += __shfl_xor_sync(0xffffffffu, v, 16);
   v += __shfl_xor_sync(0xffffffffu, v, 8);
@@ -544,44 +553,63 @@ __global__ void __launch_bounds__(kHeadMaxThreads, 3) head_kernel(const __grid_c
 
   float m = -INFINITY, S = 0.f, Sx = 0.f, Sy = 0.f, Sz = 0.f;
   constexpr int UNROLL = 4;
+  // one 16-byte vector (8 depth bins of keypoint k at pixel gp) into the running sums; m already bounds its logits
+  auto accumulate = [&](const uint4& raw, int gp) {
+    const float fw = (float)(gp & 63), fh = (float)(gp >> 6);
+    const uint32_t xs[4] = {raw.x, raw.y, raw.z, raw.w};
+    float s8 = 0.f, sz8 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float e0 = ex2_ftz(fmaf(bf16lo_to_f32(xs[i]), kLog2e, -m));
+      const float e1 = ex2_ftz(fmaf(bf16hi_to_f32(xs[i]), kLog2e, -m));
+      s8 += e0 + e1;
+      sz8 = fmaf(e0, dbase + (float)(2 * i), sz8);
+      sz8 = fmaf(e1, dbase + (float)(2 * i + 1), sz8);
+    }
+    S += s8;
+    Sx = fmaf(s8, fw, Sx);
+    Sy = fmaf(s8, fh, Sy);
+    Sz += sz8;
+  };
+  // online-softmax rescale to a new bound (rare after the first few pixels)
+  auto raise_max = [&](const __nv_bfloat162 mx) {
+    const float vmax = fmaxf(__low2float(mx), __high2float(mx)) * kLog2e;
+    if (vmax > m) {
+      const float f = exp2f(m - vmax);
+      S *= f; Sx *= f; Sy *= f; Sz *= f;
+      m = vmax;
+    }
+  };
+  auto vec_max = [](const uint4& raw) {
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    return __hmax2(__hmax2(h2[0], h2[1]), __hmax2(h2[2], h2[3]));
+  };
   if (kvalid) {
-    for (int pix0 = slot; pix0 < ppc; pix0 += slots * UNROLL) {
+    // main loop: UNROLL loads in flight per thread, no predicates (whole groups only), pointer-increment addressing,
+    // ONE running-max test per group of UNROLL vectors (the loop is issue-bound: every instruction per logit counts)
+    const int step = slots * UNROLL;
+    const int groups_n = ppc / step;
+    const size_t ustride = (size_t)slots * vpp;
+    const uint4* ptr = base + (size_t)slot * vpp;
+    int gp = chunk * ppc + slot;
+    for (int it = 0; it < groups_n; ++it) {
       uint4 raw[UNROLL];
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const int pix = pix0 + u * slots;
-        if (pix < ppc) raw[u] = ld_stream(base + (size_t)pix * vpp);
-      }
+      for (int u = 0; u < UNROLL; ++u) raw[u] = ld_stream(ptr + u * ustride);
+      ptr += (size_t)step * vpp;
+      __nv_bfloat162 mx = vec_max(raw[0]);
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const int pix = pix0 + u * slots;
-        if (pix >= ppc) continue;
-        const int gp = chunk * ppc + pix;
-        const float fw = (float)(gp & 63), fh = (float)(gp >> 6);
-        // vector max with packed bf16 ops, then one conversion
-        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
-        const __nv_bfloat162 mx = __hmax2(__hmax2(h2[0], h2[1]), __hmax2(h2[2], h2[3]));
-        const float vmax = fmaxf(__low2float(mx), __high2float(mx)) * kLog2e;
-        if (vmax > m) {  // online-softmax rescale (rare after the first few pixels)
-          const float f = exp2f(m - vmax);
-          S *= f; Sx *= f; Sy *= f; Sz *= f;
-          m = vmax;
-        }
-        const uint32_t xs[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
-        float s8 = 0.f, sz8 = 0.f;
+      for (int u = 1; u < UNROLL; ++u) mx = __hmax2(mx, vec_max(raw[u]));
+      raise_max(mx);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float e0 = exp2f(fmaf(bf16lo_to_f32(xs[i]), kLog2e, -m));
-          const float e1 = exp2f(fmaf(bf16hi_to_f32(xs[i]), kLog2e, -m));
-          s8 += e0 + e1;
-          sz8 = fmaf(e0, dbase + (float)(2 * i), sz8);
-          sz8 = fmaf(e1, dbase + (float)(2 * i + 1), sz8);
-        }
-        S += s8;
-        Sx = fmaf(s8, fw, Sx);
-        Sy = fmaf(s8, fh, Sy);
-        Sz += sz8;
-      }
+      for (int u = 0; u < UNROLL; ++u) accumulate(raw[u], gp + u * slots);
+      gp += step;
+    }
+    // ragged tail (slots * UNROLL does not divide the chunk, e.g. 3 slots): one vector at a time
+    for (int pix = groups_n * step + slot; pix < ppc; pix += slots) {
+      const uint4 raw = ld_stream(base + (size_t)pix * vpp);
+      raise_max(vec_max(raw));
+      accumulate(raw, chunk * ppc + pix);
     }
   }
   // merge the 8 depth-vector lanes of each keypoint, then the pixel slots through shared memory

@@ -47,8 +47,7 @@ __global__ void pack_input_s2d_kernel(const float* __restrict__ x, uint4* __rest
   }
 }
 
-// uint8 variant: fuses the caller-side `images.float() / 255.` of scripts/test.py:83-86 into the packing pass.
-// One thread per s2d pixel; reads 2 bytes (uchar2) per channel-row.
+// scalar uint8 variant (any even W): one thread per s2d pixel; reads 2 bytes (uchar2) per channel-row.
 __global__ void pack_input_s2d_u8_kernel(const uint8_t* __restrict__ x, uint4* __restrict__ out, int B, int H, int W,
                                          int out_pitch, int out_off) {
   const int Ws = W >> 1, Hs = H >> 1;
@@ -82,6 +81,52 @@ __global__ void pack_input_s2d_u8_kernel(const uint8_t* __restrict__ x, uint4* _
     const size_t o = ((size_t)n * Hs + hs) * out_pitch + out_off + ws;
     out[2 * o] = o0;
     out[2 * o + 1] = o1;
+  }
+}
+
+// uint8 variant: fuses the caller-side `images.float() / 255.` of scripts/test.py:83-86 into the packing pass.
+// One thread per FOUR consecutive s2d pixels of a row: six 8-byte loads (3 channels x 2 input rows x 8 pixels) and
+// 128 contiguous output bytes (the one-pixel-per-thread version issued six 2-byte loads per 32 output bytes and ran at
+// 27 % of HBM peak).  Requires W % 8 == 0 (the launcher falls back to the scalar kernel otherwise).
+__global__ void __launch_bounds__(256) pack_input_s2d_u8x4_kernel(const uint8_t* __restrict__ x, uint4* __restrict__ out,
+                                                                 int B, int H, int W, int out_pitch, int out_off) {
+  const int Wq = W >> 3, Hs = H >> 1;
+  const size_t total = (size_t)B * Hs * Wq;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int wq = (int)(i % Wq);
+    const int hs = (int)((i / Wq) % Hs);
+    const int n = (int)(i / ((size_t)Wq * Hs));
+    uint2 raw[3][2];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int hp = 0; hp < 2; ++hp)
+        raw[c][hp] = __ldg(reinterpret_cast<const uint2*>(x + (((size_t)n * 3 + c) * H + (2 * hs + hp)) * W + 8 * wq));
+    uint4* dst = out + 2 * (((size_t)n * Hs + hs) * out_pitch + out_off + 4 * wq);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {  // s2d pixel j of the group = input columns 2j, 2j+1
+      float v[12];
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int hp = 0; hp < 2; ++hp) {
+          const uint32_t word = (j < 2) ? raw[c][hp].x : raw[c][hp].y;
+          const uint32_t two = (word >> (16 * (j & 1))) & 0xffffu;
+          v[(hp * 2 + 0) * 3 + c] = (float)(two & 0xffu) / 255.0f;
+          v[(hp * 2 + 1) * 3 + c] = (float)(two >> 8) / 255.0f;
+        }
+      uint4 o0, o1;
+      o0.x = pack_bf16x2(v[0], v[1]);
+      o0.y = pack_bf16x2(v[2], v[3]);
+      o0.z = pack_bf16x2(v[4], v[5]);
+      o0.w = pack_bf16x2(v[6], v[7]);
+      o1.x = pack_bf16x2(v[8], v[9]);
+      o1.y = pack_bf16x2(v[10], v[11]);
+      o1.z = 0u;
+      o1.w = 0u;
+      dst[2 * j] = o0;
+      dst[2 * j + 1] = o1;
+    }
   }
 }
 
@@ -163,50 +208,67 @@ __global__ void nhwc_bf16_to_nchw_f32_kernel(const bf16* __restrict__ in, float*
 
 // HRNet fuse for the highest-resolution branch (no conv lands on it): out = relu(pre + sum_i upsample(up_i))
 // (HRnet.py:254-263 with i == 0); thread = (pixel, 8-channel group)
-__global__ void fuse_add_kernel(const FuseAddParams p) {
+__global__ void __launch_bounds__(256) fuse_add_kernel(const FuseAddParams p) {
   pdl_launch_dependents();
   pdl_wait();
   const int C8 = p.C >> 3;
   const size_t total = (size_t)p.B * p.H * p.W * C8;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % C8);
-    const size_t pix = i / C8;
-    const int w = (int)(pix % p.W);
-    const int h = (int)((pix / p.W) % p.H);
-    const int n = (int)(pix / ((size_t)p.W * p.H));
-    float v[8];
-    {
-      const uint4 t = __ldg(reinterpret_cast<const uint4*>(p.pre) + i);
-      const uint32_t xs[4] = {t.x, t.y, t.z, t.w};
+  const size_t nthr = (size_t)gridDim.x * blockDim.x;
+  constexpr int U = 4;  // independent 16-byte loads in flight per thread and operand (the loop is latency-bound otherwise)
+  for (size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i0 < total; i0 += U * nthr) {
+    uint4 t[U][4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        v[2 * k] = bf16lo_to_f32(xs[k]);
-        v[2 * k + 1] = bf16hi_to_f32(xs[k]);
+    for (int u = 0; u < U; ++u) {
+      const size_t i = i0 + u * nthr;
+      if (i >= total) continue;
+      const int cg = (int)(i % C8);
+      const size_t pix = i / C8;
+      const int w = (int)(pix % p.W);
+      const int h = (int)((pix / p.W) % p.H);
+      const int n = (int)(pix / ((size_t)p.W * p.H));
+      t[u][0] = __ldg(reinterpret_cast<const uint4*>(p.pre) + i);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        if (p.up[a] == nullptr) continue;
+        const int sh = p.up_shift[a];
+        const size_t upix = ((size_t)n * (p.H >> sh) + (h >> sh)) * (p.W >> sh) + (w >> sh);
+        t[u][1 + a] = __ldg(reinterpret_cast<const uint4*>(p.up[a]) + upix * C8 + cg);
       }
     }
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      if (p.up[a] == nullptr) continue;
-      const int sh = p.up_shift[a];
-      const size_t upix = ((size_t)n * (p.H >> sh) + (h >> sh)) * (p.W >> sh) + (w >> sh);
-      const uint4 t = __ldg(reinterpret_cast<const uint4*>(p.up[a]) + upix * C8 + cg);
-      const uint32_t xs[4] = {t.x, t.y, t.z, t.w};
+    for (int u = 0; u < U; ++u) {
+      const size_t i = i0 + u * nthr;
+      if (i >= total) continue;
+      float v[8];
+      {
+        const uint32_t xs[4] = {t[u][0].x, t[u][0].y, t[u][0].z, t[u][0].w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        v[2 * k] += bf16lo_to_f32(xs[k]);
-        v[2 * k + 1] += bf16hi_to_f32(xs[k]);
+        for (int k = 0; k < 4; ++k) {
+          v[2 * k] = bf16lo_to_f32(xs[k]);
+          v[2 * k + 1] = bf16hi_to_f32(xs[k]);
+        }
       }
-    }
-    if (p.relu) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+      for (int a = 0; a < 3; ++a) {
+        if (p.up[a] == nullptr) continue;
+        const uint32_t xs[4] = {t[u][1 + a].x, t[u][1 + a].y, t[u][1 + a].z, t[u][1 + a].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          v[2 * k] += bf16lo_to_f32(xs[k]);
+          v[2 * k + 1] += bf16hi_to_f32(xs[k]);
+        }
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+      }
+      uint4 o;
+      o.x = pack_bf16x2(v[0], v[1]);
+      o.y = pack_bf16x2(v[2], v[3]);
+      o.z = pack_bf16x2(v[4], v[5]);
+      o.w = pack_bf16x2(v[6], v[7]);
+      reinterpret_cast<uint4*>(p.out)[i] = o;
     }
-    uint4 o;
-    o.x = pack_bf16x2(v[0], v[1]);
-    o.y = pack_bf16x2(v[2], v[3]);
-    o.z = pack_bf16x2(v[4], v[5]);
-    o.w = pack_bf16x2(v[6], v[7]);
-    reinterpret_cast<uint4*>(p.out)[i] = o;
   }
 }
 
@@ -229,7 +291,13 @@ int launch_pack_input_s2d_u8(const uint8_t* x, void* out, int B, int H, int W, c
   const size_t total = (size_t)B * (H / 2) * (W / 2);
   const int threads = 256;
   const int blocks = (int)std::min<size_t>((total + threads - 1) / threads, 148 * 16);
-  pack_input_s2d_u8_kernel<<<blocks, threads, 0, s>>>(x, reinterpret_cast<uint4*>(out), B, H, W, out_pitch, out_off);
+  if (W % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 7u) == 0) {
+    const size_t total4 = total / 4;
+    const int blocks4 = (int)std::min<size_t>((total4 + threads - 1) / threads, 148 * 32);
+    pack_input_s2d_u8x4_kernel<<<blocks4, threads, 0, s>>>(x, reinterpret_cast<uint4*>(out), B, H, W, out_pitch, out_off);
+  } else {
+    pack_input_s2d_u8_kernel<<<blocks, threads, 0, s>>>(x, reinterpret_cast<uint4*>(out), B, H, W, out_pitch, out_off);
+  }
   count_launch();
   HRP_CUDA_CHECK(cudaGetLastError());
   return HRP_OK;
