@@ -115,3 +115,53 @@ class HostPipeline:
                 h.copy_(o, non_blocking=True)
             main.synchronize()
             yield host_out
+
+
+class EvalPipeline:
+    """The body of the reference's evaluation loop (scripts/test.py:76-182 `farward_loss` + :199-232 `test`) with every
+    stage on the GPU: decoded frames + boxes -> crop / intrinsics / k_value kernel (row f1) -> network forward ->
+    metric kernels (row f2) -> device-resident accumulation; only `summary()` reads anything back.
+
+        pipe = EvalPipeline(model, robot, reference_keypoint_id)
+        for frames, bbox, K_frame, k_bbox, gt in loader:      # pinned host tensors
+            pipe.step(frames, bbox, K_frame, k_bbox, gt["keypoints_3d"], gt["keypoints_2d_original"], gt["jointpose"])
+        print(pipe.summary())                                  # summary_add_pck + the scalar means test.py logs
+
+    `K_original` of the metrics is `K_frame` (scripts/test.py:88,163); dataset decoding, BPnP pseudo ground truth for real
+    images and visualisation stay with the reference."""
+
+    def __init__(self, model, robot, reference_keypoint_id: int, resize_hw=(256, 256)):
+        from .metrics import MetricAccumulator
+        self.model, self.robot, self.ref_id, self.resize_hw = model, robot, int(reference_keypoint_id), resize_hw
+        self.acc = MetricAccumulator()
+        self.joint_err, self.depth_err, self.rel_err = [], [], []
+        self.last = None
+
+    def step(self, frames, bbox, K_frame, k_bbox, gt_keypoints3d, gt_keypoints2d, gt_joint):
+        from .metrics import compute_metrics_batch
+        from .preprocess import crop_resize_batch
+        dev = torch.device("cuda", torch.cuda.current_device())
+        up = lambda t: torch.as_tensor(t).to(dev, non_blocking=True)
+        frames, K_frame, k_bbox = up(frames), up(K_frame), up(k_bbox)
+        images, K, k_values = crop_resize_batch(frames, torch.as_tensor(bbox), K_frame, self.resize_hw, k_bbox=k_bbox)
+        outs = self.model(images, images, k_values, K)
+        pose, rot, trans = outs[0], outs[1], outs[2]
+        res = compute_metrics_batch(self.robot, up(gt_keypoints3d), up(gt_keypoints2d), K_frame.float(), up(gt_joint),
+                                    pred_joint=pose, pred_rot=rot, pred_trans=trans, pred_depth=None, pred_xy=None,
+                                    pred_xyz_integral=None, reference_keypoint_id=self.ref_id)
+        self.acc.add(res)
+        self.joint_err.append(res[5])
+        self.depth_err.append(res[6])
+        self.rel_err.append(res[7])
+        self.last = {"images": images, "K": K, "k_values": k_values, "outputs": outs, "metrics": res}
+        return res
+
+    def summary(self) -> dict:
+        s = self.acc.summary()
+        s_rel = self.acc.summary_relative()
+        s["Relative_ADD/AUC"] = s_rel["ADD/AUC"]
+        cat = lambda v: torch.cat([x.reshape(-1) for x in v])
+        s["Joint_l1_error/mean_deg"] = float(cat(self.joint_err).mean()) / 3.141592653589793 * 180.0  # test.py:238
+        s["Depth_l1_error/mean_m"] = float(cat(self.depth_err).mean())                                # test.py:239
+        s["Relative_l1_error/mean_m"] = float(cat(self.rel_err).mean())                               # test.py:241
+        return s

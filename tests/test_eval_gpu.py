@@ -138,3 +138,97 @@ def test_metrics_summary_vs_reference_golden(rt, hrp_lib):
     for k, v in o2.items():
         assert s2[k] == pytest.approx(float(v), rel=1e-6 if k.endswith("mean") else 1e-12, abs=1e-15), k
     assert s2["ADD/median"] == float(o2["ADD/median"]) and s2["ADD_2D/median"] == float(o2["ADD_2D/median"])
+
+
+def test_eval_loop_frames_to_summary_vs_oracle_chain(hrp_lib):
+    """System parity of the widened path: frames + boxes -> crop -> network -> metrics -> summary on the GPU against the
+    same chain built from the CPU oracles (crop oracle -> fp32 reference forward -> metrics oracle).  The crop is exact.
+    The network is bf16 against fp32 and these inputs are image-like (constant padding bars, smooth gradients), where
+    bf16 rounding errors are spatially correlated and do not average out in the pooled features the way they do on the
+    config's U[0,1) noise inputs: PyTorch's own autocast-bf16 forward of the reference network is 2-15 mm / 0.4-3 px off
+    the fp32 forward here (vs 0.2-0.5 mm / < 0.1 px on noise).  The bars are therefore the north-star ones (1 mm, 0.5 px,
+    1e-2 rad) OR the torch-autocast-bf16 floor of the same chain, whichever is larger -- both numbers are logged."""
+    from horopose_b200 import arch, synth
+    from horopose_b200.models import get_rootNetwithRegInt_model
+    from horopose_b200.pipeline import EvalPipeline
+    from horopose_b200.robot import URDFRobot
+    from oracle import eval_oracle as EO
+    from oracle import horopose_oracle as O
+    rt, B = "panda", 6
+    ref_id = arch.ROBOTS[rt][2]
+    frames, boxes, Kf, k_bbox = synth.crop_inputs(B, seed=5)
+    # k = f * 1000 / side (scripts/test.py:141-152): boxes of 400..640 px keep the synthetic depth (gamma ~ 2) * k / 1000
+    # at 2-3 m (a 60-pixel box would put the robot 20 m away)
+    k_bbox = np.stack([np.array([0.0, 0.0, 400.0 + 40.0 * b, 400.0 + 40.0 * b], dtype=np.float32) for b in range(B)])
+    q, rot, trans, gt_q, gt3, gt2, _ = synth.metric_inputs(rt, B)
+    args = dict(backbone_name="resnet50", rootnet_backbone_name="hrnet32", n_iter=4, other_image_size=256.0,
+                bbox_3d_shape=[1300, 1300, 1300], reference_keypoint_id=ref_id, fix_root=True, rotation_dim=6)
+    model = get_rootNetwithRegInt_model({"robot_type": rt, "pose_params": None, "cam_params": np.eye(4),
+                                         "init_pose_from_mean": True}, args)
+    sd = synth.full_state_dict(rt)
+    model.load_state_dict(sd, strict=True)
+    pipe = EvalPipeline(model, URDFRobot(rt), ref_id)
+    for lo, hi in ((0, 4), (4, 6)):  # two ragged batches through the accumulator
+        pipe.step(torch.from_numpy(frames[lo:hi]), torch.from_numpy(boxes[lo:hi]), torch.from_numpy(Kf[lo:hi]),
+                  torch.from_numpy(k_bbox[lo:hi]), gt3[lo:hi], gt2[lo:hi], gt_q[lo:hi])
+    got = pipe.summary()
+    e3 = torch.cat(pipe.acc.dis3d).cpu().numpy()
+    e2 = torch.cat(pipe.acc.dis2d).cpu().numpy()
+    ej = torch.cat(pipe.joint_err).cpu().numpy()
+    # oracle chain (fp32) and the torch-autocast-bf16 evaluation of the same chain
+    crops = [EO.crop_resize(frames[b], boxes[b], Kf[b]) for b in range(B)]
+    x = torch.stack([c[0] for c in crops]).float() / 255.0
+    Kc = torch.stack([c[1] for c in crops])
+    Kf32 = torch.as_tensor(Kf).float()
+    kv = EO.k_value(Kf32[:, 0, 0], Kf32[:, 1, 1], k_bbox)
+    orob = O.OracleRobot(rt, str(synth.URDF_PATHS[rt]))
+
+    def chain_metrics(outs):
+        kp = orob.get_keypoints_root(outs[0], outs[1], outs[2], root=ref_id)
+        return EO.metrics_batch(kp.numpy(), gt3.numpy(), gt2.numpy(), Kf32.numpy(), outs[0].numpy(), gt_q.numpy(), ref_id, True)
+
+    with torch.no_grad():
+        m = chain_metrics(O.full_forward(sd, orob, x, x, kv, Kc))
+        sd_cuda = {k_: v.cuda() for k_, v in sd.items()}
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            feat, x_out, heat = O.full_features(sd_cuda, x.cuda(), x.cuda())
+        mf = chain_metrics(O.full_head(sd, orob, feat.float().cpu(), x_out.float().cpu(), heat.float().cpu(), kv, Kc))
+    want = EO.summary_add_pck(m["error3d"], m["error2d"])
+    ok = ~np.isnan(m["error2d"])
+    checks = [("error3d [m]", e3, m["error3d"], mf["error3d"], 1e-3),
+              ("error2d [px]", e2[ok], m["error2d"][ok], mf["error2d"][ok], 0.5),
+              ("mean_jointerror [rad]", ej, m["mean_jointerror"], mf["mean_jointerror"], 1e-2)]
+    out_dir = ROOT / "gpurun_out"
+    out_dir.mkdir(exist_ok=True)
+    with open(out_dir / "model_parity.txt", "a") as f:
+        f.write("[eval loop] frames -> crop -> network -> metrics, image-like crops, panda B=6\n")
+        for name, a, r, fl, bar in checks:
+            err, floor = float(np.abs(a - r).max()), float(np.abs(fl - r).max())
+            f.write(f"  {name:22s} max|err| vs fp32 oracle chain {err:.3e}  (north-star bar {bar:.1e}; "
+                    f"torch-autocast-bf16 floor {floor:.3e})\n")
+    for name, a, r, fl, bar in checks:
+        err, floor = float(np.abs(a - r).max()), float(np.abs(fl - r).max())
+        assert err < max(bar, 1.5 * floor), (name, err, bar, floor)
+    tol3 = max(1e-3, 1.5 * float(np.abs(mf["error3d"] - m["error3d"]).max()))
+    assert abs(got["ADD/mean"] - float(want["ADD/mean"])) < tol3
+    assert abs(got["Depth_l1_error/mean_m"] - float(m["error_depth"].mean())) < tol3
+    assert set(want) <= set(got)
+
+
+def test_uint8_forward_equals_float_forward(hrp_lib):
+    """`model(u8)` must equal `model(u8.float() / 255)` bit for bit: the fused `/255` 4-pixel packing kernel against
+    the fp32 packing kernel (same fp32 quotient, same bf16 rounding)."""
+    from horopose_b200 import synth
+    from horopose_b200.models import get_rootNetwithRegInt_model
+    x_reg, x_root, k, K = synth.inputs(3, seed=17)
+    u8 = lambda t: (t * 255.0).round().clamp(0, 255).to(torch.uint8).cuda()
+    a, b = u8(x_reg), u8(x_root)
+    args = dict(backbone_name="resnet50", rootnet_backbone_name="hrnet32", n_iter=4, other_image_size=256.0,
+                bbox_3d_shape=[1300, 1300, 1300], reference_keypoint_id=3, fix_root=True, rotation_dim=6)
+    model = get_rootNetwithRegInt_model({"robot_type": "panda", "pose_params": None, "cam_params": np.eye(4),
+                                         "init_pose_from_mean": True}, args)
+    model.load_state_dict(synth.full_state_dict("panda"), strict=True)
+    o8 = model(a, b, k.cuda(), K.cuda())
+    of = model(a.float() / 255.0, b.float() / 255.0, k.cuda(), K.cuda())
+    for x, y in zip(o8, of):
+        assert torch.equal(x, y)
