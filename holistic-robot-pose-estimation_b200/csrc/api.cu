@@ -339,6 +339,25 @@ int hrp_metrics_summary(const float* dis3d, const float* dis2d, int64_t n, doubl
   return launch_metrics_summary(p, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int hrp_pnp(const float* pts2d, const float* pts3d, const float* K, int32_t K_batched, int32_t B, int32_t N, float* pose6,
+            float* rot6d, void* stream) {
+  HRP_REQUIRE(pts2d != nullptr && pts3d != nullptr && K != nullptr && pose6 != nullptr, "null argument");
+  HRP_REQUIRE(B > 0, "empty batch");
+  HRP_REQUIRE(N >= 6 && N <= 64, "the linear initialisation needs 6..64 points");
+  PnpParams p;
+  p.B = B;
+  p.N = N;
+  p.K_batched = K_batched;
+  p.max_iters = 30;
+  p.pts2d = pts2d;
+  p.pts3d = pts3d;
+  p.K = K;
+  p.pose6 = pose6;
+  p.rot6d = rot6d;
+  p.starts = nullptr;
+  return launch_pnp(p, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int hrp_project(const float* K, const float* pts, float* uv, int32_t B, int32_t N, void* stream) {
   return launch_project(K, pts, uv, B, N, reinterpret_cast<cudaStream_t>(stream));
 }

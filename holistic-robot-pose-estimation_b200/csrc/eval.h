@@ -35,4 +35,12 @@ struct SummaryParams {
 };
 int launch_metrics_summary(const SummaryParams& p, cudaStream_t s);
 
+struct PnpParams {
+  int B, N, K_batched, max_iters;
+  const float *pts2d, *pts3d, *K;
+  float *pose6, *rot6d;
+  const double* starts;  // device [32][9] start rotations (filled by launch_pnp)
+};
+int launch_pnp(const PnpParams& p, cudaStream_t s);
+
 }  // namespace hrp

@@ -224,3 +224,22 @@ def metric_inputs(robot_type: str, batch: int, seed: int = 6):
     gt2 = torch.stack([range_uniform("m_u_" + robot_type, (batch, nkpt), -60.0, 700.0, seed),
                        range_uniform("m_v_" + robot_type, (batch, nkpt), -60.0, 540.0, seed)], dim=2)
     return q, rot, trans, gt_q, gt3, gt2, K
+
+
+def pnp_inputs(robot_type: str, batch: int, seed: int = 8, noise_px: float = 0.5):
+    """2-D / 3-D correspondences for the PnP kernel: base-frame FK keypoints of random joint states (computed by the
+    caller from `q`), a random camera pose in front of the camera, pixel noise on the projections.
+    Returns q (B,dof), rvec (B,3) angle-axis with |r| in [0.1, 3], t (B,3), K (3,3), noise (B,nkpt,2)."""
+    from .tables import JOINT_BOUNDS
+    b = np.asarray(JOINT_BOUNDS[robot_type], dtype=np.float32)
+    nkpt = {"panda": 7, "kuka": 8, "baxter": 17}[robot_type]
+    u = uniform01("pnp_q_" + robot_type, batch * b.shape[0], seed).reshape(batch, -1)
+    q = torch.from_numpy(u * (b[:, 1] - b[:, 0]) + b[:, 0])
+    d = sym_uniform("pnp_dir_" + robot_type, (batch, 3), 1.0, seed)
+    d = d / d.norm(dim=1, keepdim=True).clamp_min(1e-3)
+    rvec = d * range_uniform("pnp_ang_" + robot_type, (batch, 1), 0.1, 3.0, seed)
+    t = torch.cat([sym_uniform("pnp_txy_" + robot_type, (batch, 2), 0.2, seed),
+                   range_uniform("pnp_tz_" + robot_type, (batch, 1), 1.2, 2.5, seed)], dim=1)
+    K = torch.tensor([[615.0, 0.0, 320.0], [0.0, 615.5, 240.0], [0.0, 0.0, 1.0]])
+    noise = sym_uniform("pnp_noise_" + robot_type, (batch, nkpt, 2), noise_px, seed)
+    return q, rvec, t, K, noise

@@ -219,6 +219,17 @@ int hrp_metrics_batch(const hrp_metrics_args* args, void* stream);
 int hrp_metrics_summary(const float* dis3d, const float* dis2d, int64_t n, double* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Batched PnP.
+ * Replaces BPnP_m3d.forward (lib/utils/BPnP.py:114-152: per sample cv2.solvePnP EPNP -> ITERATIVE refinement), the
+ * ground-truth rotation source of the evaluation loop on real datasets (scripts/test.py:120-125), plus the
+ * angle_axis_to_rotation_matrix -> rotmat_to_rot6d conversion applied to its result (lib/utils/geometries.py:164-232,
+ * 117-132).  pose6 = (angle-axis, translation); N >= 6 non-coplanar points.  Forward only.
+ * ------------------------------------------------------------------------------------------------ */
+int hrp_pnp(const float* pts2d /* (B,N,2) px */, const float* pts3d /* (B,N,3) */, const float* K /* (3,3) | (B,3,3) */,
+            int32_t K_batched, int32_t B, int32_t N, float* pose6 /* (B,6) */, float* rot6d /* (B,6) or NULL */,
+            void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Whole-network inference.
  * Replaces RootNetwithRegInt.forward (lib/models/full_net.py:239-397; construction :38-192 and
  * get_rootNetwithRegInt_model :401-435 incl. the backbone.* -> rootnet_backbone.* remap :423-427) and

@@ -3,11 +3,14 @@
   f1  input pipeline: frame + bbox -> square crop -> bilinear resize to 256x256 -> uint8 CHW + updated intrinsics
       + the k_value scalar the depth head consumes.
   f2  evaluation metrics: per-batch ADD / 2-D error / joint / depth errors and the ADD / PCK AUC summary.
+  f3  batched PnP: the reference's BPnP_m3d forward, whose arithmetic is OpenCV's cv2.solvePnP (opencv-python, a
+      dependency of the reference that is not vendored in /root/reference; 4.13.0 in this image, the reference pins
+      no version): EPnP start, Levenberg-Marquardt refinement of the pixel reprojection error.
 
 Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this module; the product path
 (horopose_b200.preprocess / horopose_b200.metrics -> libhrp_b200.so) never does.  Every function cites the
 reference lines it follows (paths relative to the reference root).  Pinned against the real reference by
-tests/golden/make_golden.py (fixtures tests/golden/crop_*.npz, metrics_*.npz; re-checked by
+tests/golden/make_golden.py (fixtures tests/golden/crop.npz, metrics_*.npz, pnp_*.npz; re-checked by
 tests/test_eval_oracle.py).
 
 Arithmetic notes that matter for parity:
@@ -152,3 +155,41 @@ def summary_add_pck(dis3d, dis2d) -> dict:
     for px in PCK_PX:
         out[f"PCK_{px}_pixel"] = np.mean(d2 <= px)
     return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# f3: batched PnP (the arithmetic lives in OpenCV, a dependency of the reference: opencv-python, cv2.solvePnP)
+# ------------------------------------------------------------------------------------------------------
+def pnp_m3d(pts2d, pts3d, K) -> torch.Tensor:
+    """BPnP.py:126-148 (`BPnP_m3d.forward`, ini_pose=None): per sample EPnP as the initial guess, then the iterative
+    (Levenberg-Marquardt) refinement with useExtrinsicGuess; returns (B,6) fp32 = (angle-axis, translation)."""
+    import cv2 as cv
+    pts2d, pts3d = torch.as_tensor(pts2d), torch.as_tensor(pts3d)
+    bs, n = pts2d.shape[:2]
+    K_np = np.array(torch.as_tensor(K).detach().cpu())
+    out = torch.zeros(bs, 6)
+    for i in range(bs):
+        p2 = np.ascontiguousarray(pts2d[i].detach().cpu()).reshape((n, 1, 2))
+        p3 = np.ascontiguousarray(pts3d[i].detach().cpu()).reshape((n, 3))
+        _, r0, t0 = cv.solvePnP(objectPoints=p3, imagePoints=p2, cameraMatrix=K_np, distCoeffs=None, flags=cv.SOLVEPNP_EPNP)
+        _, r, t = cv.solvePnP(objectPoints=p3, imagePoints=p2, cameraMatrix=K_np, distCoeffs=None,
+                              flags=cv.SOLVEPNP_ITERATIVE, useExtrinsicGuess=True, rvec=r0, tvec=t0)
+        out[i] = torch.cat((torch.tensor(r, dtype=torch.float).view(3), torch.tensor(t, dtype=torch.float).view(3)))
+    return out
+
+
+def angle_axis_to_rot6d(aa: torch.Tensor) -> torch.Tensor:
+    """geometries.py:164-232 (`angle_axis_to_rotation_matrix`, eps 1e-6, first-order branch for tiny angles) followed by
+    `rotmat_to_rot6d` (:117-132, first two rows) -- scripts/test.py:123-124."""
+    aa = torch.as_tensor(aa).float()
+    th2 = (aa * aa).sum(dim=1, keepdim=True)
+    th = torch.sqrt(th2)
+    w = aa / (th + 1e-6)
+    wx, wy, wz = w[:, 0:1], w[:, 1:2], w[:, 2:3]
+    c, s = torch.cos(th), torch.sin(th)
+    k1 = 1.0 - c
+    normal = torch.cat([c + wx * wx * k1, wx * wy * k1 - wz * s, wy * s + wx * wz * k1,
+                        wz * s + wx * wy * k1, c + wy * wy * k1, -wx * s + wy * wz * k1], dim=1)
+    one = torch.ones_like(th)
+    taylor = torch.cat([one, -aa[:, 2:3], aa[:, 1:2], aa[:, 2:3], one, -aa[:, 0:1]], dim=1)
+    return torch.where(th2 > 1e-6, normal, taylor)

@@ -241,6 +241,47 @@ def golden_metrics(ns, robot_type: str):
              **res)
 
 
+PNP_BATCH = 32
+
+
+def pnp_case(robot, robot_type: str, batch: int = PNP_BATCH):
+    """pts2d / pts3d of one PnP fixture from seeds: FK keypoints in the base frame (world_3d_pts of test.py:121), moved
+    by a seeded camera pose, projected with K, plus pixel noise.  `robot` needs get_keypoints_only_fk."""
+    q, rvec, t, K, noise = synth.pnp_inputs(robot_type, batch)
+    pts3d = robot.get_keypoints_only_fk(q).float().cpu()
+    th = rvec.norm(dim=1, keepdim=True)
+    k = rvec / th
+    Kx = torch.zeros(batch, 3, 3)
+    Kx[:, 0, 1], Kx[:, 0, 2], Kx[:, 1, 0], Kx[:, 1, 2], Kx[:, 2, 0], Kx[:, 2, 1] = -k[:, 2], k[:, 1], k[:, 2], -k[:, 0], -k[:, 1], k[:, 0]
+    R = torch.eye(3)[None] + torch.sin(th)[:, :, None] * Kx + (1 - torch.cos(th))[:, :, None] * (Kx @ Kx)
+    cam = pts3d @ R.transpose(1, 2) + t[:, None, :]
+    uvw = cam @ K.T
+    pts2d = uvw[:, :, :2] / uvw[:, :, 2:3] + noise
+    return pts2d.contiguous(), pts3d.contiguous(), K, rvec, t
+
+
+def golden_pnp(ns, robot_type: str):
+    """f3: the reference's BPnP_m3d.apply + angle_axis_to_rotation_matrix + rotmat_to_rot6d (scripts/test.py:121-124)."""
+    import types
+    if "utils.BPnP" not in sys.modules:
+        sys.modules.setdefault("kornia", types.ModuleType("kornia"))       # BPnP.py:6 (used by the backward only)
+        real_tensor = torch.tensor
+        torch.tensor = lambda *a, **k: real_tensor(*a, **{kk: v for kk, v in k.items() if kk != "device"})  # BPnP.py:2
+        try:
+            import utils.BPnP  # noqa: F401
+        finally:
+            torch.tensor = real_tensor
+    BP = sys.modules["utils.BPnP"]
+    robot = ns.urdf_robot.URDFRobot(robot_type)
+    pts2d, pts3d, K, rvec, t = pnp_case(robot, robot_type)
+    out = BP.BPnP_m3d.apply(pts2d, pts3d, K)
+    rot = ns.geometries.rotmat_to_rot6d(ns.geometries.angle_axis_to_rotation_matrix(out[:, 0:3])[:, :3, :3])
+    mine = EO.pnp_m3d(pts2d, pts3d, K)
+    assert torch.equal(mine, out), "oracle PnP differs from the reference"
+    assert torch.equal(EO.angle_axis_to_rot6d(out[:, :3]), rot), "oracle rot6d differs from the reference"
+    np.savez(GOLDEN / f"pnp_{robot_type}.npz", pose6=to_np(out), rot6d=to_np(rot), pts2d=to_np(pts2d), pts3d=to_np(pts3d))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--calibrate", action="store_true")
@@ -253,6 +294,7 @@ def main():
     golden_crop(ns)
     for r in ("panda", "kuka", "baxter"):
         golden_metrics(ns, r)
+        golden_pnp(ns, r)
     if args.only_eval:
         return
     golden_geometry(ns)

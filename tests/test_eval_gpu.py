@@ -232,3 +232,51 @@ def test_uint8_forward_equals_float_forward(hrp_lib):
     of = model(a.float() / 255.0, b.float() / 255.0, k.cuda(), K.cuda())
     for x, y in zip(o8, of):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("rt", ["panda", "kuka", "baxter"])
+def test_pnp_vs_reference_golden(rt, hrp_lib):
+    """f3: the GPU solver (DLT -> Gauss-Newton, fp64) against the reference's BPnP_m3d (cv2 EPnP -> LM): both reach the
+    same minimiser of the reprojection error; fp32 outputs within 1e-5 (rad / m), rot6d within 1e-5."""
+    from horopose_b200.pnp import BPnP_m3d, pnp_rot6d
+    g = np.load(GOLDEN / f"pnp_{rt}.npz")
+    K = torch.tensor([[615.0, 0.0, 320.0], [0.0, 615.5, 240.0], [0.0, 0.0, 1.0]]).cuda()
+    p2, p3 = torch.from_numpy(g["pts2d"]).cuda(), torch.from_numpy(g["pts3d"]).cuda()
+    out = BPnP_m3d.apply(p2, p3, K).cpu().numpy()
+    TOL = 1e-5
+    assert np.abs(out - g["pose6"]).max() < TOL, np.abs(out - g["pose6"]).max()
+    r6 = pnp_rot6d(p2, p3, K[None].repeat(p2.shape[0], 1, 1)).cpu().numpy()   # batched-K variant
+    assert np.abs(r6 - g["rot6d"]).max() < TOL, np.abs(r6 - g["rot6d"]).max()
+
+
+def test_pnp_recovers_exact_pose_and_rejects_bad_input(hrp_lib):
+    """Noise-free projections: the seeded pose comes back to fp32 round-off, including rotations close to pi."""
+    from horopose_b200 import synth
+    from horopose_b200.pnp import BPnP_m3d
+    from horopose_b200.robot import URDFRobot
+    B = 256
+    q, rvec, t, K, _ = synth.pnp_inputs("baxter", B, seed=21)
+    rvec[:8] = rvec[:8] / rvec[:8].norm(dim=1, keepdim=True) * 3.1405   # near pi
+    p3 = URDFRobot("baxter").get_keypoints_only_fk(q.cuda()).double().cpu()
+    th = rvec.double().norm(dim=1, keepdim=True)
+    k = rvec.double() / th
+    Kx = torch.zeros(B, 3, 3, dtype=torch.float64)
+    Kx[:, 0, 1], Kx[:, 0, 2], Kx[:, 1, 0], Kx[:, 1, 2], Kx[:, 2, 0], Kx[:, 2, 1] = -k[:, 2], k[:, 1], k[:, 2], -k[:, 0], -k[:, 1], k[:, 0]
+    R = torch.eye(3, dtype=torch.float64)[None] + torch.sin(th)[:, :, None] * Kx + (1 - torch.cos(th))[:, :, None] * (Kx @ Kx)
+    cam = p3 @ R.transpose(1, 2) + t.double()[:, None, :]
+    uvw = cam @ K.double().T
+    p2 = uvw[:, :, :2] / uvw[:, :, 2:3]
+    out = BPnP_m3d.apply(p2.float().cuda(), p3.float().cuda(), K.cuda()).cpu().double()
+    # compare as rotation matrices (angle-axis is double-valued at pi) and translations
+    th2 = out[:, :3].norm(dim=1, keepdim=True)
+    k2 = out[:, :3] / th2
+    Kx2 = torch.zeros(B, 3, 3, dtype=torch.float64)
+    Kx2[:, 0, 1], Kx2[:, 0, 2], Kx2[:, 1, 0], Kx2[:, 1, 2], Kx2[:, 2, 0], Kx2[:, 2, 1] = -k2[:, 2], k2[:, 1], k2[:, 2], -k2[:, 0], -k2[:, 1], k2[:, 0]
+    R2 = torch.eye(3, dtype=torch.float64)[None] + torch.sin(th2)[:, :, None] * Kx2 + (1 - torch.cos(th2))[:, :, None] * (Kx2 @ Kx2)
+    # inputs were rounded to fp32 (pixels ~1e-5 px, points ~1e-7 m): the recovered pose moves by ~1e-5 at most
+    assert float((R2 - R).abs().max()) < 5e-5, float((R2 - R).abs().max())
+    assert float((out[:, 3:] - t.double()).abs().max()) < 5e-5, float((out[:, 3:] - t.double()).abs().max())
+    with pytest.raises(Exception):
+        BPnP_m3d.apply(p2[:, :5].float().cuda(), p3[:, :5].float().cuda(), K.cuda())   # < 6 points
+    with pytest.raises(NotImplementedError):
+        BPnP_m3d.apply(p2.float().cuda().requires_grad_(), p3.float().cuda(), K.cuda())

@@ -77,3 +77,17 @@ def test_shims_refuse_cpu_tensors():
         preprocess.crop_resize_batch(torch.from_numpy(frames), torch.from_numpy(boxes), torch.from_numpy(K))
     with pytest.raises(HrpError):
         metrics.summary_add_pck({"dis3d": torch.zeros(4), "dis2d": torch.zeros(4)})
+
+
+@pytest.mark.parametrize("rt", ["panda", "kuka", "baxter"])
+def test_pnp_oracle_matches_reference(rt):
+    """f3: cv2.solvePnP (EPnP -> iterative) as the reference's BPnP_m3d.forward calls it, vs the fixture written by the
+    reference itself; plus the property that the noisy correspondences recover the seeded pose to ~1e-2."""
+    cv2 = pytest.importorskip("cv2")  # noqa: F841  (the reference's own dependency; present in this image)
+    g = np.load(GOLDEN / f"pnp_{rt}.npz")
+    K = torch.tensor([[615.0, 0.0, 320.0], [0.0, 615.5, 240.0], [0.0, 0.0, 1.0]])
+    out = EO.pnp_m3d(torch.from_numpy(g["pts2d"]), torch.from_numpy(g["pts3d"]), K)
+    np.testing.assert_allclose(out.numpy(), g["pose6"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(EO.angle_axis_to_rot6d(out[:, :3]).numpy(), g["rot6d"], rtol=0, atol=2e-6)
+    q, rvec, t, _, _ = synth.pnp_inputs(rt, 32)
+    assert np.abs(g["pose6"][:, 3:] - t.numpy()).max() < 0.1       # 0.5 px noise on 7-17 points at 1-2.5 m
