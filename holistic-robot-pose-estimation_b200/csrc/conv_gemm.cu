@@ -1008,7 +1008,21 @@ int conv_geometry(const ConvLayerDesc& d, ConvParams* pp) {
   // N tile
   // N tile: 256 wide for K-heavy (tensor-bound) layers; 128 for short-K layers, whose time is the epilogue and
   // the output stream: 4 CTAs/SM fit in TMEM instead of 2 and the (small) A tile is re-read from L2
-  const int max_n = ((p.ktot <= 256 || d.has_residual) && p.Cout > 128 && p.Cout % 128 == 0) ? 128 : 256;
+  int max_n = ((p.ktot <= 256 || d.has_residual) && p.Cout > 128 && p.Cout % 128 == 0) ? 128 : 256;
+  // Small-M problems (batch-1 latency: an 8x8 or 16x16 layer is 1-2 M tiles): with 256-wide N tiles one or two CTAs
+  // stream the whole weight matrix through one SM's TMA (1.2 MB for 256 -> 256 k3: ~20 us).  Narrower N tiles spread the
+  // weight read and the MMAs over more SMs; the A tile they all re-read is tiny.  Only for Cout >= 128 (the 32 / 64
+  // channel layers keep n_tile == Cout, which the halo kernel needs) and only while the grid stays below ~1/3 of the
+  // GPU, so throughput batches are untouched.  The packed weight layout does not depend on n_tile (cout_pad == Cout).
+  {
+    static const bool small_m = !(getenv("HRP_CONV_SMALLM") != nullptr && getenv("HRP_CONV_SMALLM")[0] == '0');
+    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.nphase;
+    // (measured, Panda full model, p50: batch 1 1.99 -> 1.80 ms, batch 4 2.12 -> 1.96 ms; at 16 images a 48-CTA target
+    //  was 2.5 % slower than no splitting, hence the cap on the M-tile count and the 24-CTA target)
+    while (small_m && p.Cout >= 128 && max_n > 32 && p.Cout % (max_n / 2) == 0 && m_tiles <= 4 &&
+           m_tiles * ((p.Cout + max_n - 1) / max_n) < 24)
+      max_n /= 2;
+  }
   const int n_tiles = (p.Cout + max_n - 1) / max_n;
   p.n_tile = (((p.Cout + n_tiles - 1) / n_tiles) + 31) / 32 * 32;
   p.cout_pad = n_tiles * p.n_tile;
