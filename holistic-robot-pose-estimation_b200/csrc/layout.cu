@@ -93,9 +93,11 @@ __global__ void __launch_bounds__(256) pack_input_s2d_u8x4_kernel(const uint8_t*
   const int Wq = W >> 3, Hs = H >> 1;
   const size_t total = (size_t)B * Hs * Wq;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int wq = (int)(i % Wq);
-    const int hs = (int)((i / Wq) % Hs);
-    const int n = (int)(i / ((size_t)Wq * Hs));
+    const unsigned iu = (unsigned)i;  // total < 2^31: 32-bit div / mod
+    const int wq = (int)(iu % (unsigned)Wq);
+    const unsigned rowi = iu / (unsigned)Wq;
+    const int hs = (int)(rowi % (unsigned)Hs);
+    const int n = (int)(rowi / (unsigned)Hs);
     uint2 raw[3][2];
 #pragma unroll
     for (int c = 0; c < 3; ++c)
@@ -138,11 +140,13 @@ __global__ void maxpool3x3s2_kernel(const uint4* __restrict__ in, uint4* __restr
   const int Ho = H >> 1, Wo = W >> 1;
   const size_t total = (size_t)B * Ho * Wo * C8;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % C8);
-    size_t pix = i / C8;
-    const int wo = (int)(pix % Wo);
-    const int ho = (int)((pix / Wo) % Ho);
-    const int n = (int)(pix / ((size_t)Wo * Ho));
+    const unsigned iu = (unsigned)i;  // total < 2^31 (checked by the launcher): 32-bit div / mod
+    const int cg = (int)(iu % (unsigned)C8);
+    const unsigned pix = iu / (unsigned)C8;
+    const int wo = (int)(pix % (unsigned)Wo);
+    const unsigned rowi = pix / (unsigned)Wo;
+    const int ho = (int)(rowi % (unsigned)Ho);
+    const int n = (int)(rowi / (unsigned)Ho);
     float m[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
@@ -208,67 +212,54 @@ __global__ void nhwc_bf16_to_nchw_f32_kernel(const bf16* __restrict__ in, float*
 
 // HRNet fuse for the highest-resolution branch (no conv lands on it): out = relu(pre + sum_i upsample(up_i))
 // (HRnet.py:254-263 with i == 0); thread = (pixel, 8-channel group)
-__global__ void __launch_bounds__(256) fuse_add_kernel(const FuseAddParams p) {
+__global__ void fuse_add_kernel(const FuseAddParams p) {
   pdl_launch_dependents();
   pdl_wait();
   const int C8 = p.C >> 3;
   const size_t total = (size_t)p.B * p.H * p.W * C8;
-  const size_t nthr = (size_t)gridDim.x * blockDim.x;
-  constexpr int U = 4;  // independent 16-byte loads in flight per thread and operand (the loop is latency-bound otherwise)
-  for (size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i0 < total; i0 += U * nthr) {
-    uint4 t[U][4];
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    // 32-bit index arithmetic (the launcher guarantees total < 2^31): 64-bit div / mod cost ~100 instructions each and
+    // made this streaming kernel ALU-bound
+    const unsigned iu = (unsigned)i;
+    const unsigned cg = iu % (unsigned)C8;
+    const unsigned pix = iu / (unsigned)C8;
+    const unsigned w = pix % (unsigned)p.W;
+    const unsigned rowi = pix / (unsigned)p.W;
+    const unsigned h = rowi % (unsigned)p.H;
+    const unsigned n = rowi / (unsigned)p.H;
+    float v[8];
+    {
+      const uint4 t = __ldg(reinterpret_cast<const uint4*>(p.pre) + i);
+      const uint32_t xs[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const size_t i = i0 + u * nthr;
-      if (i >= total) continue;
-      const int cg = (int)(i % C8);
-      const size_t pix = i / C8;
-      const int w = (int)(pix % p.W);
-      const int h = (int)((pix / p.W) % p.H);
-      const int n = (int)(pix / ((size_t)p.W * p.H));
-      t[u][0] = __ldg(reinterpret_cast<const uint4*>(p.pre) + i);
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        if (p.up[a] == nullptr) continue;
-        const int sh = p.up_shift[a];
-        const size_t upix = ((size_t)n * (p.H >> sh) + (h >> sh)) * (p.W >> sh) + (w >> sh);
-        t[u][1 + a] = __ldg(reinterpret_cast<const uint4*>(p.up[a]) + upix * C8 + cg);
+      for (int k = 0; k < 4; ++k) {
+        v[2 * k] = bf16lo_to_f32(xs[k]);
+        v[2 * k + 1] = bf16hi_to_f32(xs[k]);
       }
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const size_t i = i0 + u * nthr;
-      if (i >= total) continue;
-      float v[8];
-      {
-        const uint32_t xs[4] = {t[u][0].x, t[u][0].y, t[u][0].z, t[u][0].w};
+    for (int a = 0; a < 3; ++a) {
+      if (p.up[a] == nullptr) continue;
+      const int sh = p.up_shift[a];
+      const size_t upix = ((size_t)n * (p.H >> sh) + (h >> sh)) * (p.W >> sh) + (w >> sh);
+      const uint4 t = __ldg(reinterpret_cast<const uint4*>(p.up[a]) + upix * C8 + cg);
+      const uint32_t xs[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          v[2 * k] = bf16lo_to_f32(xs[k]);
-          v[2 * k + 1] = bf16hi_to_f32(xs[k]);
-        }
+      for (int k = 0; k < 4; ++k) {
+        v[2 * k] += bf16lo_to_f32(xs[k]);
+        v[2 * k + 1] += bf16hi_to_f32(xs[k]);
       }
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        if (p.up[a] == nullptr) continue;
-        const uint32_t xs[4] = {t[u][1 + a].x, t[u][1 + a].y, t[u][1 + a].z, t[u][1 + a].w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          v[2 * k] += bf16lo_to_f32(xs[k]);
-          v[2 * k + 1] += bf16hi_to_f32(xs[k]);
-        }
-      }
-      if (p.relu) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
-      }
-      uint4 o;
-      o.x = pack_bf16x2(v[0], v[1]);
-      o.y = pack_bf16x2(v[2], v[3]);
-      o.z = pack_bf16x2(v[4], v[5]);
-      o.w = pack_bf16x2(v[6], v[7]);
-      reinterpret_cast<uint4*>(p.out)[i] = o;
     }
+    if (p.relu) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]);
+    o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]);
+    o.w = pack_bf16x2(v[6], v[7]);
+    reinterpret_cast<uint4*>(p.out)[i] = o;
   }
 }
 
@@ -291,7 +282,7 @@ int launch_pack_input_s2d_u8(const uint8_t* x, void* out, int B, int H, int W, c
   const size_t total = (size_t)B * (H / 2) * (W / 2);
   const int threads = 256;
   const int blocks = (int)std::min<size_t>((total + threads - 1) / threads, 148 * 16);
-  if (W % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 7u) == 0) {
+  if (W % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 7u) == 0 && total < (1ull << 31)) {
     const size_t total4 = total / 4;
     const int blocks4 = (int)std::min<size_t>((total4 + threads - 1) / threads, 148 * 32);
     pack_input_s2d_u8x4_kernel<<<blocks4, threads, 0, s>>>(x, reinterpret_cast<uint4*>(out), B, H, W, out_pitch, out_off);
@@ -306,6 +297,7 @@ int launch_pack_input_s2d_u8(const uint8_t* x, void* out, int B, int H, int W, c
 int launch_maxpool3x3s2(const void* in, void* out, int B, int H, int W, int C, cudaStream_t s) {
   HRP_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool needs C%8==0 and even H,W");
   const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 8);
+  HRP_REQUIRE(total < (1ull << 31), "maxpool: tensor too large for 32-bit indexing");
   const int threads = 256;
   const int blocks = (int)std::min<size_t>((total + threads - 1) / threads, 148 * 16);
   launch_ex(maxpool3x3s2_kernel, dim3(blocks), dim3(threads), 0, s, reinterpret_cast<const uint4*>(in),
@@ -334,6 +326,7 @@ int launch_nhwc_bf16_to_nchw_f32(const void* in, float* out, int B, int C, int H
 int launch_fuse_add(const FuseAddParams& p, cudaStream_t s) {
   HRP_REQUIRE(p.C % 8 == 0 && p.pre != nullptr && p.out != nullptr, "fuse_add: bad arguments");
   const size_t total = (size_t)p.B * p.H * p.W * (p.C / 8);
+  HRP_REQUIRE(total < (1ull << 31), "fuse_add: tensor too large for 32-bit indexing");
   const int threads = 256;
   const int blocks = (int)std::min<size_t>((total + threads - 1) / threads, 148 * 16);
   launch_ex(fuse_add_kernel, dim3(blocks), dim3(threads), 0, s, p);
