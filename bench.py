@@ -331,6 +331,16 @@ def main():
                      "frac": head_gbs / peaks["hbm"], "traffic": None, "kernel": "hrp::head_kernel",
                      "note": f"{HEATMAP_BYTES_PER_IMAGE[robot]} B/image x {hb} images per launch "
                              f"({hm.numel() * 2 / 1e6:.0f} MB > L2), {head_ms * 1e3:.1f} us per launch"}
+    ht = ROOT / "profiles" / "r01_ncu_head_traffic.json"
+    if ht.exists():
+        try:
+            t = json.loads(ht.read_text())
+            if t.get("robot") == robot and int(t.get("batch", 0)) > 0:
+                roofline_head["traffic"] = float(t["dram_bytes_per_launch"]) * hb / int(t["batch"])
+                roofline_head["traffic_note"] = f"{t.get('source')}, scaled to {hb} images; algorithmic bytes per launch: " \
+                                                f"{HEATMAP_BYTES_PER_IMAGE[robot] * hb}"
+        except Exception:
+            pass
     del hm
 
     # ---------------- batch-1 p50 latency (BASELINE.json configs[2], Panda) ----------------
