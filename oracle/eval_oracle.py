@@ -166,7 +166,7 @@ def pnp_m3d(pts2d, pts3d, K) -> torch.Tensor:
     import cv2 as cv
     pts2d, pts3d = torch.as_tensor(pts2d), torch.as_tensor(pts3d)
     bs, n = pts2d.shape[:2]
-    K_np = np.array(torch.as_tensor(K).detach().cpu())
+    K_np = torch.as_tensor(K).detach().cpu().numpy().copy()
     out = torch.zeros(bs, 6)
     for i in range(bs):
         p2 = np.ascontiguousarray(pts2d[i].detach().cpu()).reshape((n, 1, 2))
