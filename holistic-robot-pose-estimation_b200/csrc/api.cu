@@ -354,7 +354,6 @@ int hrp_pnp(const float* pts2d, const float* pts3d, const float* K, int32_t K_ba
   p.K = K;
   p.pose6 = pose6;
   p.rot6d = rot6d;
-  p.starts = nullptr;
   return launch_pnp(p, reinterpret_cast<cudaStream_t>(stream));
 }
 

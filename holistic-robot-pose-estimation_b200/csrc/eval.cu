@@ -383,11 +383,8 @@ __global__ void __launch_bounds__(kSumThreads) metrics_summary_kernel(SummaryPar
 int launch_metrics_summary(const SummaryParams& p, cudaStream_t s) {
   const int nthr = p.nthr_add > p.nthr_pck ? p.nthr_add : p.nthr_pck;
   const size_t smem = kSumThreads * sizeof(double) + (size_t)(nthr + 1 + 256 + 2) * sizeof(unsigned);
-  static bool once = false;
-  if (!once) {
-    cudaFuncSetAttribute(metrics_summary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    once = true;
-  }
+  // (idempotent and cheap; set on every launch so that every device of a multi-device process is covered)
+  cudaFuncSetAttribute(metrics_summary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   if (smem > 96 * 1024) {
     set_error("metrics summary: too many thresholds");
     return HRP_ERR_INVALID;

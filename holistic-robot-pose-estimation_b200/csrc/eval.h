@@ -39,7 +39,6 @@ struct PnpParams {
   int B, N, K_batched, max_iters;
   const float *pts2d, *pts3d, *K;
   float *pose6, *rot6d;
-  const double* starts;  // device [32][9] start rotations (filled by launch_pnp)
 };
 int launch_pnp(const PnpParams& p, cudaStream_t s);
 

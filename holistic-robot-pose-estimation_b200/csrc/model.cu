@@ -689,7 +689,9 @@ int capture_plan(hrp_model* m, Plan* pl) {
     // prologue overlaps the predecessor's tail and the ~5 us launch gap disappears.  Not used behind a memset
     // node or a cross-lane event wait.
     const char* pdl_env = getenv("HRP_PDL");
-    const bool pdl_on = (pdl_env != nullptr && pdl_env[0] == '1') && !m->use_simt;  // opt-in: measured no gain
+    // opt-in (measured no gain) and single-lane graphs only: with five lanes a batch-1 run produced a
+    // last-bit different pose under PDL, i.e. some cross-lane edge is not covered by the programmatic dependency
+    const bool pdl_on = (pdl_env != nullptr && pdl_env[0] == '1') && !m->use_simt && single_lane;
     bool prev_kernel[kNumLanes] = {};
     for (size_t i = 0; i < pl->ops.size() && rc == HRP_OK; ++i) {
       Op& op = pl->ops[i];

@@ -12,8 +12,6 @@
 #include "eval.h"
 #include "launch_count.h"
 
-#include <cmath>
-#include <mutex>
 
 namespace hrp {
 
@@ -183,6 +181,25 @@ __device__ double pnp_lm(double* R, double* t, const double* P3, const double* P
   return cost;
 }
 
+// start rotation of lane l: l < 24 -> the l-th proper signed axis permutation (the rotation group of the cube), else
+// one of 8 fixed generic rotations
+__device__ void pnp_start_rotation(int l, double* R) {
+  if (l < 24) {
+    const int perms[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
+    const int parity[6] = {0, 1, 1, 0, 0, 1};  // odd permutations need an odd number of -1 entries for det = +1
+    const int pi = l >> 2, k = l & 3;
+    // the four sign patterns with the required parity: enumerate s0, s1 freely, s2 fixes the parity
+    const int s0 = k & 1, s1 = (k >> 1) & 1, s2 = (s0 ^ s1 ^ parity[pi]);
+    const int sg[3] = {s0, s1, s2};
+    for (int i = 0; i < 9; ++i) R[i] = 0.0;
+    for (int i = 0; i < 3; ++i) R[i * 3 + perms[pi][i]] = sg[i] ? -1.0 : 1.0;
+  } else {
+    const double extra[8][3] = {{0.9, 0.4, -0.3},  {-0.5, 1.1, 0.7},  {1.3, -1.2, 0.6},  {-1.0, -0.9, -1.4},
+                                {0.3, 2.0, -1.1},  {2.1, 0.5, 1.2},   {-1.7, 1.5, -0.8}, {0.6, -2.2, -1.5}};
+    rodrigues(extra[l - 24], R);
+  }
+}
+
 constexpr int kPnpWarps = 4;
 constexpr int kPnpMaxPts = 64;
 
@@ -210,7 +227,7 @@ __global__ void __launch_bounds__(kPnpWarps * 32) pnp_kernel(PnpParams p) {
 
   // ---- start of this lane: rotation from the table, translation from the linear collinearity equations
   double R[9], t[3];
-  for (int k = 0; k < 9; ++k) R[k] = p.starts[lane * 9 + k];
+  pnp_start_rotation(lane, R);
   {
     double sx = 0, sy = 0, sxy2 = 0, b0 = 0, b1 = 0, b2 = 0, zmin = INFINITY;
     for (int i = 0; i < n; ++i) {
@@ -284,50 +301,7 @@ __global__ void __launch_bounds__(kPnpWarps * 32) pnp_kernel(PnpParams p) {
   }
 }
 
-// the 32 start rotations: the 24 proper signed axis permutations, then 8 fixed generic rotations (angle-axis below)
-static const double* pnp_start_table(cudaStream_t s) {
-  static double* dev = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [&] {
-    double h[32 * 9];
-    int cnt = 0;
-    const int perms[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
-    for (int pi = 0; pi < 6; ++pi)
-      for (int sg = 0; sg < 8; ++sg) {
-        double R[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        for (int i = 0; i < 3; ++i) R[i * 3 + perms[pi][i]] = ((sg >> i) & 1) ? -1.0 : 1.0;
-        const double det = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) + R[2] * (R[3] * R[7] - R[4] * R[6]);
-        if (det > 0.0 && cnt < 24) {
-          for (int k = 0; k < 9; ++k) h[cnt * 9 + k] = R[k];
-          ++cnt;
-        }
-      }
-    const double extra[8][3] = {{0.9, 0.4, -0.3},  {-0.5, 1.1, 0.7},  {1.3, -1.2, 0.6},  {-1.0, -0.9, -1.4},
-                                {0.3, 2.0, -1.1},  {2.1, 0.5, 1.2},   {-1.7, 1.5, -0.8}, {0.6, -2.2, -1.5}};
-    for (int e = 0; e < 8; ++e) {
-      const double* r = extra[e];
-      const double th = std::sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
-      const double a = std::sin(th) / th, bq = (1.0 - std::cos(th)) / (th * th);
-      const double x = r[0], y = r[1], z = r[2];
-      double* R = h + (24 + e) * 9;
-      R[0] = 1.0 - bq * (y * y + z * z); R[1] = -a * z + bq * x * y;        R[2] = a * y + bq * x * z;
-      R[3] = a * z + bq * x * y;         R[4] = 1.0 - bq * (x * x + z * z); R[5] = -a * x + bq * y * z;
-      R[6] = -a * y + bq * x * z;        R[7] = a * x + bq * y * z;         R[8] = 1.0 - bq * (x * x + y * y);
-    }
-    if (cudaMalloc(&dev, sizeof(h)) == cudaSuccess) cudaMemcpy(dev, h, sizeof(h), cudaMemcpyHostToDevice);
-    else dev = nullptr;
-  });
-  (void)s;
-  return dev;
-}
-
-int launch_pnp(const PnpParams& p0, cudaStream_t s) {
-  PnpParams p = p0;
-  p.starts = pnp_start_table(s);
-  if (p.starts == nullptr) {
-    set_error("pnp: could not allocate the start-rotation table");
-    return HRP_ERR_CUDA;
-  }
+int launch_pnp(const PnpParams& p, cudaStream_t s) {
   pnp_kernel<<<(p.B + kPnpWarps - 1) / kPnpWarps, kPnpWarps * 32, 0, s>>>(p);
   count_launch();
   HRP_CUDA_CHECK(cudaGetLastError());

@@ -30,25 +30,30 @@ def _cuda(t: torch.Tensor, dtype) -> torch.Tensor:
 
 
 def crop_resize_batch(frames: torch.Tensor, bbox: torch.Tensor, K: torch.Tensor, resize_hw=(256, 256),
-                      k_bbox: torch.Tensor | None = None, k_from_crop_K: bool = False):
+                      k_bbox: torch.Tensor | None = None, k_from_crop_K: bool = False, check_bbox: bool = True):
     """frames (B,H,W,3) uint8 CUDA (HWC, as decoded); bbox (B,4) integer (wmin,hmin,wmax,hmax), inside the frame;
     K (B,3,3) camera matrix of the full frame (kept in float64 for the principal-point shift, as the reference does).
     Returns (images uint8 (B,3,h,w), K float32 (B,3,3)[, k_value float32 (B)]) -- the dataset's "images" / "K"
     entries (dream.py:324-332) and, when `k_bbox` (B,4) is given, scripts/test.py's `k_values` (fx, fy taken from
-    `K` like `args.use_origin_bbox`, or from the crop's K when `k_from_crop_K`)."""
+    `K` like `args.use_origin_bbox`, or from the crop's K when `k_from_crop_K`).
+    `check_bbox=False` skips the host-side box validation (a device->host sync when `bbox` lives on the GPU); the
+    kernel then reads whatever the box addresses, so only pass boxes that are known to lie inside the frame."""
     if tuple(resize_hw) != (int(resize_hw[0]), int(resize_hw[0])) or int(resize_hw[0]) % 4:
         raise NotImplementedError("only square crops with a side that is a multiple of 4 are on the path (256 x 256)")
     if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[-1] != 3:
         raise ValueError(f"frames must be uint8 (B,H,W,3), got {frames.dtype} {tuple(frames.shape)}")
     B, H, W, _ = frames.shape
     frames = _cuda(frames, torch.uint8)
-    bb_host = bbox.detach().cpu().to(torch.int64)
-    # the reference pastes image[hmin:hmax, wmin:wmax] into a (hmax-hmin, wmax-wmin) window: numpy raises on a box that
-    # leaves the frame or is empty (roboutils.py:137)
-    if bb_host.shape != (B, 4) or bool(((bb_host[:, 0] < 0) | (bb_host[:, 1] < 0) | (bb_host[:, 2] > W) | (bb_host[:, 3] > H)
-                                       | (bb_host[:, 2] <= bb_host[:, 0]) | (bb_host[:, 3] <= bb_host[:, 1])).any()):
-        raise ValueError("bbox must be (B,4) = (wmin, hmin, wmax, hmax) inside the frame with positive extent")
-    bb = bb_host.to(torch.int32).to(frames.device)
+    if tuple(bbox.shape) != (B, 4):
+        raise ValueError(f"bbox must be (B,4) = (wmin, hmin, wmax, hmax), got {tuple(bbox.shape)}")
+    if check_bbox:
+        bb_host = bbox.detach().cpu().to(torch.int64)
+        # the reference pastes image[hmin:hmax, wmin:wmax] into a (hmax-hmin, wmax-wmin) window: numpy raises on a box
+        # that leaves the frame or is empty (roboutils.py:137)
+        if bool(((bb_host[:, 0] < 0) | (bb_host[:, 1] < 0) | (bb_host[:, 2] > W) | (bb_host[:, 3] > H)
+                 | (bb_host[:, 2] <= bb_host[:, 0]) | (bb_host[:, 3] <= bb_host[:, 1])).any()):
+            raise ValueError("bbox must be (wmin, hmin, wmax, hmax) inside the frame with positive extent")
+    bb = bbox.detach().to(device=frames.device, dtype=torch.int32).contiguous()
     Kd = _cuda(K.to(frames.device), torch.float64)
     out = int(resize_hw[0])
     images = torch.empty(B, 3, out, out, dtype=torch.uint8, device=frames.device)
