@@ -133,7 +133,7 @@ def run_reference(args):
     if rank != 0:
         return
     sample = 64
-    rate, cores, times = cpu_forward_rate(ROBOT, sample, runs=args.steps, warmup=max(1, min(args.warmup, 2)))
+    rate, cores, times = cpu_forward_rate(ROBOT, sample, runs=args.steps, warmup=args.warmup)
     ms = 1e3 * statistics.median(times)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
