@@ -1,4 +1,5 @@
-"""Summarise an `ncu --page source --csv` dump: top stall locations and stall-reason totals."""
+"""Summarise an `ncu -i X.ncu-rep --page source --csv > X.csv` dump: top stall locations and stall-reason totals.
+    python tools/ncu_stalls.py X.csv [n_lines]"""
 import csv
 import sys
 
