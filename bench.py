@@ -158,6 +158,7 @@ def main():
     ap.add_argument("--robot", default=ROBOT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     ap.add_argument("--profile-range", action="store_true",
                     help="wrap the timed device-resident steps in cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     args = ap.parse_args()
@@ -366,6 +367,47 @@ def main():
                    "iters": 200}
         del pm
 
+    # ---------------- the other BASELINE.json configs (device-resident, informational; N = 1 only) ----------------
+    # configs[1] Panda depthnet B=256, configs[2] Panda full B=64, configs[4] Baxter full B=256 per GPU
+    other = None
+    if not args.no_other_configs and world == 1:
+        def rate(fn, n_img, iters=5):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(iters):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return n_img * iters / (a.elapsed_time(b) * 1e-3)
+
+        def rep_to(t, n):
+            r = (n + t.shape[0] - 1) // t.shape[0]
+            return t.repeat(r, *([1] * (t.dim() - 1)))[:n].contiguous()
+
+        other = {}
+        try:
+            from horopose_b200.models import get_rootnet
+            dn = get_rootnet("hrnet32")
+            dn.chunk, dn.inflight = 256, 1
+            dn.load_state_dict(synth.depthnet_state_dict(), strict=True)
+            xd, kd = rep_to(x_root_d, 256).float() / 255.0, rep_to(k_d, 256)
+            other["panda_depthnet_b256"] = {"images_per_sec": rate(lambda: dn(xd, kd), 256), "gflop_per_image": 23.30}
+            del dn, xd
+            for name, rb, nb, gf in (("panda_full_b64", "panda", 64, 38.72), ("baxter_full_b256", "baxter", 256, 40.07)):
+                mm = get_rootNetwithRegInt_model({"robot_type": rb, "pose_params": None, "cam_params": np.eye(4),
+                                                  "init_pose_from_mean": True},
+                                                 dict(margs, reference_keypoint_id=arch.ROBOTS[rb][2]))
+                mm.chunk, mm.inflight = nb, 1
+                mm.load_state_dict(synth.full_state_dict(rb), strict=True)
+                a_, b_, c_, d_ = rep_to(x_reg_d, nb), rep_to(x_root_d, nb), rep_to(k_d, nb), rep_to(K_d, nb)
+                other[name] = {"images_per_sec": rate(lambda: mm(a_, b_, c_, d_), nb), "gflop_per_image": gf}
+                del mm
+        except Exception as e:  # informational: never fail the bench line on it
+            other["error"] = str(e)
+
     # ---------------- reference algorithm on the host cores (bounded sample) ----------------
     cpu = None
     if not args.no_cpu_baseline:
@@ -390,6 +432,7 @@ def main():
         "roofline_layers": layers,
         "cpu_baseline": cpu,
         "latency_b1": latency,
+        "other_configs": other,
     }
     print(json.dumps(line))
     if world > 1:

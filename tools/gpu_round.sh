@@ -12,5 +12,5 @@ timeout 300 python tools/bench_conv.py 256 > gpurun_out/bench_conv256.txt 2>&1
 # launch list of the bench command itself (one timed step of the 512-image workload), with DRAM traffic per launch
 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
   --clock-control none --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline \
-  --no-latency --profile-range > gpurun_out/ncu_launch_bench.log 2>&1
+  --no-latency --no-other-configs --profile-range > gpurun_out/ncu_launch_bench.log 2>&1
 wc -l gpurun_out/launches.csv
