@@ -651,10 +651,12 @@ int autotune_plan(hrp_model* m, Plan* pl) {
 }
 
 int capture_plan(hrp_model* m, Plan* pl) {
-  // Lanes pay off only when a kernel cannot fill the GPU by itself (small batches: batch-1 latency).  From ~64 images
-  // on, every conv launch is a full persistent grid and concurrent lanes only contend for SMs, shared memory and L2
-  // (measured on B200, chunk 512: 12.9k img/s on one stream vs 12.6k on five).  HRP_SINGLE_LANE=0/1 overrides.
-  bool single_lane = pl->B >= 64;
+  // Lanes pay off while some kernels cannot fill the GPU by themselves (the 8x8 / 16x16 layers of a 64-image chunk are
+  // 32 / 128 tiles for 148 SMs).  Measured on B200, Panda full model, one stream vs five lanes: 32 images 5.28 -> 3.75 ms,
+  // 64 images 6.94 -> 5.91 ms, 128 images 10.64 -> 10.28 ms, 256 images 19.26 -> 19.18 ms (a tie); at 512 images every
+  // launch is a full persistent grid and lanes only contend for SMs, shared memory and L2 (12.9k img/s on one stream vs
+  // 12.6k on five).  HRP_SINGLE_LANE=0/1 overrides.
+  bool single_lane = pl->B > 256;
   if (const char* sl = getenv("HRP_SINGLE_LANE")) single_lane = (sl[0] == '1');
   if (single_lane)
     for (auto& op : pl->ops) op.lane = 0;
