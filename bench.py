@@ -410,7 +410,7 @@ def main():
 
     # ---------------- reference algorithm on the host cores (bounded sample) ----------------
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # rank 0 at N = 1 only
         rate, cores, times = cpu_forward_rate(robot, 64, runs=3, warmup=1)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"3 forwards of 64 images ({sum(times):.1f} s), fp32 PyTorch oracle port of the reference forward"}
