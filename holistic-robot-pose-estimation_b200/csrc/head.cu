@@ -531,20 +531,22 @@ __device__ __forceinline__ void softmax_merge(float& m, float& S, float& Sx, flo
   m = M;
 }
 
-// Streaming layout: a warp owns a group of 4 keypoints (32 lanes x 16 B = the 512 contiguous bytes those
-// keypoints occupy in a pixel row); lane = (keypoint in group, 8-bin depth vector).  `slots` warps per group
-// walk different pixels.  Every thread keeps a fixed (keypoint, depth vector) -> 5 fp32 accumulators.
+// Streaming layout: thread t of a CTA owns the 16-byte vector (t mod vpp) of a pixel row -- a fixed (keypoint, 8-bin
+// depth vector) -> 5 fp32 accumulators -- and walks the pixels slot, slot + slots, ... (slot = t / vpp); a warp reads
+// 512 contiguous bytes per load instruction.
 __global__ void __launch_bounds__(kHeadMaxThreads, 3) head_kernel(const __grid_constant__ HeadParams p) {
   __shared__ HeadSmem sm;
   const int nk = p.nkpt;
-  const int groups = (nk + 3) >> 2;
-  const int slots = (blockDim.x >> 5) / groups;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kg = warp % groups, slot = warp / groups;
-  const int k = kg * 4 + (lane >> 3);
-  const bool kvalid = (k < nk);
-  const int vec = lane & 7;
   const int vpp = nk * 8;                 // 16-byte vectors per pixel
+  // thread -> (pixel slot, vector of the pixel row): consecutive threads take consecutive 16-byte vectors, so every lane
+  // of every warp is busy for any keypoint count (a warp-per-4-keypoints mapping left 12 % / 15 % of the lanes idle for
+  // 7 / 17 keypoints); vpp is a multiple of 8, so the 8 depth vectors of a keypoint stay in one aligned 8-lane group
+  const int slots = (int)blockDim.x / vpp;
+  const int slot = (int)threadIdx.x / vpp;
+  const int kv = (int)threadIdx.x - slot * vpp;
+  const int k = kv >> 3;
+  const bool kvalid = (slot < slots);
+  const int vec = kv & 7;
   const int b = blockIdx.x / p.chunks, chunk = blockIdx.x - b * p.chunks;
   const int ppc = 4096 / p.chunks;        // pixels per chunk
   const float dbase = (float)(vec * 8);
@@ -669,10 +671,11 @@ int launch_head(const HeadParams& p, cudaStream_t s) {
   HRP_REQUIRE(p.depth_in != nullptr || (p.feat != nullptr && p.depth_w != nullptr && p.k_value != nullptr),
               "head: a root-depth source is required");
   HRP_REQUIRE(p.ref_kpt >= 0 && p.ref_kpt < p.nkpt, "reference keypoint out of range");
-  const int groups = (p.nkpt + 3) / 4;
-  const int slots = std::max(1, std::min(4, (kHeadMaxThreads / 32) / groups));
-  const int threads = groups * slots * 32;
-  HRP_REQUIRE(threads <= kHeadMaxThreads && slots <= kHeadMaxSlots, "too many keypoints for the head kernel");
+  const int vpp = p.nkpt * 8;
+  const int slots = std::max(1, std::min(4, kHeadMaxThreads / vpp));
+  const int threads = (slots * vpp + 31) / 32 * 32;
+  HRP_REQUIRE(vpp <= kHeadMaxThreads && threads <= kHeadMaxThreads && slots <= kHeadMaxSlots,
+              "too many keypoints for the head kernel");
   head_kernel<<<p.B * p.chunks, threads, 0, s>>>(p);
   count_launch();
   HRP_CUDA_CHECK(cudaGetLastError());
