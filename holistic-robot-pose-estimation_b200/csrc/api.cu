@@ -406,6 +406,22 @@ int hrp_head(const hrp_head_args* a, void* stream) {
   return launch_head(p, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int hrp_head_backward_heatmap(const void* heatmap, const float* uvd, const float* grad_uvd, const void* workspace,
+                              int64_t workspace_bytes, int32_t B, int32_t nkpt, int32_t ref_kpt, int32_t fix_root,
+                              int32_t out_fp32, void* grad_heatmap, void* stream) {
+  HRP_REQUIRE(heatmap != nullptr && uvd != nullptr && grad_uvd != nullptr && grad_heatmap != nullptr, "null argument");
+  HRP_REQUIRE(workspace != nullptr, "the workspace of the preceding hrp_head call is required");
+  int64_t need = 0;
+  int rc = hrp_head_workspace_bytes(B, nkpt, &need);
+  if (rc != HRP_OK) return rc;
+  HRP_REQUIRE(workspace_bytes >= need, "workspace too small");
+  const float* partials = reinterpret_cast<const float*>(reinterpret_cast<const char*>(workspace) +
+                                                         ((size_t)B * sizeof(unsigned int) + 255) / 256 * 256);
+  return launch_head_backward_heatmap(reinterpret_cast<const bf16*>(heatmap), partials, uvd, grad_uvd, B, nkpt, ref_kpt,
+                                      fix_root, head_default_chunks(B), out_fp32 != 0, grad_heatmap,
+                                      reinterpret_cast<cudaStream_t>(stream));
+}
+
 int hrp_copy_device(void* dst, const void* src, int64_t bytes, void* stream) {
   HRP_REQUIRE(dst != nullptr && src != nullptr && bytes >= 0, "bad argument");
   HRP_CUDA_CHECK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, reinterpret_cast<cudaStream_t>(stream)));

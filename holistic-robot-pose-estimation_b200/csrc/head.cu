@@ -654,6 +654,106 @@ __global__ void __launch_bounds__(kHeadMaxThreads, 3) head_kernel(const __grid_c
   head_finalize(p, sm, b);
 }
 
+// ------------------------------------------------------------------------------------------------------
+// backward of the heatmap integral w.r.t. the logits (first piece)
+// ------------------------------------------------------------------------------------------------------
+// u = sum_i p_i w_i / 64 - 0.5 with p = softmax over the 64^3 voxels of a keypoint (integral.py:97-135; the `/ sum`
+// renormalisation of the resnet branch has zero net Jacobian at sum = 1), so
+//   dL/dx_i = p_i * (g_u (w_i - E[w]) + g_v (h_i - E[h]) + g_d (d_i - E[d])) / 64.
+// The softmax statistics are NOT recomputed: the forward left the per-chunk (max, sum) partials in the workspace.
+// Same thread -> (pixel slot, 16-byte vector) mapping as the forward; one heatmap read, one gradient write.
+struct HeadBwdParams {
+  int B, nkpt, ref_kpt, fix_root, chunks;
+  const bf16* heatmap;
+  const float* partials;
+  const float* uvd;
+  const float* grad_uvd;
+  void* grad_out;
+};
+
+template <bool F32>
+__global__ void __launch_bounds__(kHeadMaxThreads) head_bwd_heatmap_kernel(const HeadBwdParams p) {
+  const int nk = p.nkpt;
+  const int vpp = nk * 8;
+  const int slots = (int)blockDim.x / vpp;
+  const int slot = (int)threadIdx.x / vpp;
+  if (slot >= slots) return;
+  const int kv = (int)threadIdx.x - slot * vpp;
+  const int k = kv >> 3, vec = kv & 7;
+  const int b = blockIdx.x / p.chunks, chunk = blockIdx.x - b * p.chunks;
+  const int ppc = 4096 / p.chunks;
+  // global softmax statistics of (b, k) from the forward's per-chunk partials
+  float M = -INFINITY;
+  for (int c = 0; c < p.chunks; ++c) M = fmaxf(M, __ldg(p.partials + (((size_t)b * p.chunks + c) * nk + k) * 5));
+  float S = 0.f;
+  for (int c = 0; c < p.chunks; ++c) {
+    const float* pp = p.partials + (((size_t)b * p.chunks + c) * nk + k) * 5;
+    S = fmaf(__ldg(pp + 1), exp2f(__ldg(pp) - M), S);
+  }
+  const float invS = 1.0f / S;
+  const float* gq = p.grad_uvd + ((size_t)b * nk + k) * 3;
+  const float* uq = p.uvd + ((size_t)b * nk + k) * 3;
+  const bool fixed_d = (p.fix_root != 0) && (k == p.ref_kpt);   // uvd[:, ref, 2] = 0 (integral.py:134): no gradient
+  const float gu = gq[0] * (1.0f / 64.0f), gv = gq[1] * (1.0f / 64.0f), gd = fixed_d ? 0.0f : gq[2] * (1.0f / 64.0f);
+  const float Ew = (uq[0] + 0.5f) * 64.0f, Eh = (uq[1] + 0.5f) * 64.0f, Ed = fixed_d ? 0.0f : (uq[2] + 0.5f) * 64.0f;
+  const float dbase = (float)(vec * 8) - Ed;
+  const size_t row0 = ((size_t)b * 4096 + (size_t)chunk * ppc);
+  const uint4* src = reinterpret_cast<const uint4*>(p.heatmap + row0 * (size_t)(nk * 64)) + kv;
+  for (int pix = slot; pix < ppc; pix += slots) {
+    const int gp = chunk * ppc + pix;
+    const float cwh = fmaf(gu, (float)(gp & 63) - Ew, gv * ((float)(gp >> 6) - Eh));
+    const uint4 raw = ld_stream(src + (size_t)pix * vpp);
+    const uint32_t xs[4] = {raw.x, raw.y, raw.z, raw.w};
+    float g[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float p0 = ex2_ftz(fmaf(bf16lo_to_f32(xs[i]), kLog2e, -M)) * invS;
+      const float p1 = ex2_ftz(fmaf(bf16hi_to_f32(xs[i]), kLog2e, -M)) * invS;
+      g[2 * i] = p0 * fmaf(gd, dbase + (float)(2 * i), cwh);
+      g[2 * i + 1] = p1 * fmaf(gd, dbase + (float)(2 * i + 1), cwh);
+    }
+    const size_t vidx = (row0 + pix) * (size_t)vpp + kv;  // index of this 8-logit vector
+    if (F32) {
+      float4* dst = reinterpret_cast<float4*>(p.grad_out) + 2 * vidx;
+      dst[0] = make_float4(g[0], g[1], g[2], g[3]);
+      dst[1] = make_float4(g[4], g[5], g[6], g[7]);
+    } else {
+      uint4 o;
+      o.x = pack_bf16x2(g[0], g[1]);
+      o.y = pack_bf16x2(g[2], g[3]);
+      o.z = pack_bf16x2(g[4], g[5]);
+      o.w = pack_bf16x2(g[6], g[7]);
+      reinterpret_cast<uint4*>(p.grad_out)[vidx] = o;
+    }
+  }
+}
+
+int launch_head_backward_heatmap(const bf16* heatmap, const float* partials, const float* uvd, const float* grad_uvd, int B,
+                                 int nkpt, int ref_kpt, int fix_root, int chunks, bool out_fp32, void* grad_out,
+                                 cudaStream_t s) {
+  HRP_REQUIRE(B > 0 && nkpt > 0 && nkpt <= kMaxKpt && chunks > 0 && 4096 % chunks == 0, "bad head-backward dims");
+  HRP_REQUIRE(ref_kpt >= 0 && ref_kpt < nkpt, "reference keypoint out of range");
+  const int vpp = nkpt * 8;
+  const int slots = std::max(1, std::min(4, kHeadMaxThreads / vpp));
+  const int threads = (slots * vpp + 31) / 32 * 32;
+  HeadBwdParams p;
+  p.B = B;
+  p.nkpt = nkpt;
+  p.ref_kpt = ref_kpt;
+  p.fix_root = fix_root;
+  p.chunks = chunks;
+  p.heatmap = heatmap;
+  p.partials = partials;
+  p.uvd = uvd;
+  p.grad_uvd = grad_uvd;
+  p.grad_out = grad_out;
+  if (out_fp32) head_bwd_heatmap_kernel<true><<<B * chunks, threads, 0, s>>>(p);
+  else head_bwd_heatmap_kernel<false><<<B * chunks, threads, 0, s>>>(p);
+  count_launch();
+  HRP_CUDA_CHECK(cudaGetLastError());
+  return HRP_OK;
+}
+
 int head_default_chunks(int B) {
   // enough CTAs to cover 148 SMs x ~8 resident CTAs a few times over, power of two <= 64
   int chunks = 64;

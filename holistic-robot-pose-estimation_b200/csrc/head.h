@@ -75,6 +75,9 @@ struct HeadParams {
 int launch_head(const HeadParams& p, cudaStream_t s);
 size_t head_partials_elems(int B, int nkpt, int chunks);
 int head_default_chunks(int B);
+int launch_head_backward_heatmap(const bf16* heatmap, const float* partials, const float* uvd, const float* grad_uvd, int B,
+                                 int nkpt, int ref_kpt, int fix_root, int chunks, bool out_fp32, void* grad_out,
+                                 cudaStream_t s);
 
 struct FkParams {
   int B, rot_dim, root, use_b2c;

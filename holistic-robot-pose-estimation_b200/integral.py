@@ -3,6 +3,7 @@
 forward(out, K=..., root_trans=...) takes the reference's heatmap-logit tensor (B, nkpt*64, 64, 64) (channel =
 k*64 + d) and returns (pred_uvd_jts (B,nkpt,3), pred_xyz_jts (B,nkpt,3)).  The logits are bridged to the kernel's
 pixel-major bf16 layout (one extra pass; inside the full model the final conv writes that layout directly).
+When the logits require a gradient (training), the soft-argmax backward runs on the GPU as well (`_IntegralUVD`).
 """
 from __future__ import annotations
 
@@ -38,7 +39,7 @@ def _workspace(device, B, nkpt):
 
 
 def run_head(heatmap_nhwc, K, root_depth, *, nkpt, ref_kpt, fix_root=True, image_size=256.0, depth_factor=1.3,
-             robot=None, pose=None, rot=None, want_uv=False):
+             robot=None, pose=None, rot=None, want_uv=False, workspace=None):
     """heatmap_nhwc: (B,64,64,nkpt*64) bf16 CUDA.  Returns dict of fp32 CUDA tensors."""
     assert heatmap_nhwc.is_cuda and heatmap_nhwc.dtype == torch.bfloat16 and heatmap_nhwc.is_contiguous()
     B = heatmap_nhwc.shape[0]
@@ -65,13 +66,65 @@ def run_head(heatmap_nhwc, K, root_depth, *, nkpt, ref_kpt, fix_root=True, image
     if want_uv:
         out["uv_int"] = torch.empty(B, nkpt, 2, dtype=torch.float32, device=dev)
         a.uv_int = out["uv_int"].data_ptr()
-    ws = _workspace(dev, B, nkpt)
+    ws = workspace if workspace is not None else _workspace(dev, B, nkpt)
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
     a.uvd, a.xyz_int = out["uvd"].data_ptr(), out["xyz_int"].data_ptr()
     a.root_uv, a.trans = out["root_uv"].data_ptr(), out["trans"].data_ptr()
     with torch.cuda.device(dev):
         check(_lib.lib().hrp_head(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
     return out
+
+
+class _IntegralUVD(torch.autograd.Function):
+    """uvd = soft-argmax(heatmap logits) with a gradient to the logits (first piece): the
+    forward is the fused head kernel, the backward `hrp_head_backward_heatmap`, which re-uses the softmax statistics
+    the forward left in its (private, saved) workspace -- one heatmap read and one gradient write."""
+
+    @staticmethod
+    def forward(ctx, out, K, root_depth, nkpt, rootid, fixroot, image_size, depth_factor):
+        hm = ops.nchw_to_nhwc_bf16(out.detach().float().contiguous(), cpad=out.shape[1])
+        need = C.c_int64(0)
+        check(_lib.lib().hrp_head_workspace_bytes(out.shape[0], nkpt, C.byref(need)))
+        ws = torch.zeros(need.value, dtype=torch.uint8, device=out.device)
+        r = run_head(hm, K, root_depth, nkpt=nkpt, ref_kpt=rootid, fix_root=fixroot, image_size=image_size,
+                     depth_factor=depth_factor, workspace=ws)
+        ctx.save_for_backward(hm, r["uvd"], ws)
+        ctx.cfg = (nkpt, rootid, fixroot, tuple(out.shape))
+        return r["uvd"]
+
+    @staticmethod
+    def backward(ctx, grad_uvd):
+        hm, uvd, ws = ctx.saved_tensors
+        nkpt, rootid, fixroot, shape = ctx.cfg
+        B = hm.shape[0]
+        g = grad_uvd.detach().to(torch.float32).contiguous()
+        grad = torch.empty(B, 64, 64, nkpt * 64, dtype=torch.float32, device=hm.device)
+        with torch.cuda.device(hm.device):
+            check(_lib.lib().hrp_head_backward_heatmap(
+                C.c_void_p(hm.data_ptr()), C.c_void_p(uvd.data_ptr()), C.c_void_p(g.data_ptr()), C.c_void_p(ws.data_ptr()),
+                C.c_int64(ws.numel()), C.c_int32(B), C.c_int32(nkpt), C.c_int32(rootid), C.c_int32(int(fixroot)),
+                C.c_int32(1), C.c_void_p(grad.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return grad.permute(0, 3, 1, 2).reshape(shape), None, None, None, None, None, None, None
+
+
+def _inv_intrinsics(K):
+    """integral.py:56-73: the divisions run in float64, the result is stored as float32."""
+    Kd = K.double()
+    inv = torch.zeros_like(Kd)
+    inv[:, 0, 0], inv[:, 1, 1] = 1.0 / Kd[:, 0, 0], 1.0 / Kd[:, 1, 1]
+    inv[:, 0, 2], inv[:, 1, 2] = -Kd[:, 0, 2] / Kd[:, 0, 0], -Kd[:, 1, 2] / Kd[:, 1, 1]
+    inv[:, 2, 2] = 1.0
+    return inv.float()
+
+
+def _uvd_to_xyz(uvd, image_size, inv_k, root_trans, depth_factor):
+    """transforms.py:33-73 on (B,nkpt,3) tensors (a few hundred bytes per image: left to torch so that autograd carries
+    the gradient from xyz back to uvd, K and root_trans)."""
+    u = (uvd[:, :, 0:1] + 0.5) * image_size
+    v = (uvd[:, :, 1:2] + 0.5) * image_size
+    z = uvd[:, :, 2:3] * depth_factor + root_trans[:, None, 2:3]
+    pix = torch.cat((u, v, torch.ones_like(u)), dim=2)
+    return torch.matmul(inv_k[:, None], pix[..., None]).squeeze(-1) * z
 
 
 class HeatmapIntegralPose(torch.nn.Module):
@@ -96,6 +149,15 @@ class HeatmapIntegralPose(torch.nn.Module):
         K, root_trans = kwargs["K"], kwargs["root_trans"]
         if not out.is_cuda:
             raise _lib.HrpError("horopose_b200 has no CPU path: tensors must live on a CUDA device")
+        if torch.is_grad_enabled() and out.requires_grad:
+            # training (lib/core/function.py:253-311): gradient to the logits through the backward kernel; xyz from uvd in
+            # torch so that K / root_trans gradients flow as in the reference
+            K = K.to(out.device).float()
+            root_trans = root_trans.to(out.device).float()
+            uvd = _IntegralUVD.apply(out, K.detach(), root_trans[:, 2].detach(), self.num_joints, self.rootid,
+                                     bool(self.fixroot), float(self.image_size), float(self.depth_factor))
+            xyz = _uvd_to_xyz(uvd, float(self.image_size), _inv_intrinsics(K), root_trans, float(self.depth_factor))
+            return uvd, xyz
         hm = ops.nchw_to_nhwc_bf16(out.detach().float().contiguous(), cpad=out.shape[1])
         r = run_head(hm, K, root_trans[:, 2].to(out.device), nkpt=self.num_joints, ref_kpt=self.rootid,
                      fix_root=self.fixroot, image_size=float(self.image_size), depth_factor=float(self.depth_factor))

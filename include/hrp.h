@@ -162,6 +162,14 @@ typedef struct hrp_head_args {
 
 int hrp_head_workspace_bytes(int32_t B, int32_t nkpt, int64_t* bytes);
 int hrp_head(const hrp_head_args* args, void* stream);
+/* Row f4 (first piece): gradient of the heatmap integral w.r.t. the logits -- what autograd computes through
+ * HeatmapIntegralPose.forward (lib/utils/integral.py:97-135) in training (lib/core/function.py:253-311).
+ * Must follow hrp_head on the SAME heatmap and workspace (it re-uses the per-chunk softmax statistics the forward
+ * left there).  uvd: the forward's output; grad_uvd (B,nkpt,3) fp32; grad_heatmap: layout of `heatmap`, bf16
+ * (out_fp32 = 0) or fp32 (out_fp32 = 1). */
+int hrp_head_backward_heatmap(const void* heatmap, const float* uvd, const float* grad_uvd, const void* workspace,
+                              int64_t workspace_bytes, int32_t B, int32_t nkpt, int32_t ref_kpt, int32_t fix_root,
+                              int32_t out_fp32, void* grad_heatmap, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Input pipeline: full camera frame + bounding box -> the 256x256 crop the network

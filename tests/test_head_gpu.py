@@ -142,3 +142,45 @@ def test_fused_head_exact_on_bf16_logits(hrp_lib):
         r2 = run_head(hm_nhwc, K.cuda(), depth.cuda(), nkpt=nkpt, ref_kpt=ref, robot=URDFRobot(rt), pose=q.cuda(),
                       rot=rot.cuda())
         assert torch.equal(r2["uvd"], r["uvd"])
+
+
+@pytest.mark.parametrize("rt", ["panda", "baxter"])
+def test_heatmap_integral_backward_vs_autograd(rt, hrp_lib):
+    """Row f4, first piece: d(loss)/d(logits) through HeatmapIntegralPose (backward kernel re-using the forward's
+    softmax statistics; xyz from uvd in torch) against torch autograd through the fp32 oracle on bf16-exact logits.
+    Tolerance: 2e-4 of the largest gradient entry (fp32, ex2.approx vs exp)."""
+    from horopose_b200 import arch, synth
+    from horopose_b200.integral import HeatmapIntegralPose
+    from make_golden import HEATMAP_STRESS_GAIN, heatmap_logits
+    from oracle import horopose_oracle as O
+    dof, nkpt, ref = arch.ROBOTS[rt]
+    layer = HeatmapIntegralPose(backbone="resnet50", num_joints=nkpt, depth_dim=64, height_dim=64, width_dim=64,
+                                norm_type="softmax", image_size=256.0, bbox_3d_shape=[1300, 1300, 1300], rootid=ref,
+                                fixroot=True)
+    B = 2
+    _, _, k, K = synth.inputs(B, seed=13)
+    root_trans = torch.zeros(B, 3)
+    root_trans[:, 2] = synth.range_uniform("root_z", (B,), 0.8, 2.5, 13)
+    G1 = synth.sym_uniform("g_uvd", (B, nkpt, 3), 1.0, 3)
+    G2 = synth.sym_uniform("g_xyz", (B, nkpt, 3), 1.0, 4)
+    for gain in (1.0, HEATMAP_STRESS_GAIN):
+        logits = heatmap_logits(rt, B, gain=gain).bfloat16().float()        # exactly representable in bf16
+        with torch.enable_grad():   # (tests/golden/make_golden.py switches autograd off process-wide on import)
+            x = logits.clone().cuda().requires_grad_(True)
+            uvd, xyz = layer(x, root_trans=root_trans.cuda(), K=K.cuda())
+            ((uvd * G1.cuda()).sum() + (xyz * G2.cuda()).sum()).backward()
+            xo = logits.clone().requires_grad_(True)
+            uvd_o, xyz_o = O.heatmap_integral(xo, nkpt, K, root_trans, ref, fixroot=True, image_size=256.0,
+                                              depth_factor=float(layer.depth_factor))
+            ((uvd_o * G1).sum() + (xyz_o * G2).sum()).backward()
+        assert np.abs(uvd.detach().cpu().numpy() - uvd_o.detach().numpy()).max() < 1e-5
+        assert np.abs(xyz.detach().cpu().numpy() - xyz_o.detach().numpy()).max() < 1e-5
+        got, want = x.grad.cpu(), xo.grad
+        assert got.shape == want.shape
+        scale = float(want.abs().max())
+        assert scale > 0
+        err = float((got - want).abs().max())
+        assert err < 2e-4 * scale, (gain, err, scale)
+        # the reference keypoint's depth is pinned to 0 (integral.py:134): its depth expectation gets no gradient,
+        # and gradients of one keypoint's logits sum to zero (softmax)
+        assert float(got.double().reshape(B, nkpt, -1).sum(dim=2).abs().max()) < 5e-2 * scale   # 262144 fp32 terms
