@@ -74,3 +74,26 @@ def test_c_abi_exports_every_declared_symbol():
     n = ctypes.c_int64(0)
     assert lib.hrp_conv_packed_weight_elems(None, ctypes.byref(n)) == -1
     assert b"null" in lib.hrp_last_error()
+
+
+def test_new_entry_points_validate_arguments_without_a_gpu():
+    """Rows f1-f4: every new C entry point rejects bad arguments (status -1 + message) before touching CUDA."""
+    from horopose_b200 import _lib
+    from horopose_b200.metrics import MetricsArgs
+    from horopose_b200.preprocess import CropArgs
+    lib = _lib.lib()
+    assert lib.hrp_crop_resize(None, None) == -1 and b"null" in lib.hrp_last_error()
+    a = CropArgs(B=1, frame_h=480, frame_w=640, out_size=250)            # not a multiple of 4
+    assert lib.hrp_crop_resize(ctypes.byref(a), None) == -1 and b"out_size" in lib.hrp_last_error()
+    assert lib.hrp_metrics_batch(None, None) == -1
+    m = MetricsArgs(B=4, nkpt=40, dof=7, ref_kpt=0)                      # more keypoints than a warp has lanes
+    assert lib.hrp_metrics_batch(ctypes.byref(m), None) == -1 and b"nkpt" in lib.hrp_last_error()
+    n = ctypes.c_int64(0)
+    assert lib.hrp_metrics_workspace_bytes(512, 17, 15, ctypes.byref(n)) == 0 and n.value == (3 * 17 + 15) * 512 * 4
+    assert lib.hrp_metrics_summary(None, None, ctypes.c_int64(10), None, None) == -1
+    one = ctypes.c_float(0.0)
+    p = ctypes.byref(one)
+    assert lib.hrp_pnp(p, p, p, 0, 4, 5, p, None, None) == -1 and b"6..64" in lib.hrp_last_error()   # < 6 points
+    assert lib.hrp_head_backward_heatmap(None, p, p, p, ctypes.c_int64(0), 1, 7, 3, 1, 1, p, None) == -1
+    assert lib.hrp_head_backward_heatmap(p, p, p, p, ctypes.c_int64(8), 1, 7, 3, 1, 1, p, None) == -1
+    assert b"workspace" in lib.hrp_last_error()
