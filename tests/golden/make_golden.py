@@ -160,6 +160,48 @@ def golden_integral(ns, robot_type: str, batch: int = 2):
     np.savez(GOLDEN / f"integral_{robot_type}.npz", **data)
 
 
+GRAD_SAMPLES = 4096
+
+
+def grad_digest(g: torch.Tensor) -> dict:
+    """Small, order-independent digest of a (B, nkpt*64, 64, 64) gradient tensor: the three axis marginals, the largest
+    magnitude and GRAD_SAMPLES seeded entries (the full tensor is 7.3 MB per image)."""
+    B = g.shape[0]
+    flat = g.reshape(B, -1)
+    idx = torch.from_numpy((synth.uniform01("grad_idx", GRAD_SAMPLES, 1).astype(np.float64) * flat.shape[1]).astype(np.int64))
+    return {"sum_hw": to_np(g.sum(dim=(2, 3))), "sum_cw": to_np(g.sum(dim=(1, 3))), "sum_ch": to_np(g.sum(dim=(1, 2))),
+            "absmax": np.float32(g.abs().max()), "samples": to_np(flat[:, idx])}
+
+
+def golden_integral_backward(ns, robot_type: str, batch: int = 2):
+    """f4 (first piece): autograd of the REFERENCE's HeatmapIntegralPose w.r.t. its bf16-exact logits, for the loss
+    sum(uvd * G1) + sum(xyz * G2); stored as a digest.  The oracle's autograd must reproduce it."""
+    dof, nkpt, ref = arch.ROBOTS[robot_type]
+    _, _, k, K = synth.inputs(batch, seed=13)
+    root_trans = torch.zeros(batch, 3)
+    root_trans[:, 2] = synth.range_uniform("root_z", (batch,), 0.8, 2.5, 13)
+    G1 = synth.sym_uniform("g_uvd", (batch, nkpt, 3), 1.0, 3)
+    G2 = synth.sym_uniform("g_xyz", (batch, nkpt, 3), 1.0, 4)
+    layer = ns.integral.HeatmapIntegralPose(backbone="resnet50", num_joints=nkpt, depth_dim=64, height_dim=64,
+                                            width_dim=64, norm_type="softmax", image_size=256.0,
+                                            bbox_3d_shape=[1300, 1300, 1300], rootid=ref, fixroot=True)
+    data = {}
+    for tag, gain in (("", 1.0), ("_peaky", HEATMAP_STRESS_GAIN)):
+        logits = heatmap_logits(robot_type, batch, gain=gain).bfloat16().float()
+        with torch.enable_grad():
+            x = logits.clone().requires_grad_(True)
+            uvd, xyz = layer(x, root_trans=root_trans, K=K)
+            ((uvd * G1).sum() + (xyz * G2).sum()).backward()
+            xo = logits.clone().requires_grad_(True)
+            ou, ox = O.heatmap_integral(xo, nkpt, K, root_trans, ref, fixroot=True, image_size=256.0,
+                                        depth_factor=float(layer.depth_factor))
+            ((ou * G1).sum() + (ox * G2).sum()).backward()
+        assert torch.equal(x.grad, xo.grad), f"oracle autograd differs from the reference ({robot_type}{tag})"
+        for kk, v in grad_digest(x.grad).items():
+            data[kk + tag] = v
+    np.savez(GOLDEN / f"integral_backward_{robot_type}.npz", **data)
+
+
 def golden_geometry(ns):
     r6 = synth.sym_uniform("rot6d", (64, 6), 1.0, 4)
     R = ns.geometries.rot6d_to_rotmat(r6)
@@ -295,6 +337,8 @@ def main():
     for r in ("panda", "kuka", "baxter"):
         golden_metrics(ns, r)
         golden_pnp(ns, r)
+    for r in ("panda", "baxter"):
+        golden_integral_backward(ns, r)
     if args.only_eval:
         return
     golden_geometry(ns)

@@ -184,3 +184,13 @@ def test_heatmap_integral_backward_vs_autograd(rt, hrp_lib):
         # the reference keypoint's depth is pinned to 0 (integral.py:134): its depth expectation gets no gradient,
         # and gradients of one keypoint's logits sum to zero (softmax)
         assert float(got.double().reshape(B, nkpt, -1).sum(dim=2).abs().max()) < 5e-2 * scale   # 262144 fp32 terms
+        # and against the digest of the REFERENCE's own autograd (tests/golden/make_golden.py: golden_integral_backward)
+        from make_golden import grad_digest
+        gold = np.load(GOLDEN / f"integral_backward_{rt}.npz")
+        tag = "" if gain == 1.0 else "_peaky"
+        dg = grad_digest(got)
+        amax = float(gold["absmax" + tag])
+        assert abs(float(dg["absmax"]) - amax) < 2e-4 * amax
+        assert np.abs(dg["samples"] - gold["samples" + tag]).max() < 2e-4 * amax
+        for m in ("sum_hw", "sum_cw", "sum_ch"):   # sums of 4096 / nkpt*4096 entries: rounding noise adds up
+            assert np.abs(dg[m] - gold[m + tag]).max() < 5e-2 * amax, m
