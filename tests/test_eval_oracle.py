@@ -23,8 +23,12 @@ def test_crop_oracle_matches_reference_bytes():
     assert any(int(max(b[2] - b[0], b[3] - b[1])) == 256 for b in boxes)  # identity branch is covered
     for b in range(CROP_BATCH):
         img, Kn = EO.crop_resize(frames[b], boxes[b], K[b])
-        # byte work: exact.  (torch's CPU bilinear is the same compiled kernel on every x86 host of this image.)
-        assert np.array_equal(img.numpy(), g["images"][b]), f"crop {b}"
+        # byte work: the fixture holds the reference's bytes.  The oracle calls torch's CPU bilinear kernel, whose
+        # AVX2 / AVX-512 builds may contract multiply-adds differently; a different host may therefore flip the
+        # truncation of a value that sits within one fp32 ulp of an integer: allow single-LSB flips on < 0.01 % of the
+        # bytes here (0 observed in the generating container).  The CUDA kernel is compared EXACTLY to the fixture.
+        diff = np.abs(img.numpy().astype(np.int16) - g["images"][b].astype(np.int16))
+        assert diff.max() <= 1 and (diff != 0).mean() < 1e-4, f"crop {b}: max diff {diff.max()}, {(diff != 0).sum()} bytes"
         assert np.array_equal(Kn.numpy(), g["K"][b]), f"K {b}"
     Kt = torch.as_tensor(K).float()
     kv = EO.k_value(Kt[:, 0, 0], Kt[:, 1, 1], k_bbox)
