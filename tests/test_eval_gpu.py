@@ -41,9 +41,15 @@ def test_crop_resize_vs_oracle_random_boxes_and_ragged_frames(hrp_lib):
     boxes[12] = (100, 100, 103, 103)
     img, Kn, kv = crop_resize_batch(torch.from_numpy(frames).cuda(), torch.from_numpy(boxes).cuda(),
                                     torch.from_numpy(K).cuda(), k_bbox=torch.from_numpy(k_bbox).cuda(), k_from_crop_K=True)
+    def same_bytes(a, o):
+        # the live oracle is torch's CPU bilinear on THIS host: a different vector ISA build may flip the truncation of a
+        # value within one fp32 ulp of an integer (see tests/test_eval_oracle.py); the committed fixture is compared exactly
+        d = np.abs(a.astype(np.int16) - o.astype(np.int16))
+        return d.max() <= 1 and (d != 0).mean() < 1e-4
+
     for b in range(40):
         o_img, o_K = EO.crop_resize(frames[b], boxes[b], K[b])
-        assert np.array_equal(img[b].cpu().numpy(), o_img.numpy()), (b, boxes[b])
+        assert same_bytes(img[b].cpu().numpy(), o_img.numpy()), (b, boxes[b])
         assert np.array_equal(Kn[b].cpu().numpy(), o_K.numpy()), (b, boxes[b])
     assert np.array_equal(kv.cpu().numpy(), EO.k_value(Kn[:, 0, 0].cpu(), Kn[:, 1, 1].cpu(), k_bbox).numpy())
     # odd frame size
@@ -52,7 +58,7 @@ def test_crop_resize_vs_oracle_random_boxes_and_ragged_frames(hrp_lib):
     img2, K2 = crop_resize_batch(torch.from_numpy(f2).cuda(), torch.from_numpy(b2).cuda(), torch.from_numpy(K[:3]).cuda())
     for b in range(3):
         o_img, o_K = EO.crop_resize(f2[b], b2[b], K[b])
-        assert np.array_equal(img2[b].cpu().numpy(), o_img.numpy()), b
+        assert same_bytes(img2[b].cpu().numpy(), o_img.numpy()), b
         assert np.array_equal(K2[b].cpu().numpy(), o_K.numpy()), b
     with pytest.raises(ValueError):
         crop_resize_batch(torch.from_numpy(f2).cuda(), torch.tensor([[0, 0, 518, 10]] * 3).cuda(), torch.from_numpy(K[:3]).cuda())
