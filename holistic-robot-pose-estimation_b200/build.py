@@ -1,6 +1,7 @@
 """In-tree build of libhrp_b200.so (hand-written sm_100a CUDA behind the C ABI of include/hrp.h).
 
-`python -m horopose_b200.build` or `__graft_entry__.build()` compiles every .cu under csrc/ with
+`python -m horopose_b200.build` or `__graft_entry__.build()` compiles every .cu under csrc/ (plus the hardware probes
+of tools/probe/ when HRP_BUILD_PROBES=1) with
 nvcc -gencode arch=compute_100a,code=sm_100a and links one shared library next to this file.  The build is
 incremental (object files under build/, rebuilt when a source or header is newer).  nvcc cross-compiles
 without a GPU.
@@ -44,6 +45,15 @@ def _newest_header_mtime() -> float:
 def build(verbose: bool = False, force: bool = False) -> Path:
     BUILD_DIR.mkdir(exist_ok=True)
     srcs = sorted(CSRC.glob("*.cu"))
+    probes = os.environ.get("HRP_BUILD_PROBES") == "1"
+    if probes:  # hardware probes (tools/probe/): profiling aids, not part of the product library by default
+        srcs.append(REPO / "tools" / "probe" / "probe.cu")
+    stale_probe = BUILD_DIR / "probe.o"
+    if not probes and stale_probe.exists():
+        stale_probe.unlink()
+        force_link = True
+    else:
+        force_link = False
     hdr_m = _newest_header_mtime()
     jobs = []
     objs = []
@@ -67,7 +77,7 @@ def build(verbose: bool = False, force: bool = False) -> Path:
             for out in ex.map(run, jobs):
                 if verbose and out.strip():
                     print(out)
-    if jobs or not LIB_PATH.exists() or force:
+    if jobs or not LIB_PATH.exists() or force or force_link:
         cmd = [_nvcc(), "-shared", "-o", str(LIB_PATH), *map(str, objs), "-gencode",
                "arch=compute_100a,code=sm_100a", "-cudart", "static"]
         out = run(cmd)

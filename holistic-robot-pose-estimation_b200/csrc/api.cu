@@ -8,6 +8,7 @@
 #include "ops.h"
 
 #include <new>
+#include <vector>
 
 namespace hrp {
 static thread_local std::string g_err;
@@ -22,6 +23,8 @@ using namespace hrp;
 struct hrp_robot {
   RobotTable host;
   RobotTable* dev = nullptr;
+  LinkRowDev* full_rows = nullptr;  // optional unpruned tree (hrp_robot_set_full_tree) for hrp_link_fk(all_links = 1)
+  int n_full = 0;
 };
 
 struct hrp_conv {
@@ -226,7 +229,67 @@ int hrp_robot_dims(const hrp_robot* robot, int32_t* nkpt, int32_t* dof) {
 void hrp_robot_destroy(hrp_robot* robot) {
   if (robot == nullptr) return;
   if (robot->dev) cudaFree(robot->dev);
+  if (robot->full_rows) cudaFree(robot->full_rows);
   delete robot;
+}
+
+int hrp_robot_set_full_tree(hrp_robot* robot, const hrp_link_row* rows, int32_t n_links) {
+  HRP_REQUIRE(robot != nullptr && rows != nullptr && n_links > 0 && n_links <= 4096, "bad argument");
+  std::vector<LinkRowDev> h((size_t)n_links);
+  for (int i = 0; i < n_links; ++i) {
+    const hrp_link_row& row = rows[i];
+    if (!(row.parent < i && row.parent >= -1) || row.jtype < 0 || row.jtype > 2 || row.qcol >= robot->host.dof ||
+        (row.jtype != 0 && row.qcol < 0)) {
+      set_error("invalid link row " + std::to_string(i));
+      return HRP_ERR_INVALID;
+    }
+    LinkRowDev& d = h[i];
+    memset(&d, 0, sizeof(d));
+    d.parent = row.parent;
+    d.jtype = row.jtype;
+    d.qcol = row.qcol;
+    d.qmul = (float)row.qmul;
+    d.qoff = (float)row.qoff;
+    for (int e = 0; e < 12; ++e) d.origin[e] = (float)row.origin[e];
+    for (int a = 0; a < 3; ++a) d.axis[a] = (float)row.axis[a];
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) d.axis_outer[a * 3 + b] = (float)(row.axis[a] * row.axis[b]);
+  }
+  if (robot->full_rows) cudaFree(robot->full_rows);
+  robot->full_rows = nullptr;
+  robot->n_full = 0;
+  HRP_CUDA_CHECK(cudaMalloc(&robot->full_rows, h.size() * sizeof(LinkRowDev)));
+  HRP_CUDA_CHECK(cudaMemcpy(robot->full_rows, h.data(), h.size() * sizeof(LinkRowDev), cudaMemcpyHostToDevice));
+  robot->n_full = n_links;
+  return HRP_OK;
+}
+
+int hrp_link_fk(hrp_robot* robot, const float* q, int32_t B, int32_t all_links, float global_scale, float* out_T,
+                void* stream) {
+  HRP_REQUIRE(robot != nullptr && q != nullptr && out_T != nullptr && B > 0, "bad argument");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (all_links) {
+    if (robot->full_rows == nullptr) {
+      set_error("hrp_link_fk(all_links = 1) needs hrp_robot_set_full_tree first");
+      return HRP_ERR_STATE;
+    }
+    return launch_link_fk_all(robot->full_rows, robot->n_full, q, robot->host.dof, B, out_T, s);
+  }
+  return launch_twl(robot->dev, robot->host.n_links, robot->host.nkpt, q, B, global_scale, out_T, s);
+}
+
+int hrp_inv_intrinsics(const float* K, float* Kinv, int32_t B, void* stream) {
+  return launch_inv_intrinsics(K, Kinv, B, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int hrp_uvd_to_xyz(const float* uvd, const float* Kinv, const float* root_trans, float image_size, float depth_factor,
+                   int32_t return_relative, int32_t B, int32_t N, float* xyz, void* stream) {
+  return launch_uvd_to_xyz(uvd, Kinv, root_trans, image_size, depth_factor, return_relative, B, N, xyz,
+                           reinterpret_cast<cudaStream_t>(stream));
+}
+
+int hrp_uvz2xyz_singlepoint(const float* uv, const float* z, const float* K, int32_t B, float* xyz, void* stream) {
+  return launch_uvz2xyz(uv, z, K, B, xyz, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int hrp_fk(hrp_robot* robot, const float* q, const float* rot, int32_t rot_dim, const float* trans, int32_t root,

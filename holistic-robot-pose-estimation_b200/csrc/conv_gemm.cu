@@ -347,7 +347,10 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
           *sptr = o;
         }
         if (pool) {
-          // global average pool: the 32 rows of a warp belong to one image (host checks bw*bh >= 32)
+          // global average pool: the 32 rows of a warp belong to one image (host checks bw*bh >= 32).  Bitwise
+          // reproducibility: the within-warp tree is fixed, and on the path the pooled maps are 8x8 = two warps per
+          // image, i.e. exactly two atomicAdd contributions per (image, channel) onto a zeroed accumulator -- fp32
+          // addition is commutative, so their arrival order cannot change the result (tests: bitwise replay)
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             float x = valid ? v[i] : 0.f;

@@ -328,9 +328,11 @@ __global__ void __launch_bounds__(kSumThreads) metrics_summary_kernel(SummaryPar
   __syncthreads();
   double acc = 0.0;
   unsigned tab[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned n_nan = 0;  // an image without in-frame ground-truth keypoints has error2d = 0/0 (metrics.py:67-70)
   for (long long i = threadIdx.x; i < n; i += kSumThreads) {
     const float df = d[i];
     const double x = (double)df;
+    n_nan += (df != df) ? 1u : 0u;
     acc += x;
     long long j = nthr;  // above every threshold (or NaN)
     if (x <= (double)(nthr - 1) * delta) {
@@ -345,6 +347,7 @@ __global__ void __launch_bounds__(kSumThreads) metrics_summary_kernel(SummaryPar
     for (int t = 0; t < 8; ++t) tab[t] += (df <= p.table_thr[(pck ? 8 : 0) + t]) ? 1u : 0u;  // fp32 compare (weak python scalar)
   }
   const double total = block_sum_f64(acc, shd);
+  const bool any_nan = block_sum_f64((double)n_nan, shd) > 0.0;
   for (int t = 0; t < 8; ++t) {
     const double c = block_sum_f64((double)tab[t], shd);
     if (threadIdx.x == 0) out[3 + t] = c / (double)n;
@@ -373,6 +376,9 @@ __global__ void __launch_bounds__(kSumThreads) metrics_summary_kernel(SummaryPar
     const float m_lo = block_select(d, n, n / 2 - 1, sel_hist, sel_hist + 256);
     med = (m_lo + m_hi) * 0.5f;  // exact unless m_lo + m_hi overflows
   }
+  // np.median propagates NaN (and np.mean does through `total`); the radix select orders bit patterns of non-negative
+  // finite floats only
+  if (any_nan) med = __int_as_float(0x7fc00000);
   if (threadIdx.x == 0) {
     out[0] = total / (double)n;
     out[1] = (double)med;

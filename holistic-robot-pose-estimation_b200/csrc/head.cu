@@ -213,12 +213,187 @@ int launch_fk(const FkParams& p, cudaStream_t s) {
   HRP_REQUIRE(!p.use_b2c || (p.rot != nullptr && p.trans != nullptr), "rotation / translation required");
   HRP_REQUIRE(!p.use_b2c || p.rot_dim == 6 || p.rot_dim == 4, "rotation must be 6-D or a quaternion");
   const int smem = kMaxLinks * 12 * kFkThreads * (int)sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(fk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr = true;
-  }
+  // (set on every launch: the attribute is per device, and a process may drive several GPUs)
+  HRP_CUDA_CHECK(cudaFuncSetAttribute(fk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   fk_kernel<<<(p.B + kFkThreads - 1) / kFkThreads, kFkThreads, smem, s>>>(p);
+  count_launch();
+  HRP_CUDA_CHECK(cudaGetLastError());
+  return HRP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// link transforms: URDFRobot.get_TWL (urdf_robot.py:107-111) and URDF.link_fk_batch over ALL links
+// (urdf.py:3061-3149) -- one thread per sample
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFkThreads) twl_kernel(const RobotTable* __restrict__ rb, const float* __restrict__ q, int B,
+                                                         float scale, float* __restrict__ out) {
+  extern __shared__ float fk_smem[];
+  const int b = blockIdx.x * kFkThreads + threadIdx.x;
+  if (b >= B) return;
+  float* T = fk_smem + threadIdx.x;
+  float qv[kMaxDof];
+  for (int i = 0; i < rb->dof; ++i) qv[i] = q[(size_t)b * rb->dof + i];
+  fk_tree(rb, qv, T, kFkThreads);
+  for (int k = 0; k < rb->nkpt; ++k) {
+    const float* Tl = T + (size_t)rb->kp_link[k] * 12 * kFkThreads;
+    float* o = out + ((size_t)b * rb->nkpt + k) * 16;
+#pragma unroll
+    for (int e = 0; e < 12; ++e) o[e] = ((e & 3) == 3) ? Tl[e * kFkThreads] * scale : Tl[e * kFkThreads];
+    o[12] = 0.f; o[13] = 0.f; o[14] = 0.f; o[15] = 1.f;
+  }
+}
+
+int launch_twl(const RobotTable* robot, int n_links, int nkpt, const float* q, int B, float scale, float* out_T,
+               cudaStream_t s) {
+  HRP_REQUIRE(robot != nullptr && q != nullptr && out_T != nullptr && B > 0, "bad get_TWL arguments");
+  (void)n_links; (void)nkpt;
+  const int smem = kMaxLinks * 12 * kFkThreads * (int)sizeof(float);
+  HRP_CUDA_CHECK(cudaFuncSetAttribute(twl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  twl_kernel<<<(B + kFkThreads - 1) / kFkThreads, kFkThreads, smem, s>>>(robot, q, B, scale, out_T);
+  count_launch();
+  HRP_CUDA_CHECK(cudaGetLastError());
+  return HRP_OK;
+}
+
+__global__ void link_fk_all_kernel(const LinkRowDev* __restrict__ rows, int n_links, const float* __restrict__ q, int dof,
+                                   int B, float* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float* Tb = out + (size_t)b * n_links * 16;
+  for (int i = 0; i < n_links; ++i) {
+    const LinkRowDev& r = rows[i];
+    float* Ti = Tb + (size_t)i * 16;
+    Ti[12] = 0.f; Ti[13] = 0.f; Ti[14] = 0.f; Ti[15] = 1.f;
+    if (r.parent < 0) {
+#pragma unroll
+      for (int e = 0; e < 12; ++e) Ti[e] = (e == 0 || e == 5 || e == 10) ? 1.f : 0.f;
+      continue;
+    }
+    float child[12];
+    const float* O = r.origin;
+    if (r.jtype == 0) {
+#pragma unroll
+      for (int e = 0; e < 12; ++e) child[e] = O[e];
+    } else {
+      const float cfg = r.qmul * q[(size_t)b * dof + r.qcol] + r.qoff;
+      if (r.jtype == 1) {  // same Rodrigues form as fk_tree (urdf.py:2447-2462)
+        float sn, c;
+        sincosf(cfg, &sn, &c);
+        const float* ax = r.axis;
+        const float* oo = r.axis_outer;
+        const float omc = 1.0f - c;
+        float M[9];
+        M[0] = (c + oo[0] * omc);
+        M[1] = (oo[1] * omc) + (-ax[2]) * sn;
+        M[2] = (oo[2] * omc) + ax[1] * sn;
+        M[3] = (oo[3] * omc) + ax[2] * sn;
+        M[4] = (c + oo[4] * omc);
+        M[5] = (oo[5] * omc) + (-ax[0]) * sn;
+        M[6] = (oo[6] * omc) + (-ax[1]) * sn;
+        M[7] = (oo[7] * omc) + ax[0] * sn;
+        M[8] = (c + oo[8] * omc);
+#pragma unroll
+        for (int rr = 0; rr < 3; ++rr) {
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc)
+            child[rr * 4 + cc] = fmaf(O[rr * 4 + 2], M[6 + cc], fmaf(O[rr * 4 + 1], M[3 + cc], O[rr * 4 + 0] * M[cc]));
+          child[rr * 4 + 3] = O[rr * 4 + 3];
+        }
+      } else {
+        const float t0 = r.axis[0] * cfg, t1 = r.axis[1] * cfg, t2 = r.axis[2] * cfg;
+#pragma unroll
+        for (int rr = 0; rr < 3; ++rr) {
+          child[rr * 4 + 0] = O[rr * 4 + 0];
+          child[rr * 4 + 1] = O[rr * 4 + 1];
+          child[rr * 4 + 2] = O[rr * 4 + 2];
+          child[rr * 4 + 3] = fmaf(O[rr * 4 + 2], t2, fmaf(O[rr * 4 + 1], t1, O[rr * 4 + 0] * t0)) + O[rr * 4 + 3];
+        }
+      }
+    }
+    rigid_mul(Tb + (size_t)r.parent * 16, 1, child, 1, Ti, 1);  // (this thread wrote the parent's transform itself)
+  }
+}
+
+int launch_link_fk_all(const LinkRowDev* rows, int n_links, const float* q, int dof, int B, float* out_T, cudaStream_t s) {
+  HRP_REQUIRE(rows != nullptr && q != nullptr && out_T != nullptr && B > 0 && n_links > 0 && dof > 0, "bad link-FK arguments");
+  link_fk_all_kernel<<<(B + 63) / 64, 64, 0, s>>>(rows, n_links, q, dof, B, out_T);
+  count_launch();
+  HRP_CUDA_CHECK(cudaGetLastError());
+  return HRP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// standalone geometry operators (the fused head computes the same expressions in head_finalize)
+// ------------------------------------------------------------------------------------------------------
+// get_intrinsic_matrix_batch(inv=True) (integral.py:56-73, transforms.py:145-162): divisions in fp64, stored fp32
+__global__ void inv_intrinsics_kernel(const float* __restrict__ K, float* __restrict__ Ki, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* k = K + (size_t)b * 9;
+  float* o = Ki + (size_t)b * 9;
+  const double fx = (double)k[0], fy = (double)k[4], cx = (double)k[2], cy = (double)k[5];
+  o[0] = (float)(1.0 / fx); o[1] = 0.f; o[2] = (float)(-cx / fx);
+  o[3] = 0.f; o[4] = (float)(1.0 / fy); o[5] = (float)(-cy / fy);
+  o[6] = 0.f; o[7] = 0.f; o[8] = 1.f;
+}
+
+int launch_inv_intrinsics(const float* K, float* Kinv, int B, cudaStream_t s) {
+  HRP_REQUIRE(K != nullptr && Kinv != nullptr && B > 0, "bad intrinsics arguments");
+  inv_intrinsics_kernel<<<(B + 127) / 128, 128, 0, s>>>(K, Kinv, B);
+  count_launch();
+  HRP_CUDA_CHECK(cudaGetLastError());
+  return HRP_OK;
+}
+
+// uvd_to_xyz (transforms.py:33-73) with a GENERAL 3x3 inverse intrinsic matrix, as the reference's batched matmul
+__global__ void uvd_to_xyz_kernel(const float* __restrict__ uvd, const float* __restrict__ Kinv,
+                                  const float* __restrict__ root_trans, float image_size, float depth_factor, int relative,
+                                  int B, int N, float* __restrict__ xyz) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * N) return;
+  const int b = i / N;
+  const float* k = Kinv + (size_t)b * 9;
+  const float u = (uvd[(size_t)i * 3] + 0.5f) * image_size, v = (uvd[(size_t)i * 3 + 1] + 0.5f) * image_size;
+  const float dz = uvd[(size_t)i * 3 + 2] * depth_factor;
+  const float az = dz + root_trans[(size_t)b * 3 + 2];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    float h = fmaf(k[r * 3 + 2], 1.0f, fmaf(k[r * 3 + 1], v, k[r * 3] * u));
+    h *= az;
+    if (relative) h -= root_trans[(size_t)b * 3 + r];
+    xyz[(size_t)i * 3 + r] = h;
+  }
+}
+
+int launch_uvd_to_xyz(const float* uvd, const float* Kinv, const float* root_trans, float image_size, float depth_factor,
+                      int return_relative, int B, int N, float* xyz, cudaStream_t s) {
+  HRP_REQUIRE(uvd != nullptr && Kinv != nullptr && root_trans != nullptr && xyz != nullptr && B > 0 && N > 0,
+              "bad uvd_to_xyz arguments");
+  uvd_to_xyz_kernel<<<(B * N + 127) / 128, 128, 0, s>>>(uvd, Kinv, root_trans, image_size, depth_factor, return_relative, B, N,
+                                                      xyz);
+  count_launch();
+  HRP_CUDA_CHECK(cudaGetLastError());
+  return HRP_OK;
+}
+
+// uvz2xyz_singlepoint (transforms.py:133-143): xyz = Kinv(K) * [u z, v z, z]
+__global__ void uvz2xyz_kernel(const float* __restrict__ uv, const float* __restrict__ z, const float* __restrict__ K, int B,
+                               float* __restrict__ xyz) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* k = K + (size_t)b * 9;
+  const double fx = (double)k[0], fy = (double)k[4], cx = (double)k[2], cy = (double)k[5];
+  const float ifx = (float)(1.0 / fx), ify = (float)(1.0 / fy), icx = (float)(-cx / fx), icy = (float)(-cy / fy);
+  const float zz = z[b];
+  const float a = uv[(size_t)b * 2] * zz, c = uv[(size_t)b * 2 + 1] * zz;
+  xyz[(size_t)b * 3] = fmaf(icx, zz, ifx * a);
+  xyz[(size_t)b * 3 + 1] = fmaf(icy, zz, ify * c);
+  xyz[(size_t)b * 3 + 2] = zz;
+}
+
+int launch_uvz2xyz(const float* uv, const float* z, const float* K, int B, float* xyz, cudaStream_t s) {
+  HRP_REQUIRE(uv != nullptr && z != nullptr && K != nullptr && xyz != nullptr && B > 0, "bad uvz2xyz arguments");
+  uvz2xyz_kernel<<<(B + 127) / 128, 128, 0, s>>>(uv, z, K, B, xyz);
   count_launch();
   HRP_CUDA_CHECK(cudaGetLastError());
   return HRP_OK;

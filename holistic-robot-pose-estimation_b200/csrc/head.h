@@ -89,6 +89,27 @@ struct FkParams {
   float* rot_out;      // (B,rot_dim) rotation at `root` (get_rotation_at_specific_root) or null
 };
 int launch_fk(const FkParams& p, cudaStream_t s);
+
+// One link of an UNPRUNED kinematic tree (URDF.link_fk_batch over all links, urdf.py:3061-3149): any number of links,
+// rows in parent-before-child order in global memory.
+struct LinkRowDev {
+  int parent, jtype, qcol, pad;
+  float qmul, qoff;
+  float origin[12];
+  float axis[3];
+  float axis_outer[9];
+};
+// out_T (B, n_links, 4, 4) row-major homogeneous transforms of every link (base frame)
+int launch_link_fk_all(const LinkRowDev* rows, int n_links, const float* q, int dof, int B, float* out_T, cudaStream_t s);
+// out_T (B, nkpt, 4, 4): transforms of the keypoint links of the pruned table, translation scaled by `scale`
+// (URDFRobot.get_TWL, urdf_robot.py:107-111)
+int launch_twl(const RobotTable* robot, int n_links, int nkpt, const float* q, int B, float scale, float* out_T,
+               cudaStream_t s);
+// standalone geometry operators of the head (transforms.py:33-73,133-162; integral.py:56-73)
+int launch_inv_intrinsics(const float* K, float* Kinv, int B, cudaStream_t s);
+int launch_uvd_to_xyz(const float* uvd, const float* Kinv, const float* root_trans, float image_size, float depth_factor,
+                      int return_relative, int B, int N, float* xyz, cudaStream_t s);
+int launch_uvz2xyz(const float* uv, const float* z, const float* K, int B, float* xyz, cudaStream_t s);
 int launch_project(const float* K, const float* pts, float* uv, int B, int N, cudaStream_t s);
 int launch_depth(const float* feat, const float* w, float b, const float* k, float* out, int B, float out_scale,
                  cudaStream_t s);

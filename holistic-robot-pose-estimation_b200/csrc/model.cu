@@ -16,6 +16,8 @@
 #include <cmath>
 #include <map>
 #include <memory>
+#include <mutex>
+#include <sstream>
 #include <string>
 #include <vector>
 
@@ -92,6 +94,12 @@ struct Plan {
   cudaStream_t cap[kNumLanes] = {};
   cudaEvent_t fork_ev = nullptr, join_ev[kNumLanes] = {};
   cudaEvent_t done_ev = nullptr;
+  // every forward that used this plan's buffers records busy_ev on its stream when it has enqueued its last kernel; the
+  // next user -- possibly on another stream -- waits on it first, so two forwards never overlap on one set of
+  // activation buffers / pooled accumulators / head counters
+  cudaEvent_t busy_ev = nullptr;
+  bool busy_recorded = false;
+  uint64_t last_use = 0;  // LRU stamp (hrp_model::use_counter)
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
   int n_kernels = 0;
@@ -108,6 +116,10 @@ struct Plan {
     }
     if (fork_ev) cudaEventDestroy(fork_ev);
     if (done_ev) cudaEventDestroy(done_ev);
+    if (busy_ev) {
+      if (busy_recorded) cudaEventSynchronize(busy_ev);  // eviction / destruction: the last user must have finished
+      cudaEventDestroy(busy_ev);
+    }
     if (stream) cudaStreamDestroy(stream);
     for (void* p : owned) cudaFree(p);
   }
@@ -126,8 +138,16 @@ struct hrp_model {
   bool finalized = false;
   std::map<std::string, HostTensor> host;
   std::map<std::string, ConvWeights> wcache;
-  std::map<std::string, int> tune_cache;  // conv shape signature -> 1 persistent kernel, 0 one-tile-per-CTA kernel
-  bool autotune = true;
+  // conv shape signature -> kernel variant (0 one tile per CTA, 1 persistent, 2 halo).  Filled from the committed tuning
+  // table (hrp_model_set_tuning: the default, deterministic) and / or by the timed autotune (HRP_AUTOTUNE=1).
+  std::map<std::string, int> tune_cache;
+  bool autotune = false;
+  bool pin_variants = false;                   // HRP_CONV_PERSISTENT / HRP_CONV_VARIANT pin the kernel: no table, no tuning
+  std::mutex mu;                               // guards plans / tune_cache / stream_slot and serialises enqueueing
+  std::map<cudaStream_t, int> stream_slot;     // caller stream -> plan replica (round-robin over desc.inflight)
+  int next_slot = 0;
+  uint64_t use_counter = 0;
+  int max_plans = 8;                           // LRU bound on cached plans (HRP_MAX_PLANS)
   std::vector<void*> owned;
   const hrp_robot* robot = nullptr;
   RegressorTable* reg_pose = nullptr;
@@ -598,27 +618,41 @@ int launch_op(const hrp_model* m, const Op& op, cudaStream_t s) {
   return HRP_ERR_STATE;
 }
 
-// Pick, per conv shape, the faster of the two tcgen05 kernels (persistent vs one-tile-per-CTA) by timing both on
-// the plan's own buffers (3 launches each, CUDA events).  Decisions are cached by shape signature.
+// Kernel variant per conv: the committed tuning table (hrp_model_set_tuning) decides where it has an entry -- the same
+// choice on every box and every run, so results are bitwise reproducible --, the shape heuristics of conv_plan_finalize
+// elsewhere.  With HRP_AUTOTUNE=1 shapes missing from the table are timed on the plan's own buffers instead (3 launches
+// per variant, CUDA events) and the winners are added to the cache (hrp_model_get_tuning dumps it: that is how the table
+// is produced, tools/make_tuning.py).
+void tune_key(const Op& op, char* key, size_t len) {
+  const ConvParams& q = op.conv.p;
+  snprintf(key, len, "%d:%d:%d:%d:%d:%d:%d:%d:%d:%d:%d:%d:%d", q.B, q.Hin, q.Win, q.Cin, q.Cout, q.Hout, q.ntaps, q.nphase,
+           q.src_sh, op.conv.epi, q.pre[0] != nullptr, q.pool_out != nullptr, q.out != nullptr);
+}
+
+void apply_variant(Op& op, int pick) {
+  op.conv.halo = (pick == 2) && op.conv.halo_ok;
+  if (pick < 2) op.conv.persistent = (pick == 1);
+}
+
 int autotune_plan(hrp_model* m, Plan* pl) {
-  if (!m->autotune || m->use_simt) return HRP_OK;
+  if (m->use_simt || m->pin_variants) return HRP_OK;
   cudaStream_t s = nullptr;
-  HRP_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-  cudaEvent_t e0, e1;
-  HRP_CUDA_CHECK(cudaEventCreate(&e0));
-  HRP_CUDA_CHECK(cudaEventCreate(&e1));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
   char key[256];
   int rc = HRP_OK;
   for (auto& op : pl->ops) {
     if (op.kind != OP_CONV) continue;
-    const ConvParams& q = op.conv.p;
-    snprintf(key, sizeof(key), "%d:%d:%d:%d:%d:%d:%d:%d:%d:%d:%d:%d:%d", q.B, q.Hin, q.Win, q.Cin, q.Cout, q.Hout, q.ntaps,
-             q.nphase, q.src_sh, op.conv.epi, q.pre[0] != nullptr, q.pool_out != nullptr, q.out != nullptr);
+    tune_key(op, key, sizeof(key));
     auto it = m->tune_cache.find(key);
     if (it != m->tune_cache.end()) {
-      op.conv.halo = (it->second == 2) && op.conv.halo_ok;
-      if (it->second < 2) op.conv.persistent = (it->second == 1);
+      apply_variant(op, it->second);
       continue;
+    }
+    if (!m->autotune) continue;  // heuristic default of conv_plan_finalize
+    if (s == nullptr) {
+      HRP_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+      HRP_CUDA_CHECK(cudaEventCreate(&e0));
+      HRP_CUDA_CHECK(cudaEventCreate(&e1));
     }
     float best[3] = {0.f, 0.f, 0.f};
     const int nvar = op.conv.halo_ok ? 3 : 2;
@@ -640,13 +674,12 @@ int autotune_plan(hrp_model* m, Plan* pl) {
     if (rc != HRP_OK) break;
     int pick = (best[1] < best[0]) ? 1 : 0;
     if (nvar == 3 && best[2] < best[pick]) pick = 2;
-    op.conv.halo = (pick == 2);
-    op.conv.persistent = (pick == 1);
+    apply_variant(op, pick);
     m->tune_cache[key] = pick;
   }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  cudaStreamDestroy(s);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  if (s) cudaStreamDestroy(s);
   return rc;
 }
 
@@ -791,13 +824,54 @@ int build_plan(hrp_model* m, int B, Plan** out_plan, int replica) {
   return HRP_OK;
 }
 
+// Plans are cached per (batch, replica).  The nominal-chunk plans live for the model's lifetime; plans of other batch
+// sizes (ragged tails, callers that vary B) are bounded by an LRU of max_plans entries so that a stream of distinct
+// batch sizes cannot grow device memory without limit.  Caller holds m->mu.
 int get_plan(hrp_model* m, int B, int replica, Plan** out) {
   auto it = m->plans.find(std::make_pair(B, replica));
   if (it != m->plans.end()) {
+    it->second->last_use = ++m->use_counter;
     *out = it->second.get();
     return HRP_OK;
   }
-  return build_plan(m, B, out, replica);
+  while ((int)m->plans.size() >= m->max_plans) {
+    auto victim = m->plans.end();
+    for (auto jt = m->plans.begin(); jt != m->plans.end(); ++jt) {
+      if (jt->first.first == m->desc.chunk) continue;  // nominal plans are never evicted
+      if (victim == m->plans.end() || jt->second->last_use < victim->second->last_use) victim = jt;
+    }
+    if (victim == m->plans.end()) break;
+    if (m->last_plan == victim->second.get()) m->last_plan = nullptr;
+    m->plans.erase(victim);  // ~Plan waits for the plan's last user (busy_ev) before freeing its buffers
+  }
+  int rc = build_plan(m, B, out, replica);
+  if (rc == HRP_OK) (*out)->last_use = ++m->use_counter;
+  return rc;
+}
+
+// Replica used by a single-chunk forward enqueued on `user`: callers that drive the model from several streams (e.g. two
+// batches in flight, bench.py's strong-scaling mode) get distinct plan replicas -- up to desc.inflight of them --, so
+// their forwards overlap instead of serialising on one set of buffers.  Caller holds m->mu.
+int replica_of_stream(hrp_model* m, cudaStream_t user) {
+  if (m->desc.inflight <= 1) return 0;
+  auto it = m->stream_slot.find(user);
+  if (it != m->stream_slot.end()) return it->second;
+  const int slot = m->next_slot;
+  m->next_slot = (m->next_slot + 1) % m->desc.inflight;
+  m->stream_slot[user] = slot;
+  return slot;
+}
+
+// Serialise the users of one plan: wait for the previous forward on this plan (any stream), and mark this one.
+int plan_acquire(Plan* pl, cudaStream_t s) {
+  if (pl->busy_ev == nullptr) HRP_CUDA_CHECK(cudaEventCreateWithFlags(&pl->busy_ev, cudaEventDisableTiming));
+  if (pl->busy_recorded) HRP_CUDA_CHECK(cudaStreamWaitEvent(s, pl->busy_ev, 0));
+  return HRP_OK;
+}
+int plan_release(Plan* pl, cudaStream_t s) {
+  HRP_CUDA_CHECK(cudaEventRecord(pl->busy_ev, s));
+  pl->busy_recorded = true;
+  return HRP_OK;
 }
 
 int run_plan_body(hrp_model* m, Plan* pl, cudaStream_t s) {
@@ -846,8 +920,10 @@ int hrp_model_create(const hrp_model_desc* desc, hrp_model** out) {
   e = getenv("HRP_CONV_IMPL");
   m->use_simt = (e != nullptr && std::string(e) == "simt");
   e = getenv("HRP_AUTOTUNE");
-  m->autotune = !(e != nullptr && e[0] == '0') && getenv("HRP_CONV_PERSISTENT") == nullptr &&
-                getenv("HRP_CONV_VARIANT") == nullptr;
+  m->autotune = (e != nullptr && e[0] == '1');
+  m->pin_variants = getenv("HRP_CONV_PERSISTENT") != nullptr || getenv("HRP_CONV_VARIANT") != nullptr;
+  e = getenv("HRP_MAX_PLANS");
+  if (e != nullptr && atoi(e) >= 1) m->max_plans = atoi(e);
   *out = m;
   return HRP_OK;
 }
@@ -884,6 +960,7 @@ int hrp_model_set_robot(hrp_model* model, const hrp_robot* robot) {
 
 int hrp_model_finalize(hrp_model* m) {
   HRP_REQUIRE(m != nullptr, "null model");
+  std::lock_guard<std::mutex> lock(m->mu);
   if (m->finalized) return HRP_OK;
   HRP_CUDA_CHECK(cudaSetDevice(m->device));
   const HostTensor* dw = find(m, "depth_layer.weight");
@@ -936,6 +1013,7 @@ static int forward_impl(hrp_model* m, const void* x_reg_v, const void* x_root_v,
     set_error("forward before hrp_model_finalize");
     return HRP_ERR_STATE;
   }
+  std::lock_guard<std::mutex> lock(m->mu);  // plans, workspaces and graph launches of one handle are serialised
   HRP_CUDA_CHECK(cudaSetDevice(m->device));
   const bool full = (m->desc.kind == HRP_MODEL_FULL);
   const int chunk = m->desc.chunk;
@@ -947,7 +1025,7 @@ static int forward_impl(hrp_model* m, const void* x_reg_v, const void* x_root_v,
   for (int c = 0; c < nchunks; ++c) {
     const int b0 = c * chunk;
     const int nb = std::min(chunk, B - b0);
-    const int replica = multi ? (c % m->desc.inflight) : 0;
+    const int replica = multi ? (c % m->desc.inflight) : replica_of_stream(m, user);
     Plan* pl = nullptr;
     int rc = get_plan(m, nb, replica, &pl);
     if (rc != HRP_OK) return rc;
@@ -957,6 +1035,8 @@ static int forward_impl(hrp_model* m, const void* x_reg_v, const void* x_root_v,
       HRP_CUDA_CHECK(cudaStreamWaitEvent(s, m->fork_ev, 0));
       used.push_back(pl);
     }
+    rc = plan_acquire(pl, s);
+    if (rc != HRP_OK) return rc;
     rc = in_u8 ? launch_pack_input_s2d_u8(x_root8 + b0 * img, pl->s2d_root, nb, kImg, kImg, s, kS2dPitch, kS2dPad)
                : launch_pack_input_s2d(x_root + b0 * img, pl->s2d_root, nb, kImg, kImg, s, kS2dPitch, kS2dPad);
     if (rc != HRP_OK) return rc;
@@ -969,6 +1049,8 @@ static int forward_impl(hrp_model* m, const void* x_reg_v, const void* x_root_v,
     if (rc != HRP_OK) return rc;
     if (!full) {
       rc = launch_depth(pl->feat, m->depth_w, m->depth_b, k_value + b0, depth_mm + b0, nb, 1.0f, s);
+      if (rc != HRP_OK) return rc;
+      rc = plan_release(pl, s);
       if (rc != HRP_OK) return rc;
       continue;
     }
@@ -1009,6 +1091,8 @@ static int forward_impl(hrp_model* m, const void* x_reg_v, const void* x_root_v,
     hp.uv_int = out->uv_int ? out->uv_int + (size_t)b0 * nk * 2 : nullptr;
     hp.uv_fk = out->uv_fk ? out->uv_fk + (size_t)b0 * nk * 2 : nullptr;
     rc = launch_head(hp, s);
+    if (rc != HRP_OK) return rc;
+    rc = plan_release(pl, s);
     if (rc != HRP_OK) return rc;
   }
   if (multi)
@@ -1083,10 +1167,13 @@ int hrp_model_profile(hrp_model* m, int32_t batch, int32_t iters, char* buf, int
     set_error("profile before finalize");
     return HRP_ERR_STATE;
   }
+  std::lock_guard<std::mutex> lock(m->mu);
   Plan* pl = nullptr;
   int rc = get_plan(m, batch, 0, &pl);
   if (rc != HRP_OK) return rc;
   cudaStream_t s = pl->stream;
+  rc = plan_acquire(pl, s);
+  if (rc != HRP_OK) return rc;
   cudaEvent_t e0, e1;
   HRP_CUDA_CHECK(cudaEventCreate(&e0));
   HRP_CUDA_CHECK(cudaEventCreate(&e1));
@@ -1130,8 +1217,42 @@ int hrp_model_profile(hrp_model* m, int32_t batch, int32_t iters, char* buf, int
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
+  rc = plan_release(pl, s);
+  if (rc != HRP_OK) return rc;
   if ((int64_t)out.size() + 1 > buflen) {
     set_error("profile buffer too small: need " + std::to_string(out.size() + 1));
+    return HRP_ERR_INVALID;
+  }
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return HRP_OK;
+}
+
+int hrp_model_set_tuning(hrp_model* m, const char* text) {
+  HRP_REQUIRE(m != nullptr && text != nullptr, "null argument");
+  std::lock_guard<std::mutex> lock(m->mu);
+  std::istringstream in(text);
+  std::string line;
+  while (std::getline(in, line)) {
+    if (line.empty() || line[0] == '#') continue;
+    std::istringstream ls(line);
+    std::string key;
+    int variant = -1;
+    if (!(ls >> key >> variant) || variant < 0 || variant > 2) {
+      set_error("malformed tuning line: " + line);
+      return HRP_ERR_INVALID;
+    }
+    m->tune_cache[key] = variant;
+  }
+  return HRP_OK;
+}
+
+int hrp_model_get_tuning(hrp_model* m, char* buf, int64_t buflen) {
+  HRP_REQUIRE(m != nullptr && buf != nullptr && buflen > 0, "bad argument");
+  std::lock_guard<std::mutex> lock(m->mu);
+  std::string out;
+  for (auto& kv : m->tune_cache) out += kv.first + " " + std::to_string(kv.second) + "\n";
+  if ((int64_t)out.size() + 1 > buflen) {
+    set_error("tuning buffer too small: need " + std::to_string(out.size() + 1));
     return HRP_ERR_INVALID;
   }
   memcpy(buf, out.c_str(), out.size() + 1);

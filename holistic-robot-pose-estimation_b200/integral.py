@@ -30,7 +30,9 @@ _workspaces = {}
 def _workspace(device, B, nkpt):
     need = C.c_int64(0)
     check(_lib.lib().hrp_head_workspace_bytes(B, nkpt, C.byref(need)))
-    key = (device, B, nkpt)
+    # one workspace per (device, stream, shape): the kernel keeps per-image counters and partial sums there, so two
+    # streams running the head concurrently must not share it
+    key = (device, torch.cuda.current_stream(device).cuda_stream, B, nkpt)
     ws = _workspaces.get(key)
     if ws is None:
         ws = torch.zeros(need.value, dtype=torch.uint8, device=device)
@@ -57,7 +59,7 @@ def run_head(heatmap_nhwc, K, root_depth, *, nkpt, ref_kpt, fix_root=True, image
         pose = pose.detach().to(device=dev, dtype=torch.float32).contiguous()
         rot = rot.detach().to(device=dev, dtype=torch.float32).contiguous()
         keep += [pose, rot]
-        a.robot, a.pose, a.rot = robot.handle(), pose.data_ptr(), rot.data_ptr()
+        a.robot, a.pose, a.rot = robot.handle(dev), pose.data_ptr(), rot.data_ptr()
         out["xyz_fk"] = torch.empty(B, nkpt, 3, dtype=torch.float32, device=dev)
         a.xyz_fk = out["xyz_fk"].data_ptr()
         if want_uv:

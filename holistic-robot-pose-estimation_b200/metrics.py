@@ -89,7 +89,17 @@ def compute_metrics_batch(robot, gt_keypoints3d, gt_keypoints2d, K_original, gt_
 def summary_add_pck(alldis) -> dict:
     """metrics.py:122-162.  alldis['dis3d'] / ['dis2d']: per-image errors (CUDA tensors, or lists of them)."""
     def cat(v):
-        return _f32(torch.cat([x.reshape(-1) for x in v]) if isinstance(v, (list, tuple)) else v).reshape(-1)
+        # the reference accumulates python floats / numpy values (scripts/test.py:199-232): those are uploaded once here;
+        # CUDA tensors (or lists of them) stay on the device; CPU *tensors* are refused like everywhere else (no CPU path)
+        def up(x):
+            if torch.is_tensor(x):
+                return _f32(x)
+            if not torch.cuda.is_available():
+                raise _lib.HrpError("horopose_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+            return torch.as_tensor(x, dtype=torch.float32).to(torch.device("cuda", torch.cuda.current_device()))
+        if isinstance(v, (list, tuple)):
+            v = torch.cat([up(x).reshape(-1) for x in v])
+        return _f32(up(v)).reshape(-1)
     d3, d2 = cat(alldis["dis3d"]), cat(alldis["dis2d"])
     assert d3.shape[0] == d2.shape[0]
     out = torch.empty(22, dtype=torch.float64, device=d3.device)

@@ -46,6 +46,25 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+TUNING_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tuning", "b200.txt")
+
+
+def _tuning_table() -> str:
+    """Committed kernel-variant table (produced on B200 by tools/make_tuning.py).  $HRP_TUNING=0 disables it (shape
+    heuristics only), $HRP_TUNING=<path> selects another file."""
+    sel = os.environ.get("HRP_TUNING", "")
+    if sel == "0":
+        return ""
+    path = sel if sel else TUNING_PATH
+    try:
+        with open(path) as f:
+            return f.read()
+    except FileNotFoundError:
+        if sel:
+            raise
+        return ""
+
+
 class _EngineModule(nn.Module):
     """Common plumbing: weight hand-over and lazy finalisation on the first CUDA forward."""
 
@@ -122,6 +141,9 @@ class _EngineModule(nn.Module):
                     shape = (C.c_int64 * a.ndim)(*a.shape)
                     check(L.hrp_model_set_tensor(h, k.encode(), a.ctypes.data_as(C.POINTER(C.c_float)), shape, a.ndim))
                 self._pre_finalize(h)
+                table = _tuning_table()
+                if table:
+                    check(L.hrp_model_set_tuning(h, table.encode()))
                 check(L.hrp_model_finalize(h))
             except Exception:
                 L.hrp_model_destroy(h)
@@ -130,6 +152,12 @@ class _EngineModule(nn.Module):
 
     def _pre_finalize(self, h):
         pass
+
+    def tuning(self) -> str:
+        """Current kernel-variant table of the handle (committed entries + anything tuned with HRP_AUTOTUNE=1)."""
+        buf = C.create_string_buffer(1 << 20)
+        check(_lib.lib().hrp_model_get_tuning(self._handle, buf, len(buf)))
+        return buf.value.decode()
 
     def activation(self, name: str) -> torch.Tensor:
         """Debug/test hook: copy of a named intermediate activation as fp32 NCHW (or (B,2048) for feat / xf)."""

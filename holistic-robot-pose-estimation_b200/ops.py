@@ -91,13 +91,15 @@ class ConvOp:
         epi.out = self.out.data_ptr() if self.out is not None else None
         epi.pool_out = self.pool_out.data_ptr() if self.pool_out is not None else None
         self.handle = C.c_void_p(0)
-        check(L.hrp_conv_create(C.byref(self.desc), _ptr(x), _ptr(self.w_packed), C.byref(epi),
-                                C.byref(self.handle)))
+        with torch.cuda.device(dev):
+            check(L.hrp_conv_create(C.byref(self.desc), _ptr(x), _ptr(self.w_packed), C.byref(epi),
+                                    C.byref(self.handle)))
 
     def run(self, impl: int = IMPL_TCGEN05):
         if self.pool_out is not None:
             self.pool_out.zero_()
-        check(_lib.lib().hrp_conv_run(self.handle, C.c_int32(impl), _stream()))
+        with torch.cuda.device(self.x.device):
+            check(_lib.lib().hrp_conv_run(self.handle, C.c_int32(impl), _stream()))
         return self.out if self.out is not None else self.pool_out
 
     def __del__(self):
@@ -114,7 +116,8 @@ def pack_input_s2d(x: torch.Tensor) -> torch.Tensor:
     assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == 3
     B, _, H, W = x.shape
     out = torch.empty(B, H // 2, W // 2, 16, dtype=torch.bfloat16, device=x.device)
-    check(_lib.lib().hrp_pack_input_s2d(_ptr(x), _ptr(out), B, H, W, _stream()))
+    with torch.cuda.device(x.device):
+        check(_lib.lib().hrp_pack_input_s2d(_ptr(x), _ptr(out), B, H, W, _stream()))
     return out
 
 
@@ -122,7 +125,8 @@ def maxpool3x3s2(x: torch.Tensor) -> torch.Tensor:
     assert x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous()
     B, H, W, Cc = x.shape
     out = torch.empty(B, H // 2, W // 2, Cc, dtype=torch.bfloat16, device=x.device)
-    check(_lib.lib().hrp_maxpool3x3s2(_ptr(x), _ptr(out), B, H, W, Cc, _stream()))
+    with torch.cuda.device(x.device):
+        check(_lib.lib().hrp_maxpool3x3s2(_ptr(x), _ptr(out), B, H, W, Cc, _stream()))
     return out
 
 
@@ -131,7 +135,8 @@ def nchw_to_nhwc_bf16(x: torch.Tensor, cpad: int | None = None) -> torch.Tensor:
     B, Cc, H, W = x.shape
     cpad = pad_channels(Cc) if cpad is None else cpad
     out = torch.empty(B, H, W, cpad, dtype=torch.bfloat16, device=x.device)
-    check(_lib.lib().hrp_nchw_f32_to_nhwc_bf16(_ptr(x), _ptr(out), B, Cc, H, W, cpad, _stream()))
+    with torch.cuda.device(x.device):
+        check(_lib.lib().hrp_nchw_f32_to_nhwc_bf16(_ptr(x), _ptr(out), B, Cc, H, W, cpad, _stream()))
     return out
 
 
@@ -140,5 +145,6 @@ def nhwc_bf16_to_nchw(x: torch.Tensor, c: int | None = None) -> torch.Tensor:
     B, H, W, cpad = x.shape
     c = cpad if c is None else c
     out = torch.empty(B, c, H, W, dtype=torch.float32, device=x.device)
-    check(_lib.lib().hrp_nhwc_bf16_to_nchw_f32(_ptr(x), _ptr(out), B, c, H, W, cpad, _stream()))
+    with torch.cuda.device(x.device):
+        check(_lib.lib().hrp_nhwc_bf16_to_nchw_f32(_ptr(x), _ptr(out), B, c, H, W, cpad, _stream()))
     return out

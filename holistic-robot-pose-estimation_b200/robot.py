@@ -33,17 +33,57 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
     return t.detach().to(torch.float32).contiguous()
 
 
+# where the reference looks for the robot descriptions, relative to the working directory (lib/config.py:21,33-36;
+# its Baxter path is an absolute path on the authors' machine, the deps/ layout is used here instead)
+_REFERENCE_URDF = {
+    "panda": "data/deps/panda-description/panda.urdf",
+    "kuka": "data/deps/kuka-description/iiwa_description/urdf/iiwa7.urdf",
+    "baxter": "data/deps/baxter-description/baxter_description/urdf/baxter.urdf",
+}
+
+
+def resolve_urdf_path(robot_type: str, urdf_path: str | None = None) -> str:
+    """Explicit argument > $HRP_URDF_<ROBOT> > the reference's `data/deps/...` location under the working directory.
+    `urdf_path="synthetic"` (or `synth.use_synthetic_urdfs()`, which sets the environment variables) selects the
+    mesh-free fixtures shipped for tests and benchmarks.  There is NO silent fallback: a real checkpoint evaluated on
+    approximate kinematics would give silently wrong keypoints."""
+    if urdf_path == "synthetic":
+        from . import synth
+        return str(synth.URDF_PATHS[robot_type])
+    if urdf_path is not None:
+        return str(urdf_path)
+    env = os.environ.get(f"HRP_URDF_{robot_type.upper()}")
+    if env:
+        return env
+    if os.path.exists(_REFERENCE_URDF[robot_type]):
+        return os.path.abspath(_REFERENCE_URDF[robot_type])
+    raise _lib.HrpError(
+        f"no URDF for robot {robot_type!r}: pass urdf_path=..., set HRP_URDF_{robot_type.upper()}, or place the "
+        f"description at ./{_REFERENCE_URDF[robot_type]} as the reference does (lib/config.py:33-36); "
+        "urdf_path='synthetic' selects the test fixture explicitly")
+
+
+class _LinkFkView:
+    """`URDFRobot.robot.link_fk_batch(cfgs, use_names=True)` of the reference (urdf_robot.py:108 ->
+    urdfpytorch/urdf.py:3061-3149): transforms of EVERY link of the description, computed by one CUDA kernel."""
+
+    def __init__(self, owner):
+        self._owner = owner
+
+    def link_fk_batch(self, cfgs, use_names=True):
+        T = self._owner._link_fk_all(cfgs)
+        names = self._owner.tree.link_names
+        if use_names:
+            return {n: T[:, i] for i, n in enumerate(names)}
+        raise NotImplementedError("link_fk_batch(use_names=False) returns Link objects in the reference (off-path)")
+
+
 class URDFRobot:
     def __init__(self, robot_type: str, urdf_path: str | None = None):
         if robot_type not in _DOF:
             raise NotImplementedError(f"robot type {robot_type!r} is outside the hot path (panda / kuka / baxter)")
         self.robot_type = robot_type
-        if urdf_path is None:
-            urdf_path = os.environ.get(f"HRP_URDF_{robot_type.upper()}")
-        if urdf_path is None:
-            from . import synth
-            urdf_path = str(synth.URDF_PATHS[robot_type])  # synthetic fixture (the reference ships no URDFs)
-        self.urdf_path = str(urdf_path)
+        self.urdf_path = resolve_urdf_path(robot_type, urdf_path)
         self.dof = _DOF[robot_type]
         self.tree = urdf.load_urdf(self.urdf_path)
         self.actuated_joint_names = tables.JOINT_NAMES[robot_type]
@@ -56,8 +96,8 @@ class URDFRobot:
         self.link_names, offsets = self._link_names_and_offsets()
         self._offsets_np = offsets
         self.offsets = torch.as_tensor(offsets, dtype=torch.float32).unsqueeze(0).unsqueeze(-1)  # (1,nkpt,3,1)
-        self._handle = None
-        self._device = None
+        self._handles = {}   # device index -> hrp_robot handle (tables live in that device's memory)
+        self.robot = _LinkFkView(self)
 
     # urdf_robot.py:52-80
     def _link_names_and_offsets(self):
@@ -80,7 +120,12 @@ class URDFRobot:
             while i >= 0 and i not in keep:
                 keep.add(i)
                 i = t.parent[i]
-        order = sorted(keep)
+        rows, remap = self._rows(sorted(keep))
+        kp = (C.c_int32 * len(self.link_names))(*[remap[t.link_index(n)] for n in self.link_names])
+        return rows, kp
+
+    def _rows(self, order):
+        t = self.tree
         remap = {old: new for new, old in enumerate(order)}
         rows = (LinkRow * len(order))()
         for new, old in enumerate(order):
@@ -89,24 +134,31 @@ class URDFRobot:
             r.jtype, r.qcol, r.qmul, r.qoff = t.jtype[old], t.qcol[old], t.qmul[old], t.qoff[old]
             r.origin[:] = list(np.asarray(t.origin[old], dtype=np.float64).reshape(-1))
             r.axis[:] = list(np.asarray(t.axis[old], dtype=np.float64))
-        kp = (C.c_int32 * len(self.link_names))(*[remap[t.link_index(n)] for n in self.link_names])
-        return rows, kp
+        return rows, remap
 
-    def handle(self):
-        dev = torch.cuda.current_device()
-        if self._handle is None or self._device != dev:
+    def handle(self, device=None):
+        """hrp_robot handle whose tables live on `device` (default: the current CUDA device)."""
+        dev = torch.cuda.current_device() if device is None else torch.device(device).index
+        if dev is None:
+            dev = torch.cuda.current_device()
+        h = self._handles.get(dev)
+        if h is None:
             rows, kp = self._pruned_rows()
             off = np.ascontiguousarray(self._offsets_np * self.global_scale, dtype=np.float64)
             h = C.c_void_p(0)
-            check(_lib.lib().hrp_robot_create(rows, len(rows), kp, off.ctypes.data_as(C.POINTER(C.c_double)),
-                                              len(self.link_names), self.dof, C.byref(h)))
-            self._handle, self._device = h, dev
-        return self._handle
+            with torch.cuda.device(dev):
+                check(_lib.lib().hrp_robot_create(rows, len(rows), kp, off.ctypes.data_as(C.POINTER(C.c_double)),
+                                                  len(self.link_names), self.dof, C.byref(h)))
+                full, _ = self._rows(list(range(len(self.tree.link_names))))
+                check(_lib.lib().hrp_robot_set_full_tree(h, full, len(full)))
+            self._handles[dev] = h
+        return h
 
     def __del__(self):
         try:
-            if self._handle:
-                _lib.lib().hrp_robot_destroy(self._handle)
+            for h in self._handles.values():
+                _lib.lib().hrp_robot_destroy(h)
+            self._handles = {}
         except Exception:
             pass
 
@@ -126,14 +178,31 @@ class URDFRobot:
         pts = torch.empty(B, nk, 3, dtype=torch.float32, device=q.device) if want_pts else None
         rout = torch.empty(B, rot_dim, dtype=torch.float32, device=q.device) if want_rot else None
         with torch.cuda.device(q.device):
-            check(_lib.lib().hrp_fk(self.handle(), C.c_void_p(q.data_ptr()),
+            check(_lib.lib().hrp_fk(self.handle(q.device), C.c_void_p(q.data_ptr()),
                                     C.c_void_p(rot.data_ptr() if use_b2c else 0), rot_dim,
                                     C.c_void_p(trans.data_ptr() if use_b2c else 0), int(root), int(use_b2c),
                                     C.c_void_p(pts.data_ptr() if pts is not None else 0),
                                     C.c_void_p(rout.data_ptr() if rout is not None else 0), B, _stream()))
         return pts, rout
 
+    def _link_fk(self, q, all_links: bool):
+        q = _f32(q)
+        B = q.shape[0]
+        assert q.shape[1] == self.dof, (q.shape, self.dof)
+        L = len(self.tree.link_names) if all_links else len(self.link_names)
+        out = torch.empty(B, L, 4, 4, dtype=torch.float32, device=q.device)
+        with torch.cuda.device(q.device):
+            check(_lib.lib().hrp_link_fk(self.handle(q.device), C.c_void_p(q.data_ptr()), B, int(all_links),
+                                         C.c_float(self.global_scale), C.c_void_p(out.data_ptr()), _stream()))
+        return out
+
+    def _link_fk_all(self, q):
+        return self._link_fk(q, True)
+
     # ---- reference API (urdf_robot.py) ----------------------------------------------------------------
+    def get_TWL(self, cfgs):  # :107-111 -> (B, nkpt, 4, 4)
+        return self._link_fk(cfgs, False)
+
     def get_keypoints(self, jointcfgs, b2c_rot, b2c_trans):  # :82-105
         return self._fk(jointcfgs, b2c_rot, b2c_trans, root=0)[0]
 

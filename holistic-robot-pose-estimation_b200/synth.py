@@ -38,6 +38,15 @@ URDF_PATHS = {
 GAMMA_RES = 0.25
 
 
+def use_synthetic_urdfs() -> None:
+    """Point $HRP_URDF_<ROBOT> at the mesh-free URDF fixtures (tests, bench.py, smoke): `URDFRobot(robot_type)` and
+    `RootNetwithRegInt(init, args)` with the reference signatures then resolve them.  An explicit opt-in: without it
+    (and without a real description) constructing a robot raises instead of silently using approximate kinematics."""
+    import os
+    for rt, path in URDF_PATHS.items():
+        os.environ.setdefault(f"HRP_URDF_{rt.upper()}", str(path))
+
+
 def uniform01(key: str, n: int, seed: int = 0) -> np.ndarray:
     """n floats in [0,1) with 24 random bits each; depends only on (key, seed)."""
     s = (zlib.crc32(key.encode()) << 32) | (seed & 0xFFFFFFFF)

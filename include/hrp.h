@@ -10,7 +10,9 @@
  * hrp_status; the message is available from hrp_last_error() (thread-local).  Device pointers are owned by
  * the caller (PyTorch allocates them and passes data_ptr()); handles own their packed weights, workspaces
  * and CUDA graphs.  `stream` is a cudaStream_t passed as void*; launches are asynchronous on it.
- * Handles are bound to the device that was current at creation and are not thread-safe.
+ * Handles are bound to the device that was current at creation.  hrp_model entry points take a per-handle lock and
+ * order successive users of one plan's buffers with events, so a handle may be driven from several threads / streams;
+ * the other handle types are not thread-safe.
  */
 #ifndef HRP_H_
 #define HRP_H_
@@ -130,6 +132,27 @@ int hrp_fk(hrp_robot* robot, const float* q, const float* rot, int32_t rot_dim, 
            int32_t use_b2c, float* out_xyz, float* out_rot, int32_t B, void* stream);
 /* K (B,3,3), pts (B,N,3) -> uv (B,N,2), device fp32 */
 int hrp_project(const float* K, const float* pts, float* uv, int32_t B, int32_t N, void* stream);
+/* Link transforms.  all_links = 0: URDFRobot.get_TWL (lib/utils/urdf_robot.py:107-111) -- out_T (B,nkpt,4,4), the
+ * base-frame transforms of the keypoint links in link_names order, translation scaled by global_scale.
+ * all_links = 1: URDF.link_fk_batch (lib/utils/urdfpytorch/urdf.py:3061-3149) over EVERY link of the description --
+ * out_T (B,n_links,4,4) in the row order handed to hrp_robot_set_full_tree (any link count; rows parent-before-child). */
+int hrp_robot_set_full_tree(hrp_robot* robot, const hrp_link_row* rows, int32_t n_links);
+int hrp_link_fk(hrp_robot* robot, const float* q, int32_t B, int32_t all_links, float global_scale, float* out_T,
+                void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Standalone geometry operators of the head (the fused head kernel evaluates the same expressions on chip).
+ *   hrp_inv_intrinsics: get_intrinsic_matrix_batch(f, c, bsz, inv=True) (lib/utils/integral.py:56-73,
+ *     lib/utils/transforms.py:145-162): K (B,3,3) -> K^-1 (B,3,3), divisions in fp64, stored fp32.
+ *   hrp_uvd_to_xyz: uvd_to_xyz (lib/utils/transforms.py:33-73): uvd (B,N,3), K^-1 (B,3,3), root_trans (B,3) ->
+ *     xyz (B,N,3) metres; return_relative subtracts root_trans.
+ *   hrp_uvz2xyz_singlepoint: uvz2xyz_singlepoint (lib/utils/transforms.py:133-143): uv (B,2) px, z (B), K (B,3,3) ->
+ *     xyz (B,3).
+ * ------------------------------------------------------------------------------------------------ */
+int hrp_inv_intrinsics(const float* K, float* Kinv, int32_t B, void* stream);
+int hrp_uvd_to_xyz(const float* uvd, const float* Kinv, const float* root_trans, float image_size, float depth_factor,
+                   int32_t return_relative, int32_t B, int32_t N, float* xyz, void* stream);
+int hrp_uvz2xyz_singlepoint(const float* uv, const float* z, const float* K, int32_t B, float* xyz, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused head: 3-D heatmap soft-argmax -> uvd -> xyz, root translation, FK and projections in one kernel.
@@ -259,7 +282,8 @@ typedef struct hrp_model_desc {
   float image_size;      /* 256 */
   float depth_factor;    /* bbox_3d_shape[2] * 1e-3 */
   int32_t chunk;         /* images per pass through the network (L2-sized sub-batch) */
-  int32_t inflight;      /* number of chunk replicas executing concurrently (1..4) */
+  int32_t inflight;      /* plan replicas (1..4): consecutive chunks of one large batch alternate between them, and
+                            single-chunk forwards enqueued on DIFFERENT caller streams get different replicas */
 } hrp_model_desc;
 
 /* device fp32 outputs; any pointer may be NULL.  Shapes as returned by the reference forward (8-tuple). */
@@ -298,21 +322,17 @@ int hrp_model_depthnet_forward(hrp_model* model, const float* x, const float* k_
  * pointer; C < 0 means an fp32 (B,|C|) vector), and per-plan statistics */
 int hrp_model_activation(hrp_model* model, const char* name, const void** ptr, int32_t* B, int32_t* H, int32_t* W,
                          int32_t* C);
-/* hardware probe (profiling aid): cycles to issue / complete `reps` back-to-back tcgen05.mma (SS mode, bf16, K=16)
- * of shape M x N on `ctas` CTAs; dev_out2 = {issue cycles, completion cycles} of CTA 0 */
-int hrp_probe_mma_rate(int32_t M, int32_t N, int32_t reps, int32_t kdistinct, long long* dev_out2, int32_t ctas);
-/* hardware probe: one 128x32xCK product whose swizzled K-major A operand starts `shift` rows into a [rows x ck] bf16
- * shared-memory tile (bo_mode 1 sets the descriptor base_offset field); D (128x32 fp32) is written to out_dev */
-int hrp_probe_desc_shift(int32_t ck, int32_t rows, int32_t shift, int32_t bo_mode, const void* A_dev, const void* B_dev,
-                         float* out_dev);
-/* hardware probe: cycles for `warps` (1, 4 or 8) warps of one CTA to issue `reps` tcgen05.ld.32x32b.x32 each (4 KiB per
- * instruction), waiting after every load (wait_each = 1) or only at the end; dev_out2[0] = cycles */
-int hrp_probe_tmem_ld_rate(int32_t warps, int32_t reps, int32_t wait_each, long long* dev_out2);
 /* asynchronous device-to-device copy on `stream` (used by the shims to snapshot activations) */
 int hrp_copy_device(void* dst, const void* src, int64_t bytes, void* stream);
 /* per-operation timing of one plan (eager, CUDA events, `iters` back-to-back launches per op): tab-separated text
  * name, kind, lane, in HxW, Cin, Cout, out HxW, taps, n_tile, epilogue, CTAs, stages, us, TFLOP/s, GB/s */
 int hrp_model_profile(hrp_model* model, int32_t batch, int32_t iters, char* buf, int64_t buflen);
+/* Kernel-variant table: text lines "<conv shape signature> <variant>" (variant 0 one tile per CTA, 1 persistent,
+ * 2 halo-tile).  The shim loads the committed table (tuning/b200.txt) before finalize so that every box and every run
+ * picks the same kernels (bitwise reproducible results); shapes without an entry use shape heuristics, or -- with
+ * HRP_AUTOTUNE=1 in the environment -- are timed at plan build.  get_tuning dumps the current table (set + tuned). */
+int hrp_model_set_tuning(hrp_model* model, const char* text);
+int hrp_model_get_tuning(hrp_model* model, char* buf, int64_t buflen);
 int hrp_model_stats(const hrp_model* model, int32_t batch, double* flops, int32_t* kernels, int64_t* activation_bytes);
 
 #ifdef __cplusplus

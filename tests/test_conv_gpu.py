@@ -284,3 +284,83 @@ def test_halo_not_eligible_raises(hrp_lib):
     op = ops.ConvOp(x, torch.randn(128, 128, 3, 3) * 0.03, stride=1, pad=1, relu=True)
     with pytest.raises(_lib.HrpError):
         _lib.check(_lib.lib().hrp_conv_set_variant(op.handle, C.c_int32(2)))
+
+
+# ---- persistent kernel (conv_gemm_persistent): forced with hrp_conv_set_variant(1) ----
+# ~35 % of a 512-image step runs on this kernel, but at the small shapes of CASES the planner may prefer the
+# one-tile-per-CTA kernel, so the variant is pinned here and checked against fp32 F.conv2d on every conv class, with the
+# batch enlarged where needed so that a persistent CTA walks several tiles (accumulator / staging rings wrap).
+@pytest.mark.parametrize("case", CASES, ids=[c[0] + "_persist" for c in CASES])
+def test_persistent_conv_vs_torch(case, hrp_lib):
+    import ctypes as C
+    import zlib
+    from horopose_b200 import _lib, ops
+    name, B, Cin, H, W, Cout, k, stride, pad = case
+    B = max(B, 3) * (8 if H * W <= 1024 else 2)      # >= ~200 M tiles x N tiles: more tiles than SMs
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator().manual_seed(zlib.crc32((name + "p").encode()) % 1000)
+    x = _bf16_round(torch.randn(B, Cin, H, W, generator=g)).cuda()
+    w = _bf16_round(torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5)
+    scale = (torch.rand(Cout, generator=g) + 0.5)
+    bias = torch.randn(Cout, generator=g) * 0.1
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    conv = F.conv2d(x, w.cuda(), stride=stride, padding=pad) * scale.cuda()[None, :, None, None] + \
+        bias.cuda()[None, :, None, None]
+    L = _lib.lib()
+    # (a) plain epilogue, (b) one residual (EPI_RES: TMA-prefetched into the staging ring), (c) two addends (EPI_PRE)
+    res1 = _bf16_round(torch.randn(B, Cout, Ho, Wo, generator=g)).cuda()
+    res2 = _bf16_round(torch.randn(B, Cout, Ho, Wo, generator=g)).cuda()
+    for tag, pre, ref in (("plain", (), conv), ("res", (res1,), conv + res1), ("pre2", (res1, res2), conv + res1 + res2)):
+        op = ops.ConvOp(_nhwc(x), w, stride=stride, pad=pad, relu=True, scale=scale, bias=bias,
+                        pre=[_nhwc(t) for t in pre])
+        _lib.check(L.hrp_conv_set_variant(op.handle, C.c_int32(1)))
+        assert L.hrp_conv_variant(op.handle) == 1
+        op.out.fill_(float("nan"))
+        got = op.run(ops.IMPL_TCGEN05)
+        torch.cuda.synchronize()
+        assert torch.isfinite(got.float()).all(), f"{name}[{tag}]: unwritten output"
+        _report(f"{name}[persist,{tag}]", got, torch.relu(ref).permute(0, 2, 3, 1).contiguous())
+        # same operands as the one-tile-per-CTA kernel (the K order differs with vertical tap sharing): one bf16 ulp
+        got = got.clone()
+        _lib.check(L.hrp_conv_set_variant(op.handle, C.c_int32(0)))
+        got_tile = op.run(ops.IMPL_TCGEN05)
+        torch.cuda.synchronize()
+        diff = (got_tile.float() - got.float()).abs().max().item()
+        assert diff <= 2.0 ** -6 * max(1.0, ref.abs().max().item()), f"{name}[{tag}]: persistent vs tile differ by {diff}"
+
+
+def test_persistent_full_epilogue_deconv_and_pool(hrp_lib):
+    """Persistent kernel on the remaining epilogue / geometry classes: nearest-upsampled + post addends (EPI_FULL), the
+    4-phase deconv, and the pooled fp32 output."""
+    import ctypes as C
+    from horopose_b200 import _lib, ops
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(15)
+    B, Cc, H = 6, 64, 32
+    x = _bf16_round(torch.randn(B, Cc, H, H, generator=g)).cuda()
+    w = _bf16_round(torch.randn(Cc, Cc, 3, 3, generator=g) / (Cc * 9) ** 0.5)
+    res = _bf16_round(torch.randn(B, Cc, H, H, generator=g)).cuda()
+    up1 = _bf16_round(torch.randn(B, Cc, H // 2, H // 2, generator=g)).cuda()
+    post = _bf16_round(torch.randn(B, Cc, H, H, generator=g)).cuda()
+    op = ops.ConvOp(_nhwc(x), w, stride=1, pad=1, relu=True, pre=[_nhwc(res)], up=[(_nhwc(up1), 1)], post=_nhwc(post))
+    _lib.check(L.hrp_conv_set_variant(op.handle, C.c_int32(1)))
+    ref = F.conv2d(x, w.cuda(), padding=1) + res + F.interpolate(up1, scale_factor=2, mode="nearest")
+    ref = (torch.relu(ref) + post).permute(0, 2, 3, 1).contiguous()
+    _report("persist[full]", op.run(), ref)
+    # deconv
+    xd = _bf16_round(torch.randn(4, 256, 16, 16, generator=g)).cuda()
+    wd = _bf16_round(torch.randn(256, 64, 4, 4, generator=g) / (256 * 4) ** 0.5)
+    opd = ops.ConvOp(_nhwc(xd), wd, kind=ops.DECONV_K4S2P1, relu=True)
+    _lib.check(L.hrp_conv_set_variant(opd.handle, C.c_int32(1)))
+    refd = torch.relu(F.conv_transpose2d(xd, wd.cuda(), stride=2, padding=1)).permute(0, 2, 3, 1).contiguous()
+    _report("persist[deconv]", opd.run(), refd)
+    # pooled output, 24 images of 8x8: 12 tiles, pool accumulators of different images in one tile
+    xp = _bf16_round(torch.randn(24, 128, 8, 8, generator=g)).cuda()
+    wp = _bf16_round(torch.randn(256, 128, 1, 1, generator=g) / 128 ** 0.5)
+    opp = ops.ConvOp(_nhwc(xp), wp, relu=True, pool=True, write_out=False)
+    _lib.check(L.hrp_conv_set_variant(opp.handle, C.c_int32(1)))
+    refp = torch.relu(F.conv2d(xp, wp.cuda())).mean(dim=(2, 3))
+    gotp = opp.run().clone()
+    torch.cuda.synchronize()
+    assert torch.allclose(gotp, refp, rtol=1e-4, atol=1e-4), (gotp - refp).abs().max()
+    assert torch.equal(opp.run(), gotp)   # two contributions per (image, channel): order-independent, bitwise stable

@@ -146,6 +146,32 @@ def test_metrics_summary_vs_reference_golden(rt, hrp_lib):
     assert s2["ADD/median"] == float(o2["ADD/median"]) and s2["ADD_2D/median"] == float(o2["ADD_2D/median"])
 
 
+def test_metrics_summary_nan_and_host_lists(hrp_lib):
+    """An image without in-frame ground-truth keypoints has error2d = 0/0 (metrics.py:67-70): np.mean / np.median then
+    give NaN, the threshold counts treat it as 'above' -- the kernel must do the same.  And `alldis` may be the list of
+    python floats that scripts/test.py:199-232 builds."""
+    import math
+    from horopose_b200.metrics import summary_add_pck
+    from oracle import eval_oracle as EO
+    g = torch.Generator().manual_seed(9)
+    e3 = (torch.rand(400, generator=g) * 0.12).numpy()
+    e2 = (torch.rand(400, generator=g) * 25.0).numpy()
+    e2[17] = float("nan")
+    e2[203] = float("nan")
+    got = summary_add_pck({"dis3d": [float(v) for v in e3], "dis2d": [float(v) for v in e2]})   # host python floats
+    want = EO.summary_add_pck(e3, e2)
+    for k, v in want.items():
+        v = float(v)
+        if math.isnan(v):
+            assert math.isnan(got[k]), (k, got[k])
+        else:
+            assert got[k] == pytest.approx(v, rel=1e-6 if k.endswith("mean") else 1e-12, abs=1e-15), k
+    assert math.isnan(got["ADD_2D/median"]) and math.isnan(got["ADD_2D/mean"]) and not math.isnan(got["ADD/median"])
+    # mixed list of CUDA tensors and numpy chunks
+    got2 = summary_add_pck({"dis3d": [torch.from_numpy(e3[:100]).cuda(), e3[100:]], "dis2d": [e2[:100], torch.from_numpy(e2[100:]).cuda()]})
+    assert got2["ADD/median"] == got["ADD/median"] and got2["PCK/AUC"] == got["PCK/AUC"]
+
+
 def test_eval_loop_frames_to_summary_vs_oracle_chain(hrp_lib):
     """System parity of the widened path: frames + boxes -> crop -> network -> metrics -> summary on the GPU against the
     same chain built from the CPU oracles (crop oracle -> fp32 reference forward -> metrics oracle).  The crop is exact.

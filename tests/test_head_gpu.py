@@ -194,3 +194,65 @@ def test_heatmap_integral_backward_vs_autograd(rt, hrp_lib):
         assert np.abs(dg["samples"] - gold["samples" + tag]).max() < 2e-4 * amax
         for m in ("sum_hw", "sum_cw", "sum_ch"):   # sums of 4096 / nkpt*4096 entries: rounding noise adds up
             assert np.abs(dg[m] - gold[m + tag]).max() < 5e-2 * amax, m
+
+
+@pytest.mark.parametrize("rt", ROBOT_TYPES)
+def test_link_transforms_vs_reference_golden(rt, hrp_lib):
+    """URDF.link_fk_batch over ALL links (urdf.py:3061-3149) and URDFRobot.get_TWL (urdf_robot.py:107-111) against the
+    reference's own transforms (fixture `all_link_fk`), 1e-5 relative."""
+    from horopose_b200 import synth
+    from horopose_b200.robot import URDFRobot
+    g = np.load(GOLDEN / f"fk_{rt}.npz")
+    robot = URDFRobot(rt)
+    q, _, _ = synth.fk_inputs(rt, 64)
+    fk = robot.robot.link_fk_batch(q.cuda(), use_names=True)
+    names = [str(n) for n in g["all_link_names"]]
+    assert sorted(fk.keys()) == sorted(names)
+    for i, n in enumerate(names):
+        assert _rel(fk[n].cpu(), g["all_link_fk"][:, i]) < 1e-5, n
+        assert torch.equal(fk[n][:, 3].cpu(), torch.tensor([0.0, 0.0, 0.0, 1.0]).expand(64, 4)), n
+    twl = robot.get_TWL(q.cuda())
+    assert twl.shape == (64, len(robot.link_names), 4, 4)
+    for k, n in enumerate(robot.link_names):
+        assert _rel(twl[:, k].cpu(), g["all_link_fk"][:, names.index(n)]) < 1e-5, n
+        # the pruned-tree kernel and the all-link kernel evaluate the same chain in the same order
+        assert torch.equal(twl[:, k], fk[n]), n
+    # keypoints = TWL * offset (urdf_robot.py:104): consistent with the FK kernel
+    pts = (twl[:, :, :3, :3] @ robot.offsets.cuda() + twl[:, :, :3, 3:]).squeeze(-1)
+    assert _rel(pts.cpu(), g["keypoints_only_fk"]) < 1e-5
+    # ragged batch (not a multiple of the CTA size) and global_scale
+    robot.global_scale = 2.0
+    robot._handles = {}
+    t2 = robot.get_TWL(q[:37].cuda())
+    assert torch.allclose(t2[..., :3, 3], twl[:37, ..., :3, 3] * 2.0, rtol=1e-6, atol=0)
+    assert torch.equal(t2[..., :3, :3], twl[:37, ..., :3, :3])
+
+
+def test_geometry_operators_vs_oracle(hrp_lib):
+    """Standalone uvd_to_xyz / uvz2xyz_singlepoint / get_intrinsic_matrix_batch (transforms.py:33-73,133-162,
+    integral.py:56-73) against the CPU oracle: fp32, 1e-5 relative; K^-1 bit-exact (fp64 divisions, fp32 store)."""
+    from horopose_b200 import synth, transforms as T
+    from oracle import horopose_oracle as O
+    B, N = 257, 17
+    _, _, _, K = synth.inputs(B, seed=19)
+    K[:, 1, 1] = K[:, 0, 0] * 1.013   # fx != fy
+    uvd = synth.sym_uniform("geo_uvd", (B, N, 3), 0.25, 19)
+    root = torch.cat([synth.sym_uniform("geo_txy", (B, 2), 0.3, 19), synth.range_uniform("geo_tz", (B, 1), 0.8, 2.5, 19)], 1)
+    inv_ref = O.inv_intrinsics(K)
+    inv = T.get_intrinsic_matrix_batch((K[:, 0, 0].cuda(), K[:, 1, 1].cuda()), (K[:, 0, 2].cuda(), K[:, 1, 2].cuda()),
+                                       bsz=B, inv=True)
+    assert torch.equal(inv.cpu(), inv_ref)
+    fwd = T.get_intrinsic_matrix_batch((K[:, 0, 0], K[:, 1, 1]), (K[:, 0, 2], K[:, 1, 2]), bsz=B, inv=False)
+    assert fwd.is_cuda and torch.equal(fwd.cpu(), K)
+    xyz_ref = O.uvd_to_xyz(uvd, 256.0, inv_ref, root, 1.3)
+    xyz = T.uvd_to_xyz(uvd.cuda(), 256.0, inv, root.cuda(), 1.3)
+    assert _rel(xyz.cpu(), xyz_ref) < 1e-5
+    rel = T.uvd_to_xyz(uvd.cuda(), 256.0, inv, root.cuda(), 1.3, return_relative=True)
+    assert _rel(rel.cpu(), xyz_ref - root[:, None]) < 1e-5
+    uv = (uvd[:, 0, :2] + 0.5) * 256.0
+    z = root[:, 2:3]
+    p_ref = O.uvz2xyz_singlepoint(uv, z, K)
+    p = T.uvz2xyz_singlepoint(uv.cuda(), z.cuda(), K.cuda())
+    assert _rel(p.cpu(), p_ref) < 1e-5
+    with pytest.raises(Exception):
+        T.uvd_to_xyz(uvd, 256.0, inv_ref, root, 1.3)   # CPU tensors: no CPU path

@@ -136,13 +136,13 @@ def test_chunking_ragged_batches_and_graph_replay(hrp_lib):
     """B=5 with chunk=2, 2 replicas in flight: multi-chunk + ragged tail must equal per-image runs; replays must be
     bit-identical (graph state, pooled-feature zeroing, head counters)."""
     from horopose_b200 import synth
-    # autotune may pick different (equally valid) kernels for different batch sizes, whose fp32 accumulation orders
-    # differ; pin the shape-based choice so that per-image results are independent of how the batch is chunked
-    os.environ["HRP_AUTOTUNE"] = "0"
+    # the tuning table may name different (equally valid) kernels for different batch sizes, whose fp32 accumulation
+    # orders differ; use the shape heuristics alone so that per-image results are independent of how the batch is chunked
+    os.environ["HRP_TUNING"] = "0"
     try:
         _check_chunking(synth)
     finally:
-        del os.environ["HRP_AUTOTUNE"]
+        del os.environ["HRP_TUNING"]
 
 
 def _check_chunking(synth):
@@ -152,8 +152,7 @@ def _check_chunking(synth):
     b = [t.clone() for t in m(x_reg, x_root, k, K)]
     torch.cuda.synchronize()
     for n, u, v in zip(NAMES, a, b):
-        # the pooled epilogue uses fp32 atomics: summation order may change run to run (1e-6 level)
-        assert torch.allclose(u, v, rtol=0, atol=5e-5), n
+        assert torch.equal(u, v), n   # replays are bit-identical (fixed kernel choice, fixed-order reductions)
     m1 = _model("panda", chunk=1, inflight=1)
     for i in range(5):
         o = m1(x_reg[i:i + 1], x_root[i:i + 1], k[i:i + 1], K[i:i + 1])
@@ -268,3 +267,189 @@ def test_full_size_batch_properties(hrp_lib):
         assert float((u[:2] - v).abs().max()) < TOL[n], (n, float((u[:2] - v).abs().max()))
     uv = O.point_projection_from_3d(KK.cpu(), a[NAMES.index("xyz_int")].cpu())
     assert torch.isfinite(uv).all()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# parity at the BASELINE.json sizes: the plans the bench actually runs (Panda 64, Baxter 256, Kuka 512 images per chunk;
+# depthnet 256) are compared with the fp32 oracle on 64 distinct images (4 seeds x 16), k_value over the full
+# U[500,3000] range of SURVEY.md section 8(d) C1.  The batch is the 64 images repeated to the plan size, so every replica
+# must agree with the oracle (and the copies with one another).
+# ------------------------------------------------------------------------------------------------------------------
+def _inputs64(k_range=(500.0, 3000.0)):
+    from horopose_b200 import synth
+    parts = [synth.inputs(16, seed=s, k_range=k_range) for s in (101, 102, 103, 104)]
+    return tuple(torch.cat([p[i] for p in parts]) for i in range(4))
+
+
+def _oracle_full(rt, x_reg, x_root, k, K, sd=None, step=16):
+    from horopose_b200 import synth
+    from oracle import horopose_oracle as O
+    sd = synth.full_state_dict(rt) if sd is None else sd
+    robot = O.OracleRobot(rt, str(synth.URDF_PATHS[rt]))
+    outs = []
+    with torch.no_grad():
+        for i in range(0, x_reg.shape[0], step):
+            outs.append(O.full_forward(sd, robot, x_reg[i:i + step], x_root[i:i + step], k[i:i + step], K[i:i + step]))
+    return [torch.cat([o[j] for o in outs]) for j in range(8)]
+
+
+def _floor_full(rt, x_reg, x_root, k, K, oracle_outs, sd=None, step=16):
+    """torch-autocast-bf16 evaluation of the same network on the GPU (the bf16 noise floor), max |err| per output."""
+    from horopose_b200 import synth
+    from oracle import horopose_oracle as O
+    sd = synth.full_state_dict(rt) if sd is None else sd
+    sd_cuda = {k_: v.cuda() for k_, v in sd.items()}
+    robot = O.OracleRobot(rt, str(synth.URDF_PATHS[rt]))
+    outs = []
+    with torch.no_grad():
+        for i in range(0, x_reg.shape[0], step):
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                feat, x_out, heat = O.full_features(sd_cuda, x_reg[i:i + step].cuda(), x_root[i:i + step].cuda())
+            outs.append(O.full_head(sd, robot, feat.float().cpu(), x_out.float().cpu(), heat.float().cpu(), k[i:i + step],
+                                    K[i:i + step]))
+    cat = [torch.cat([o[j] for o in outs]) for j in range(8)]
+    return {n: float((a - b).abs().max()) for n, a, b in zip(NAMES, cat, oracle_outs)}
+
+
+def _proj_err(K, got, ref):
+    from oracle import horopose_oracle as O
+    ok = ref[..., 2] > 0.2
+    return float((O.point_projection_from_3d(K, got) - O.point_projection_from_3d(K, ref))[ok].abs().max())
+
+
+@pytest.mark.parametrize("rt,plan_b", [("panda", 64), ("baxter", 256), ("kuka", 512)])
+def test_baseline_size_plans_vs_oracle(rt, plan_b, hrp_lib):
+    x_reg, x_root, k, K = _inputs64()
+    ref = _oracle_full(rt, x_reg, x_root, k, K)
+    floor = _floor_full(rt, x_reg, x_root, k, K, ref)
+    reps = plan_b // 64
+    rep = lambda t: t.repeat(reps, *([1] * (t.dim() - 1))).cuda()
+    model = _model(rt, chunk=plan_b, inflight=1)
+    outs = [o.cpu() for o in model(rep(x_reg), rep(x_root), rep(k), rep(K))]
+    _log(f"[{rt}] 64 distinct images (k in U[500,3000]) x {reps} through the {plan_b}-image plan vs the fp32 oracle")
+    worst = {}
+    for n, o, r in zip(NAMES, outs, ref):
+        o = o.view(reps, 64, *o.shape[1:])
+        worst[n] = float((o - r[None]).abs().max())
+        spread = float((o - o[:1]).abs().max())          # copies of an image inside one batch
+        _log(f"  out {n:8s} max|err| {worst[n]:.3e} (tol {TOL[n]:.1e}; torch-autocast-bf16 floor {floor[n]:.3e}; "
+             f"spread between the {reps} copies {spread:.1e})")
+        assert spread <= 5e-5, (n, spread)
+    for n in ("xyz_int", "xyz_fk"):
+        j = NAMES.index(n)
+        e = max(_proj_err(K, outs[j].view(reps, 64, -1, 3)[i], ref[j]) for i in range(reps))
+        _log(f"  out proj({n}) max|err| {e:.3e} px (tol 0.5)")
+        assert e < 0.5, (n, e)
+    for n in NAMES:
+        assert worst[n] < TOL[n], (rt, plan_b, n, worst[n], TOL[n])
+
+
+def test_depthnet_baseline_size_vs_oracle(hrp_lib):
+    """BASELINE.json configs[1]: standalone depthnet through its 256-image plan, 32 distinct images x 8, k in U[500,3000]."""
+    from horopose_b200 import synth
+    from horopose_b200.models import get_rootnet
+    from oracle import horopose_oracle as O
+    _, x_root, k, _ = _inputs64()
+    x_root, k = x_root[:32], k[:32]
+    sd = synth.depthnet_state_dict()
+    with torch.no_grad():
+        ref = torch.cat([O.depthnet_forward(sd, x_root[i:i + 16], k[i:i + 16]) for i in (0, 16)])
+    m = get_rootnet("hrnet32")
+    m.chunk, m.inflight = 256, 1
+    m.load_state_dict(sd, strict=True)
+    out = m(x_root.repeat(8, 1, 1, 1).cuda(), k.repeat(8).cuda()).cpu().view(8, 32, 1)
+    err = float((out - ref.view(1, 32, 1)).abs().max())
+    _log(f"[depthnet] 32 distinct images x 8 through the 256-image plan, k in U[500,3000]: depth_mm max|err| {err:.3f} mm "
+         f"(tol 1 mm; depth range {float(ref.min()):.0f}..{float(ref.max()):.0f} mm)")
+    assert err < 1.0
+
+
+def test_raw_reference_init_floor_is_logged(hrp_lib):
+    """with the reference's RAW init (gamma_res = 1 on the last BN of every residual block)
+    the network is a chaotic map and no bf16 evaluation -- PyTorch's own included -- meets 1 mm / 0.5 px.  This test logs
+    this path's error and the torch-autocast-bf16 floor side by side on that recipe; it asserts only that this path is
+    not worse than 2x the floor (the bars themselves are asserted on the gamma_res = 0.25 recipe above)."""
+    from horopose_b200 import arch, synth
+    from horopose_b200.models import get_rootNetwithRegInt_model
+    from oracle import horopose_oracle as O
+    rt = "panda"
+    sd = synth.full_state_dict(rt, with_bn_stats=False)
+    for name in arch.residual_last_bn_names(arch.full_model_spec(rt)):
+        sd[name + ".weight"] = sd[name + ".weight"] / synth.GAMMA_RES      # back to gamma ~ U[0.5,1.5]
+    robot = O.OracleRobot(rt, str(synth.URDF_PATHS[rt]))
+    xc = synth.inputs(8, seed=7)
+    with torch.no_grad():
+        O.full_forward(sd, robot, *xc, calib=lambda name, mean, var: (mean, var.clamp_min(1e-3)))   # BN calibration
+    x_reg, x_root, k, K = synth.inputs(8, seed=11, k_range=(500.0, 3000.0))
+    ref = _oracle_full(rt, x_reg, x_root, k, K, sd=sd, step=8)
+    floor = _floor_full(rt, x_reg, x_root, k, K, ref, sd=sd, step=8)
+    init = {"robot_type": rt, "pose_params": None, "cam_params": np.eye(4), "init_pose_from_mean": True}
+    m = get_rootNetwithRegInt_model(init, _args(rt))
+    m.chunk = 8
+    m.load_state_dict(sd, strict=True)
+    outs = [o.cpu() for o in m(x_reg.cuda(), x_root.cuda(), k.cuda(), K.cuda())]
+    _log(f"[{rt}] RAW reference init (gamma_res = 1), B=8, k in U[500,3000]: this path vs the torch-autocast-bf16 floor")
+    for n, o, r in zip(NAMES, outs, ref):
+        e = float((o - r).abs().max())
+        _log(f"  out {n:8s} max|err| {e:.3e}  torch-autocast-bf16 floor {floor[n]:.3e}  (north-star bar {TOL[n]:.1e})")
+        assert e <= 2.0 * floor[n] + TOL[n], (n, e, floor[n])
+
+
+def test_default_path_is_bitwise_reproducible(hrp_lib):
+    """Kernel selection comes from the committed tuning table (or shape heuristics), never from timing, and every
+    reduction has a fixed order: replays on one handle, a second handle, and a second stream give identical bits."""
+    from horopose_b200 import synth
+    xs = [t.cuda() for t in synth.inputs(8, seed=77)]
+    m1 = _model("kuka", chunk=8, inflight=1)
+    a = [t.clone() for t in m1(*xs)]
+    b = [t.clone() for t in m1(*xs)]
+    m2 = _model("kuka", chunk=8, inflight=1)
+    c = [t.clone() for t in m2(*xs)]
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        d = [t.clone() for t in m1(*xs)]
+    torch.cuda.synchronize()
+    for n, u, v, w, z in zip(NAMES, a, b, c, d):
+        assert torch.equal(u, v), ("replay", n)
+        assert torch.equal(u, w), ("second handle", n)
+        assert torch.equal(u, z), ("second stream", n)
+    assert m1.tuning() == m2.tuning()
+
+
+def test_streams_get_their_own_plan_replicas(hrp_lib):
+    """Two caller streams on one handle (inflight = 2): forwards overlap on distinct plan replicas; with more streams
+    than replicas the shared plan is serialised by its busy event.  Results equal the serial ones bit for bit."""
+    from horopose_b200 import synth
+    m = _model("panda", chunk=4, inflight=2)
+    batches = [[t.cuda() for t in synth.inputs(4, seed=200 + i)] for i in range(6)]
+    serial = [[t.clone() for t in m(*b)] for b in batches]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    outs = [None] * 6
+    for i, b in enumerate(batches):
+        s = streams[i % 3]
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            outs[i] = m(*b)
+    torch.cuda.synchronize()
+    for i in range(6):
+        for n, u, v in zip(NAMES, serial[i], outs[i]):
+            assert torch.equal(u, v), (i, n)
+
+
+def test_plan_cache_is_bounded(hrp_lib, monkeypatch):
+    """A caller that varies the batch size cannot grow device memory without bound: plans other than the nominal chunk
+    are evicted LRU (HRP_MAX_PLANS), and an evicted batch size is simply re-planned with the same results."""
+    from horopose_b200 import synth
+    monkeypatch.setenv("HRP_MAX_PLANS", "2")
+    m = _model("panda", chunk=4, inflight=1)
+    xs = [t.cuda() for t in synth.inputs(4, seed=300)]
+    first = {}
+    for B in (1, 2, 3, 4, 1, 3, 2):
+        out = [t.clone() for t in m(*[t[:B] for t in xs])]
+        torch.cuda.synchronize()
+        if B in first:
+            for n, u, v in zip(NAMES, first[B], out):
+                assert torch.equal(u, v), (B, n)
+        first[B] = out

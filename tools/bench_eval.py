@@ -10,6 +10,8 @@ import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import horopose_b200  # noqa
+from horopose_b200 import synth as _synth
+_synth.use_synthetic_urdfs()
 from horopose_b200 import synth
 from horopose_b200.metrics import compute_metrics_batch, summary_add_pck
 from horopose_b200.pnp import BPnP_m3d

@@ -7,6 +7,8 @@ import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import horopose_b200  # noqa
+from horopose_b200 import synth as _synth
+_synth.use_synthetic_urdfs()
 from horopose_b200 import arch
 from horopose_b200.integral import run_head
 from horopose_b200.robot import URDFRobot

@@ -1,0 +1,39 @@
+"""Summarise an ncu launch list (gpu__time_duration, sm__pipe_tensor_cycles_active, dram bytes per launch) of one bench
+step: per-kernel-family share of the step, time-weighted tensor-pipe utilisation (whole step / conv kernels only) and
+DRAM traffic.    python tools/ncu_launch_table.py launches.csv [out.json]"""
+import collections
+import csv
+import json
+import re
+import sys
+
+rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 10 and r[0].isdigit()]
+UNIT = {"ns": 1.0, "us": 1e3, "ms": 1e6, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "%": 1.0}
+per, names = collections.defaultdict(dict), {}
+for r in rows:
+    per[r[0]][r[-3]] = float(r[-1].replace(",", "")) * UNIT.get(r[-2], 1.0)
+    names[r[0]] = re.sub(r"\(.*", "", r[4]).replace("void ", "").replace("hrp::", "")
+T, P, D = "gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "dram__bytes_"
+agg = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0])
+for i, m in per.items():
+    a = agg[names[i]]
+    a[0] += 1
+    a[1] += m.get(T, 0.0)
+    a[2] += m.get(T, 0.0) * m.get(P, 0.0)
+    a[3] += m.get(D + "read.sum", 0.0) + m.get(D + "write.sum", 0.0)
+tot_t = sum(a[1] for a in agg.values())
+tot_p = sum(a[2] for a in agg.values())
+tot_b = sum(a[3] for a in agg.values())
+conv = {k: a for k, a in agg.items() if k.startswith("conv_")}
+ct, cp = sum(a[1] for a in conv.values()), sum(a[2] for a in conv.values())
+print(f"{len(per)} launches, {tot_t / 1e6:.2f} ms serialised under ncu, {tot_b / 1e9:.2f} GB DRAM traffic")
+print(f"time-weighted sm__pipe_tensor_cycles_active: whole step {tot_p / tot_t:.1f} %, conv kernels only {cp / max(ct, 1):.1f} %"
+      f" (conv share of the step {ct / tot_t * 100:.1f} %)")
+for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+    print(f"  {k:58s} {a[0]:4d} launches {a[1] / 1e3:9.1f} us {a[1] / tot_t * 100:5.1f}%  tensor pipe {a[2] / max(a[1], 1):5.1f} %  "
+          f"{a[3] / 1e6:9.1f} MB")
+if len(sys.argv) > 2:
+    json.dump({"kernels": len(per), "serialised_ms": tot_t / 1e6, "dram_bytes_per_step": tot_b,
+               "tensor_pipe_pct_step": tot_p / tot_t, "tensor_pipe_pct_conv": cp / max(ct, 1),
+               "families": {k: {"launches": a[0], "us": a[1] / 1e3, "tensor_pipe_pct": a[2] / max(a[1], 1), "dram_mb": a[3] / 1e6}
+                            for k, a in agg.items()}}, open(sys.argv[2], "w"), indent=1)

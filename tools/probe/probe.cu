@@ -1,7 +1,7 @@
 // Hardware probe (not on the product path): issue-to-completion time of back-to-back tcgen05.mma instructions as
 // a function of (M, N), operands in shared memory (SS mode), bf16, K=16 per instruction.  Used to size the N tile
 // and to decide which layers can be tensor-bound at all.
-#include "../../include/hrp.h"
+#include "hrp_probe.h"
 #include "hrp_common.cuh"
 
 namespace hrp {

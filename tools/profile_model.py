@@ -9,6 +9,8 @@ import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import horopose_b200  # noqa
+from horopose_b200 import synth as _synth
+_synth.use_synthetic_urdfs()
 from horopose_b200 import _lib, arch, synth
 from horopose_b200.models import get_rootNetwithRegInt_model
 
