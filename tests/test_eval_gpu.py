@@ -178,20 +178,24 @@ def test_eval_loop_frames_to_summary_vs_oracle_chain(hrp_lib):
     The network is bf16 against fp32 and these inputs are image-like (constant padding bars, smooth gradients), where
     bf16 rounding errors are spatially correlated and do not average out in the pooled features the way they do on the
     config's U[0,1) noise inputs: PyTorch's own autocast-bf16 forward of the reference network is 2-15 mm / 0.4-3 px off
-    the fp32 forward here (vs 0.2-0.5 mm / < 0.1 px on noise).  The bars are therefore the north-star ones (1 mm, 0.5 px,
-    1e-2 rad) OR the torch-autocast-bf16 floor of the same chain, whichever is larger -- both numbers are logged."""
+    the fp32 forward here (vs 0.2-0.5 mm / < 0.1 px on noise) -- weights and activations rounded to bf16 contribute
+    equally (profiles/r02_exp_precision_sources.txt), so no storage trick short of a wider type removes it.  The
+    north-star bars (stated on the config's synthetic inputs) are NOT met on these inputs by any bf16 evaluation; what is
+    asserted over 24 frames is that this path is statistically no worse than PyTorch's own bf16: its RMS error against
+    the fp32 chain must not exceed 1.25 x the RMS error of torch-autocast-bf16 (the maxima are logged beside them), and
+    the joint angles (which do not depend on the root depth) meet their 1e-2 rad bar outright."""
     from horopose_b200 import arch, synth
     from horopose_b200.models import get_rootNetwithRegInt_model
     from horopose_b200.pipeline import EvalPipeline
     from horopose_b200.robot import URDFRobot
     from oracle import eval_oracle as EO
     from oracle import horopose_oracle as O
-    rt, B = "panda", 6
+    rt, B = "panda", 24
     ref_id = arch.ROBOTS[rt][2]
     frames, boxes, Kf, k_bbox = synth.crop_inputs(B, seed=5)
     # k = f * 1000 / side (scripts/test.py:141-152): boxes of 400..640 px keep the synthetic depth (gamma ~ 2) * k / 1000
     # at 2-3 m (a 60-pixel box would put the robot 20 m away)
-    k_bbox = np.stack([np.array([0.0, 0.0, 400.0 + 40.0 * b, 400.0 + 40.0 * b], dtype=np.float32) for b in range(B)])
+    k_bbox = np.stack([np.array([0.0, 0.0, 400.0 + 40.0 * (b % 6), 400.0 + 40.0 * (b % 6)], dtype=np.float32) for b in range(B)])
     q, rot, trans, gt_q, gt3, gt2, _ = synth.metric_inputs(rt, B)
     args = dict(backbone_name="resnet50", rootnet_backbone_name="hrnet32", n_iter=4, other_image_size=256.0,
                 bbox_3d_shape=[1300, 1300, 1300], reference_keypoint_id=ref_id, fix_root=True, rotation_dim=6)
@@ -200,7 +204,7 @@ def test_eval_loop_frames_to_summary_vs_oracle_chain(hrp_lib):
     sd = synth.full_state_dict(rt)
     model.load_state_dict(sd, strict=True)
     pipe = EvalPipeline(model, URDFRobot(rt), ref_id)
-    for lo, hi in ((0, 4), (4, 6)):  # two ragged batches through the accumulator
+    for lo, hi in ((0, 4), (4, 6), (6, 24)):  # ragged batches through the accumulator
         pipe.step(torch.from_numpy(frames[lo:hi]), torch.from_numpy(boxes[lo:hi]), torch.from_numpy(Kf[lo:hi]),
                   torch.from_numpy(k_bbox[lo:hi]), gt3[lo:hi], gt2[lo:hi], gt_q[lo:hi])
     got = pipe.summary()
@@ -233,14 +237,18 @@ def test_eval_loop_frames_to_summary_vs_oracle_chain(hrp_lib):
     out_dir = ROOT / "gpurun_out"
     out_dir.mkdir(exist_ok=True)
     with open(out_dir / "model_parity.txt", "a") as f:
-        f.write("[eval loop] frames -> crop -> network -> metrics, image-like crops, panda B=6\n")
+        f.write(f"[eval loop] frames -> crop -> network -> metrics, image-like crops, panda B={B}\n")
         for name, a, r, fl, bar in checks:
             err, floor = float(np.abs(a - r).max()), float(np.abs(fl - r).max())
-            f.write(f"  {name:22s} max|err| vs fp32 oracle chain {err:.3e}  (north-star bar {bar:.1e}; "
-                    f"torch-autocast-bf16 floor {floor:.3e})\n")
+            rms, rms_floor = float(np.sqrt(np.mean((a - r) ** 2))), float(np.sqrt(np.mean((fl - r) ** 2)))
+            f.write(f"  {name:22s} vs fp32 oracle chain: max {err:.3e} rms {rms:.3e}  (north-star bar {bar:.1e}; "
+                    f"torch-autocast-bf16 floor: max {floor:.3e} rms {rms_floor:.3e})\n")
     for name, a, r, fl, bar in checks:
-        err, floor = float(np.abs(a - r).max()), float(np.abs(fl - r).max())
-        assert err < max(bar, 1.5 * floor), (name, err, bar, floor)
+        rms, rms_floor = float(np.sqrt(np.mean((a - r) ** 2))), float(np.sqrt(np.mean((fl - r) ** 2)))
+        if name.startswith("mean_jointerror"):
+            assert float(np.abs(a - r).max()) < bar, (name, float(np.abs(a - r).max()), bar)
+        else:
+            assert rms <= 1.25 * rms_floor + 1e-9, (name, rms, rms_floor)
     tol3 = max(1e-3, 1.5 * float(np.abs(mf["error3d"] - m["error3d"]).max()))
     assert abs(got["ADD/mean"] - float(want["ADD/mean"])) < tol3
     assert abs(got["Depth_l1_error/mean_m"] - float(m["error_depth"].mean())) < tol3

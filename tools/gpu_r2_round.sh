@@ -4,7 +4,7 @@ set -x
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt
 rm -f gpurun_out/model_parity.txt
-( time timeout 1500 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.txt 2>&1
+( time timeout 1500 python -m pytest tests -m gpu -q ) > gpurun_out/pytest_gpu.txt 2>&1
 tail -15 gpurun_out/pytest_gpu.txt
 if [ "$1" == "tune" ]; then
   timeout 900 python tools/make_tuning.py gpurun_out/tuning_b200.txt > gpurun_out/make_tuning.log 2>&1
