@@ -46,6 +46,7 @@ static ConvLayerDesc to_internal(const hrp_conv_desc* d) {
   o.pad = d->pad;
   o.relu = d->relu;
   o.has_residual = 0;
+  o.head_fold = 0;
   o.in_wpitch = o.in_wpad = 0;
   return o;
 }
@@ -140,6 +141,21 @@ int hrp_conv_set_variant(hrp_conv* conv, int32_t variant) {
 int hrp_conv_variant(const hrp_conv* conv) {
   if (conv == nullptr) return -1;
   return conv->plan.halo ? 2 : (conv->plan.persistent ? 1 : 0);
+}
+
+int hrp_conv_describe(const hrp_conv* conv, char* buf, int64_t buflen) {
+  HRP_REQUIRE(conv != nullptr && buf != nullptr && buflen > 0, "bad argument");
+  const ConvPlan& pl = conv->plan;
+  if (pl.halo)
+    snprintf(buf, (size_t)buflen, "halo pair=%d T=%d bands=%d ring=%d NR=%d smem=%d grid=%u", pl.hp.pair, pl.hp.T, pl.hp.n_abuf,
+             pl.hp.nring, pl.hp.NR, pl.halo_smem, pl.halo_grid);
+  else if (pl.persistent)
+    snprintf(buf, (size_t)buflen, "persistent epi=%d n_tile=%d stages=%d nstag=%d vsh=%d wres=%d smem=%d grid=%u", pl.epi,
+             pl.p.n_tile, pl.pcfg.stages, pl.pcfg.nstag, pl.pcfg.vsh, pl.pcfg.wres, pl.psmem, pl.pgrid);
+  else
+    snprintf(buf, (size_t)buflen, "tile epi=%d n_tile=%d stages=%d smem=%d grid=%u", pl.epi, pl.p.n_tile, pl.stages,
+             pl.smem_bytes, pl.grid.x * pl.grid.z);
+  return HRP_OK;
 }
 
 int hrp_conv_set_timeline(hrp_conv* conv, long long* dev_buf) {
@@ -314,6 +330,30 @@ int hrp_fk(hrp_robot* robot, const float* q, const float* rot, int32_t rot_dim, 
   p.pts = out_xyz;
   p.rot_out = out_rot;
   return launch_fk(p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int hrp_fk_backward(hrp_robot* robot, const float* q, const float* rot, const float* trans, int32_t root, int32_t use_b2c,
+                    const float* grad_xyz, float* grad_q, float* grad_rot, float* grad_trans, int32_t B, void* stream) {
+  HRP_REQUIRE(robot != nullptr && q != nullptr && grad_xyz != nullptr && grad_q != nullptr && B > 0, "bad argument");
+  HRP_REQUIRE(root >= 0 && root < robot->host.nkpt, "root keypoint out of range");
+  FkBwdParams p;
+  p.B = B;
+  p.root = root;
+  p.use_b2c = use_b2c;
+  p.q = q;
+  p.rot = rot;
+  p.trans = trans;
+  p.robot = robot->dev;
+  p.grad_pts = grad_xyz;
+  p.grad_q = grad_q;
+  p.grad_rot = grad_rot;
+  p.grad_trans = grad_trans;
+  return launch_fk_backward(p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int hrp_project_backward(const float* K, const float* pts, const float* grad_uv, float* grad_pts, int32_t B, int32_t N,
+                         void* stream) {
+  return launch_project_backward(K, pts, grad_uv, grad_pts, B, N, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // ---- input pipeline / metrics (eval.cu) ----------------------------------------------------------------

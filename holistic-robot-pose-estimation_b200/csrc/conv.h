@@ -27,6 +27,7 @@ struct ConvParams {
   int Hout, Wout, Cout;   // output tensor
   int os, oh0, ow0;       // output pixel stride / offset
   int nphase;             // 1, or 4 for ConvTranspose2d(k4,s2,p1): phase z = (ph,pw) shifts taps and output
+  int shared_phase;       // kConvUp2: the 4 phases share weight rows and taps (only the output pixel differs)
   int ntaps, ck, cpt;     // taps, channels per k-block (16/32/64), k-blocks per tap (Cin/ck)
   int n_tiles;            // cout_pad / n_tile
   int n_tile, cout_pad;   // N tile (multiple of 32, <= 256); weight rows per phase (multiple of n_tile)
@@ -47,6 +48,12 @@ struct ConvParams {
   bf16* out;              // (B,Hout,Wout,Cout) bf16, may be null when only pooled output is wanted
   float* pool_out;        // optional (B,Cout) fp32: mean over the Hout*Wout pixels of post-activation values
   float pool_scale;       // 1/(Hout*Wout)
+  // optional soft-argmax fold (final 1x1 conv of the keypoint head, full_net.py:78,296-297 + integral.py:109-135): instead
+  // of writing the (B, 64*64, nkpt*64) logits, every epilogue warp reduces its 32 pixels x 32 depth bins of a keypoint to
+  // an online-softmax partial (max, sum e, sum e*w, sum e*h, sum e*d in the log2 domain) and writes it to
+  // head_partials[(image * head_chunks + chunk) * head_nkpt + keypoint][5]; head.cu merges the chunks per image.
+  float* head_partials;
+  int head_chunks, head_nkpt;
   // raw pointers for the SIMT cross-check path
   const bf16* in;         // (B,Hin,Win,Cin) source tensor base
   const bf16* w;          // (nphase*cout_pad, ktot) packed weights
@@ -90,7 +97,8 @@ struct HaloParams {
   int tiles_per_img, units_per_img, total_units;
   int n_abuf;            // band buffers in flight
   int nacc, nacc_shift;  // accumulators in the TMEM ring (power of two)
-  int a_buf_bytes, a_offset, stag_offset, res_offset, bar_offset;
+  int nring;             // output / residual ring buffers (2..4), one 128-position tile each
+  int a_buf_bytes, a_offset, ring_offset, bar_offset;
   uint32_t div_magic;    // P / Wp == (P * div_magic) >> 20
   const float* scale;
   const float* bias;
@@ -123,7 +131,11 @@ struct ConvPlan {
 };
 
 // Layer description used to build a plan.
-enum ConvKind { kConv = 0, kDeconvK4S2P1 = 1, kStemS2D = 2 };
+// kConvUp2: 1x1 conv whose output is nearest-upsampled by 2 -- every row pixel feeds its 2x2 output pixels through four
+// phases that share ONE weight matrix and the unshifted tap; the epilogue's addends are indexed at the OUTPUT resolution.
+// This is how the branch-0 sum of an HRNet fuse layer (HRnet.py:254-263: y0 = relu(x0 + up2(bn(conv1x1(x1))) + ...)) runs
+// inside a conv epilogue instead of a separate elementwise kernel.
+enum ConvKind { kConv = 0, kDeconvK4S2P1 = 1, kStemS2D = 2, kConvUp2 = 3 };
 
 struct ConvLayerDesc {
   int kind;              // ConvKind
@@ -133,6 +145,7 @@ struct ConvLayerDesc {
   int kh, kw, stride, pad;
   int relu;
   int has_residual;      // a same-resolution addend (pre[0]) will be attached: keeps the N tile <= 128
+  int head_fold;         // the epilogue reduces the logits to soft-argmax partials (ConvParams::head_partials): N tile 128
   // kStemS2D only: the s2d input has padded rows (in_wpitch pixels per row, the image starts at column in_wpad, the
   // padding is zero).  The horizontal taps of one kernel row are then ONE contiguous K block of nw*16 channels
   // (overlapping TMA windows, pixel stride 32 B): 4x fewer, 4x longer TMA rows than one box per tap.  0 = dense.

@@ -44,6 +44,14 @@ constexpr int EPI_PRE = 1;    // + up to three same-resolution addends before th
 constexpr int EPI_FULL = 2;   // + nearest-upsampled addends, post-ReLU addend, pooled output
 constexpr int EPI_RES = 3;    // + exactly one residual, TMA-prefetched into the staging tile (no per-row predicates or
                               //   global loads: the generic flavours spend ~60 issue slots per 8 channels on them)
+constexpr int EPI_HEAD = 4;   // persistent kernel only: logits -> per-warp soft-argmax partials, nothing is stored
+constexpr float kLog2eF = 1.4426950408889634f;
+
+__device__ __forceinline__ float ex2_ftz_f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __device__ __forceinline__ void add_bf16x8(float* v, const uint4& x) {
   v[0] += bf16lo_to_f32(x.x); v[1] += bf16hi_to_f32(x.x);
@@ -98,7 +106,7 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
   // residual (pre[0]) prefetched by TMA into a dedicated staging buffer behind the pipeline stages; without a
   // residual the staging buffer aliases the (by then idle) stages
   constexpr bool GENERIC = (EPI == EPI_PRE || EPI == EPI_FULL);
-  const bool has_res = (EPI == EPI_RES) || (GENERIC && (p.pre[0] != nullptr) && (p.out != nullptr));
+  const bool has_res = (EPI == EPI_RES) || (GENERIC && (p.pre[0] != nullptr) && (p.out != nullptr) && p.os == 1);
   uint8_t* const stag_base = has_res ? smem + (size_t)stages * stage_bytes : smem;
   const int nkb = p.ntaps * p.cpt;
   // vertical tap sharing (3x3 stride-1 convs): one iteration = (channel chunk, dw); its A buffer holds bh+2 image
@@ -149,7 +157,8 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
       // running counters instead of div/mod: this single thread's scalar latency IS the producer's throughput
       int s = 0, tap = 0, cc = 0;
       uint32_t par = 0;
-      const int brow = phase * p.cout_pad + c_base;
+      const int brow = (p.shared_phase ? 0 : phase * p.cout_pad) + c_base;
+      const int tph = p.shared_phase ? 0 : ph, tpw = p.shared_phase ? 0 : pw;  // tap shift of the deconv phases
       for (int it = 0; it < n_iters; ++it) {
         mbar_wait(&bars->empty[s], par ^ 1);
         uint8_t* sa = smem + (size_t)s * stage_bytes;
@@ -166,7 +175,7 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
           uint8_t* sb = sa + kStageABytes;
           for (int j = 0; j < nsub; ++j) {
             tma_load_4d(sa + j * A_SUB_BYTES, &maps.a[p.tap_map[tap]], &bars->full[s], cc * CK,
-                        w0 + p.tap_dw[tap] + pw, h0 + p.tap_dh[tap] + ph, n0);
+                        w0 + p.tap_dw[tap] + tpw, h0 + p.tap_dh[tap] + tph, n0);
             tma_load_2d(sb + j * b_sub_bytes, &maps.b, &bars->full[s], (it * SUB + j) * CK, brow);
             if (++cc == p.cpt) {
               cc = 0;
@@ -453,7 +462,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
   const int cko = p.cko;
   const int nblk_full = n_tile / cko;
   constexpr bool GENERIC = (EPI == EPI_PRE || EPI == EPI_FULL);
-  const bool has_res = (EPI == EPI_RES) || (GENERIC && (p.pre[0] != nullptr) && (p.out != nullptr));
+  const bool has_res = (EPI == EPI_RES) || (GENERIC && (p.pre[0] != nullptr) && (p.out != nullptr) && p.os == 1);
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
 
   if (warp == 0 && lane == 0) {
@@ -480,9 +489,10 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
     tmem_relinquish();
   }
   if (warp >= 2 && warp < 10) {
+    const float mul = (EPI == EPI_HEAD) ? kLog2eF : 1.0f;  // soft-argmax fold: logits in the log2 domain (ex2 below)
     for (int i = threadIdx.x - 64; i < p.cout_pad; i += kEpiThreadsP) {
-      sb_smem[i] = (i < p.Cout) ? __ldg(p.scale + i) : 0.f;
-      sb_smem[p.cout_pad + i] = (i < p.Cout) ? __ldg(p.bias + i) : 0.f;
+      sb_smem[i] = (i < p.Cout) ? __ldg(p.scale + i) * mul : 0.f;
+      sb_smem[p.cout_pad + i] = (i < p.Cout) ? __ldg(p.bias + i) * mul : 0.f;
     }
   }
   tc_fence_before();
@@ -517,9 +527,13 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      if (wres) {  // the whole (single) N tile of packed weights stays in shared memory for the CTA's lifetime
+      if (wres) {
+        // the packed weights of this CTA's N tile stay in shared memory for the CTA's lifetime.  With several N tiles the
+        // grid is a multiple of n_tiles (host), so every tile this CTA walks (blockIdx.x + i * gridDim.x) has the same
+        // n_blk = blockIdx.x % n_tiles: the A tiles stream through the pipeline alone and the L2 -> SM traffic halves.
+        const int wrow0 = (p.n_tiles > 1) ? (int)(blockIdx.x % (unsigned)p.n_tiles) * n_tile : 0;
         mbar_expect_tx(&bars->w_full, (uint32_t)(nkb * b_sub_bytes));
-        for (int kb = 0; kb < nkb; ++kb) tma_load_2d(smem + (size_t)kb * b_sub_bytes, &maps.b, &bars->w_full, kb * CK, 0);
+        for (int kb = 0; kb < nkb; ++kb) tma_load_2d(smem + (size_t)kb * b_sub_bytes, &maps.b, &bars->w_full, kb * CK, wrow0);
         pdl_wait();
       }
       int s = 0;
@@ -530,7 +544,8 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
         (void)th; (void)tw; (void)tn;
         const int sbuf = li & (nstag - 1);
         const uint32_t spar = (uint32_t)((li >> nstag_shift) & 1);
-        const int brow = phase * p.cout_pad + c_base;
+        const int brow = (p.shared_phase ? 0 : phase * p.cout_pad) + c_base;
+        const int tph = p.shared_phase ? 0 : ph, tpw = p.shared_phase ? 0 : pw;
         int tap = 0, cc = 0, dwi = 0;
         auto load_residual = [&]() {
           mbar_wait(&bars->stag_free[sbuf], spar ^ 1);  // the store that last used this buffer has drained
@@ -564,7 +579,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
             mbar_expect_tx(&bars->full[s], (uint32_t)(nsub * (A_SUB_BYTES + (wres ? 0 : b_sub_bytes))));
             for (int j = 0; j < nsub; ++j) {
               tma_load_4d(sa + j * A_SUB_BYTES, &maps.a[p.tap_map[tap]], &bars->full[s], cc * CK,
-                          w0 + p.tap_dw[tap] + pw, h0 + p.tap_dh[tap] + ph, n0);
+                          w0 + p.tap_dw[tap] + tpw, h0 + p.tap_dh[tap] + tph, n0);
               if (!wres) tma_load_2d(sb + j * b_sub_bytes, &maps.b, &bars->full[s], (it * SUB + j) * CK, brow);
               if (++cc == p.cpt) {
                 cc = 0;
@@ -761,6 +776,49 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
         uint32_t acc[32];
         tmem_ld32(taddr + (uint32_t)c0, acc);
         tmem_ld_wait();
+        if (EPI == EPI_HEAD) {
+          // Soft-argmax fold.  This thread owns pixel (h, w) of image n0 (tile = two image rows: bw 64, bh 2, bn 1) and the
+          // 32 depth bins d0..d0+31 of keypoint kp: online-softmax partial over its 32 logits (log2 domain), then a
+          // fixed-order butterfly over the warp's 32 pixels; lane 0 writes the 5-tuple.  Nothing is stored otherwise.
+          const int cabs = c_base + c0;
+          const int kp = cabs >> 6;
+          const float d0 = (float)(cabs & 63);
+          const float fw = (float)(w0 + (row & (p.bw - 1))), fh = (float)(h0 + (row >> p.bw_shift));
+          float t[32];
+          float m = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            t[i] = fmaf(__uint_as_float(acc[i]), sc[c0 + i], sh_[c0 + i]);
+            m = fmaxf(m, t[i]);
+          }
+          float S = 0.f, Sz = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float e = ex2_ftz_f(t[i] - m);
+            S += e;
+            Sz = fmaf(e, d0 + (float)i, Sz);
+          }
+          float Sx = S * fw, Sy = S * fh;
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const float m2 = __shfl_xor_sync(0xffffffffu, m, off), S2 = __shfl_xor_sync(0xffffffffu, S, off);
+            const float Sx2 = __shfl_xor_sync(0xffffffffu, Sx, off), Sy2 = __shfl_xor_sync(0xffffffffu, Sy, off);
+            const float Sz2 = __shfl_xor_sync(0xffffffffu, Sz, off);
+            const float M = fmaxf(m, m2);
+            const float f1 = ex2_ftz_f(m - M), f2 = ex2_ftz_f(m2 - M);
+            S = S * f1 + S2 * f2;
+            Sx = Sx * f1 + Sx2 * f2;
+            Sy = Sy * f1 + Sy2 * f2;
+            Sz = Sz * f1 + Sz2 * f2;
+            m = M;
+          }
+          if (lane == 0) {
+            const int chunk = ((th * 4 + q) << 1) | ((cabs >> 5) & 1);
+            float* dst = p.head_partials + (((size_t)n0 * p.head_chunks + chunk) * p.head_nkpt + kp) * 5;
+            dst[0] = m; dst[1] = S; dst[2] = Sx; dst[3] = Sy; dst[4] = Sz;
+          }
+          continue;
+        }
         for (int ks = 1; ks < ksplit; ++ks) {  // partial sums of the K-split accumulators
           uint32_t part[32];
           tmem_ld32(taddr + (uint32_t)(ks * n_tile + c0), part);
@@ -933,6 +991,20 @@ int conv_geometry(const ConvLayerDesc& d, ConvParams* pp) {
         p.tap_dw[a * 2 + b] = (int8_t)(-b);  // + pw in the kernel
         p.tap_map[a * 2 + b] = 0;
       }
+  } else if (d.kind == kConvUp2) {
+    HRP_REQUIRE(d.kh == 1 && d.kw == 1 && d.stride == 1 && d.pad == 0, "the upsampling conv is a 1x1 conv");
+    p.Hout = d.Hin * 2;
+    p.Wout = d.Win * 2;
+    p.Hm = d.Hin;
+    p.Wm = d.Win;
+    p.Hs = d.Hin;
+    p.Ws = d.Win;
+    p.os = 2;
+    p.nphase = 4;
+    p.shared_phase = 1;
+    p.ntaps = 1;
+    p.tap_dh[0] = p.tap_dw[0] = 0;
+    p.tap_map[0] = 0;
   } else if (d.kind == kStemS2D) {
     HRP_REQUIRE(d.Cin == 16 && d.stride == 2, "s2d stem expects the 16-channel space-to-depth input");
     // d.Hin/d.Win are the s2d dims (H/2, W/2); output of the original stride-2 conv has the same size
@@ -1022,12 +1094,20 @@ int conv_geometry(const ConvLayerDesc& d, ConvParams* pp) {
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.nphase;
     // (measured, Panda full model, p50: batch 1 1.99 -> 1.80 ms, batch 4 2.12 -> 1.96 ms; at 16 images a 48-CTA target
     //  was 2.5 % slower than no splitting, hence the cap on the M-tile count and the 24-CTA target)
-    while (small_m && p.Cout >= 128 && max_n > 32 && p.Cout % (max_n / 2) == 0 && m_tiles <= 4 &&
+    while (small_m && !d.head_fold && p.Cout >= 128 && max_n > 32 && p.Cout % (max_n / 2) == 0 && m_tiles <= 4 &&
            m_tiles * ((p.Cout + max_n - 1) / max_n) < 24)
       max_n /= 2;
   }
-  const int n_tiles = (p.Cout + max_n - 1) / max_n;
+  int n_tiles = (p.Cout + max_n - 1) / max_n;
   p.n_tile = (((p.Cout + n_tiles - 1) / n_tiles) + 31) / 32 * 32;
+  if (d.head_fold) {
+    // soft-argmax fold: every N tile holds whole keypoints (64 depth bins each): 128-wide tiles, Cout padded with
+    // zero weight rows (Panda 448 -> 512, Baxter 1088 -> 1152); the epilogue skips the padding columns
+    HRP_REQUIRE(d.kind == kConv && d.kh == 1 && d.kw == 1 && d.stride == 1 && p.Cout % 64 == 0,
+                "the soft-argmax fold needs a 1x1 conv whose channels are keypoints x 64 depth bins");
+    p.n_tile = 128;
+    n_tiles = (p.Cout + 127) / 128;
+  }
   p.cout_pad = n_tiles * p.n_tile;
   p.cko = (p.n_tile % 64 == 0) ? 64 : 32;  // channel block of the TMA-store epilogue
   p.pool_scale = 1.f / (float)(p.Hout * p.Wout);
@@ -1052,13 +1132,13 @@ int conv_geometry(const ConvLayerDesc& d, ConvParams* pp) {
 }
 
 size_t conv_packed_weight_elems(const ConvParams& p) {
-  return (size_t)p.nphase * p.cout_pad * p.ktot + (p.pair_off > 0 ? (size_t)64 * 9 * 64 : 0);
+  return (size_t)(p.shared_phase ? 1 : p.nphase) * p.cout_pad * p.ktot + (p.pair_off > 0 ? (size_t)64 * 6 * 64 : 0);
 }
 
 int conv_pack_weights(const ConvLayerDesc& d, const ConvParams& p, int cin_ref, const float* w, uint16_t* out) {
   const size_t total = conv_packed_weight_elems(p);
   memset(out, 0, total * sizeof(uint16_t));
-  if (d.kind == kConv) {
+  if (d.kind == kConv || d.kind == kConvUp2) {
     HRP_REQUIRE(cin_ref <= p.Cin, "reference Cin exceeds stored Cin");
     for (int co = 0; co < p.Cout; ++co)
       for (int ci = 0; ci < cin_ref; ++ci)
@@ -1069,18 +1149,23 @@ int conv_pack_weights(const ConvLayerDesc& d, const ConvParams& p, int cin_ref, 
           }
     if (p.pair_off > 0) {
       // Pixel-pair view (conv_halo.cu): two horizontally adjacent pixels form one 64-channel position, so the layer
-      // becomes a 64 -> 64 channel 3x3 conv over (H, W/2) whose matrix has structured zero blocks:
+      // becomes a 64 -> 64 channel 3x3 conv over (H, W/2) whose per-tap matrices have structured zero blocks:
       //   Wpair[dh][dj][po*32+co][pi*32+ci] = W[co][ci][dh][dw],  dw = 2*dj + pi - po  (zero when |dw| > 1)
+      // dj = 0 is a full 64 x 64 tile; dj = -1 only has the block (po = 0, pi = 1) and dj = +1 only (po = 1, pi = 0),
+      // which share ONE tile.  Packed as 64 rows x 6 tiles x 64 K columns: tiles 0..2 = (dh, dj = 0), tiles 3..5 = the
+      // merged (dh, dj = -1 | +1) tiles.
       uint16_t* pw = out + p.pair_off;
+      const size_t pitch = 6 * 64;
       for (int i = 0; i < 3; ++i)
         for (int dj = -1; dj <= 1; ++dj)
           for (int po = 0; po < 2; ++po)
             for (int pi = 0; pi < 2; ++pi) {
               const int dw = 2 * dj + pi - po;
               if (dw < -1 || dw > 1) continue;
+              const int tile = (dj == 0) ? i : 3 + i;
               for (int co = 0; co < 32; ++co)
                 for (int ci = 0; ci < cin_ref; ++ci)
-                  pw[(size_t)(po * 32 + co) * 576 + (size_t)(i * 3 + dj + 1) * 64 + pi * 32 + ci] =
+                  pw[(size_t)(po * 32 + co) * pitch + (size_t)tile * 64 + pi * 32 + ci] =
                       f32_to_bf16_bits(w[(((size_t)co * cin_ref + ci) * 3 + i) * 3 + (dw + 1)]);
             }
     }
@@ -1173,6 +1258,7 @@ static void set_smem_attr_once() {
     HRP_SET_ATTR_P(16, EPI_PLAIN); HRP_SET_ATTR_P(16, EPI_PRE); HRP_SET_ATTR_P(16, EPI_FULL); HRP_SET_ATTR_P(16, EPI_RES);
     HRP_SET_ATTR_P(32, EPI_PLAIN); HRP_SET_ATTR_P(32, EPI_PRE); HRP_SET_ATTR_P(32, EPI_FULL); HRP_SET_ATTR_P(32, EPI_RES);
     HRP_SET_ATTR_P(64, EPI_PLAIN); HRP_SET_ATTR_P(64, EPI_PRE); HRP_SET_ATTR_P(64, EPI_FULL); HRP_SET_ATTR_P(64, EPI_RES);
+    HRP_SET_ATTR_P(64, EPI_HEAD);
 #undef HRP_SET_ATTR_P
   });
 }
@@ -1210,7 +1296,7 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed, con
     if (rc != HRP_OK) return rc;
   }
   {
-    uint64_t dims[2] = {(uint64_t)p.ktot, (uint64_t)p.nphase * p.cout_pad};
+    uint64_t dims[2] = {(uint64_t)p.ktot, (uint64_t)(p.shared_phase ? 1 : p.nphase) * p.cout_pad};
     uint64_t strides[1] = {(uint64_t)p.ktot * 2};
     uint32_t box[2] = {(uint32_t)p.ck, (uint32_t)p.n_tile};
     int rc = conv_encode_map(&plan->maps.b, w_packed, 2, dims, strides, box, p.ck);
@@ -1243,7 +1329,7 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed, con
   stages = std::max(1, std::min(stages, n_iters));
   plan->stages = stages;
   const int staging = (p.out != nullptr) ? kTileM * p.n_tile * 2 : 0;
-  const bool res_v1 = (p.pre[0] != nullptr) && (p.out != nullptr);
+  const bool res_v1 = (p.pre[0] != nullptr) && (p.out != nullptr) && p.os == 1;
   plan->bar_offset = res_v1 ? stages * stage_bytes + staging : std::max(stages * stage_bytes, staging);
   plan->smem_bytes = plan->bar_offset + (int)sizeof(PipeBarriers) + 2 * p.n_tile * (int)sizeof(float) + 1024;
   p.n_tiles = p.cout_pad / p.n_tile;
@@ -1253,6 +1339,14 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed, con
   const bool res_only = !full && p.pre[0] != nullptr && p.pre[1] == nullptr && p.pre[2] == nullptr && p.out != nullptr &&
                         p.nphase == 1 && p.os == 1;
   plan->epi = full ? EPI_FULL : (res_only ? EPI_RES : (pre ? EPI_PRE : EPI_PLAIN));
+  if (p.head_partials != nullptr) {
+    HRP_REQUIRE(!full && !pre && p.out == nullptr && p.ck == 64 && p.n_tile == 128 && p.nphase == 1,
+                "the soft-argmax fold takes no addends and writes no tensor");
+    HRP_REQUIRE(p.bw == 64 && p.bh == 2 && p.bn == 1 && p.Hm == 64 && p.Wm == 64,
+                "the soft-argmax fold is specialised for 64 x 64 heatmaps (tile = two image rows)");
+    HRP_REQUIRE(p.head_chunks == p.tiles_h * 8 && p.head_nkpt * 64 == p.Cout, "soft-argmax partial layout mismatch");
+    plan->epi = EPI_HEAD;
+  }
 
   // ---- persistent variant (default) ----
   {
@@ -1269,10 +1363,11 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed, con
     const char* pe = getenv("HRP_CONV_PERSISTENT");
     if (pe != nullptr && (pe[0] == '0' || pe[0] == '1')) plan->persistent = (pe[0] == '1');
     else plan->persistent = (p.n_tile == 128 && p.ktot >= 256 && p.ktot <= 1024 && p.pre[0] == nullptr);
+    if (p.head_partials != nullptr) plan->persistent = true;  // the fold lives in the persistent kernel's epilogue
     PersistCfg& c = plan->pcfg;
-    const bool has_res = (p.pre[0] != nullptr) && (p.out != nullptr);
+    // (output-strided layers -- deconv, upsampling conv -- read pre[0] with plain loads in the generic epilogue)
+    const bool has_res = (p.pre[0] != nullptr) && (p.out != nullptr) && p.os == 1;
     if (has_res) {
-      HRP_REQUIRE(p.nphase == 1 && p.os == 1, "residual addends are not supported on deconvolutions");
       uint64_t dims[4] = {(uint64_t)p.Cout, (uint64_t)p.Wout, (uint64_t)p.Hout, (uint64_t)p.B};
       uint64_t strides[3] = {(uint64_t)p.Cout * 2, (uint64_t)p.Wout * p.Cout * 2, (uint64_t)p.Hout * p.Wout * p.Cout * 2};
       uint32_t box[4] = {(uint32_t)p.cko, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
@@ -1293,7 +1388,12 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed, con
                          p.tap_dh[8] == 1 && p.tap_dw[8] == 1 && p.bn == 1 && p.Hs == p.Hm && p.Ws == p.Wm);
     c.vsh = (vsh_ok && !(e1 != nullptr && e1[0] == '0')) ? 1 : 0;
     const int wbytes = p.ntaps * p.cpt * b_sub;
-    c.wres = (p.n_tiles == 1 && p.nphase == 1 && wbytes <= 80 * 1024 && !(e2 != nullptr && e2[0] == '0')) ? 1 : 0;
+    // resident weights: one N tile always; several N tiles when the grid can be made a multiple of n_tiles without
+    // idling more than ~5 % of the SMs (each CTA then owns ONE N tile for all its M tiles)
+    const int grid_nt = (p.n_tiles > 1) ? (num_sms / p.n_tiles) * p.n_tiles : num_sms;
+    const bool multi_ok = p.n_tiles > 1 && p.nphase == 1 && grid_nt * 20 >= num_sms * 19 &&
+                          (long long)p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles >= 2LL * num_sms;
+    c.wres = ((p.n_tiles == 1 || multi_ok) && p.nphase == 1 && wbytes <= 80 * 1024 && !(e2 != nullptr && e2[0] == '0')) ? 1 : 0;
     c.a_bytes = c.vsh ? (p.bh + 2) * p.bw * p.ck * 2 : kStageABytes;
     c.a_region = (c.a_bytes + 1023) / 1024 * 1024;
     const int b_region = c.wres ? 0 : (c.vsh ? 3 * b_sub : p.n_tile * 128);
@@ -1341,7 +1441,7 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed, con
     while (cols < 2 * ks * p.n_tile) cols <<= 1;
     c.tmem_cols = cols;
     plan->psmem = c.bar_offset + tail;
-    plan->pgrid = (unsigned)std::min(c.total_tiles, num_sms);
+    plan->pgrid = (unsigned)std::min(c.total_tiles, (c.wres && p.n_tiles > 1) ? grid_nt : num_sms);
   }
   // ---- halo-tile variant for narrow 3x3 stride-1 layers (conv_halo.cu) ----
   plan->halo_ok = plan->halo = false;
@@ -1353,7 +1453,7 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed, con
   // HRP_CONV_VARIANT=tile|persist|halo pins the kernel (tests, profiling); halo falls back where it is not eligible
   if (const char* v = getenv("HRP_CONV_VARIANT")) {
     const std::string vs(v);
-    if (vs == "tile") { plan->persistent = false; plan->halo = false; }
+    if (vs == "tile" && plan->epi != EPI_HEAD) { plan->persistent = false; plan->halo = false; }
     else if (vs == "persist") { plan->persistent = true; plan->halo = false; }
     else if (vs == "halo") { plan->halo = plan->halo_ok; }
   }
@@ -1364,6 +1464,13 @@ int conv_plan_launch(const ConvPlan& plan, cudaStream_t stream) {
   set_smem_attr_once();
   const ConvParams& p = plan.p;
   if (plan.halo) return conv_halo_launch(plan, stream);
+  if (plan.epi == EPI_HEAD) {
+    launch_ex(conv_gemm_persistent<64, EPI_HEAD>, dim3(plan.pgrid), dim3(kThreadsP), (size_t)plan.psmem, stream, plan.maps, p,
+              plan.pcfg);
+    count_launch();
+    HRP_CUDA_CHECK(cudaGetLastError());
+    return HRP_OK;
+  }
   if (plan.persistent) {
 #define HRP_LAUNCH_P(CKV, EPIV) \
   launch_ex(conv_gemm_persistent<CKV, EPIV>, dim3(plan.pgrid), dim3(kThreadsP), (size_t)plan.psmem, stream, plan.maps, p, plan.pcfg)

@@ -34,7 +34,8 @@ struct __align__(16) HaloBars {
   uint64_t a_empty[4];
   uint64_t acc_full[8];
   uint64_t acc_empty[8];
-  uint64_t res_full[2];
+  uint64_t ring_full[4];    // output / residual ring: buffer may be used by the epilogue (residual tile landed, if any)
+  uint64_t ring_ready[4];   // ... holds a finished output tile (one arrival per epilogue warp of the owning group)
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -48,16 +49,26 @@ __device__ __forceinline__ void halo_stamp(long long* tl, int ev) {
   }
 }
 
-constexpr int kHaloThreads = 352;  // producer, MMA issuer A, 2 x 4 epilogue warps, MMA issuer B
+constexpr int kHaloThreads = 384;  // producer, MMA issuer A, 2 x 4 epilogue warps, MMA issuer B, store warp
 
-__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
-  uint4 r;
-  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-  return r;
-}
+// CTA-order tile iterator shared by every role: unit u (T tiles of one image), tile m inside it
+struct HaloTileIter {
+  int u, m;
+  __device__ __forceinline__ bool valid(const HaloParams& hp) const { return u < hp.total_units; }
+  __device__ __forceinline__ void next(const HaloParams& hp) {
+    ++m;
+    const int uu = u % hp.units_per_img;
+    if (m >= hp.T || uu * hp.T + m >= hp.tiles_per_img) {
+      m = 0;
+      u += (int)gridDim.x;
+    }
+  }
+};
 
-// PAIR: the 64-channel positions are pixel pairs of a 32-channel layer; the weight matrix then has zero blocks
-// (tap column dj = -1 only sees the right pixel of its pair, dj = +1 only the left one), whose K steps are skipped.
+// PAIR: the 64-channel positions are pixel pairs of a 32-channel layer.  Tap column dj = -1 then only feeds the LEFT
+// output pixel of a pair from the RIGHT input pixel of the neighbouring pair (and dj = +1 the mirror image), so those
+// taps are N = 32, K = 32 products: the packed matrix holds three full 64 x 64 tiles (dj = 0) and three tiles in which
+// the dj = -1 block (rows 0..31, K columns 32..63) and the dj = +1 block (rows 32..63, K columns 0..31) share one tile.
 template <int CK, int NOUT, bool RES, bool PAIR>
 __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                     const __grid_constant__ CUtensorMap map_b,
@@ -68,21 +79,22 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   constexpr uint32_t LAYOUT = (CK == 64) ? 2u : 4u;  // SWIZZLE_128B / SWIZZLE_64B
   constexpr uint32_t SBO = 8 * ROWB;
   constexpr int B_SUB = NOUT * ROWB;              // one tap of the packed weights
-  constexpr int STAG = kTileM * NOUT * 2;         // one output staging buffer
+  constexpr int NWT = PAIR ? 6 : 9;               // weight tiles resident in shared memory
+  constexpr int STAG = kTileM * NOUT * 2;         // one ring buffer (output tile / residual tile)
   constexpr int CH16 = NOUT / 8;                  // 16-byte chunks per output pixel
 
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = smem_align1024(smem_dyn);
   uint8_t* const sW = smem;
   uint8_t* const sA = smem + hp.a_offset;
-  uint8_t* const sStag = smem + hp.stag_offset;
-  uint8_t* const sRes = smem + hp.res_offset;  // per epilogue group: residual tile, TMA-swizzled (RES only)
+  uint8_t* const sRing = smem + hp.ring_offset;
   HaloBars* bars = reinterpret_cast<HaloBars*>(smem + hp.bar_offset);
   float* sb_smem = reinterpret_cast<float*>(bars + 1);  // [2][NOUT] folded-BN scale / shift
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int Wp = hp.Wp, T = hp.T, upi = hp.units_per_img;
+  const int NB = hp.nring;
 
   if (threadIdx.x == 0) {
     halo_stamp(hp.tl, 0);
@@ -93,9 +105,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     for (int i = 0; i < 4; ++i) {
       mbar_init(&bars->a_full[i], 1);
       mbar_init(&bars->a_empty[i], 2);  // both MMA issuers release a band
+      mbar_init(&bars->ring_full[i], 1);
+      mbar_init(&bars->ring_ready[i], 4);  // one arrival per epilogue warp of the owning group
     }
-    mbar_init(&bars->res_full[0], 1);
-    mbar_init(&bars->res_full[1], 1);
     for (int i = 0; i < 8; ++i) {
       mbar_init(&bars->acc_full[i], 1);
       mbar_init(&bars->acc_empty[i], 4);  // one arrival per epilogue warp of the owning group
@@ -124,8 +136,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      mbar_expect_tx(&bars->w_full, (uint32_t)(9 * B_SUB));
-      for (int t = 0; t < 9; ++t) tma_load_2d(sW + t * B_SUB, &map_b, &bars->w_full, t * CK, 0);
+      mbar_expect_tx(&bars->w_full, (uint32_t)(NWT * B_SUB));
+      for (int t = 0; t < NWT; ++t) tma_load_2d(sW + t * B_SUB, &map_b, &bars->w_full, t * CK, 0);
       pdl_wait();
       int abuf = 0;
       uint32_t par = 0;
@@ -151,6 +163,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     // at N = 32..64 one MMA occupies the tensor pipe for only 40-48 cycles.
     {
       const uint32_t idesc = make_idesc_bf16(kTileM, (uint32_t)NOUT);
+      const uint32_t idesc_half = make_idesc_bf16(kTileM, (uint32_t)(NOUT / 2));
       const uint32_t dhi = (uint32_t)(make_kmajor_desc(0, SBO, LAYOUT) >> 32);
       const uint32_t dlo = (uint32_t)make_kmajor_desc(0, SBO, LAYOUT);
       const uint32_t w_lo = dlo + (smem_u32(sW) >> 4);
@@ -192,17 +205,38 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           const uint32_t taddr = tmem_base + acc * NOUT;
           const uint32_t a_tile = a_unit0 + (uint32_t)(m * kTileM * (ROWB >> 4));
           if (elect_one()) {
+            if (PAIR) {
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              const int dh = tap / 3 - 1, dw = tap % 3 - 1;
-              const uint32_t al = a_tile + (uint32_t)(dh * wp_units + dw * (ROWB >> 4));
-              const uint32_t bl = w_lo + (uint32_t)(tap * (B_SUB >> 4));
-              const int k_lo = (PAIR && tap % 3 == 0) ? KSTEPS / 2 : 0;
-              const int k_hi = (PAIR && tap % 3 == 2) ? KSTEPS / 2 : KSTEPS;
+              for (int dh = -1; dh <= 1; ++dh) {
+                const uint32_t ac = a_tile + (uint32_t)(dh * wp_units);
+                const uint32_t bc = w_lo + (uint32_t)((dh + 1) * (B_SUB >> 4));        // dj = 0: full 64 x 64 tile
+                const uint32_t bm = w_lo + (uint32_t)((dh + 4) * (B_SUB >> 4));        // merged dj = -1 / +1 tile
 #pragma unroll
-              for (int k = k_lo; k < k_hi; ++k)
-                umma_bf16_ss(taddr, ((uint64_t)dhi << 32) | (al + 2 * k), ((uint64_t)dhi << 32) | (bl + 2 * k), idesc,
-                             (tap != 0 || k != k_lo) ? 1u : 0u);
+                for (int k = 0; k < KSTEPS; ++k)
+                  umma_bf16_ss(taddr, ((uint64_t)dhi << 32) | (ac + 2 * k), ((uint64_t)dhi << 32) | (bc + 2 * k), idesc,
+                               (dh != -1 || k != 0) ? 1u : 0u);
+                // dj = -1: left output pixels (accumulator columns 0..31) <- right input pixel of pair p-1 (K steps 2, 3)
+#pragma unroll
+                for (int k = KSTEPS / 2; k < KSTEPS; ++k)
+                  umma_bf16_ss(taddr, ((uint64_t)dhi << 32) | (ac - (uint32_t)(ROWB >> 4) + 2 * k),
+                               ((uint64_t)dhi << 32) | (bm + 2 * k), idesc_half, 1u);
+                // dj = +1: right output pixels (columns 32..63, weight rows 32..63) <- left input pixel of pair p+1
+#pragma unroll
+                for (int k = 0; k < KSTEPS / 2; ++k)
+                  umma_bf16_ss(taddr + (uint32_t)(NOUT / 2), ((uint64_t)dhi << 32) | (ac + (uint32_t)(ROWB >> 4) + 2 * k),
+                               ((uint64_t)dhi << 32) | (bm + (uint32_t)((NOUT / 2) * ROWB >> 4) + 2 * k), idesc_half, 1u);
+              }
+            } else {
+#pragma unroll
+              for (int tap = 0; tap < 9; ++tap) {
+                const int dh = tap / 3 - 1, dw = tap % 3 - 1;
+                const uint32_t al = a_tile + (uint32_t)(dh * wp_units + dw * (ROWB >> 4));
+                const uint32_t bl = w_lo + (uint32_t)(tap * (B_SUB >> 4));
+#pragma unroll
+                for (int k = 0; k < KSTEPS; ++k)
+                  umma_bf16_ss(taddr, ((uint64_t)dhi << 32) | (al + 2 * k), ((uint64_t)dhi << 32) | (bl + 2 * k), idesc,
+                               (tap != 0 || k != 0) ? 1u : 0u);
+              }
             }
             umma_commit(&bars->acc_full[acc]);
           }
@@ -227,87 +261,108 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         o[14] = (long long)tc;
       }
     }
+  } else if (warp == 11) {
+    // ===================== store warp: drains the output ring, prefetches the residual tiles ==========
+    // Ring buffer b = tile % NB serves tile after tile: [residual tile lands (RES)] -> epilogue group updates it in place
+    // -> bulk store to global -> residual of tile + NB is fetched into it.  One thread owns every bulk store and every
+    // residual load, so the epilogue warps never wait for a store to drain and the residual prefetch distance is NB tiles.
+    if (elect_one()) {
+      const int HW = hp.H * hp.W;
+      auto tile_range = [&](const HaloTileIter& it, int* pix_lo, int* npix) -> size_t {
+        const int n = it.u / upi, uu = it.u - n * upi;
+        const int Pt = (uu * T + it.m) * kTileM, Pe = Pt + kTileM;
+        const int rf = (int)(((uint32_t)Pt * hp.div_magic) >> 20), wf = Pt - rf * Wp;
+        const int re = (int)(((uint32_t)Pe * hp.div_magic) >> 20), we = Pe - re * Wp;
+        const int lo = min(rf * hp.W + min(wf, hp.W), HW), hi = min(re * hp.W + min(we, hp.W), HW);
+        *pix_lo = lo;
+        *npix = hi - lo;
+        return (size_t)n * HW;
+      };
+      auto fill = [&](const HaloTileIter& it, int buf) {  // make ring buffer `buf` usable for tile `it`
+        if (RES) {
+          int lo, np;
+          const size_t ib = tile_range(it, &lo, &np);
+          mbar_expect_tx(&bars->ring_full[buf], (uint32_t)STAG);
+          tma_load_2d(sRing + (size_t)buf * STAG, &map_r, &bars->ring_full[buf], 0, (int)(ib + (size_t)lo));
+        } else {
+          mbar_arrive(&bars->ring_full[buf]);
+        }
+      };
+      HaloTileIter ahead{(int)blockIdx.x, 0};  // next tile whose ring buffer has not been prepared yet
+      for (int b = 0; b < NB && ahead.valid(hp); ++b) {
+        fill(ahead, b);
+        ahead.next(hp);
+      }
+      int buf = 0;
+      uint32_t par = 0;
+      for (HaloTileIter it{(int)blockIdx.x, 0}; it.valid(hp); it.next(hp)) {
+        mbar_wait(&bars->ring_ready[buf], par);
+        int lo, np;
+        const size_t ib = tile_range(it, &lo, &np);
+        if (np > 0) {
+          bf16* dst = hp.out + (ib + lo) * NOUT;
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+                       "r"(smem_u32(sRing + (size_t)buf * STAG)), "r"((uint32_t)(np * NOUT * 2))
+                       : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem read out: the buffer can be refilled
+        if (ahead.valid(hp)) {
+          fill(ahead, buf);
+          ahead.next(hp);
+        }
+        if (++buf == NB) {
+          buf = 0;
+          par ^= 1;
+        }
+      }
+      halo_stamp(hp.tl, 5);
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      halo_stamp(hp.tl, 7);
+    }
   } else {
     // ===================== epilogue: warps 2..9, TMEM lane quarter = warp % 4, group = (warp - 2) / 4 ==========
     const int q = warp & 3;
     const int grp = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int HW = hp.H * hp.W;
-    const bool leader = (threadIdx.x == 64 + grp * 128);
-    uint8_t* const stag = sStag + (size_t)grp * STAG;
-    // CTA-order tile iterator; this group takes every other tile
-    int u = blockIdx.x, m = 0;
+    HaloTileIter it{(int)blockIdx.x, 0};
     uint32_t tc = 0;
-    auto step = [&]() {
-      ++m;
-      ++tc;
-      const int uu = u % upi;
-      if (m >= T || uu * T + m >= hp.tiles_per_img) {
-        m = 0;
-        u += gridDim.x;
-      }
-    };
-    // this thread's output position in tile (u_, m_): pixel index inside the image (-1 = junk) and the image base
-    auto my_pixel = [&](int u_, int m_, size_t* img_base) -> int {
-      const int n = u_ / upi, uu = u_ - n * upi;
-      const int P = (uu * T + m_) * kTileM + row;
-      const int r = (int)(((uint32_t)P * hp.div_magic) >> 20), w = P - r * Wp;
-      *img_base = (size_t)n * HW;
-      return ((w < hp.W) && (r < hp.H)) ? r * hp.W + w : -1;
-    };
-    // first pixel of tile (u_, m_) and its image: the tile's valid outputs are the contiguous pixels [pix_lo, pix_hi)
-    auto tile_pix_lo = [&](int u_, int m_, size_t* img_base) -> int {
-      const int n = u_ / upi, uu = u_ - n * upi;
-      const int Pt = (uu * T + m_) * kTileM;
-      const int rf = (int)(((uint32_t)Pt * hp.div_magic) >> 20), wf = Pt - rf * Wp;
-      *img_base = (size_t)n * HW;
-      return min(rf * hp.W + min(wf, hp.W), HW);
-    };
-    // Residual tile = 128 pixel rows starting at the tile's first pixel, fetched by TMA into this group's buffer with
-    // the 64-/128-byte swizzle (row-per-lane reads are then bank-conflict free); rows past the tile are never used.
-    uint8_t* const rbuf = sRes + (size_t)grp * STAG;
-    auto load_residual = [&](int u_, int m_) {
-      if (u_ >= hp.total_units) return;
-      size_t ib;
-      const int lo = tile_pix_lo(u_, m_, &ib);
-      mbar_expect_tx(&bars->res_full[grp], (uint32_t)STAG);
-      tma_load_2d(rbuf, &map_r, &bars->res_full[grp], 0, (int)(ib + (size_t)lo));
-    };
+    int buf = 0;
     uint32_t rpar = 0;
-    if (grp == 1 && u < hp.total_units) step();
-    if (RES && leader) load_residual(u, m);
-    while (u < hp.total_units) {
-      const int n = u / upi, uu = u - n * upi;
-      const int Pt = (uu * T + m) * kTileM;
-      // this thread's output position and the tile's contiguous pixel range [pix_lo, pix_hi)
-      size_t img_base;
-      const int pix = my_pixel(u, m, &img_base);
-      const bool valid = pix >= 0;
+    if (grp == 1 && it.valid(hp)) {  // group 1 takes the odd tiles
+      it.next(hp);
+      tc = 1;
+      buf = 1 % NB;
+      rpar = (NB == 1) ? 1u : 0u;
+    }
+    while (it.valid(hp)) {
+      const int n = it.u / upi, uu = it.u - n * upi;
+      const int Pt = (uu * T + it.m) * kTileM;
+      // this thread's output position and the tile's first pixel
+      const int P = Pt + row;
+      const int r = (int)(((uint32_t)P * hp.div_magic) >> 20), w = P - r * Wp;
+      const bool valid = (w < hp.W) && (r < hp.H);
       const int rf = (int)(((uint32_t)Pt * hp.div_magic) >> 20), wf = Pt - rf * Wp;
-      const int Pe = Pt + kTileM;
-      const int re = (int)(((uint32_t)Pe * hp.div_magic) >> 20), we = Pe - re * Wp;
       const int pix_lo = min(rf * hp.W + min(wf, hp.W), HW);
-      const int pix_hi = min(re * hp.W + min(we, hp.W), HW);
+      const int sr = r * hp.W + w - pix_lo;  // this thread's row in the ring buffer (valid lanes only)
       const uint32_t acc = tc & (uint32_t)(hp.nacc - 1);
-      // the bulk store that last read this group's staging buffer must have drained
-      if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+      uint8_t* const rbuf = sRing + (size_t)buf * STAG;
       mbar_wait(&bars->acc_full[acc], (tc >> hp.nacc_shift) & 1);
       tc_fence_after();
+      mbar_wait(&bars->ring_full[buf], rpar);  // store of tile - NB drained (and this tile's residual landed)
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * NOUT;
-      const int sr = pix - pix_lo;  // this thread's row in the staging / residual tile (valid lanes only)
-      if (RES) {
-        mbar_wait(&bars->res_full[grp], rpar);
-        rpar ^= 1;
-      }
       const uint8_t* const rrow = rbuf + (size_t)sr * (NOUT * 2);
       const int rsw = (CH16 == 8) ? (sr & 7) : ((sr >> 1) & 3);
       uint4 o[CH16];
+      // the whole accumulator row (32 or 64 columns) is fetched with one round trip: both loads in flight, one wait
+      uint32_t acc_all[NOUT];
+#pragma unroll
+      for (int c0 = 0; c0 < NOUT; c0 += 32) tmem_ld32(taddr + (uint32_t)c0, reinterpret_cast<uint32_t(&)[32]>(acc_all[c0]));
+      tmem_ld_wait();
 #pragma unroll
       for (int c0 = 0; c0 < NOUT; c0 += 32) {
-        uint32_t a[32];
-        tmem_ld32(taddr + (uint32_t)c0, a);
-        tmem_ld_wait();
+        const uint32_t* a = acc_all + c0;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const int cg = c0 + g * 8;
@@ -348,22 +403,11 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
-      // residual of this group's NEXT tile: in flight while this tile is stored and the next accumulator completes
-      int u2 = u, m2 = m;
-      {
-        const int u0 = u, m0 = m;
-        const uint32_t tc0 = tc;
-        step();
-        if (u < hp.total_units) step();
-        u2 = u;
-        m2 = m;
-        u = u0;
-        m = m0;
-        tc = tc0;
-      }
-      // Staging rows are dense pixels (64 or 128 bytes apart): written chunk-by-chunk in lane order every 16-byte
-      // store would hit the same 4 banks (8- / 16-way conflict).  Row sr therefore writes its chunks in the
-      // rotated order (c + rot(sr)) % CH16, which spreads every quarter-warp over all 32 banks.
+      // The output row replaces the residual row IN PLACE: this thread has read all the chunks of its row above, and a
+      // row is touched by one thread only (the TMA swizzle and the rotation below both permute chunks inside a row).
+      // Ring rows are dense pixels (64 or 128 bytes apart): written chunk-by-chunk in lane order every 16-byte store
+      // would hit the same 4 banks (8- / 16-way conflict).  Row sr therefore writes its chunks in the rotated order
+      // (c + rot(sr)) % CH16, which spreads every quarter-warp over all 32 banks.
       if (valid) {
         const int rot = (CH16 == 8) ? (sr & 7) : ((sr >> 1) & 3);
 #pragma unroll
@@ -381,32 +425,23 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
 #pragma unroll
           for (int i = 0; i < CH16; ++i) o[i] = t[i];
         }
-        uint8_t* const srow = stag + (size_t)sr * (NOUT * 2);
+        uint8_t* const srow = rbuf + (size_t)sr * (NOUT * 2);
 #pragma unroll
         for (int c = 0; c < CH16; ++c) *reinterpret_cast<uint4*>(srow + (((c + rot) & (CH16 - 1)) << 4)) = o[c];
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-      if (leader) {
-        const int npix = pix_hi - pix_lo;
-        if (npix > 0) {
-          bf16* dst = hp.out + (img_base + pix_lo) * NOUT;
-          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(stag)),
-                       "r"((uint32_t)(npix * NOUT * 2))
-                       : "memory");
-        }
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        // every thread of the group has consumed the residual tile (it is read before the staging stores and the
-        // barrier above): fetch the one of this group's next tile
-        if (RES) load_residual(u2, m2);
-      }
-      u = u2;
-      m = m2;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk copy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->ring_ready[buf]);
+      // this group's next tile: two tiles further in CTA order
+      it.next(hp);
+      if (it.valid(hp)) it.next(hp);
       tc += 2;
+      buf += 2;
+      if (buf >= NB) {
+        buf -= NB;
+        rpar ^= 1;
+      }
     }
-    if (leader) halo_stamp(hp.tl, 5 + grp);
-    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    if (leader) halo_stamp(hp.tl, 7 + grp);
   }
 
   __syncthreads();
@@ -472,13 +507,33 @@ int conv_halo_plan(ConvPlan* plan, const ConvLayerDesc& d, const bf16* in) {
     if ((int)(((uint64_t)(uint32_t)P * h.div_magic) >> 20) != P / Wp || (uint64_t)P * h.div_magic >= (1ull << 32))
       return HRP_OK;  // (never happens for the shapes on the path; stay on the generic kernels if it does)
   const int rowb = C * 2;
-  const int w_bytes = 9 * C * rowb;
-  const int stag_bytes = 2 * kTileM * C * 2;
-  const int res_bytes = (p.pre[0] != nullptr) ? stag_bytes : 0;  // residual tiles (one per epilogue group)
+  const int w_bytes = (pair ? 6 : 9) * C * rowb;   // pair view: three full taps + three merged half-tap tiles
+  // Buffering.  Output / residual ring (`nring` tiles): the residual tile is fetched into the buffer the output tile is then
+  // built in (in place), so the ring depth is also the residual prefetch distance.  Bands: T tiles per band, nbuf bands; the
+  // MMA warps run (nbuf - 1) * T tiles ahead of the band being loaded and need ~2 tiles to cover a DRAM round trip.
+  // Measured on B200 at 512 images (profiles/r02_halo_sweep.txt, us per launch, round-1 kernel -> best configuration):
+  //   pixel pairs (32 ch @ 64x64)      67.6 -> 59.9  T=1 bands=3 ring=4   (T=2/b3/r2 62.5, T=3/b2/r2 65.9)
+  //   pixel pairs + residual            95.8 -> 69.7  T=1 bands=3 ring=4   (ring=3 76.2, ring=2 98.4)
+  //   64 ch @ 32x32                     47.2 -> 43.3  T=3 bands=2 ring=2   (T=2/b2 47.8, T=1/b4 48.6)
+  //   64 ch @ 32x32 + residual          59.2 -> 47.7  T=1 bands=3 ring=3   (T=2/b2/r3 50.1, ring=4/T=1/b2 55.0)
+  // i.e. a deep ring wins whenever it still leaves two tiles of band look-ahead; otherwise large bands win.
+  const bool res = (p.pre[0] != nullptr);
   const int tail = (int)sizeof(HaloBars) + 2 * C * 4 + 1024;
-  const int avail = 227 * 1024 - tail - stag_bytes - res_bytes - (w_bytes + 1023) / 1024 * 1024;
-  int best_T = 0, best_NR = 0, best_nbuf = 0;
-  for (int T = 4; T >= 1 && best_T == 0; --T) {
+  const int w_pad = (w_bytes + 1023) / 1024 * 1024;
+  struct Cand { int T, ring; };
+  static const Cand pref_pair[] = {{1, 4}, {2, 4}, {2, 3}, {2, 2}, {1, 3}, {1, 2}};
+  static const Cand pref_res[] = {{1, 3}, {2, 3}, {1, 4}, {1, 2}};
+  static const Cand pref_plain[] = {{3, 2}, {2, 2}, {4, 2}, {1, 2}};
+  const Cand* pref = pair ? pref_pair : (res ? pref_res : pref_plain);
+  const int npref = pair ? 6 : 4;
+  const char* eT = getenv("HRP_HALO_T");
+  const char* eN = getenv("HRP_HALO_NBUF");
+  const char* eR = getenv("HRP_HALO_NRING");
+  int best_T = 0, best_NR = 0, best_nbuf = 0, nring = 0;
+  for (int ci = 0; ci < npref && best_T == 0; ++ci) {
+    const int T = (eT != nullptr) ? atoi(eT) : pref[ci].T;
+    const int ring = (eR != nullptr) ? std::max(2, std::min(4, atoi(eR))) : pref[ci].ring;
+    if (T < 1 || T > 4) continue;
     const int upi = (h.tiles_per_img + T - 1) / T;
     int NR = 0;
     for (int uu = 0; uu < upi; ++uu) {
@@ -488,24 +543,28 @@ int conv_halo_plan(ConvPlan* plan, const ConvLayerDesc& d, const bf16* in) {
     }
     if (NR > 256) continue;
     const int a_buf = (NR * Wp * rowb + 1023) / 1024 * 1024;
-    const int nbuf = std::min(4, avail / a_buf);
-    if (nbuf >= 2 || (T == 1 && nbuf >= 1)) {
-      best_T = T;
-      best_NR = NR;
-      best_nbuf = std::min(nbuf, 3);
-    }
+    const int avail = 227 * 1024 - tail - ring * kTileM * C * 2 - w_pad;
+    int nbuf = (avail > 0) ? std::min(4, avail / a_buf) : 0;
+    if (eN != nullptr) nbuf = std::min(nbuf, std::max(1, atoi(eN)));
+    const int look = (nbuf - 1) * T;
+    if (nbuf < 2 || (look < 2 && ci + 1 < npref && eT == nullptr)) continue;  // (the last candidate may run with 1 tile ahead)
+    best_T = T;
+    best_NR = NR;
+    best_nbuf = nbuf;
+    nring = ring;
   }
+  const int ring_bytes = nring * kTileM * C * 2;
   if (best_T == 0) return HRP_OK;
   h.T = best_T;
   h.NR = best_NR;
   h.n_abuf = best_nbuf;
+  h.nring = nring;
   h.units_per_img = (h.tiles_per_img + h.T - 1) / h.T;
   h.total_units = h.units_per_img * d.B;
   h.a_buf_bytes = (h.NR * Wp * rowb + 1023) / 1024 * 1024;
   h.a_offset = (w_bytes + 1023) / 1024 * 1024;
-  h.stag_offset = h.a_offset + h.n_abuf * h.a_buf_bytes;
-  h.res_offset = h.stag_offset + stag_bytes;
-  h.bar_offset = h.res_offset + res_bytes;
+  h.ring_offset = h.a_offset + h.n_abuf * h.a_buf_bytes;
+  h.bar_offset = h.ring_offset + ring_bytes;
   h.scale = p.scale;
   h.bias = p.bias;
   h.res = p.pre[0];
@@ -530,8 +589,8 @@ int conv_halo_plan(ConvPlan* plan, const ConvLayerDesc& d, const bf16* in) {
     if (rc != HRP_OK) return rc;
   }
   if (pair) {
-    uint64_t dims[2] = {(uint64_t)9 * 64, 64};
-    uint64_t strides[1] = {(uint64_t)9 * 64 * 2};
+    uint64_t dims[2] = {(uint64_t)6 * 64, 64};
+    uint64_t strides[1] = {(uint64_t)6 * 64 * 2};
     uint32_t box[2] = {64u, 64u};
     int rc = conv_encode_map(&plan->halo_map_b, p.w + p.pair_off, 2, dims, strides, box, 64);
     if (rc != HRP_OK) return rc;

@@ -16,9 +16,9 @@ __global__ void conv_simt_kernel(const ConvParams p) {
   const int h = (int)((rowpix / p.Wm) % p.Hm);
   const int n = (int)(rowpix / ((size_t)p.Wm * p.Hm));
   float acc = 0.f;
-  const bf16* wrow = p.w + ((size_t)phase * p.cout_pad + c) * p.ktot;
+  const bf16* wrow = p.w + ((size_t)(p.shared_phase ? 0 : phase) * p.cout_pad + c) * p.ktot;
   for (int t = 0; t < p.ntaps; ++t) {
-    const int hs = h + p.tap_dh[t] + ph, ws = w + p.tap_dw[t] + pw;
+    const int hs = h + p.tap_dh[t] + (p.shared_phase ? 0 : ph), ws = w + p.tap_dw[t] + (p.shared_phase ? 0 : pw);
     if (hs < 0 || hs >= p.Hs || ws < 0 || ws >= p.Ws) continue;
     const int hp = p.tap_map[t] >> 1, wp = p.tap_map[t] & 1;
     const bf16* src = p.in + p.src_off + ((size_t)hp * p.Win + wp) * p.Cin + (size_t)n * p.src_img +

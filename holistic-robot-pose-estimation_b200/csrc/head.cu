@@ -222,6 +222,179 @@ int launch_fk(const FkParams& p, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------------
+// FK backward (row f4): one thread per sample, link transforms in shared memory like fk_kernel
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cross3(const float* a, const float* b, float* c) {
+  c[0] = a[1] * b[2] - a[2] * b[1];
+  c[1] = a[2] * b[0] - a[0] * b[2];
+  c[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+// d loss / d q from a force `w` (gradient w.r.t. a base-frame point `x` attached to link `l`): every moving ancestor joint
+// contributes  revolute: a . ((x - o) x w),  prismatic: a . w  (a, o = joint axis / origin in the base frame)
+__device__ void fk_bwd_point(const RobotTable* __restrict__ rb, const float* T, int stride, int l, const float* x,
+                             const float* w, float sign, float* gq) {
+  for (int i = l; i >= 0 && rb->parent[i] >= 0; i = rb->parent[i]) {
+    const int jt = rb->jtype[i];
+    if (jt == 0) continue;
+    const float* Ti = T + (size_t)i * 12 * stride;
+    const float* ax = rb->axis[i];
+    float a[3], d[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+      a[r] = Ti[(r * 4 + 0) * stride] * ax[0] + Ti[(r * 4 + 1) * stride] * ax[1] + Ti[(r * 4 + 2) * stride] * ax[2];
+    float g;
+    if (jt == 1) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) d[r] = x[r] - Ti[(r * 4 + 3) * stride];
+      float c[3];
+      cross3(d, w, c);
+      g = a[0] * c[0] + a[1] * c[1] + a[2] * c[2];
+    } else {
+      g = a[0] * w[0] + a[1] * w[1] + a[2] * w[2];
+    }
+    gq[rb->qcol[i]] += sign * rb->qmul[i] * g;
+  }
+}
+
+// d loss / d q from a torque `tau` on the rotation of link `l` (d R_l = [a]x R_l dq for every revolute ancestor)
+__device__ void fk_bwd_rotation(const RobotTable* __restrict__ rb, const float* T, int stride, int l, const float* tau,
+                                float sign, float* gq) {
+  for (int i = l; i >= 0 && rb->parent[i] >= 0; i = rb->parent[i]) {
+    if (rb->jtype[i] != 1) continue;
+    const float* Ti = T + (size_t)i * 12 * stride;
+    const float* ax = rb->axis[i];
+    float g = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+      g += (Ti[(r * 4 + 0) * stride] * ax[0] + Ti[(r * 4 + 1) * stride] * ax[1] + Ti[(r * 4 + 2) * stride] * ax[2]) * tau[r];
+    gq[rb->qcol[i]] += sign * rb->qmul[i] * g;
+  }
+}
+
+__global__ void __launch_bounds__(kFkThreads) fk_bwd_kernel(const FkBwdParams p) {
+  extern __shared__ float fk_smem[];
+  const int b = blockIdx.x * kFkThreads + threadIdx.x;
+  if (b >= p.B) return;
+  const RobotTable* rb = p.robot;
+  float* T = fk_smem + threadIdx.x;
+  const int S = kFkThreads;
+  float q[kMaxDof], gq[kMaxDof];
+  for (int i = 0; i < rb->dof; ++i) {
+    q[i] = p.q[(size_t)b * rb->dof + i];
+    gq[i] = 0.f;
+  }
+  fk_tree(rb, q, T, S);
+  float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+  if (p.use_b2c) rot6d_to_rows(p.rot + (size_t)b * 6, R);
+  // root frame: p_k = Rr^T (x_k - o_r)
+  const int lr = (p.root > 0) ? rb->kp_link[p.root] : -1;
+  float Rr[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f}, orr[3] = {0.f, 0.f, 0.f};
+  if (lr >= 0) {
+    const float* Tr = T + (size_t)lr * 12 * S;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) Rr[r * 3 + c] = Tr[(r * 4 + c) * S];
+      orr[r] = Tr[(r * 4 + 3) * S];
+    }
+  }
+  float gt[3] = {0.f, 0.f, 0.f}, gR[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float g_or[3] = {0.f, 0.f, 0.f}, tau_r[3] = {0.f, 0.f, 0.f};
+  for (int k = 0; k < rb->nkpt; ++k) {
+    const int l = rb->kp_link[k];
+    const float* Tl = T + (size_t)l * 12 * S;
+    const float o0 = rb->kp_off[k][0], o1 = rb->kp_off[k][1], o2 = rb->kp_off[k][2];
+    float x[3], v[3], pk[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+      x[r] = fmaf(Tl[(r * 4 + 2) * S], o2, fmaf(Tl[(r * 4 + 1) * S], o1, Tl[(r * 4 + 0) * S] * o0)) + Tl[(r * 4 + 3) * S];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) v[r] = x[r] - orr[r];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) pk[c] = Rr[0 * 3 + c] * v[0] + Rr[1 * 3 + c] * v[1] + Rr[2 * 3 + c] * v[2];  // Rr^T v
+    const float* g = p.grad_pts + ((size_t)b * rb->nkpt + k) * 3;
+    float gp[3];
+    if (p.use_b2c) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        gt[r] += g[r];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) gR[r * 3 + c] = fmaf(g[r], pk[c], gR[r * 3 + c]);   // out_r = R_row_r . p_k + t_r
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gp[c] = R[0 * 3 + c] * g[0] + R[1 * 3 + c] * g[1] + R[2 * 3 + c] * g[2];  // R^T g
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gp[c] = g[c];
+    }
+    float w[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) w[r] = Rr[r * 3 + 0] * gp[0] + Rr[r * 3 + 1] * gp[1] + Rr[r * 3 + 2] * gp[2];   // Rr gp
+    fk_bwd_point(rb, T, S, l, x, w, 1.0f, gq);
+    if (lr >= 0) {
+      float c[3];
+      cross3(v, w, c);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        g_or[r] += w[r];
+        tau_r[r] += c[r];
+      }
+    }
+  }
+  if (lr >= 0) {
+    fk_bwd_point(rb, T, S, lr, orr, g_or, -1.0f, gq);      // the root origin moves with its own ancestors
+    fk_bwd_rotation(rb, T, S, lr, tau_r, -1.0f, gq);       // ... and so does the root orientation
+  }
+  for (int i = 0; i < rb->dof; ++i) p.grad_q[(size_t)b * rb->dof + i] = gq[i];
+  if (p.use_b2c) {
+    if (p.grad_trans != nullptr)
+      for (int r = 0; r < 3; ++r) p.grad_trans[(size_t)b * 3 + r] = gt[r];
+    if (p.grad_rot != nullptr) {
+      // rows x = a/|a|, z = (x x b)/|x x b|, y = z x x  (geometries.py:100-115); cross adjoints: c = u x v ->
+      // gu += v x gc, gv += gc x u
+      const float* rr = p.rot + (size_t)b * 6;
+      const float a[3] = {rr[0], rr[1], rr[2]}, bb[3] = {rr[3], rr[4], rr[5]};
+      const float na = sqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+      const float x[3] = {R[0], R[1], R[2]}, z[3] = {R[6], R[7], R[8]};
+      float wv[3];
+      cross3(x, bb, wv);
+      const float nw = sqrtf(wv[0] * wv[0] + wv[1] * wv[1] + wv[2] * wv[2]);
+      float gx[3] = {gR[0], gR[1], gR[2]}, gy[3] = {gR[3], gR[4], gR[5]}, gz[3] = {gR[6], gR[7], gR[8]};
+      float t1[3];
+      cross3(x, gy, t1);   // y = z x x : gz += x x gy
+      for (int r = 0; r < 3; ++r) gz[r] += t1[r];
+      cross3(gy, z, t1);   //            gx += gy x z
+      for (int r = 0; r < 3; ++r) gx[r] += t1[r];
+      const float zg = z[0] * gz[0] + z[1] * gz[1] + z[2] * gz[2];
+      float gw[3];
+      for (int r = 0; r < 3; ++r) gw[r] = (gz[r] - z[r] * zg) / nw;   // z = w / |w|
+      cross3(bb, gw, t1);  // w = x x b : gx += b x gw
+      for (int r = 0; r < 3; ++r) gx[r] += t1[r];
+      float gb[3];
+      cross3(gw, x, gb);   //             gb = gw x x
+      const float xg = x[0] * gx[0] + x[1] * gx[1] + x[2] * gx[2];
+      for (int r = 0; r < 3; ++r) {
+        p.grad_rot[(size_t)b * 6 + r] = (gx[r] - x[r] * xg) / na;     // x = a / |a|
+        p.grad_rot[(size_t)b * 6 + 3 + r] = gb[r];
+      }
+    }
+  }
+}
+
+int launch_fk_backward(const FkBwdParams& p, cudaStream_t s) {
+  HRP_REQUIRE(p.B > 0 && p.q != nullptr && p.robot != nullptr && p.grad_pts != nullptr && p.grad_q != nullptr,
+              "bad FK-backward arguments");
+  HRP_REQUIRE(!p.use_b2c || (p.rot != nullptr && p.trans != nullptr), "rotation / translation required");
+  const int smem = kMaxLinks * 12 * kFkThreads * (int)sizeof(float);
+  HRP_CUDA_CHECK(cudaFuncSetAttribute(fk_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  fk_bwd_kernel<<<(p.B + kFkThreads - 1) / kFkThreads, kFkThreads, smem, s>>>(p);
+  count_launch();
+  HRP_CUDA_CHECK(cudaGetLastError());
+  return HRP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
 // link transforms: URDFRobot.get_TWL (urdf_robot.py:107-111) and URDF.link_fk_batch over ALL links
 // (urdf.py:3061-3149) -- one thread per sample
 // ------------------------------------------------------------------------------------------------------
@@ -427,6 +600,35 @@ __global__ void project_kernel(const float* __restrict__ K, const float* __restr
 int launch_project(const float* K, const float* pts, float* uv, int B, int N, cudaStream_t s) {
   HRP_REQUIRE(K != nullptr && pts != nullptr && uv != nullptr && B > 0 && N > 0, "bad projection arguments");
   project_kernel<<<(B * N + 127) / 128, 128, 0, s>>>(K, pts, uv, B, N);
+  count_launch();
+  HRP_CUDA_CHECK(cudaGetLastError());
+  return HRP_OK;
+}
+
+__global__ void project_bwd_kernel(const float* __restrict__ K, const float* __restrict__ pts, const float* __restrict__ guv,
+                                   float* __restrict__ gpts, int B, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * N) return;
+  const int b = i / N;
+  float k[9];
+#pragma unroll
+  for (int e = 0; e < 9; ++e) k[e] = __ldg(K + (size_t)b * 9 + e);
+  const float x = pts[(size_t)i * 3], y = pts[(size_t)i * 3 + 1], z = pts[(size_t)i * 3 + 2];
+  const float v0 = fmaf(k[2], z, fmaf(k[1], y, k[0] * x));
+  const float v1 = fmaf(k[5], z, fmaf(k[4], y, k[3] * x));
+  const float v2 = fmaf(k[8], z, fmaf(k[7], y, k[6] * x));
+  const float u0 = v0 / v2, u1 = v1 / v2;
+  const float g0 = guv[(size_t)i * 2] / v2, g1 = guv[(size_t)i * 2 + 1] / v2;
+  // d u0 / d p_j = (K0j - u0 K2j) / v2 ,  d u1 / d p_j = (K1j - u1 K2j) / v2
+#pragma unroll
+  for (int j = 0; j < 3; ++j) gpts[(size_t)i * 3 + j] = g0 * (k[j] - u0 * k[6 + j]) + g1 * (k[3 + j] - u1 * k[6 + j]);
+}
+
+int launch_project_backward(const float* K, const float* pts, const float* grad_uv, float* grad_pts, int B, int N,
+                            cudaStream_t s) {
+  HRP_REQUIRE(K != nullptr && pts != nullptr && grad_uv != nullptr && grad_pts != nullptr && B > 0 && N > 0,
+              "bad projection-backward arguments");
+  project_bwd_kernel<<<(B * N + 127) / 128, 128, 0, s>>>(K, pts, grad_uv, grad_pts, B, N);
   count_launch();
   HRP_CUDA_CHECK(cudaGetLastError());
   return HRP_OK;
@@ -827,6 +1029,66 @@ __global__ void __launch_bounds__(kHeadMaxThreads, 3) head_kernel(const __grid_c
   if (!sm.is_last) return;
   __threadfence();
   head_finalize(p, sm, b);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// finish from partials written by the final conv's epilogue (soft-argmax fold): one CTA per image
+// ------------------------------------------------------------------------------------------------------
+constexpr int kFoldThreads = 256;
+
+__global__ void __launch_bounds__(kFoldThreads) head_from_partials_kernel(const __grid_constant__ HeadParams p) {
+  __shared__ HeadSmem sm;
+  __shared__ float red[kFoldThreads / 32][5];
+  const int b = blockIdx.x;
+  const int nk = p.nkpt;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = 0; k < nk; ++k) {
+    // chunk-parallel merge in a fixed order: strided per-thread pass, warp butterfly, then the 8 warps in order
+    float m = -INFINITY, S = 0.f, Sx = 0.f, Sy = 0.f, Sz = 0.f;
+    for (int c = threadIdx.x; c < p.chunks; c += kFoldThreads) {
+      const float* pp = p.partials + (((size_t)b * p.chunks + c) * nk + k) * 5;
+      softmax_merge(m, S, Sx, Sy, Sz, __ldcg(pp), __ldcg(pp + 1), __ldcg(pp + 2), __ldcg(pp + 3), __ldcg(pp + 4));
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m, off), S2 = __shfl_xor_sync(0xffffffffu, S, off);
+      const float Sx2 = __shfl_xor_sync(0xffffffffu, Sx, off), Sy2 = __shfl_xor_sync(0xffffffffu, Sy, off);
+      const float Sz2 = __shfl_xor_sync(0xffffffffu, Sz, off);
+      softmax_merge(m, S, Sx, Sy, Sz, m2, S2, Sx2, Sy2, Sz2);
+    }
+    if (lane == 0) {
+      red[warp][0] = m; red[warp][1] = S; red[warp][2] = Sx; red[warp][3] = Sy; red[warp][4] = Sz;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float M = -INFINITY, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+      for (int w = 0; w < kFoldThreads / 32; ++w) softmax_merge(M, a1, a2, a3, a4, red[w][0], red[w][1], red[w][2], red[w][3], red[w][4]);
+      float* dst = p.merged + ((size_t)b * nk + k) * 5;
+      __stcg(dst, M);
+      __stcg(dst + 1, a1);
+      __stcg(dst + 2, a2);
+      __stcg(dst + 3, a3);
+      __stcg(dst + 4, a4);
+    }
+    __syncthreads();
+  }
+  __threadfence_block();
+  HeadParams q = p;          // head_finalize merges `chunks` partials per keypoint: hand it the single merged one
+  q.partials = p.merged;
+  q.chunks = 1;
+  head_finalize(q, sm, b);
+}
+
+int launch_head_from_partials(const HeadParams& p, cudaStream_t s) {
+  HRP_REQUIRE(p.B > 0 && p.nkpt > 0 && p.nkpt <= kMaxKpt, "bad head dims");
+  HRP_REQUIRE(p.K != nullptr && p.partials != nullptr && p.merged != nullptr && p.chunks > 0, "head: null tensor");
+  HRP_REQUIRE(p.depth_in != nullptr || (p.feat != nullptr && p.depth_w != nullptr && p.k_value != nullptr),
+              "head: a root-depth source is required");
+  HRP_REQUIRE(p.ref_kpt >= 0 && p.ref_kpt < p.nkpt, "reference keypoint out of range");
+  head_from_partials_kernel<<<p.B, kFoldThreads, 0, s>>>(p);
+  count_launch();
+  HRP_CUDA_CHECK(cudaGetLastError());
+  return HRP_OK;
 }
 
 // ------------------------------------------------------------------------------------------------------

@@ -42,6 +42,7 @@ struct HeadParams {
   int chunks;               // CTAs per image
   float* partials;          // workspace (B, chunks, nkpt, 5)
   unsigned int* counters;   // workspace (B) zero-initialised; self-resetting
+  float* merged;            // launch_head_from_partials only: workspace (B, nkpt, 5) for the per-image merged partials
   const float* K;           // (B,3,3)
   // root depth: either depth_in (B) [m], or gamma = depth_w . feat + depth_b ; depth = gamma*k_value/1000
   const float* depth_in;
@@ -73,6 +74,10 @@ struct HeadParams {
 };
 
 int launch_head(const HeadParams& p, cudaStream_t s);
+// Soft-argmax folded into the final conv's epilogue (conv_gemm.cu EPI_HEAD): `partials` already holds the per-warp
+// partials (B, chunks, nkpt, 5) the conv wrote; this kernel merges them per image (fixed order) and finishes the sample
+// exactly as the fused head does (uvd -> xyz, root depth, regressors, FK, projections).  `heatmap` is not read.
+int launch_head_from_partials(const HeadParams& p, cudaStream_t s);
 size_t head_partials_elems(int B, int nkpt, int chunks);
 int head_default_chunks(int B);
 int launch_head_backward_heatmap(const bf16* heatmap, const float* partials, const float* uvd, const float* grad_uvd, int B,
@@ -89,6 +94,26 @@ struct FkParams {
   float* rot_out;      // (B,rot_dim) rotation at `root` (get_rotation_at_specific_root) or null
 };
 int launch_fk(const FkParams& p, cudaStream_t s);
+
+// Reverse mode of launch_fk: gradients of a scalar loss w.r.t. joint angles, 6-D rotation and
+// translation given d loss / d keypoints -- what autograd computes through URDFRobot.get_keypoints[_root] in training
+// (lib/core/function.py:253-311).  Analytic: geometric Jacobian of the kinematic tree (revolute: axis x lever arm,
+// prismatic: axis; mimic joints scaled), rigid root inverse, Gram-Schmidt-by-cross of the 6-D rotation.
+struct FkBwdParams {
+  int B, root, use_b2c;
+  const float* q;         // (B,dof)
+  const float* rot;       // (B,6) or null
+  const float* trans;     // (B,3) or null
+  const RobotTable* robot;
+  const float* grad_pts;  // (B,nkpt,3)
+  float* grad_q;          // (B,dof)
+  float* grad_rot;        // (B,6) or null
+  float* grad_trans;      // (B,3) or null
+};
+int launch_fk_backward(const FkBwdParams& p, cudaStream_t s);
+// reverse mode of launch_project w.r.t. the points: uv = (K p)[:2] / (K p)[2]
+int launch_project_backward(const float* K, const float* pts, const float* grad_uv, float* grad_pts, int B, int N,
+                            cudaStream_t s);
 
 // One link of an UNPRUNED kinematic tree (URDF.link_fk_batch over all links, urdf.py:3061-3149): any number of links,
 // rows in parent-before-child order in global memory.

@@ -87,9 +87,15 @@ struct Plan {
   bf16* s2d_root = nullptr;
   float* feat = nullptr;     // (B,2048) pooled HRNet feature
   float* xf = nullptr;       // (B,2048) pooled ResNet feature
-  int heatmap = -1;          // activation id
+  int heatmap = -1;          // activation id (-1 when the soft-argmax is folded into the final conv's epilogue)
   void* head_ws = nullptr;
   int head_chunks = 0;
+  bool single_lane = false;        // the whole program is captured on one stream (large chunks)
+  size_t arena_bytes = 0;          // activation arena (liveness-aliased when single_lane), else the sum of all tensors
+  size_t act_bytes_sum = 0;        // what one-buffer-per-tensor would need
+  float* fold_partials = nullptr;  // (B, fold_chunks, nkpt, 5) written by the final conv's epilogue (EPI_HEAD)
+  float* fold_merged = nullptr;    // (B, nkpt, 5)
+  int fold_chunks = 0;
   cudaStream_t stream = nullptr;         // launch stream of this replica (when inflight > 1)
   cudaStream_t cap[kNumLanes] = {};
   cudaEvent_t fork_ev = nullptr, join_ev[kNumLanes] = {};
@@ -162,6 +168,8 @@ struct hrp_model {
   int device = 0;
   bool use_graph = true;
   bool use_simt = false;
+  bool fuse0_epilogue = true;  // HRNet fuse, branch 0: the sum runs in an upsampling conv's epilogue (no fuse_add kernel)
+  bool head_fold = true;   // soft-argmax partials computed by the final conv's epilogue: the heatmap never reaches HBM
   std::string prefix_root;  // "rootnet_backbone." (full) or "backbone." (depthnet)
 
   ~hrp_model() {
@@ -313,25 +321,51 @@ struct Builder {
   hrp_model* m;
   Plan* pl;
   int rc = HRP_OK;
+  // set before the conv() call of the final 1x1 layer: its epilogue then writes soft-argmax partials instead of logits
+  float* fold_partials = nullptr;
+  int fold_chunks = 0, fold_nkpt = 0;
+  // Activation memory.  Pass 1 (dry): the program is traversed without touching the device -- only tensor shapes and
+  // the reads / writes of every op are recorded; plan_arena() then gives every tensor an offset in ONE arena, re-using
+  // the space of tensors whose last reader has already run (valid when the ops execute in program order, i.e. for
+  // single-lane plans; multi-lane plans keep one region per tensor).  Pass 2 builds the real plans on those addresses.
+  bool dry = false;
+  char* arena = nullptr;
+  std::vector<size_t> offsets;   // per activation id (pass 2)
 
   int new_act(int H, int W, int C) {
     Act a;
     a.H = H;
     a.W = W;
     a.C = C;
-    void* p = nullptr;
-    if (rc == HRP_OK) {
-      cudaError_t e = cudaMalloc(&p, (size_t)pl->B * H * W * C * sizeof(bf16));
-      if (e != cudaSuccess) {
-        set_error(std::string("activation allocation failed: ") + cudaGetErrorString(e));
-        rc = HRP_ERR_CUDA;
+    const int id = (int)pl->acts.size();
+    if (!dry && rc == HRP_OK) {
+      if (id >= (int)offsets.size()) {
+        set_error("internal: activation count differs between the planning passes");
+        rc = HRP_ERR_STATE;
       } else {
-        pl->owned.push_back(p);
+        a.ptr = reinterpret_cast<bf16*>(arena + offsets[id]);
       }
     }
-    a.ptr = reinterpret_cast<bf16*>(p);
     pl->acts.push_back(a);
-    return (int)pl->acts.size() - 1;
+    return id;
+  }
+
+  // dry pass: record an op by its reads / writes only
+  int dry_op(int lane, int in, const Epi* epi, int out) {
+    Op op;
+    op.lane = lane;
+    if (in >= 0) op.reads.push_back(in);
+    if (epi != nullptr) {
+      for (int i = 0; i < 3; ++i) {
+        if (epi->pre[i] >= 0) op.reads.push_back(epi->pre[i]);
+        if (epi->up[i] >= 0) op.reads.push_back(epi->up[i]);
+      }
+      if (epi->post >= 0) op.reads.push_back(epi->post);
+    }
+    op.writes = out;
+    pl->ops.push_back(op);
+    if (out >= 0) pl->acts[out].producer = (int)pl->ops.size() - 1;
+    return out;
   }
 
   // conv + (bias) + BN + addends + ReLU; returns the output activation id (or -1 when only pooled)
@@ -343,7 +377,7 @@ struct Builder {
     d.kind = kind;
     d.B = pl->B;
     d.in_wpitch = d.in_wpad = 0;
-    if (raw_in != nullptr) {
+    if (raw_in != nullptr || in < 0) {
       d.Hin = raw_H;
       d.Win = raw_W;
       d.Cin = raw_C;
@@ -362,11 +396,17 @@ struct Builder {
     d.pad = pad;
     d.relu = relu ? 1 : 0;
     d.has_residual = (epi.pre[0] >= 0) ? 1 : 0;
+    d.head_fold = (fold_partials != nullptr) ? 1 : 0;
     Op op;
     op.kind = OP_CONV;
     op.lane = lane;
     rc = conv_geometry(d, &op.conv.p);
     if (rc != HRP_OK) return -1;
+    if (dry) {
+      fold_partials = nullptr;
+      const int o = write_out ? new_act(op.conv.p.Hout, op.conv.p.Wout, cout) : -1;
+      return dry_op(lane, in, &epi, o);
+    }
     ConvWeights cw;
     rc = get_weights(m, name, bn, d, op.conv.p, &cw);
     if (rc != HRP_OK) return -1;
@@ -380,6 +420,12 @@ struct Builder {
     p.scale = cw.scale;
     p.bias = cw.bias;
     p.pool_out = pool_out;
+    if (fold_partials != nullptr) {
+      p.head_partials = fold_partials;
+      p.head_chunks = fold_chunks;
+      p.head_nkpt = fold_nkpt;
+      fold_partials = nullptr;
+    }
     if (in >= 0) op.reads.push_back(in);
     for (int i = 0; i < 3; ++i) {
       if (epi.pre[i] >= 0) {
@@ -415,6 +461,7 @@ struct Builder {
       const ConvParams& q = op.conv.p;
       double macs;
       if (kind == kDeconvK4S2P1) macs = (double)pl->B * q.Hout * q.Wout * 4.0 * q.Cin * cout;
+      else if (kind == kConvUp2) macs = (double)pl->B * q.Hm * q.Wm * q.Cin * cout;  // the reference's 1x1 conv at low resolution
       else if (kind == kStemS2D) macs = (double)pl->B * q.Hout * q.Wout * (double)k * k * 3.0 * cout;
       else macs = (double)pl->B * q.Hout * q.Wout * (double)k * k * q.Cin * cout;
       op.conv.flops = 2.0 * macs;
@@ -432,6 +479,7 @@ struct Builder {
     const Act a = pl->acts[in];
     const int out = new_act(a.H / 2, a.W / 2, a.C);
     if (rc != HRP_OK) return -1;
+    if (dry) return dry_op(lane, in, nullptr, out);
     Op op;
     op.kind = OP_MAXPOOL;
     op.name = "maxpool";
@@ -454,6 +502,12 @@ struct Builder {
     const Act a = pl->acts[pre];
     const int out = new_act(a.H, a.W, a.C);
     if (rc != HRP_OK) return -1;
+    if (dry) {
+      Epi e2 = epi;
+      for (int i = 0; i < 3; ++i) e2.pre[i] = -1;
+      e2.post = -1;
+      return dry_op(lane, pre, &e2, out);
+    }
     Op op;
     op.kind = OP_FUSEADD;
     op.name = "fuse_add";
@@ -480,6 +534,7 @@ struct Builder {
   }
 
   void memset_op(int lane, void* ptr, size_t bytes) {
+    if (dry) return;
     Op op;
     op.kind = OP_MEMSET;
     op.lane = lane;
@@ -563,6 +618,20 @@ struct Builder {
           Epi e;
           int nup = 0, npre = 0;
           e.pre[npre++] = xs[i];
+          if (i == 0 && m->fuse0_epilogue) {
+            // y0 = relu(x0 + up2(f01(x1)) + up4(f02(x2)) + up8(f03(x3))): the j = 1 term's 1x1 conv runs as an upsampling
+            // conv (4 output phases, one weight matrix) whose epilogue adds x0 and the other (low-resolution) terms and
+            // applies the ReLU -- the sum never takes a separate elementwise pass
+            for (int j = 2; j < nb; ++j) {
+              const std::string f = mn + ".fuse_layers.0." + std::to_string(j);
+              e.up[nup] = conv(j, f + ".0", f + ".1", xs[j], C[0], 1, 1, 0, false);
+              e.up_shift[nup] = j;
+              ++nup;
+            }
+            const std::string f1 = mn + ".fuse_layers.0.1";
+            fused[0] = conv(0, f1 + ".0", f1 + ".1", xs[1], C[0], 1, 1, 0, true, e, kConvUp2);
+            continue;
+          }
           for (int j = i + 1; j < nb; ++j) {  // 1x1 conv + BN at the low resolution, upsampled in the consumer
             const std::string f = mn + ".fuse_layers." + std::to_string(i) + "." + std::to_string(j);
             e.up[nup] = conv(j, f + ".0", f + ".1", xs[j], C[i], 1, 1, 0, false);
@@ -570,6 +639,7 @@ struct Builder {
             ++nup;
           }
           if (i == 0) {
+            // branch 0 has no conv of its own to carry the sum.  HRP_FUSE0_EPI=0: standalone elementwise kernel.
             fused[i] = fuse_add(0, xs[0], e);
             continue;
           }
@@ -641,7 +711,7 @@ int autotune_plan(hrp_model* m, Plan* pl) {
   char key[256];
   int rc = HRP_OK;
   for (auto& op : pl->ops) {
-    if (op.kind != OP_CONV) continue;
+    if (op.kind != OP_CONV || op.conv.p.head_partials != nullptr) continue;  // (the fold lives in one kernel only)
     tune_key(op, key, sizeof(key));
     auto it = m->tune_cache.find(key);
     if (it != m->tune_cache.end()) {
@@ -689,8 +759,7 @@ int capture_plan(hrp_model* m, Plan* pl) {
   // 64 images 6.94 -> 5.91 ms, 128 images 10.64 -> 10.28 ms, 256 images 19.26 -> 19.18 ms (a tie); at 512 images every
   // launch is a full persistent grid and lanes only contend for SMs, shared memory and L2 (12.9k img/s on one stream vs
   // 12.6k on five).  HRP_SINGLE_LANE=0/1 overrides.
-  bool single_lane = pl->B > 256;
-  if (const char* sl = getenv("HRP_SINGLE_LANE")) single_lane = (sl[0] == '1');
+  const bool single_lane = pl->single_lane;
   if (single_lane)
     for (auto& op : pl->ops) op.lane = 0;
   // cross-lane dependencies -> events
@@ -763,15 +832,153 @@ int capture_plan(hrp_model* m, Plan* pl) {
   return HRP_OK;
 }
 
+// The network program (both planning passes run exactly this): HRNet-w32 root-depth net, and for the full model the
+// ResNet-50 trunk, the deconv head and the final 1x1 conv (with or without the soft-argmax fold).
+void emit_program(Builder& b, hrp_model* m, Plan* pl, bool fold) {
+  const bool full = (m->desc.kind == HRP_MODEL_FULL);
+  b.memset_op(0, pl->feat, (size_t)pl->B * 2048 * 4);
+  if (full) b.memset_op(kLaneRN, pl->xf, (size_t)pl->B * 2048 * 4);
+  b.hrnet32(m->prefix_root, pl->s2d_root, pl->feat);
+  if (!full || b.rc != HRP_OK) return;
+  int x = b.resnet50("reg_backbone.", pl->s2d_reg, pl->xf);
+  const int dc[3] = {256, 256, 256};
+  for (int i = 0; i < 3 && b.rc == HRP_OK; ++i)
+    x = b.conv(kLaneRN, "deconv_layers." + std::to_string(3 * i), "deconv_layers." + std::to_string(3 * i + 1), x, dc[i], 4, 2,
+               1, true, Epi(), kDeconvK4S2P1);
+  b.tap("deconv", x);
+  if (fold) {
+    // the final 1x1 conv reduces its logits to per-warp soft-argmax partials in its epilogue: 64 rows / 2 rows per tile
+    // x 4 warps x 2 depth halves = 256 chunks per image; the (B, 4096, nkpt*64) heatmap is never materialised
+    b.fold_partials = pl->fold_partials != nullptr ? pl->fold_partials : reinterpret_cast<float*>(16);  // (dry pass: a flag)
+    b.fold_chunks = pl->fold_chunks;
+    b.fold_nkpt = m->desc.nkpt;
+    b.conv(kLaneRN, "final_layer", "", x, m->desc.nkpt * 64, 1, 1, 0, false, Epi(), kConv, false);
+    pl->heatmap = -1;
+  } else {
+    x = b.conv(kLaneRN, "final_layer", "", x, m->desc.nkpt * 64, 1, 1, 0, false);
+    b.tap("heatmap", x);
+    pl->heatmap = x;
+  }
+}
+
+// Offsets of every activation in one arena.  alias = false: one region per tensor.  alias = true (single-lane plans: the
+// ops run in program order): a tensor's region is released once its last reader has been emitted and re-used, best fit,
+// by later tensors.  An op's output never shares memory with its own inputs (they are released only AFTER the op);
+// tensors with a tap, without a reader inside the program (the heatmap: read by the head kernel) are pinned.
+size_t plan_arena(const Plan& dry, bool alias, std::vector<size_t>* offsets, size_t* sum_bytes) {
+  const int n = (int)dry.acts.size();
+  std::vector<size_t> bytes(n);
+  std::vector<int> def(n, 0), last(n, -1);
+  size_t sum = 0;
+  for (int i = 0; i < n; ++i) {
+    const Act& a = dry.acts[i];
+    bytes[i] = ((size_t)dry.B * a.H * a.W * a.C * sizeof(bf16) + 1023) / 1024 * 1024;
+    sum += bytes[i];
+    def[i] = std::max(a.producer, 0);
+  }
+  for (size_t o = 0; o < dry.ops.size(); ++o)
+    for (int a : dry.ops[o].reads) last[a] = std::max(last[a], (int)o);
+  for (auto& kv : dry.taps) last[kv.second] = 1 << 30;
+  if (dry.heatmap >= 0) last[dry.heatmap] = 1 << 30;
+  for (int i = 0; i < n; ++i)
+    if (last[i] < 0) last[i] = 1 << 30;
+  *sum_bytes = sum;
+  offsets->assign(n, 0);
+  if (!alias) {
+    size_t off = 0;
+    for (int i = 0; i < n; ++i) {
+      (*offsets)[i] = off;
+      off += bytes[i];
+    }
+    return off;
+  }
+  struct Blk { size_t off, size; };
+  std::vector<Blk> free_list;             // sorted by offset, coalesced
+  std::vector<std::pair<int, int>> live;  // (last reader op, act id)
+  size_t end = 0;
+  auto release = [&](size_t off, size_t size) {
+    size_t i = 0;
+    while (i < free_list.size() && free_list[i].off < off) ++i;
+    free_list.insert(free_list.begin() + i, Blk{off, size});
+    if (i + 1 < free_list.size() && free_list[i].off + free_list[i].size == free_list[i + 1].off) {
+      free_list[i].size += free_list[i + 1].size;
+      free_list.erase(free_list.begin() + i + 1);
+    }
+    if (i > 0 && free_list[i - 1].off + free_list[i - 1].size == free_list[i].off) {
+      free_list[i - 1].size += free_list[i].size;
+      free_list.erase(free_list.begin() + i);
+    }
+  };
+  for (int i = 0; i < n; ++i) {  // activation ids are created in program order
+    for (size_t j = 0; j < live.size();) {
+      if (live[j].first < def[i]) {
+        release((*offsets)[live[j].second], bytes[live[j].second]);
+        live.erase(live.begin() + j);
+      } else {
+        ++j;
+      }
+    }
+    int best = -1;
+    for (size_t j = 0; j < free_list.size(); ++j)
+      if (free_list[j].size >= bytes[i] && (best < 0 || free_list[j].size < free_list[best].size)) best = (int)j;
+    if (best >= 0) {
+      (*offsets)[i] = free_list[best].off;
+      free_list[best].off += bytes[i];
+      free_list[best].size -= bytes[i];
+      if (free_list[best].size == 0) free_list.erase(free_list.begin() + best);
+    } else if (!free_list.empty() && free_list.back().off + free_list.back().size == end) {
+      (*offsets)[i] = free_list.back().off;  // grow the arena from the free block that touches its end
+      end = free_list.back().off + bytes[i];
+      free_list.pop_back();
+    } else {
+      (*offsets)[i] = end;
+      end += bytes[i];
+    }
+    live.push_back(std::make_pair(last[i], i));
+  }
+  // self-check (cheap, ~1e5 pairs): tensors whose lifetimes [def, last reader] intersect must not share memory
+  for (int i = 0; i < n; ++i)
+    for (int j = i + 1; j < n; ++j) {
+      const bool life = def[i] <= last[j] && def[j] <= last[i];
+      const bool mem = (*offsets)[i] < (*offsets)[j] + bytes[j] && (*offsets)[j] < (*offsets)[i] + bytes[i];
+      if (life && mem) return 0;  // (reported by the caller)
+    }
+  return end;
+}
+
 int build_plan(hrp_model* m, int B, Plan** out_plan, int replica) {
   std::unique_ptr<Plan> pl(new Plan());
   pl->B = B;
-  Builder b{m, pl.get()};
+  // Lanes pay off while some kernels cannot fill the GPU by themselves (see capture_plan); large chunks run on one stream
+  pl->single_lane = B > 256;
+  if (const char* sl = getenv("HRP_SINGLE_LANE")) pl->single_lane = (sl[0] == '1');
+  const bool full = (m->desc.kind == HRP_MODEL_FULL);
+  const bool fold = full && m->head_fold && !m->use_simt;
   auto dmalloc = [&](size_t bytes, void** p) -> int {
     HRP_CUDA_CHECK(cudaMalloc(p, bytes));
     pl->owned.push_back(*p);
     return HRP_OK;
   };
+  // ---- pass 1: shapes and liveness only ----
+  std::vector<size_t> offsets;
+  {
+    Plan dry;
+    dry.B = B;
+    dry.fold_chunks = 256;
+    dry.s2d_root = dry.s2d_reg = reinterpret_cast<bf16*>(16);  // (never dereferenced: marks the stems' raw inputs)
+    Builder bd{m, &dry};
+    bd.dry = true;
+    emit_program(bd, m, &dry, fold);
+    if (bd.rc != HRP_OK) return bd.rc;
+    const char* al = getenv("HRP_ALIAS");
+    const bool alias = pl->single_lane && !(al != nullptr && al[0] == '0');
+    pl->arena_bytes = plan_arena(dry, alias, &offsets, &pl->act_bytes_sum);
+    if (pl->arena_bytes == 0) {
+      set_error("internal: activation arena planning produced overlapping live tensors");
+      return HRP_ERR_STATE;
+    }
+  }
+  // ---- device buffers ----
   static_assert(kS2dPitch == kImg / 2 + 2 * kS2dPad, "s2d padding");
   const size_t s2d_bytes = (size_t)B * (kImg / 2) * kS2dPitch * 16 * sizeof(bf16);
   int rc = dmalloc(s2d_bytes, reinterpret_cast<void**>(&pl->s2d_root));
@@ -779,36 +986,43 @@ int build_plan(hrp_model* m, int B, Plan** out_plan, int replica) {
   HRP_CUDA_CHECK(cudaMemset(pl->s2d_root, 0, s2d_bytes));  // the padding columns stay zero: the pack kernel skips them
   rc = dmalloc((size_t)B * 2048 * 4, reinterpret_cast<void**>(&pl->feat));
   if (rc != HRP_OK) return rc;
-  b.memset_op(0, pl->feat, (size_t)B * 2048 * 4);
-  const bool full = (m->desc.kind == HRP_MODEL_FULL);
   if (full) {
     rc = dmalloc(s2d_bytes, reinterpret_cast<void**>(&pl->s2d_reg));
     if (rc != HRP_OK) return rc;
     HRP_CUDA_CHECK(cudaMemset(pl->s2d_reg, 0, s2d_bytes));
     rc = dmalloc((size_t)B * 2048 * 4, reinterpret_cast<void**>(&pl->xf));
     if (rc != HRP_OK) return rc;
-    b.memset_op(kLaneRN, pl->xf, (size_t)B * 2048 * 4);
   }
-  b.hrnet32(m->prefix_root, pl->s2d_root, pl->feat);
-  if (full && b.rc == HRP_OK) {
-    int x = b.resnet50("reg_backbone.", pl->s2d_reg, pl->xf);
-    const int dc[3] = {256, 256, 256};
-    for (int i = 0; i < 3 && b.rc == HRP_OK; ++i)
-      x = b.conv(kLaneRN, "deconv_layers." + std::to_string(3 * i), "deconv_layers." + std::to_string(3 * i + 1), x, dc[i],
-                 4, 2, 1, true, Epi(), kDeconvK4S2P1);
-    b.tap("deconv", x);
-    x = b.conv(kLaneRN, "final_layer", "", x, m->desc.nkpt * 64, 1, 1, 0, false);
-    b.tap("heatmap", x);
-    pl->heatmap = x;
-    if (b.rc == HRP_OK) {
-      pl->head_chunks = head_default_chunks(B);
-      const size_t ws = ((size_t)B * 4 + 255) / 256 * 256 + head_partials_elems(B, m->desc.nkpt, pl->head_chunks) * 4;
-      rc = dmalloc(ws, &pl->head_ws);
-      if (rc != HRP_OK) return rc;
-      HRP_CUDA_CHECK(cudaMemset(pl->head_ws, 0, ws));
+  if (fold) {
+    pl->fold_chunks = 256;
+    rc = dmalloc((size_t)B * pl->fold_chunks * m->desc.nkpt * 5 * sizeof(float), reinterpret_cast<void**>(&pl->fold_partials));
+    if (rc != HRP_OK) return rc;
+    rc = dmalloc((size_t)B * m->desc.nkpt * 5 * sizeof(float), reinterpret_cast<void**>(&pl->fold_merged));
+    if (rc != HRP_OK) return rc;
+  }
+  void* arena = nullptr;
+  {
+    cudaError_t e = cudaMalloc(&arena, std::max<size_t>(pl->arena_bytes, 1024));
+    if (e != cudaSuccess) {
+      set_error(std::string("activation arena allocation failed (") + std::to_string(pl->arena_bytes >> 20) + " MiB): " +
+                cudaGetErrorString(e));
+      return HRP_ERR_CUDA;
     }
+    pl->owned.push_back(arena);
   }
+  // ---- pass 2: the real program on the planned addresses ----
+  Builder b{m, pl.get()};
+  b.arena = reinterpret_cast<char*>(arena);
+  b.offsets = offsets;
+  emit_program(b, m, pl.get(), fold);
   if (b.rc != HRP_OK) return b.rc;
+  if (full && pl->heatmap >= 0) {
+    pl->head_chunks = head_default_chunks(B);
+    const size_t ws = ((size_t)B * 4 + 255) / 256 * 256 + head_partials_elems(B, m->desc.nkpt, pl->head_chunks) * 4;
+    rc = dmalloc(ws, &pl->head_ws);
+    if (rc != HRP_OK) return rc;
+    HRP_CUDA_CHECK(cudaMemset(pl->head_ws, 0, ws));
+  }
   {
     const int64_t launches_before = g_launch_count.load();
     rc = autotune_plan(m, pl.get());
@@ -922,6 +1136,10 @@ int hrp_model_create(const hrp_model_desc* desc, hrp_model** out) {
   e = getenv("HRP_AUTOTUNE");
   m->autotune = (e != nullptr && e[0] == '1');
   m->pin_variants = getenv("HRP_CONV_PERSISTENT") != nullptr || getenv("HRP_CONV_VARIANT") != nullptr;
+  e = getenv("HRP_FUSE0_EPI");
+  m->fuse0_epilogue = !(e != nullptr && e[0] == '0');
+  e = getenv("HRP_HEAD_FOLD");
+  m->head_fold = !(e != nullptr && e[0] == '0');
   e = getenv("HRP_MAX_PLANS");
   if (e != nullptr && atoi(e) >= 1) m->max_plans = atoi(e);
   *out = m;
@@ -1063,10 +1281,17 @@ static int forward_impl(hrp_model* m, const void* x_reg_v, const void* x_root_v,
     hp.fix_root = m->desc.fix_root;
     hp.image_size = m->desc.image_size;
     hp.depth_factor = m->desc.depth_factor;
-    hp.heatmap = pl->acts[pl->heatmap].ptr;
-    hp.chunks = pl->head_chunks;
-    hp.counters = reinterpret_cast<unsigned int*>(pl->head_ws);
-    hp.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(pl->head_ws) + ((size_t)nb * 4 + 255) / 256 * 256);
+    const bool folded = (pl->fold_partials != nullptr);
+    if (folded) {
+      hp.partials = pl->fold_partials;
+      hp.merged = pl->fold_merged;
+      hp.chunks = pl->fold_chunks;
+    } else {
+      hp.heatmap = pl->acts[pl->heatmap].ptr;
+      hp.chunks = pl->head_chunks;
+      hp.counters = reinterpret_cast<unsigned int*>(pl->head_ws);
+      hp.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(pl->head_ws) + ((size_t)nb * 4 + 255) / 256 * 256);
+    }
     hp.K = K + (size_t)b0 * 9;
     hp.feat = pl->feat;
     hp.depth_w = m->depth_w;
@@ -1090,7 +1315,7 @@ static int forward_impl(hrp_model* m, const void* x_reg_v, const void* x_root_v,
     hp.xyz_fk = out->xyz_fk ? out->xyz_fk + (size_t)b0 * nk * 3 : nullptr;
     hp.uv_int = out->uv_int ? out->uv_int + (size_t)b0 * nk * 2 : nullptr;
     hp.uv_fk = out->uv_fk ? out->uv_fk + (size_t)b0 * nk * 2 : nullptr;
-    rc = launch_head(hp, s);
+    rc = folded ? launch_head_from_partials(hp, s) : launch_head(hp, s);
     if (rc != HRP_OK) return rc;
     rc = plan_release(pl, s);
     if (rc != HRP_OK) return rc;
@@ -1227,6 +1452,32 @@ int hrp_model_profile(hrp_model* m, int32_t batch, int32_t iters, char* buf, int
   return HRP_OK;
 }
 
+int hrp_model_plan_memory(hrp_model* m, int32_t batch, int32_t alias, int64_t* arena_bytes, int64_t* tensor_bytes,
+                          int32_t* n_tensors, int32_t* n_ops) {
+  HRP_REQUIRE(m != nullptr && batch > 0 && arena_bytes != nullptr, "bad argument");
+  std::lock_guard<std::mutex> lock(m->mu);
+  Plan dry;
+  dry.B = batch;
+  dry.fold_chunks = 256;
+  dry.s2d_root = dry.s2d_reg = reinterpret_cast<bf16*>(16);
+  Builder bd{m, &dry};
+  bd.dry = true;
+  emit_program(bd, m, &dry, m->desc.kind == HRP_MODEL_FULL && m->head_fold && !m->use_simt);
+  if (bd.rc != HRP_OK) return bd.rc;
+  std::vector<size_t> offsets;
+  size_t sum = 0;
+  const size_t arena = plan_arena(dry, alias != 0, &offsets, &sum);
+  if (arena == 0) {
+    set_error("internal: activation arena planning produced overlapping live tensors");
+    return HRP_ERR_STATE;
+  }
+  *arena_bytes = (int64_t)arena;
+  if (tensor_bytes) *tensor_bytes = (int64_t)sum;
+  if (n_tensors) *n_tensors = (int32_t)dry.acts.size();
+  if (n_ops) *n_ops = (int32_t)dry.ops.size();
+  return HRP_OK;
+}
+
 int hrp_model_set_tuning(hrp_model* m, const char* text) {
   HRP_REQUIRE(m != nullptr && text != nullptr, "null argument");
   std::lock_guard<std::mutex> lock(m->mu);
@@ -1266,11 +1517,7 @@ int hrp_model_stats(const hrp_model* model, int32_t batch, double* flops, int32_
       const Plan* pl = kv.second.get();
       if (flops) *flops = pl->flops;
       if (kernels) *kernels = pl->n_kernels + ((model->desc.kind == HRP_MODEL_FULL) ? 3 : 2);
-      if (activation_bytes) {
-        int64_t t = 0;
-        for (auto& a : pl->acts) t += (int64_t)pl->B * a.H * a.W * a.C * 2;
-        *activation_bytes = t;
-      }
+      if (activation_bytes) *activation_bytes = (int64_t)pl->arena_bytes;  // (one-buffer-per-tensor would be act_bytes_sum)
       return HRP_OK;
     }
   set_error("no plan for this batch size yet");

@@ -153,6 +153,12 @@ class _EngineModule(nn.Module):
     def _pre_finalize(self, h):
         pass
 
+    def stats(self, batch: int) -> dict:
+        """FLOPs, kernel count and activation-arena bytes of the plan built for `batch` images."""
+        fl, kn, ab = C.c_double(0), C.c_int32(0), C.c_int64(0)
+        check(_lib.lib().hrp_model_stats(self._handle, int(batch), C.byref(fl), C.byref(kn), C.byref(ab)))
+        return {"flops": fl.value, "kernels": kn.value, "activation_bytes": ab.value}
+
     def tuning(self) -> str:
         """Current kernel-variant table of the handle (committed entries + anything tuned with HRP_AUTOTUNE=1)."""
         buf = C.create_string_buffer(1 << 20)

@@ -13,7 +13,7 @@ import torch
 from . import _lib
 from ._lib import ConvDesc, ConvEpilogue, check
 
-CONV, DECONV_K4S2P1, STEM_S2D = 0, 1, 2
+CONV, DECONV_K4S2P1, STEM_S2D, CONV_UP2 = 0, 1, 2, 3
 IMPL_TCGEN05, IMPL_SIMT_CHECK = 0, 1
 
 
@@ -79,7 +79,7 @@ class ConvOp:
             epi.up_shift[i] = s
         epi.post = post.data_ptr() if post is not None else None
         # output dims: create with a dummy out first to learn Hout/Wout is awkward -> compute here
-        if kind == DECONV_K4S2P1:
+        if kind in (DECONV_K4S2P1, CONV_UP2):
             Hout, Wout = 2 * Hin, 2 * Win
         elif kind == STEM_S2D:
             Hout, Wout = Hin, Win

@@ -63,6 +63,62 @@ def resolve_urdf_path(robot_type: str, urdf_path: str | None = None) -> str:
         "urdf_path='synthetic' selects the test fixture explicitly")
 
 
+class _FKFunction(torch.autograd.Function):
+    """Keypoints from (q, rot6d, trans) with gradients: forward = the FK kernel, backward =
+    `hrp_fk_backward` (analytic geometric Jacobian, rigid root inverse, 6-D rotation adjoint) -- what torch autograd
+    computes through URDFRobot.get_keypoints[_root] in the reference's training losses (lib/core/function.py:253-311)."""
+
+    @staticmethod
+    def forward(ctx, robot, root, q, rot, trans):
+        use_b2c = rot is not None
+        with torch.no_grad():
+            pts = robot._fk_raw(q, rot, trans, root=root)[0]
+        ctx.robot, ctx.root, ctx.use_b2c = robot, int(root), use_b2c
+        ctx.save_for_backward(q, rot if use_b2c else q.new_zeros(0), trans if use_b2c else q.new_zeros(0))
+        return pts
+
+    @staticmethod
+    def backward(ctx, grad_pts):
+        q, rot, trans = ctx.saved_tensors
+        robot, use_b2c = ctx.robot, ctx.use_b2c
+        q32 = _f32(q)
+        g = _f32(grad_pts)
+        B = q32.shape[0]
+        gq = torch.empty(B, robot.dof, dtype=torch.float32, device=q32.device)
+        grot = torch.empty(B, 6, dtype=torch.float32, device=q32.device) if use_b2c else None
+        gtr = torch.empty(B, 3, dtype=torch.float32, device=q32.device) if use_b2c else None
+        r32 = _f32(rot) if use_b2c else None
+        t32 = _f32(trans) if use_b2c else None
+        with torch.cuda.device(q32.device):
+            check(_lib.lib().hrp_fk_backward(
+                robot.handle(q32.device), C.c_void_p(q32.data_ptr()), C.c_void_p(r32.data_ptr() if use_b2c else 0),
+                C.c_void_p(t32.data_ptr() if use_b2c else 0), ctx.root, int(use_b2c), C.c_void_p(g.data_ptr()),
+                C.c_void_p(gq.data_ptr()), C.c_void_p(grot.data_ptr() if use_b2c else 0),
+                C.c_void_p(gtr.data_ptr() if use_b2c else 0), B, _stream()))
+        return None, None, gq, grot, gtr
+
+
+class _ProjectFunction(torch.autograd.Function):
+    """point_projection_from_3d_tensor with a gradient to the points (hrp_project_backward)."""
+
+    @staticmethod
+    def forward(ctx, K, pts):
+        ctx.save_for_backward(K, pts)
+        with torch.no_grad():
+            return _project_raw(K, pts)
+
+    @staticmethod
+    def backward(ctx, grad_uv):
+        K, pts = ctx.saved_tensors
+        K32, p32, g = _f32(K), _f32(pts), _f32(grad_uv)
+        B, N = p32.shape[0], p32.shape[1]
+        gp = torch.empty(B, N, 3, dtype=torch.float32, device=p32.device)
+        with torch.cuda.device(p32.device):
+            check(_lib.lib().hrp_project_backward(C.c_void_p(K32.data_ptr()), C.c_void_p(p32.data_ptr()),
+                                                  C.c_void_p(g.data_ptr()), C.c_void_p(gp.data_ptr()), B, N, _stream()))
+        return None, gp
+
+
 class _LinkFkView:
     """`URDFRobot.robot.link_fk_batch(cfgs, use_names=True)` of the reference (urdf_robot.py:108 ->
     urdfpytorch/urdf.py:3061-3149): transforms of EVERY link of the description, computed by one CUDA kernel."""
@@ -164,6 +220,15 @@ class URDFRobot:
 
     # ---- kernels --------------------------------------------------------------------------------------
     def _fk(self, q, rot=None, trans=None, root=0, want_pts=True, want_rot=False):
+        needs_grad = torch.is_grad_enabled() and any(t is not None and torch.is_tensor(t) and t.requires_grad
+                                                     for t in (q, rot, trans))
+        if needs_grad and want_pts and not want_rot:
+            if rot is not None and rot.shape[1] != 6:
+                raise NotImplementedError("gradients are implemented for the 6-D rotation representation (rotation_dim 6)")
+            return _FKFunction.apply(self, root, q, rot, trans), None
+        return self._fk_raw(q, rot, trans, root=root, want_pts=want_pts, want_rot=want_rot)
+
+    def _fk_raw(self, q, rot=None, trans=None, root=0, want_pts=True, want_rot=False):
         q = _f32(q)
         B = q.shape[0]
         assert q.shape[1] == self.dof, (q.shape, self.dof)
@@ -225,7 +290,13 @@ class URDFRobot:
 
 
 def point_projection_from_3d_tensor(camera_K, points):
-    """transforms.py:17-21: (B,3,3), (B,N,3) -> (B,N,2) on the GPU."""
+    """transforms.py:17-21: (B,3,3), (B,N,3) -> (B,N,2) on the GPU (differentiable w.r.t. the points)."""
+    if torch.is_grad_enabled() and torch.is_tensor(points) and points.requires_grad:
+        return _ProjectFunction.apply(camera_K, points)
+    return _project_raw(camera_K, points)
+
+
+def _project_raw(camera_K, points):
     K, pts = _f32(camera_K), _f32(points)
     B, N = pts.shape[0], pts.shape[1]
     uv = torch.empty(B, N, 2, dtype=torch.float32, device=pts.device)

@@ -48,11 +48,13 @@ int64_t hrp_launch_count(void);
  * ------------------------------------------------------------------------------------------------ */
 typedef struct hrp_conv hrp_conv;
 
-enum { HRP_CONV = 0, HRP_DECONV_K4S2P1 = 1, HRP_STEM_S2D = 2 };
+/* HRP_CONV_UP2: 1x1 conv + nearest upsampling by 2 (the addends of the epilogue live at the OUTPUT resolution): the branch-0
+ * term of an HRNet fuse layer, HRnet.py:197-208,254-263 */
+enum { HRP_CONV = 0, HRP_DECONV_K4S2P1 = 1, HRP_STEM_S2D = 2, HRP_CONV_UP2 = 3 };
 enum { HRP_IMPL_TCGEN05 = 0, HRP_IMPL_SIMT_CHECK = 1 };
 
 typedef struct hrp_conv_desc {
-  int32_t kind;               /* HRP_CONV | HRP_DECONV_K4S2P1 | HRP_STEM_S2D */
+  int32_t kind;               /* HRP_CONV | HRP_DECONV_K4S2P1 | HRP_STEM_S2D | HRP_CONV_UP2 */
   int32_t B, Hin, Win, Cin;   /* input (B,Hin,Win,Cin) bf16 NHWC; HRP_STEM_S2D: the (B,H/2,W/2,16) s2d tensor */
   int32_t Cout;
   int32_t kh, kw, stride, pad;
@@ -85,6 +87,8 @@ void hrp_conv_destroy(hrp_conv* conv);
 int hrp_conv_set_variant(hrp_conv* conv, int32_t variant);
 int hrp_conv_variant(const hrp_conv* conv);
 int hrp_conv_set_timeline(hrp_conv* conv, long long* dev_buf);
+/* one-line description of the planned launch (kernel variant, tiling, buffering, shared memory, grid) */
+int hrp_conv_describe(const hrp_conv* conv, char* buf, int64_t buflen);
 
 /* ------------------------------------------------------------------------------------------------
  * Input / layout kernels.
@@ -132,6 +136,14 @@ int hrp_fk(hrp_robot* robot, const float* q, const float* rot, int32_t rot_dim, 
            int32_t use_b2c, float* out_xyz, float* out_rot, int32_t B, void* stream);
 /* K (B,3,3), pts (B,N,3) -> uv (B,N,2), device fp32 */
 int hrp_project(const float* K, const float* pts, float* uv, int32_t B, int32_t N, void* stream);
+/* Row f4 (training support): reverse mode of hrp_fk / hrp_project -- the gradients torch autograd computes through
+ * URDFRobot.get_keypoints[_root] and point_projection_from_3d_tensor inside the reference's training losses
+ * (lib/core/function.py:253-311).  rot is the 6-D representation; grad_xyz (B,nkpt,3) -> grad_q (B,dof), grad_rot (B,6),
+ * grad_trans (B,3) (the latter two NULL for the only_fk variants, use_b2c = 0); grad_uv (B,N,2) -> grad_pts (B,N,3). */
+int hrp_fk_backward(hrp_robot* robot, const float* q, const float* rot, const float* trans, int32_t root, int32_t use_b2c,
+                    const float* grad_xyz, float* grad_q, float* grad_rot, float* grad_trans, int32_t B, void* stream);
+int hrp_project_backward(const float* K, const float* pts, const float* grad_uv, float* grad_pts, int32_t B, int32_t N,
+                         void* stream);
 /* Link transforms.  all_links = 0: URDFRobot.get_TWL (lib/utils/urdf_robot.py:107-111) -- out_T (B,nkpt,4,4), the
  * base-frame transforms of the keypoint links in link_names order, translation scaled by global_scale.
  * all_links = 1: URDF.link_fk_batch (lib/utils/urdfpytorch/urdf.py:3061-3149) over EVERY link of the description --
@@ -333,6 +345,11 @@ int hrp_model_profile(hrp_model* model, int32_t batch, int32_t iters, char* buf,
  * HRP_AUTOTUNE=1 in the environment -- are timed at plan build.  get_tuning dumps the current table (set + tuned). */
 int hrp_model_set_tuning(hrp_model* model, const char* text);
 int hrp_model_get_tuning(hrp_model* model, char* buf, int64_t buflen);
+/* Host-only planning pass (no device work; callable before finalize once the tensors are set): the network program for
+ * `batch` images is traversed for tensor shapes and liveness and the activation arena is laid out -- alias = 1 re-uses the
+ * memory of tensors whose last reader has run (single-lane plans), alias = 0 gives every tensor its own region. */
+int hrp_model_plan_memory(hrp_model* model, int32_t batch, int32_t alias, int64_t* arena_bytes, int64_t* tensor_bytes,
+                          int32_t* n_tensors, int32_t* n_ops);
 int hrp_model_stats(const hrp_model* model, int32_t batch, double* flops, int32_t* kernels, int64_t* activation_bytes);
 
 #ifdef __cplusplus

@@ -202,6 +202,40 @@ def golden_integral_backward(ns, robot_type: str, batch: int = 2):
     np.savez(GOLDEN / f"integral_backward_{robot_type}.npz", **data)
 
 
+def golden_fk_backward(ns, robot_type: str, batch: int = 16):
+    """f4 (second piece): autograd of the REFERENCE's URDFRobot.get_keypoints_root / get_keypoints_only_fk_at_specific_root
+    and point_projection_from_3d_tensor for the loss sum(pts * G) (+ sum(uv * G2)); the gradients themselves are stored
+    (a few hundred floats).  The oracle's autograd is checked against them here."""
+    robot = ns.urdf_robot.URDFRobot(robot_type)
+    q0, rot0, trans0 = synth.fk_inputs(robot_type, batch, seed=9)
+    _, _, _, K = synth.inputs(batch, seed=5)
+    nk = len(robot.link_names)
+    G = synth.sym_uniform("g_fk_" + robot_type, (batch, nk, 3), 1.0, 5)
+    G2 = synth.sym_uniform("g_uv_" + robot_type, (batch, nk, 2), 1.0, 6)
+    orob = O.OracleRobot(robot_type, str(synth.URDF_PATHS[robot_type]))
+    data = {}
+    for root in sorted({0, 3, nk - 1}):
+        grads = []
+        for rb, proj in ((robot, ns.transforms.point_projection_from_3d_tensor), (orob, O.point_projection_from_3d)):
+            with torch.enable_grad():
+                q, rot, trans = (t.clone().requires_grad_(True) for t in (q0, rot0, trans0))
+                pts = rb.get_keypoints_root(q, rot, trans, root=root)
+                uv = proj(K, pts)
+                ((pts * G).sum() + 1e-3 * (uv * G2).sum()).backward()
+                grads.append((q.grad.clone(), rot.grad.clone(), trans.grad.clone()))
+        for a, b_, nm in zip(grads[0], grads[1], ("q", "rot", "trans")):
+            err = float((a - b_).abs().max() / a.abs().max().clamp_min(1e-12))
+            assert err < 2e-5, f"oracle autograd differs from the reference ({robot_type} root {root} {nm}: {err})"
+        data[f"grad_q_root{root}"], data[f"grad_rot_root{root}"], data[f"grad_trans_root{root}"] = (to_np(g) for g in grads[0])
+        with torch.enable_grad():
+            q = q0.clone().requires_grad_(True)
+            pts = robot.get_keypoints_only_fk_at_specific_root(q, root=root) if root > 0 else robot.get_keypoints_only_fk(q)
+            (pts * G).sum().backward()
+        data[f"grad_q_only_fk_root{root}"] = to_np(q.grad)
+    np.savez(GOLDEN / f"fk_backward_{robot_type}.npz", **data)
+    print(f"[fk backward {robot_type}] wrote", {k: v.shape for k, v in data.items()})
+
+
 def golden_geometry(ns):
     r6 = synth.sym_uniform("rot6d", (64, 6), 1.0, 4)
     R = ns.geometries.rot6d_to_rotmat(r6)
@@ -328,17 +362,24 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--calibrate", action="store_true")
     ap.add_argument("--only-eval", action="store_true", help="only the crop / metrics fixtures (rows f1, f2)")
+    ap.add_argument("--only-fk-backward", action="store_true", help="only the FK / projection autograd fixtures (row f4)")
     args = ap.parse_args()
     if args.calibrate:
         calibrate()
         return
     ns = ref_harness.setup({k: str(v) for k, v in synth.URDF_PATHS.items()})
+    if args.only_fk_backward:
+        for r in ("panda", "kuka", "baxter"):
+            golden_fk_backward(ns, r)
+        return
     golden_crop(ns)
     for r in ("panda", "kuka", "baxter"):
         golden_metrics(ns, r)
         golden_pnp(ns, r)
     for r in ("panda", "baxter"):
         golden_integral_backward(ns, r)
+    for r in ("panda", "kuka", "baxter"):
+        golden_fk_backward(ns, r)
     if args.only_eval:
         return
     golden_geometry(ns)

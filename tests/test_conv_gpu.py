@@ -364,3 +364,36 @@ def test_persistent_full_epilogue_deconv_and_pool(hrp_lib):
     torch.cuda.synchronize()
     assert torch.allclose(gotp, refp, rtol=1e-4, atol=1e-4), (gotp - refp).abs().max()
     assert torch.equal(opp.run(), gotp)   # two contributions per (image, channel): order-independent, bitwise stable
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("nb", [2, 4])
+def test_upsampling_conv_carries_the_branch0_fuse(nb, variant, hrp_lib):
+    """HRNet fuse layer, output branch 0 (HRnet.py:254-263): y0 = relu(x0 + up2(bn(conv1x1(x1))) + up4(t2) + up8(t3)).  The
+    1x1 conv of the j = 1 term runs as an upsampling conv (HRP_CONV_UP2: four output phases share one weight matrix) whose
+    epilogue adds x0 (output resolution) and the remaining low-resolution terms and applies the ReLU."""
+    import ctypes as C
+    from horopose_b200 import _lib, ops
+    g = torch.Generator().manual_seed(40 + nb)
+    B, H = 5, 64
+    x0 = _bf16_round(torch.randn(B, 32, H, H, generator=g)).cuda()
+    x1 = _bf16_round(torch.randn(B, 64, H // 2, H // 2, generator=g)).cuda()
+    w = _bf16_round(torch.randn(32, 64, 1, 1, generator=g) / 8.0)
+    scale, bias = torch.rand(32, generator=g) + 0.5, torch.randn(32, generator=g) * 0.1
+    ups, ref_up = [], 0.0
+    for j in range(2, nb):
+        t = _bf16_round(torch.randn(B, 32, H >> j, H >> j, generator=g)).cuda()
+        ups.append((_nhwc(t), j))
+        ref_up = ref_up + F.interpolate(t, scale_factor=2 ** j, mode="nearest")
+    op = ops.ConvOp(_nhwc(x1), w, kind=ops.CONV_UP2, relu=True, scale=scale, bias=bias, pre=[_nhwc(x0)], up=ups)
+    _lib.check(_lib.lib().hrp_conv_set_variant(op.handle, C.c_int32(variant)))
+    y = F.conv2d(x1, w.cuda()) * scale.cuda()[None, :, None, None] + bias.cuda()[None, :, None, None]
+    ref = torch.relu(x0 + F.interpolate(y, scale_factor=2, mode="nearest") + ref_up).permute(0, 2, 3, 1).contiguous()
+    got_simt = op.run(ops.IMPL_SIMT_CHECK).clone()
+    torch.cuda.synchronize()
+    _report("up2[simt]", got_simt, ref)
+    op.out.fill_(float("nan"))
+    got = op.run(ops.IMPL_TCGEN05)
+    torch.cuda.synchronize()
+    assert torch.isfinite(got.float()).all()
+    _report(f"up2[tcgen05,{variant}]", got, ref)

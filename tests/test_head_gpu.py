@@ -256,3 +256,34 @@ def test_geometry_operators_vs_oracle(hrp_lib):
     assert _rel(p.cpu(), p_ref) < 1e-5
     with pytest.raises(Exception):
         T.uvd_to_xyz(uvd, 256.0, inv_ref, root, 1.3)   # CPU tensors: no CPU path
+
+
+@pytest.mark.parametrize("rt", ROBOT_TYPES)
+def test_fk_and_projection_backward_vs_reference_autograd(rt, hrp_lib):
+    """Row f4: gradients of sum(pts * G) + 1e-3 * sum(uv * G2) w.r.t. (q, rot6d, trans) through get_keypoints_root and
+    point_projection_from_3d_tensor, and of the only_fk variants w.r.t. q, against the gradients the REAL reference's
+    autograd produced (tests/golden/fk_backward_*.npz, written by tests/golden/make_golden.py): 1e-4 relative."""
+    from horopose_b200 import synth
+    from horopose_b200.robot import URDFRobot, point_projection_from_3d_tensor
+    g = np.load(GOLDEN / f"fk_backward_{rt}.npz")
+    robot = URDFRobot(rt)
+    q0, rot0, trans0 = (t.cuda() for t in synth.fk_inputs(rt, 16, seed=9))
+    _, _, _, K = synth.inputs(16, seed=5)
+    nk = len(robot.link_names)
+    G = synth.sym_uniform("g_fk_" + rt, (16, nk, 3), 1.0, 5).cuda()
+    G2 = synth.sym_uniform("g_uv_" + rt, (16, nk, 2), 1.0, 6).cuda()
+    for root in sorted({0, 3, nk - 1}):
+        with torch.enable_grad():   # (tests/golden/make_golden.py switches autograd off globally when imported)
+            q, rot, trans = (t.clone().requires_grad_(True) for t in (q0, rot0, trans0))
+            pts = robot.get_keypoints_root(q, rot, trans, root=root)
+            uv = point_projection_from_3d_tensor(K.cuda(), pts)
+            ((pts * G).sum() + 1e-3 * (uv * G2).sum()).backward()
+        for nm, t in (("q", q), ("rot", rot), ("trans", trans)):
+            assert _rel(t.grad.cpu(), g[f"grad_{nm}_root{root}"]) < 1e-4, (root, nm, _rel(t.grad.cpu(), g[f"grad_{nm}_root{root}"]))
+        with torch.enable_grad():
+            q = q0.clone().requires_grad_(True)
+            pts = robot.get_keypoints_only_fk_at_specific_root(q, root=root) if root > 0 else robot.get_keypoints_only_fk(q)
+            (pts * G).sum().backward()
+        assert _rel(q.grad.cpu(), g[f"grad_q_only_fk_root{root}"]) < 1e-4, root
+    # no gradient requested: the plain kernels run (no autograd graph)
+    assert not robot.get_keypoints_root(q0, rot0, trans0, root=3).requires_grad

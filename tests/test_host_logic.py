@@ -97,3 +97,39 @@ def test_new_entry_points_validate_arguments_without_a_gpu():
     assert lib.hrp_head_backward_heatmap(None, p, p, p, ctypes.c_int64(0), 1, 7, 3, 1, 1, p, None) == -1
     assert lib.hrp_head_backward_heatmap(p, p, p, p, ctypes.c_int64(8), 1, 7, 3, 1, 1, p, None) == -1
     assert b"workspace" in lib.hrp_last_error()
+
+
+def test_activation_arena_planning_runs_on_the_host():
+    """The two-pass plan builder's first pass (shapes + liveness, no device work) through the C ABI: the liveness-aliased
+    arena of a single-lane 512-image plan is a fraction of one-buffer-per-tensor, the planner's own overlap check passes,
+    and without aliasing the arena is exactly the sum of the tensors."""
+    import numpy as np
+    from horopose_b200 import _lib, synth
+    from horopose_b200.models import MODEL_DEPTHNET, MODEL_FULL, ModelDesc
+    lib = _lib.lib()
+    for kind, sd, nk, dof in ((MODEL_FULL, synth.full_state_dict("kuka", with_bn_stats=False), 8, 7),
+                              (MODEL_DEPTHNET, synth.depthnet_state_dict(with_bn_stats=False), 0, 0)):
+        desc = ModelDesc(kind, dof, nk, 3 if nk else 0, 4, 1, 256.0, 1.3, 512, 1)
+        h = ctypes.c_void_p(0)
+        assert lib.hrp_model_create(ctypes.byref(desc), ctypes.byref(h)) == 0, lib.hrp_last_error()
+        try:
+            for k, v in sd.items():
+                if v.dtype.is_floating_point and v.dim() == 4:   # the planner only asks which downsample convs exist
+                    a = np.ascontiguousarray(v.float().numpy())
+                    shape = (ctypes.c_int64 * a.ndim)(*a.shape)
+                    assert lib.hrp_model_set_tensor(h, k.encode(), a.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), shape,
+                                                    a.ndim) == 0
+            res = {}
+            for alias in (1, 0):
+                arena, total, nt, no = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int32(0), ctypes.c_int32(0)
+                rc = lib.hrp_model_plan_memory(h, 512, alias, ctypes.byref(arena), ctypes.byref(total), ctypes.byref(nt),
+                                               ctypes.byref(no))
+                assert rc == 0, lib.hrp_last_error()
+                res[alias] = (arena.value, total.value, nt.value, no.value)
+            assert res[0][0] == res[0][1] == res[1][1]            # no aliasing: arena == sum of the tensors
+            assert res[1][0] < 0.35 * res[1][1], res              # aliased: a fraction of it
+            if kind == MODEL_FULL:
+                assert 40e9 < res[1][1] < 60e9 and res[1][0] < 10e9, res   # ~47 GB of tensors at 512 images -> ~7 GB arena
+                assert 370 <= res[1][3] <= 400, res                        # conv / pool ops of the program
+        finally:
+            lib.hrp_model_destroy(h)

@@ -1,4 +1,5 @@
-"""Time / profile ONE conv shape with a chosen kernel variant: python tools/bench_one_conv.py C H B variant [res]"""
+"""Time ONE conv shape with a chosen kernel variant: python tools/bench_one_conv.py C H B variant [res] [k]
+Prints the minimum over 3 rounds of 40 back-to-back launches (CUDA events) and the planned launch configuration."""
 import ctypes as C
 import sys
 from pathlib import Path
@@ -17,14 +18,18 @@ w = torch.randn(Cc, Cc, k, k) * 0.05
 pre = (torch.randn(B, H, H, Cc, device="cuda").to(torch.bfloat16),) if res else ()
 op = ops.ConvOp(x, w, stride=1, pad=k // 2, relu=True, pre=pre)
 _lib.check(_lib.lib().hrp_conv_set_variant(op.handle, C.c_int32(variant)))
+buf = C.create_string_buffer(256)
+_lib.check(_lib.lib().hrp_conv_describe(op.handle, buf, 256))
+for _ in range(5):
+    op.run()
+torch.cuda.synchronize()
+best = 1e9
 for _ in range(3):
-    op.run()
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(10):
-    op.run()
-e1.record()
-torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / 10
-print(f"C={Cc} H={H} B={B} variant={variant} res={res}: {ms * 1e3:.1f} us  {2 * B * H * H * k * k * Cc * Cc / ms / 1e9:.1f} TFLOP/s")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(40):
+        op.run()
+    e1.record()
+    torch.cuda.synchronize()
+    best = min(best, e0.elapsed_time(e1) / 40)
+print(f"C={Cc} H={H} B={B} res={int(res)}: {best * 1e3:6.1f} us  {2 * B * H * H * k * k * Cc * Cc / best / 1e9:6.1f} TFLOP/s  [{buf.value.decode()}]")

@@ -28,7 +28,7 @@ for tl in tls:
 e1.record()
 torch.cuda.synchronize()
 print(f"C={Cc} H={H} B={B} res={res}: {e0.elapsed_time(e1) / 3 * 1e3:.1f} us per launch (events)")
-names = ["entry", "setup", "weights", "first band", "mma done", "epi0 last", "epi1 last", "epi0 drained", "epi1 drained", "exit"]
+names = ["entry", "setup", "weights", "first band", "mma done", "stores issued", "-", "stores drained", "-", "exit"]
 base = int(tls[0][0])
 for i, tl in enumerate(tls):
     t = tl.cpu().view(8, 16)
