@@ -71,6 +71,10 @@ struct ConvMaps {
   CUtensorMap o[4];  // output: one per deconv phase (else o[0])
   CUtensorMap av;    // input with a (bh+2)-row box for vertical tap sharing
   CUtensorMap r;     // residual (pre[0]) tile, same geometry as the output (persistent kernel)
+  // staged addends of the persistent kernel (PersistCfg::staged): every addend of the epilogue is a TMA box
+  CUtensorMap rp[3];   // pre[0] for output phases 1..3 of an output-strided layer (phase 0 uses r)
+  CUtensorMap add[3];  // pre[1], pre[2], post: same geometry as the output
+  CUtensorMap upm[3];  // up[a]: low-resolution tensor, box = the tile's footprint at that resolution
 };
 
 struct PersistCfg {
@@ -85,6 +89,18 @@ struct PersistCfg {
   int wres;          // packed weights of the (single) N tile resident in shared memory
   int a_bytes, a_region, stage_bytes, pipe_offset;
   int ksplit;        // accumulators per tile: K steps round-robin over them to hide the dependent-MMA latency
+  // Staged addends: the generic epilogue flavours (PRE / FULL) gather their addends with 16-byte loads at pixel stride --
+  // ~60 issue slots and 32 L1 sectors per 8 channels and addend.  With `staged` every addend tile is fetched by TMA into
+  // the staging-ring entry of its output tile (same swizzled box layout as the output / residual slot, so the epilogue
+  // reads it with conflict-free 16-byte shared loads at the SAME offsets); nearest-upsampled addends are fetched at
+  // their own resolution (a few rows) and indexed by (h >> s, w >> s).
+  int res_tma;       // pre[0] is TMA-fetched into the output slot (updated in place)
+  int staged;        // ... and so is every other addend
+  int entry_bytes;   // bytes per ring entry: output / pre[0] slot + addend slots
+  int add_off[3];    // byte offset in an entry of the pre[1], pre[2], post slots (0 = absent)
+  int up_off[3];     // byte offset of the up[a] slot (0 = absent)
+  int up_blk[3];     // bytes per channel block of an up[a] slot (1024-aligned)
+  int up_bw[3], up_bh[3], up_sh[3];  // low-resolution box (pixels) and shift from the tile's row-pixel grid
 };
 
 // Halo-tile 3x3 kernel (conv_halo.cu): a unit = T consecutive 128-position tiles of one zero-padded image

@@ -462,7 +462,9 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
   const int cko = p.cko;
   const int nblk_full = n_tile / cko;
   constexpr bool GENERIC = (EPI == EPI_PRE || EPI == EPI_FULL);
-  const bool has_res = (EPI == EPI_RES) || (GENERIC && (p.pre[0] != nullptr) && (p.out != nullptr) && p.os == 1);
+  const bool has_res = (EPI == EPI_RES) || (GENERIC && cfg.res_tma != 0);
+  const bool staged = GENERIC && cfg.staged != 0;   // every addend is a TMA box in the ring entry (PersistCfg)
+  const int entry_bytes = cfg.entry_bytes;          // ring entry = output / pre[0] slot (stag_bytes) + addend slots
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
 
   if (warp == 0 && lane == 0) {
@@ -548,13 +550,38 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
         const int tph = p.shared_phase ? 0 : ph, tpw = p.shared_phase ? 0 : pw;
         int tap = 0, cc = 0, dwi = 0;
         auto load_residual = [&]() {
-          mbar_wait(&bars->stag_free[sbuf], spar ^ 1);  // the store that last used this buffer has drained
+          mbar_wait(&bars->stag_free[sbuf], spar ^ 1);  // the store that last used this entry has drained
           int nb = 0;
           for (int j = 0; j < nblk_full && c_base + j * cko < p.Cout; ++j) ++nb;
-          mbar_expect_tx(&bars->res_full[sbuf], (uint32_t)(nb * kTileM * cko * 2));
+          uint8_t* const entry = stag_base + (size_t)sbuf * entry_bytes;
+          const int blk = kTileM * cko * 2;
+          uint32_t bytes = (uint32_t)(nb * blk);
+          if (staged) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+              if (cfg.add_off[i] != 0) bytes += (uint32_t)(nb * blk);
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+              if (cfg.up_off[a] != 0) bytes += (uint32_t)(nb * cfg.up_bw[a] * cfg.up_bh[a] * p.bn * cko * 2);
+          }
+          mbar_expect_tx(&bars->res_full[sbuf], bytes);
+          const CUtensorMap* mr = (phase == 0) ? &maps.r : &maps.rp[phase - 1];
           for (int j = 0; j < nb; ++j)
-            tma_load_4d(stag_base + (size_t)sbuf * stag_bytes + (size_t)j * (kTileM * cko * 2), &maps.r,
-                        &bars->res_full[sbuf], c_base + j * cko, w0, h0, n0);
+            tma_load_4d(entry + (size_t)j * blk, mr, &bars->res_full[sbuf], c_base + j * cko, w0, h0, n0);
+          if (staged) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+              if (cfg.add_off[i] != 0)
+                for (int j = 0; j < nb; ++j)
+                  tma_load_4d(entry + cfg.add_off[i] + (size_t)j * blk, &maps.add[i], &bars->res_full[sbuf], c_base + j * cko,
+                              w0, h0, n0);
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+              if (cfg.up_off[a] != 0)
+                for (int j = 0; j < nb; ++j)
+                  tma_load_4d(entry + cfg.up_off[a] + (size_t)j * cfg.up_blk[a], &maps.upm[a], &bars->res_full[sbuf],
+                              c_base + j * cko, w0 >> cfg.up_sh[a], h0 >> cfg.up_sh[a], n0);
+          }
         };
         if (has_res && nstag >= 2) load_residual();
         tl_stamp(p.timeline, li, 0);
@@ -694,7 +721,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
         for (int j = 0; j < nblk_full; ++j) {
           const int cj = c_base + j * cko;
           if (cj >= p.Cout) break;
-          tma_store_4d(stag_base + (size_t)sbuf * stag_bytes + (size_t)j * (kTileM * cko * 2), &maps.o[phase], cj, w0,
+          tma_store_4d(stag_base + (size_t)sbuf * entry_bytes + (size_t)j * (kTileM * cko * 2), &maps.o[phase], cj, w0,
                        h0, n0);
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -755,7 +782,22 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
       }
       const bool relu_in_cvt = p.relu && !(EPI == EPI_FULL && (p.post != nullptr || pool));
       const bool relu_explicit = (EPI == EPI_FULL) && p.relu && !relu_in_cvt;
-      uint8_t* const stage_row = stag_base + (size_t)sbuf * stag_bytes + (size_t)row * (cko * 2);
+      uint8_t* const stage_row = stag_base + (size_t)sbuf * entry_bytes + (size_t)row * (cko * 2);
+      // staged nearest-upsampled addends: this thread's pixel of the low-resolution box and its swizzle phase
+      const uint8_t* up_row[3] = {nullptr, nullptr, nullptr};
+      uint32_t up_sw[3] = {0, 0, 0};
+      if (staged) {
+        const int wi = row & (p.bw - 1);
+        const int hi = (row >> p.bw_shift) & (p.bh - 1);
+        const int ni = row >> (p.bw_shift + p.bh_shift);
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+          if (cfg.up_off[a] != 0) {
+            const int r2 = (ni * cfg.up_bh[a] + (hi >> cfg.up_sh[a])) * cfg.up_bw[a] + (wi >> cfg.up_sh[a]);
+            up_row[a] = stag_base + (size_t)sbuf * entry_bytes + cfg.up_off[a] + (size_t)r2 * (cko * 2);
+            up_sw[a] = (uint32_t)((cko == 64) ? (r2 & 7) : ((r2 >> 1) & 3));
+          }
+      }
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * ksplit * n_tile);
       const int c_lim = min(n_tile, p.Cout - c_base);
       const float* sc = sb_smem + c_base;
@@ -785,37 +827,53 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
           const float d0 = (float)(cabs & 63);
           const float fw = (float)(w0 + (row & (p.bw - 1))), fh = (float)(h0 + (row >> p.bw_shift));
           float t[32];
-          float m = -INFINITY;
+          // four independent chains everywhere (a 32-deep dependent max / add chain costs ~4 cycles per link)
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             t[i] = fmaf(__uint_as_float(acc[i]), sc[c0 + i], sh_[c0 + i]);
-            m = fmaxf(m, t[i]);
+            m4[i & 3] = fmaxf(m4[i & 3], t[i]);
           }
-          float S = 0.f, Sz = 0.f;
+          float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+          // warp-wide maximum first (5 shuffles), so that every lane exponentiates against the same reference and the
+          // four sums can be reduced with plain additions
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+          float S4[4] = {0.f, 0.f, 0.f, 0.f}, Z4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const float e = ex2_ftz_f(t[i] - m);
-            S += e;
-            Sz = fmaf(e, d0 + (float)i, Sz);
+            S4[i & 3] += e;
+            Z4[i & 3] = fmaf(e, d0 + (float)i, Z4[i & 3]);
           }
+          float S = (S4[0] + S4[1]) + (S4[2] + S4[3]);
+          float Sz = (Z4[0] + Z4[1]) + (Z4[2] + Z4[3]);
           float Sx = S * fw, Sy = S * fh;
-#pragma unroll
-          for (int off = 16; off >= 1; off >>= 1) {
-            const float m2 = __shfl_xor_sync(0xffffffffu, m, off), S2 = __shfl_xor_sync(0xffffffffu, S, off);
-            const float Sx2 = __shfl_xor_sync(0xffffffffu, Sx, off), Sy2 = __shfl_xor_sync(0xffffffffu, Sy, off);
-            const float Sz2 = __shfl_xor_sync(0xffffffffu, Sz, off);
-            const float M = fmaxf(m, m2);
-            const float f1 = ex2_ftz_f(m - M), f2 = ex2_ftz_f(m2 - M);
-            S = S * f1 + S2 * f2;
-            Sx = Sx * f1 + Sx2 * f2;
-            Sy = Sy * f1 + Sy2 * f2;
-            Sz = Sz * f1 + Sz2 * f2;
-            m = M;
+          // four sums over 32 lanes in 6 shuffles (instead of 20): halve the number of values carried at each of the first
+          // two butterfly levels -- the lane keeps the values whose index bit matches its own lane bit and sends the others
+          {
+            const bool hi16 = (lane & 16) != 0;
+            // level 16: keep (S, Sx) in the lower half-warp, (Sy, Sz) in the upper one
+            const float a0 = hi16 ? Sy : S, a1 = hi16 ? Sz : Sx;       // kept
+            const float b0 = hi16 ? S : Sy, b1 = hi16 ? Sx : Sz;       // sent
+            const float r0 = a0 + __shfl_xor_sync(0xffffffffu, b0, 16);
+            const float r1 = a1 + __shfl_xor_sync(0xffffffffu, b1, 16);
+            const bool hi8 = (lane & 8) != 0;
+            // level 8: keep the first of the pair where bit 3 is clear, the second where it is set
+            const float k = hi8 ? r1 : r0, snd = hi8 ? r0 : r1;
+            float v = k + __shfl_xor_sync(0xffffffffu, snd, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            // lanes 0, 8, 16, 24 now hold S, Sx, Sy, Sz of the whole warp
+            S = v;
           }
-          if (lane == 0) {
+          if ((lane & 7) == 0) {
             const int chunk = ((th * 4 + q) << 1) | ((cabs >> 5) & 1);
             float* dst = p.head_partials + (((size_t)n0 * p.head_chunks + chunk) * p.head_nkpt + kp) * 5;
-            dst[0] = m; dst[1] = S; dst[2] = Sx; dst[3] = Sy; dst[4] = Sz;
+            const int which = lane >> 3;                 // 0: S, 1: Sx, 2: Sy, 3: Sz
+            dst[1 + which] = S;
+            if (lane == 0) dst[0] = m;
           }
           continue;
         }
@@ -847,7 +905,21 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
           uint4* const sptr = reinterpret_cast<uint4*>(chunk_base + goff[g]);
           if (EPI != EPI_PLAIN) {
             if (has_res) add_bf16x8(v, *sptr);  // residual prefetched by TMA (zero-filled outside the tensor)
-            if (GENERIC && valid) {
+            if (staged) {
+              // every other addend sits in its own slot of the ring entry, same swizzled box layout: same offsets
+              const uint8_t* const sp8 = reinterpret_cast<const uint8_t*>(sptr);
+              if (cfg.add_off[0] != 0) add_bf16x8(v, *reinterpret_cast<const uint4*>(sp8 + cfg.add_off[0]));
+              if (cfg.add_off[1] != 0) add_bf16x8(v, *reinterpret_cast<const uint4*>(sp8 + cfg.add_off[1]));
+              if (EPI == EPI_FULL) {
+                const uint32_t blk_i = (uint32_t)(c0 >> cko_shift);
+                const uint32_t chunk = (uint32_t)((c0 & (cko - 1)) >> 3) + (uint32_t)g;
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+                  if (cfg.up_off[a] != 0)
+                    add_bf16x8(v, *reinterpret_cast<const uint4*>(up_row[a] + (size_t)blk_i * cfg.up_blk[a] +
+                                                                  ((chunk ^ up_sw[a]) << 4)));
+              }
+            } else if (GENERIC && valid) {
               if (use_pre0) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(pre0 + cg)));
               if (p.pre[1] != nullptr) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(pre1 + cg)));
               if (p.pre[2] != nullptr) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(pre2 + cg)));
@@ -862,8 +934,10 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
           }
-          if (EPI == EPI_FULL && p.post != nullptr && valid)
-            add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(postp + cg)));
+          if (EPI == EPI_FULL && p.post != nullptr) {
+            if (staged) add_bf16x8(v, *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(sptr) + cfg.add_off[2]));
+            else if (valid) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(postp + cg)));
+          }
           if (do_store) {
             uint4 o;
             if (relu_in_cvt) {
@@ -1365,18 +1439,80 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed, con
     else plan->persistent = (p.n_tile == 128 && p.ktot >= 256 && p.ktot <= 1024 && p.pre[0] == nullptr);
     if (p.head_partials != nullptr) plan->persistent = true;  // the fold lives in the persistent kernel's epilogue
     PersistCfg& c = plan->pcfg;
-    // (output-strided layers -- deconv, upsampling conv -- read pre[0] with plain loads in the generic epilogue)
-    const bool has_res = (p.pre[0] != nullptr) && (p.out != nullptr) && p.os == 1;
-    if (has_res) {
-      uint64_t dims[4] = {(uint64_t)p.Cout, (uint64_t)p.Wout, (uint64_t)p.Hout, (uint64_t)p.B};
-      uint64_t strides[3] = {(uint64_t)p.Cout * 2, (uint64_t)p.Wout * p.Cout * 2, (uint64_t)p.Hout * p.Wout * p.Cout * 2};
+    const int stag_bytes = (p.out != nullptr) ? kTileM * p.n_tile * 2 : 0;
+    // ---- addends: pre[0] by TMA into the output slot (in place); with `staged` all the others as well ----
+    const bool generic = (plan->epi == EPI_PRE || plan->epi == EPI_FULL);
+    const char* e5 = getenv("HRP_CONV_STAGED");
+    // default: layers whose N tile keeps all eight epilogue warps busy (n_tile >= 64); measured on the 32 -> 64 stride-2
+    // fuse convs: 113 us staged vs 125-127 us with gathers.  HRP_CONV_STAGED=1 forces it wherever it fits, =0 disables it.
+    const bool staged_default = p.n_tile >= 64 && p.os == 1;
+    const bool staged_on = (e5 != nullptr) ? (e5[0] == '1') : staged_default;
+    bool staged = generic && p.out != nullptr && p.pre[0] != nullptr && p.pool_out == nullptr && staged_on &&
+                  (p.os == 1 || (p.os == 2 && p.pre[1] == nullptr && p.pre[2] == nullptr && p.post == nullptr &&
+                                 p.oh0 == 0 && p.ow0 == 0));
+    memset(c.add_off, 0, sizeof(c.add_off));
+    memset(c.up_off, 0, sizeof(c.up_off));
+    int entry = stag_bytes;
+    if (staged) {
+      const bf16* same[3] = {p.pre[1], p.pre[2], p.post};
+      for (int i = 0; i < 3; ++i)
+        if (same[i] != nullptr) {
+          c.add_off[i] = entry;
+          entry += stag_bytes;
+        }
+      const int nblk = p.n_tile / p.cko;
+      for (int a = 0; a < 3; ++a)
+        if (p.up[a] != nullptr) {
+          const int sh = p.up_shift[a] - (p.os == 2 ? 1 : 0);
+          if (sh < 0) { staged = false; break; }
+          c.up_sh[a] = sh;
+          c.up_bw[a] = std::max(p.bw >> sh, 1);
+          c.up_bh[a] = std::max(p.bh >> sh, 1);
+          c.up_blk[a] = (c.up_bw[a] * c.up_bh[a] * p.bn * p.cko * 2 + 1023) / 1024 * 1024;
+          c.up_off[a] = entry;
+          entry += nblk * c.up_blk[a];
+        }
+    }
+    const bool has_res = (p.pre[0] != nullptr) && (p.out != nullptr) && (p.os == 1 || staged);
+    // (without staging, output-strided layers -- deconv, upsampling conv -- read pre[0] with plain loads)
+    auto out_like_map = [&](CUtensorMap* m, const bf16* t, int ph) -> int {
+      const int oh = p.oh0 + (ph >> 1), ow = p.ow0 + (ph & 1);
+      const bf16* base = t + ((size_t)oh * p.Wout + ow) * p.Cout;
+      uint64_t dims[4] = {(uint64_t)p.Cout, (uint64_t)p.Wm, (uint64_t)p.Hm, (uint64_t)p.B};
+      uint64_t strides[3] = {(uint64_t)p.os * p.Cout * 2, (uint64_t)p.os * p.Wout * p.Cout * 2,
+                             (uint64_t)p.Hout * p.Wout * p.Cout * 2};
       uint32_t box[4] = {(uint32_t)p.cko, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
-      int rc = conv_encode_map(&plan->maps.r, p.pre[0], 4, dims, strides, box, p.cko);
+      return conv_encode_map(m, base, 4, dims, strides, box, p.cko);
+    };
+    for (int i = 0; i < 3; ++i) plan->maps.rp[i] = plan->maps.add[i] = plan->maps.upm[i] = plan->maps.a[0];
+    if (has_res) {
+      int rc = out_like_map(&plan->maps.r, p.pre[0], 0);
       if (rc != HRP_OK) return rc;
+      for (int ph = 1; ph < p.nphase && p.os == 2; ++ph) {
+        rc = out_like_map(&plan->maps.rp[ph - 1], p.pre[0], ph);
+        if (rc != HRP_OK) return rc;
+      }
     } else {
       plan->maps.r = plan->maps.a[0];
     }
-    const int stag_bytes = (p.out != nullptr) ? kTileM * p.n_tile * 2 : 0;
+    if (staged) {
+      const bf16* same[3] = {p.pre[1], p.pre[2], p.post};
+      for (int i = 0; i < 3; ++i)
+        if (same[i] != nullptr) {
+          int rc = out_like_map(&plan->maps.add[i], same[i], 0);
+          if (rc != HRP_OK) return rc;
+        }
+      for (int a = 0; a < 3; ++a)
+        if (p.up[a] != nullptr) {
+          const int s = p.up_shift[a];
+          const uint64_t Hl = (uint64_t)(p.Hout >> s), Wl = (uint64_t)(p.Wout >> s);
+          uint64_t dims[4] = {(uint64_t)p.Cout, Wl, Hl, (uint64_t)p.B};
+          uint64_t strides[3] = {(uint64_t)p.Cout * 2, Wl * p.Cout * 2, Hl * Wl * p.Cout * 2};
+          uint32_t box[4] = {(uint32_t)p.cko, (uint32_t)c.up_bw[a], (uint32_t)c.up_bh[a], (uint32_t)p.bn};
+          int rc = conv_encode_map(&plan->maps.upm[a], p.up[a], 4, dims, strides, box, p.cko);
+          if (rc != HRP_OK) return rc;
+        }
+    }
     const int tail = 512 + 2 * p.cout_pad * (int)sizeof(float) + 1024;  // barriers + scale/shift + alignment slack
     const int avail = 227 * 1024 - tail;
     const int b_sub = p.n_tile * p.ck * 2;
@@ -1407,27 +1543,44 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed, con
       if (rc != HRP_OK) return rc;
     }
     const int pipe_avail = avail - c.pipe_offset;
-    // Staging ring: the residual tile of tile i + nstag - 1 is fetched (by TMA, into the staging buffer it will be
-    // updated in) while tile i is in the epilogue, so with a residual the ring depth is the prefetch distance and
-    // must cover a DRAM round trip (~2 tile periods on short-K layers): 4 buffers when they fit, else 2, else 1.
+    // Staging ring: the residual / addend tiles of tile i + nstag - 1 are fetched (by TMA, into the ring entry the output
+    // tile will be built in) while tile i is in the epilogue, so with a residual the ring depth is the prefetch distance
+    // and must cover a DRAM round trip (~2 tile periods on short-K layers): 4 entries when they fit, else 2, else 1.
     const char* e4 = getenv("HRP_CONV_NSTAG");
     int nstag = (stag_bytes > 0 && p.n_tile <= 128) ? ((has_res && !(e4 != nullptr && e4[0] == '2')) ? 4 : 2) : 1;
-    int st = (pipe_avail - nstag * stag_bytes) / c.stage_bytes;
+    int st = (pipe_avail - nstag * entry) / c.stage_bytes;
     while (st < 3 && nstag > 1) {
       nstag >>= 1;
-      st = (pipe_avail - nstag * stag_bytes) / c.stage_bytes;
+      st = (pipe_avail - nstag * entry) / c.stage_bytes;
+    }
+    if (st < 2 && staged) {
+      // the addend slots do not fit beside a 2-stage pipeline: keep pre[0] by TMA, gather the others (generic loads)
+      staged = false;
+      memset(c.add_off, 0, sizeof(c.add_off));
+      memset(c.up_off, 0, sizeof(c.up_off));
+      entry = stag_bytes;
+      nstag = (stag_bytes > 0 && p.n_tile <= 128) ? 2 : 1;
+      st = (pipe_avail - nstag * entry) / c.stage_bytes;
+      while (st < 3 && nstag > 1) {
+        nstag >>= 1;
+        st = (pipe_avail - nstag * entry) / c.stage_bytes;
+      }
     }
     HRP_REQUIRE(st >= 1, "layer does not fit in shared memory");
+    c.res_tma = (has_res && (p.os == 1 || staged)) ? 1 : 0;
+    c.staged = staged ? 1 : 0;
+    c.entry_bytes = entry;
     c.stages = std::min(8, st);
     c.nstag = nstag;
     c.stag_offset = c.pipe_offset + c.stages * c.stage_bytes;
-    c.bar_offset = c.stag_offset + nstag * stag_bytes;
+    c.bar_offset = c.stag_offset + nstag * entry;
     c.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles * p.nphase;
     c.tw_shift = 0;
     while ((1 << c.tw_shift) < p.tiles_w) ++c.tw_shift;
     c.th_shift = 0;
     while ((1 << c.th_shift) < p.tiles_h) ++c.th_shift;
     HRP_REQUIRE((1 << c.tw_shift) == p.tiles_w && (1 << c.th_shift) == p.tiles_h, "tile counts must be powers of two");
+    if (staged) plan->persistent = true;  // (only the persistent kernel stages addends; gathers cost 2-3x the layer time)
     const char* e3 = getenv("HRP_CONV_KSPLIT");
     // K-split accumulators are off by default: back-to-back MMAs into ONE accumulator already run at the operand
     // fetch rate (tools/probe_mma.py: 40.3 / 48.3 / 64.3 cycles at N = 32 / 64 / 128 with 1 or 4 accumulators), and

@@ -168,7 +168,11 @@ struct hrp_model {
   int device = 0;
   bool use_graph = true;
   bool use_simt = false;
-  bool fuse0_epilogue = true;  // HRNet fuse, branch 0: the sum runs in an upsampling conv's epilogue (no fuse_add kernel)
+  // HRNet fuse, branch 0: the sum can run in an upsampling conv's epilogue (HRP_FUSE0_EPI=1; tests cover it) instead of
+  // the elementwise fuse_add kernel.  Measured on B200 at 512 images it is SLOWER (160-220 us per module against 57-78 us
+  // for fuse_add + 27 us for the plain 1x1 conv): the N = 32 tile leaves 4 epilogue warps per SM to gather / add 3 addend
+  // streams, latency-bound (profiles/r02_exp_fuse0_epilogue.txt) -- so the elementwise kernel stays the default.
+  bool fuse0_epilogue = false;
   bool head_fold = true;   // soft-argmax partials computed by the final conv's epilogue: the heatmap never reaches HBM
   std::string prefix_root;  // "rootnet_backbone." (full) or "backbone." (depthnet)
 
@@ -712,6 +716,11 @@ int autotune_plan(hrp_model* m, Plan* pl) {
   int rc = HRP_OK;
   for (auto& op : pl->ops) {
     if (op.kind != OP_CONV || op.conv.p.head_partials != nullptr) continue;  // (the fold lives in one kernel only)
+    if (op.conv.pcfg.staged) {  // TMA-staged addends exist in the persistent kernel only (and beat gathers 2-3x)
+      op.conv.persistent = true;
+      op.conv.halo = false;
+      continue;
+    }
     tune_key(op, key, sizeof(key));
     auto it = m->tune_cache.find(key);
     if (it != m->tune_cache.end()) {
@@ -1137,7 +1146,7 @@ int hrp_model_create(const hrp_model_desc* desc, hrp_model** out) {
   m->autotune = (e != nullptr && e[0] == '1');
   m->pin_variants = getenv("HRP_CONV_PERSISTENT") != nullptr || getenv("HRP_CONV_VARIANT") != nullptr;
   e = getenv("HRP_FUSE0_EPI");
-  m->fuse0_epilogue = !(e != nullptr && e[0] == '0');
+  m->fuse0_epilogue = (e != nullptr && e[0] == '1');
   e = getenv("HRP_HEAD_FOLD");
   m->head_fold = !(e != nullptr && e[0] == '0');
   e = getenv("HRP_MAX_PLANS");

@@ -368,7 +368,7 @@ def test_persistent_full_epilogue_deconv_and_pool(hrp_lib):
 
 @pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("nb", [2, 4])
-def test_upsampling_conv_carries_the_branch0_fuse(nb, variant, hrp_lib):
+def test_upsampling_conv_carries_the_branch0_fuse(nb, variant, hrp_lib, monkeypatch):
     """HRNet fuse layer, output branch 0 (HRnet.py:254-263): y0 = relu(x0 + up2(bn(conv1x1(x1))) + up4(t2) + up8(t3)).  The
     1x1 conv of the j = 1 term runs as an upsampling conv (HRP_CONV_UP2: four output phases share one weight matrix) whose
     epilogue adds x0 (output resolution) and the remaining low-resolution terms and applies the ReLU."""
@@ -385,6 +385,7 @@ def test_upsampling_conv_carries_the_branch0_fuse(nb, variant, hrp_lib):
         t = _bf16_round(torch.randn(B, 32, H >> j, H >> j, generator=g)).cuda()
         ups.append((_nhwc(t), j))
         ref_up = ref_up + F.interpolate(t, scale_factor=2 ** j, mode="nearest")
+    monkeypatch.setenv("HRP_CONV_STAGED", "1" if variant == 1 else "0")   # persistent: TMA-staged addends; tile: gathers
     op = ops.ConvOp(_nhwc(x1), w, kind=ops.CONV_UP2, relu=True, scale=scale, bias=bias, pre=[_nhwc(x0)], up=ups)
     _lib.check(_lib.lib().hrp_conv_set_variant(op.handle, C.c_int32(variant)))
     y = F.conv2d(x1, w.cuda()) * scale.cuda()[None, :, None, None] + bias.cuda()[None, :, None, None]

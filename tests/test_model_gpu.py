@@ -276,10 +276,8 @@ def test_full_size_batch_properties(hrp_lib):
     big = _model("kuka", chunk=512, inflight=1)
     a = [t.clone() for t in big(xr, xo, kk, KK)]
     st = big.stats(512)
-    # liveness-aliased activation arena of the single-lane 512-image plan (one buffer per tensor would need ~47 GB) and no
-    # standalone fuse_add / heatmap kernels: 2 packing kernels + the graph + the head finish
+    # liveness-aliased activation arena of the single-lane 512-image plan (one buffer per tensor would need ~47 GB)
     assert st["activation_bytes"] < 10e9, st
-    assert st["kernels"] <= 392, st
     perm = torch.randperm(B, generator=g).cuda()
     b = big(xr[perm], xo[perm], kk[perm], KK[perm])
     torch.cuda.synchronize()
@@ -520,3 +518,21 @@ def test_plan_cache_is_bounded(hrp_lib, monkeypatch):
             for n, u, v in zip(NAMES, first[B], out):
                 assert torch.equal(u, v), (B, n)
         first[B] = out
+
+
+def test_branch0_fuse_in_conv_epilogue_option(hrp_lib):
+    """HRP_FUSE0_EPI=1: the branch-0 sum of every HRNet fuse layer runs in the epilogue of an upsampling conv instead of the
+    elementwise kernel (slower on B200, hence opt-in -- DESIGN.md).  Same arithmetic (fp32 sum of the same bf16 addends,
+    one rounding): the depth-coupled outputs agree with the default path to bf16 round-off of one tensor."""
+    from horopose_b200 import synth
+    xs = [t.cuda() for t in synth.inputs(2, seed=11)]
+    a = _model("panda", chunk=2)(*xs)
+    os.environ["HRP_FUSE0_EPI"] = "1"
+    try:
+        m = _model("panda", chunk=2)
+        b = m(*xs)
+        torch.cuda.synchronize()
+    finally:
+        del os.environ["HRP_FUSE0_EPI"]
+    for n, u, v in zip(NAMES, a, b):
+        assert float((u - v).abs().max()) < 0.25 * TOL[n], (n, float((u - v).abs().max()))
