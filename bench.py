@@ -508,7 +508,7 @@ def main():
                "sample": f"3 forwards of 64 images ({sum(times):.1f} s), fp32 PyTorch oracle port of the reference forward",
                "panda_b1_latency_ms": 1e3 * statistics.median(t1)}
 
-    act_gb = B * 160e6 / 1e9
+    act_gb = B * 91e6 / 1e9   # ~47 GB of intermediate tensors per 512 images (hrp_model_plan_memory)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16",

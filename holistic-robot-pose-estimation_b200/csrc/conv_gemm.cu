@@ -827,27 +827,37 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
           const float d0 = (float)(cabs & 63);
           const float fw = (float)(w0 + (row & (p.bw - 1))), fh = (float)(h0 + (row >> p.bw_shift));
           float t[32];
-          // four independent chains everywhere (a 32-deep dependent max / add chain costs ~4 cycles per link)
+          // four independent chains everywhere (a 32-deep dependent max / add chain costs ~4 cycles per link); scale /
+          // shift come as 16-byte shared loads
           float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            t[i] = fmaf(__uint_as_float(acc[i]), sc[c0 + i], sh_[c0 + i]);
-            m4[i & 3] = fmaxf(m4[i & 3], t[i]);
+          for (int i = 0; i < 32; i += 4) {
+            const float4 s4 = *reinterpret_cast<const float4*>(sc + c0 + i);
+            const float4 b4 = *reinterpret_cast<const float4*>(sh_ + c0 + i);
+            t[i + 0] = fmaf(__uint_as_float(acc[i + 0]), s4.x, b4.x);
+            t[i + 1] = fmaf(__uint_as_float(acc[i + 1]), s4.y, b4.y);
+            t[i + 2] = fmaf(__uint_as_float(acc[i + 2]), s4.z, b4.z);
+            t[i + 3] = fmaf(__uint_as_float(acc[i + 3]), s4.w, b4.w);
+            m4[0] = fmaxf(m4[0], t[i + 0]);
+            m4[1] = fmaxf(m4[1], t[i + 1]);
+            m4[2] = fmaxf(m4[2], t[i + 2]);
+            m4[3] = fmaxf(m4[3], t[i + 3]);
           }
           float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
           // warp-wide maximum first (5 shuffles), so that every lane exponentiates against the same reference and the
           // four sums can be reduced with plain additions
 #pragma unroll
           for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+          // sum e and sum e * i with the bin index i an immediate; the depth offset d0 is added once: sum e * (d0 + i)
           float S4[4] = {0.f, 0.f, 0.f, 0.f}, Z4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const float e = ex2_ftz_f(t[i] - m);
             S4[i & 3] += e;
-            Z4[i & 3] = fmaf(e, d0 + (float)i, Z4[i & 3]);
+            Z4[i & 3] = fmaf(e, (float)i, Z4[i & 3]);
           }
           float S = (S4[0] + S4[1]) + (S4[2] + S4[3]);
-          float Sz = (Z4[0] + Z4[1]) + (Z4[2] + Z4[3]);
+          float Sz = fmaf(S, d0, (Z4[0] + Z4[1]) + (Z4[2] + Z4[3]));
           float Sx = S * fw, Sy = S * fh;
           // four sums over 32 lanes in 6 shuffles (instead of 20): halve the number of values carried at each of the first
           // two butterfly levels -- the lane keeps the values whose index bit matches its own lane bit and sends the others

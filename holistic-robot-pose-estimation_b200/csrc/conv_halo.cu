@@ -34,8 +34,8 @@ struct __align__(16) HaloBars {
   uint64_t a_empty[4];
   uint64_t acc_full[8];
   uint64_t acc_empty[8];
-  uint64_t ring_full[4];    // output / residual ring: buffer may be used by the epilogue (residual tile landed, if any)
-  uint64_t ring_ready[4];   // ... holds a finished output tile (one arrival per epilogue warp of the owning group)
+  uint64_t ring_full[6];    // output / residual ring: buffer may be used by the epilogue (residual tile landed, if any)
+  uint64_t ring_ready[6];   // ... holds a finished output tile (one arrival per epilogue warp of the owning group)
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -105,6 +105,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     for (int i = 0; i < 4; ++i) {
       mbar_init(&bars->a_full[i], 1);
       mbar_init(&bars->a_empty[i], 2);  // both MMA issuers release a band
+    }
+    for (int i = 0; i < 6; ++i) {
       mbar_init(&bars->ring_full[i], 1);
       mbar_init(&bars->ring_ready[i], 4);  // one arrival per epilogue warp of the owning group
     }
@@ -293,9 +295,14 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         fill(ahead, b);
         ahead.next(hp);
       }
-      int buf = 0;
+      // The buffer of tile t is released (and refilled with the residual of tile t + NB) as soon as its store has been
+      // read out of shared memory.  Experiment (profiles/r02_halo_sweep.txt): keeping LAG = NB - 2 stores in flight before
+      // releasing a buffer left the plain kernels unchanged (61.8 vs 59.9 us: the store read is not the limiter) and slowed
+      // the residual kernels (68.7 -> 90.4 us, 47.0 -> 54.8 us) because the residual prefetch distance drops to 2 tiles.
+      const int LAG = 0;  // (LAG = NB - 2 measured slower: the residual prefetch distance shrinks to 2 tiles -- see below)
+      int buf = 0, rel_buf = 0, t_idx = 0;
       uint32_t par = 0;
-      for (HaloTileIter it{(int)blockIdx.x, 0}; it.valid(hp); it.next(hp)) {
+      for (HaloTileIter it{(int)blockIdx.x, 0}; it.valid(hp); it.next(hp), ++t_idx) {
         mbar_wait(&bars->ring_ready[buf], par);
         int lo, np;
         const size_t ib = tile_range(it, &lo, &np);
@@ -306,10 +313,19 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
                        : "memory");
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem read out: the buffer can be refilled
-        if (ahead.valid(hp)) {
-          fill(ahead, buf);
-          ahead.next(hp);
+        if (t_idx >= LAG) {
+          switch (LAG) {  // (the group count is an immediate)
+            case 0: asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); break;
+            case 1: asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); break;
+            case 2: asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); break;
+            case 3: asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory"); break;
+            default: asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory"); break;
+          }
+          if (ahead.valid(hp)) {  // the store of tile t_idx - LAG has been read out: its buffer serves tile t_idx - LAG + NB
+            fill(ahead, rel_buf);
+            ahead.next(hp);
+          }
+          if (++rel_buf == NB) rel_buf = 0;
         }
         if (++buf == NB) {
           buf = 0;
@@ -532,7 +548,7 @@ int conv_halo_plan(ConvPlan* plan, const ConvLayerDesc& d, const bf16* in) {
   int best_T = 0, best_NR = 0, best_nbuf = 0, nring = 0;
   for (int ci = 0; ci < npref && best_T == 0; ++ci) {
     const int T = (eT != nullptr) ? atoi(eT) : pref[ci].T;
-    const int ring = (eR != nullptr) ? std::max(2, std::min(4, atoi(eR))) : pref[ci].ring;
+    const int ring = (eR != nullptr) ? std::max(2, std::min(6, atoi(eR))) : pref[ci].ring;
     if (T < 1 || T > 4) continue;
     const int upi = (h.tiles_per_img + T - 1) / T;
     int NR = 0;
