@@ -63,6 +63,7 @@ struct ConvParams {
   long long src_img;
   int src_row, src_pix, src_off;
   long long* timeline;    // debug: per-role clock64 stamps of the first CTAs (null in production)
+  int dbg;                // debug ablation mask (HRP_CONV_DBG, experiments only; 0 in production)
 };
 
 struct ConvMaps {

@@ -414,6 +414,16 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
 // ------------------------------------------------------------------------------------------------------
 constexpr int kThreadsP = 352;      // warp 0 producer, warp 1 MMA, warps 2..9 epilogue, warp 10 TMA-store
 constexpr int kEpiThreadsP = 256;
+// The soft-argmax fold (EPI_HEAD) has no store warp.  Its epilogue is ~1000 instructions per warp and tile, but it is NOT
+// what bounds the layer: with the epilogue reduced to the accumulator read the kernel still takes 848 of its 960 us at
+// 512 images, and sixteen epilogue warps instead of eight changed nothing (profiles/r02_exp_final_fold.txt) -- the A
+// stream (64 KB per 128 x 128 tile, re-fetched by the four N-tile CTAs) arrives at ~19 B/cycle/SM.
+constexpr int kEpiWarpsHead = 8;
+constexpr int kThreadsPHead = 64 + 32 * kEpiWarpsHead;
+template <int EPI> struct PersistShape {
+  static constexpr int epi_warps = (EPI == 4) ? kEpiWarpsHead : kEpiThreadsP / 32;
+  static constexpr int threads = (EPI == 4) ? kThreadsPHead : kThreadsP;
+};
 
 struct __align__(16) PersistBarriers {
   uint64_t full[8];
@@ -429,7 +439,7 @@ struct __align__(16) PersistBarriers {
 };
 
 template <int CK, int EPI>
-__global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __grid_constant__ ConvMaps maps,
+__global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persistent(const __grid_constant__ ConvMaps maps,
                                                                      const __grid_constant__ ConvParams p,
                                                                      const PersistCfg cfg) {
   constexpr int SUB = 64 / CK;
@@ -476,7 +486,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->tmem_full[i], 1);
-      mbar_init(&bars->tmem_empty[i], kEpiThreadsP / 32);  // one arrival per epilogue warp
+      mbar_init(&bars->tmem_empty[i], PersistShape<EPI>::epi_warps);  // one arrival per epilogue warp
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&bars->res_full[i], 1);
@@ -490,9 +500,9 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
     tmem_alloc(&bars->tmem_base, (uint32_t)cfg.tmem_cols);
     tmem_relinquish();
   }
-  if (warp >= 2 && warp < 10) {
+  if (warp >= 2 && warp < 2 + PersistShape<EPI>::epi_warps) {
     const float mul = (EPI == EPI_HEAD) ? kLog2eF : 1.0f;  // soft-argmax fold: logits in the log2 domain (ex2 below)
-    for (int i = threadIdx.x - 64; i < p.cout_pad; i += kEpiThreadsP) {
+    for (int i = threadIdx.x - 64; i < p.cout_pad; i += 32 * PersistShape<EPI>::epi_warps) {
       sb_smem[i] = (i < p.Cout) ? __ldg(p.scale + i) * mul : 0.f;
       sb_smem[p.cout_pad + i] = (i < p.Cout) ? __ldg(p.bias + i) * mul : 0.f;
     }
@@ -708,7 +718,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
         }
       }
     }
-  } else if (warp == 10) {
+  } else if (EPI != EPI_HEAD && warp == 10) {
     // ===================== TMA-store warp: drains finished staging buffers, never stalls the epilogue ==========
     if (p.out != nullptr && elect_one()) {
       int li = 0;
@@ -814,11 +824,12 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
       if (warp == 2 && lane == 0) tl_stamp(p.timeline, li, 8);
 
 #pragma unroll 1
-      for (int c0 = half * 32; c0 < c_lim; c0 += 64) {
+      for (int c0 = half * 32; c0 < c_lim; c0 += 8 * PersistShape<EPI>::epi_warps) {
         uint32_t acc[32];
         tmem_ld32(taddr + (uint32_t)c0, acc);
         tmem_ld_wait();
         if (EPI == EPI_HEAD) {
+          if (p.dbg & 4) continue;  // (ablation: accumulator read only)
           // Soft-argmax fold.  This thread owns pixel (h, w) of image n0 (tile = two image rows: bw 64, bh 2, bn 1) and the
           // 32 depth bins d0..d0+31 of keypoint kp: online-softmax partial over its 32 logits (log2 domain), then a
           // fixed-order butterfly over the warp's 32 pixels; lane 0 writes the 5-tuple.  Nothing is stored otherwise.
@@ -852,7 +863,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_gemm_persistent(const __gri
           float S4[4] = {0.f, 0.f, 0.f, 0.f}, Z4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const float e = ex2_ftz_f(t[i] - m);
+            const float e = (p.dbg & 1) ? t[i] : ex2_ftz_f(t[i] - m);  // (dbg 1: ablation without the exponentials)
             S4[i & 3] += e;
             Z4[i & 3] = fmaf(e, (float)i, Z4[i & 3]);
           }
@@ -1359,6 +1370,7 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed, con
               "tensors must be 16-byte aligned");
   p.in = in;
   p.w = w_packed;
+  if (const char* dbg = getenv("HRP_CONV_DBG")) p.dbg = atoi(dbg);
   // A maps: one per input parity for stride-2 sources, else a single map
   const int nmaps = (p.src_sh == 2) ? 4 : 1;
   for (int m = 0; m < nmaps; ++m) {
@@ -1628,8 +1640,8 @@ int conv_plan_launch(const ConvPlan& plan, cudaStream_t stream) {
   const ConvParams& p = plan.p;
   if (plan.halo) return conv_halo_launch(plan, stream);
   if (plan.epi == EPI_HEAD) {
-    launch_ex(conv_gemm_persistent<64, EPI_HEAD>, dim3(plan.pgrid), dim3(kThreadsP), (size_t)plan.psmem, stream, plan.maps, p,
-              plan.pcfg);
+    launch_ex(conv_gemm_persistent<64, EPI_HEAD>, dim3(plan.pgrid), dim3(kThreadsPHead), (size_t)plan.psmem, stream,
+              plan.maps, p, plan.pcfg);
     count_launch();
     HRP_CUDA_CHECK(cudaGetLastError());
     return HRP_OK;
