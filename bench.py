@@ -166,8 +166,8 @@ def main():
     ap.add_argument("--global-batch", type=int, default=GLOBAL_BATCH)
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch of the weak-scaling variant")
     ap.add_argument("--overlap", type=int, default=0,
-                    help="steps in flight per GPU (caller streams = plan replicas); 0 = auto: 2 when the per-GPU batch "
-                         "is <= 128 images (a 64-image step cannot fill 148 SMs by itself), else 1")
+                    help="independent steps in flight per GPU (caller streams = plan replicas); 0 = auto: 3 up to 128 "
+                         "images per GPU (a 64-image step cannot fill 148 SMs by itself), 2 up to 256, else 1")
     ap.add_argument("--robot", default=ROBOT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
@@ -307,6 +307,12 @@ def main():
         ms_e = max(r["e2e_ms_per_step"] for r in per_rank)
         return imgs, ms, imgs / (ms * 1e-3), ms_e, imgs / (ms_e * 1e-3)
 
+    def default_overlap(b):
+        """Independent steps kept in flight per GPU (caller streams = plan replicas).  Measured
+        (profiles/r02_exp_small_shards.txt): 3 steps of single-lane PDL graphs beat one 5-lane graph by 6-9 % at 64-128
+        images and 2 steps by 2-3 % at 256; at 512 every kernel fills the GPU and one step in flight is as fast."""
+        return 3 if b <= 128 else (2 if b <= 256 else 1)
+
     def batch_of(mode):
         if mode == "strong":
             lo, hi = shard.shard_range(args.global_batch, rank, world)
@@ -316,7 +322,7 @@ def main():
     # ---------------- headline: the scaling mode asked for ----------------
     lo, hi = batch_of(args.scaling)
     B = hi - lo
-    overlap = args.overlap if args.overlap > 0 else (2 if B <= 128 else 1)
+    overlap = args.overlap if args.overlap > 0 else default_overlap(B)
     model = build_model(robot, B, overlap)
     per_rank, clocks, outs, dev_in = measure(model, host_batch(lo, hi), args.steps, args.warmup, overlap,
                                              profile=args.profile_range, clocks=True)
@@ -331,7 +337,7 @@ def main():
     other_mode = "weak" if args.scaling == "strong" else "strong"
     if world > 1 and not args.no_secondary:
         lo2, hi2 = batch_of(other_mode)
-        ov2 = args.overlap if args.overlap > 0 else (2 if hi2 - lo2 <= 128 else 1)
+        ov2 = args.overlap if args.overlap > 0 else default_overlap(hi2 - lo2)
         m2 = model if (hi2 - lo2 == B and ov2 == overlap) else build_model(robot, hi2 - lo2, ov2)
         pr2, _, _, _ = measure(m2, host_batch(lo2, hi2), max(5, args.steps // 2), args.warmup, ov2)
         imgs2, ms2, v2, e2e_ms2, e2e_v2 = summarise(pr2, max(5, args.steps // 2))
@@ -388,7 +394,9 @@ def main():
                            "frac": max(float(r[13]) / peaks["tf_sust"], float(r[14]) / peaks["hbm"])} for r in top]}
     except Exception as e:  # the per-layer view is diagnostic: never fail the bench line on it
         layers = {"error": str(e)}
-    tr = ROOT / "profiles" / "r01_ncu_traffic.json"
+    tr = ROOT / "profiles" / "r02_ncu_traffic.json"
+    if not tr.exists():
+        tr = ROOT / "profiles" / "r01_ncu_traffic.json"
     if tr.exists():
         try:
             t = json.loads(tr.read_text())
@@ -422,7 +430,9 @@ def main():
                      "frac": head_gbs / peaks["hbm"], "traffic": None, "kernel": "hrp::head_kernel",
                      "note": f"{HEATMAP_BYTES_PER_IMAGE[robot]} B/image x {hb} images per launch "
                              f"({hm.numel() * 2 / 1e6:.0f} MB > L2), {head_ms * 1e3:.1f} us per launch"}
-    ht = ROOT / "profiles" / "r01_ncu_head_traffic.json"
+    ht = ROOT / "profiles" / "r02_ncu_head_traffic.json"
+    if not ht.exists():
+        ht = ROOT / "profiles" / "r01_ncu_head_traffic.json"   # (head_kernel is unchanged since that capture)
     if ht.exists():
         try:
             t = json.loads(ht.read_text())

@@ -33,9 +33,12 @@ struct __align__(16) PipeBarriers {
   uint32_t pad;
 };
 
-// debug timeline: slot = (cta * 64 + tile_local * 8 + event) for the first 8 CTAs / 8 tiles
+// debug timeline: slot = (cta * 8 + tile_local - skip) * 16 + event for the first 8 CTAs and 8 consecutive tiles of each,
+// starting at the CTA's tile number `skip` = tl[8 * 8 * 16] (0: pipeline fill, >= 8: steady state)
 __device__ __forceinline__ void tl_stamp(long long* tl, int tile_local, int ev) {
-  if (tl != nullptr && blockIdx.x < 8 && tile_local < 8) tl[(blockIdx.x * 8 + tile_local) * 16 + ev] = clock64();
+  if (tl == nullptr || blockIdx.x >= 8) return;
+  const int t = tile_local - (int)tl[8 * 8 * 16];
+  if (t >= 0 && t < 8) tl[(blockIdx.x * 8 + t) * 16 + ev] = clock64();
 }
 
 // Epilogue flavours (template parameter EPI): the common case carries no addends and no per-row predicates at all.
@@ -1192,6 +1195,9 @@ int conv_geometry(const ConvLayerDesc& d, ConvParams* pp) {
     while (small_m && !d.head_fold && p.Cout >= 128 && max_n > 32 && p.Cout % (max_n / 2) == 0 && m_tiles <= 4 &&
            m_tiles * ((p.Cout + max_n - 1) / max_n) < 24)
       max_n /= 2;
+    // (Experiment, profiles/r02_exp_small_shards.txt: also halving the N tile of long-K layers whenever the grid stays
+    //  within one wave -- fewer operand bytes per SM for the 8x8 layers of a 64-image shard -- was neutral to slower at
+    //  every batch from 1 to 256, so the rule above stays limited to 1-4 M tiles.)
   }
   int n_tiles = (p.Cout + max_n - 1) / max_n;
   p.n_tile = (((p.Cout + n_tiles - 1) / n_tiles) + 31) / 32 * 32;

@@ -804,7 +804,10 @@ int capture_plan(hrp_model* m, Plan* pl) {
     const char* pdl_env = getenv("HRP_PDL");
     // opt-in (measured no gain) and single-lane graphs only: with five lanes a batch-1 run produced a
     // last-bit different pose under PDL, i.e. some cross-lane edge is not covered by the programmatic dependency
-    const bool pdl_on = (pdl_env != nullptr && pdl_env[0] == '1') && !m->use_simt && single_lane;
+    // Default: on for single-lane plans of <= 256 images (the kernel tails it hides are a few us each: 3-7 % of a step at
+    // 64-128 images, nothing at 512 where round 1 measured -2 %); HRP_PDL=0 / 1 overrides.
+    const bool pdl_want = (pdl_env != nullptr) ? (pdl_env[0] == '1') : (pl->B <= 256);
+    const bool pdl_on = pdl_want && !m->use_simt && single_lane;
     bool prev_kernel[kNumLanes] = {};
     for (size_t i = 0; i < pl->ops.size() && rc == HRP_OK; ++i) {
       Op& op = pl->ops[i];
@@ -958,8 +961,12 @@ size_t plan_arena(const Plan& dry, bool alias, std::vector<size_t>* offsets, siz
 int build_plan(hrp_model* m, int B, Plan** out_plan, int replica) {
   std::unique_ptr<Plan> pl(new Plan());
   pl->B = B;
-  // Lanes pay off while some kernels cannot fill the GPU by themselves (see capture_plan); large chunks run on one stream
-  pl->single_lane = B > 256;
+  // Lanes (intra-step parallelism) pay off while some kernels cannot fill the GPU by themselves (see capture_plan) AND one
+  // step is in flight.  Large chunks run on one stream; so do plans of >= 32 images when the caller keeps several steps in
+  // flight (desc.inflight >= 2: plan replicas on caller streams): independent steps then fill each other's gaps better
+  // than lanes do, and a single-lane graph can chain its kernels by programmatic dependent launch
+  // (profiles/r02_exp_small_shards.txt: 64 images 5.76 -> 5.26 ms, 128 images 9.68 -> 9.10 ms per step).
+  pl->single_lane = B > 256 || (m->desc.inflight >= 2 && B >= 32);
   if (const char* sl = getenv("HRP_SINGLE_LANE")) pl->single_lane = (sl[0] == '1');
   const bool full = (m->desc.kind == HRP_MODEL_FULL);
   const bool fold = full && m->head_fold && !m->use_simt;

@@ -66,18 +66,32 @@ class HostPipeline:
         main.synchronize()
         return host_out
 
-    # ---- stream of batches: the upload of batch i+1 overlaps the forward of batch i (a DataLoader-style eval loop) ----
-    def run_stream(self, batches):
+    # ---- stream of batches: uploads, forwards and downloads of consecutive batches overlap (a DataLoader-style eval loop) ----
+    def run_stream(self, batches, inflight: int | None = None):
         """Iterate over host batches `(x_reg_h, x_root_h, k_h, K_h)` (pinned) and yield the host outputs of each, in
-        order.  Every batch is copied host->device on the copy stream into one of two full-batch device buffer sets
-        while the previous batch is being computed; its eight outputs are copied back before it is yielded."""
+        order.  Every batch is copied host->device on the copy stream while earlier batches are being computed, and its
+        eight outputs are copied back before it is yielded.  `inflight` (default: the model's `inflight`) forwards are
+        kept enqueued, each on its own compute stream (= its own plan replica inside the model), before the oldest one
+        is waited for; with `inflight == 1` a batch is yielded before the next forward is launched.  The yielded host
+        buffers are recycled `inflight + 1` batches later."""
+        from collections import deque
         dev = torch.device("cuda", torch.cuda.current_device())
         main = torch.cuda.current_stream()
+        depth = max(1, int(inflight if inflight is not None else getattr(self.model, "inflight", 1)))
         if self.copy_stream is None:
             self.copy_stream = torch.cuda.Stream(device=dev)
-        bufs = [None, None]
-        ready = [torch.cuda.Event() for _ in range(2)]
-        free = [None, None]
+        if depth == 1:
+            streams = [main]
+        else:
+            if len(getattr(self, "_compute_streams", [])) < depth:
+                self._compute_streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
+            streams = self._compute_streams[:depth]
+            for s_ in streams:
+                s_.wait_stream(main)
+        nslots = depth + 1
+        bufs = [None] * nslots
+        ready = [torch.cuda.Event() for _ in range(nslots)]
+        free = [None] * nslots
 
         def upload(batch, slot):
             if bufs[slot] is None or any(b.shape != h.shape or b.dtype != h.dtype for b, h in zip(bufs[slot], batch)):
@@ -90,31 +104,50 @@ class HostPipeline:
                     b.copy_(h, non_blocking=True)
                 ready[slot].record(self.copy_stream)
 
-        it = iter(batches)
-        nxt = next(it, None)
-        slot = 0
-        if nxt is not None:
-            upload(nxt, slot)
-        while nxt is not None:
-            cur_slot = slot
-            B = nxt[0].shape[0]
-            nxt = next(it, None)
-            main.wait_event(ready[cur_slot])
-            outs = self.model(*bufs[cur_slot])
-            free[cur_slot] = torch.cuda.Event()
-            free[cur_slot].record(main)
-            if nxt is not None:
-                slot ^= 1
-                upload(nxt, slot)
-            key = ("stream", B, tuple(tuple(o.shape[1:]) for o in outs))
+        def host_buffers(B, outs, ring):
+            key = ("stream", B, ring, tuple(tuple(o.shape[1:]) for o in outs))
             host_out = self._host_out.get(key)
             if host_out is None:
                 host_out = tuple(torch.empty((B,) + tuple(o.shape[1:]), dtype=torch.float32).pin_memory() for o in outs)
                 self._host_out[key] = host_out
-            for o, h in zip(outs, host_out):
-                h.copy_(o, non_blocking=True)
-            main.synchronize()
-            yield host_out
+            return host_out
+
+        it = iter(batches)
+        nxt = next(it, None)
+        i = 0
+        if nxt is not None:
+            upload(nxt, 0)
+        pending = deque()
+        while nxt is not None:
+            slot = i % nslots
+            B = nxt[0].shape[0]
+            s_ = streams[i % depth]
+            nxt = next(it, None)
+            s_.wait_event(ready[slot])
+            with torch.cuda.stream(s_):
+                outs = self.model(*bufs[slot])
+                free[slot] = torch.cuda.Event()
+                free[slot].record(s_)
+                host_out = host_buffers(B, outs, i % nslots)
+                for o, h in zip(outs, host_out):
+                    h.copy_(o, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(s_)
+            pending.append((done, host_out))
+            if nxt is not None:
+                upload(nxt, (i + 1) % nslots)
+            i += 1
+            if len(pending) >= depth:
+                ev, ho = pending.popleft()
+                ev.synchronize()
+                yield ho
+        while pending:
+            ev, ho = pending.popleft()
+            ev.synchronize()
+            yield ho
+        if depth > 1:
+            for s_ in streams:
+                main.wait_stream(s_)
 
 
 class EvalPipeline:

@@ -81,7 +81,8 @@ int hrp_conv_create(const hrp_conv_desc* desc, const void* in_dev, const void* w
 int hrp_conv_out_shape(const hrp_conv* conv, int32_t* Hout, int32_t* Wout);
 int hrp_conv_run(hrp_conv* conv, int32_t impl, void* stream);
 void hrp_conv_destroy(hrp_conv* conv);
-/* debug: device buffer of 8 CTAs x 8 tiles x 16 int64 clock64() stamps per pipeline role, or NULL to disable */
+/* debug (hrp_conv_set_timeline): device buffer of 8 CTAs x 8 tiles x 16 int64 clock64() stamps per pipeline role plus
+ * ONE trailing int64 = number of each CTA's leading tiles to skip (8 * 8 * 16 + 1 elements), or NULL to disable */
 /* kernel variant of a planned conv: 0 = one tile per CTA, 1 = persistent, 2 = halo-tile (3x3 s1, Cin=Cout in {32,64});
  * set_variant(2) returns HRP_ERR_UNSUPPORTED where the halo kernel is not eligible */
 int hrp_conv_set_variant(hrp_conv* conv, int32_t variant);

@@ -503,6 +503,50 @@ def test_streams_get_their_own_plan_replicas(hrp_lib):
             assert torch.equal(u, v), (i, n)
 
 
+def test_single_lane_pdl_plans_match_lane_plans_bitwise(hrp_lib):
+    """With `inflight >= 2` a plan of >= 32 images is ONE stream of kernels chained by programmatic dependent launch
+    (steps overlap each other instead of lanes overlapping inside a step); with `inflight == 1` the same batch runs on
+    five lanes.  Same kernels, same reduction orders: the results must be identical bits -- also with three steps in
+    flight on three streams, and through the pipelined host-buffer call."""
+    from horopose_b200 import synth
+    from horopose_b200.pipeline import HostPipeline
+    base = synth.inputs(16, seed=91)
+    idx = torch.arange(32) % 16
+    host = [t[idx].contiguous() for t in base]
+    xs = [t.cuda() for t in host]
+    lanes = _model("kuka", chunk=32, inflight=1)
+    ref = [t.clone() for t in lanes(*xs)]
+    chained = _model("kuka", chunk=32, inflight=3)
+    got = [t.clone() for t in chained(*xs)]
+    # (a single-lane plan runs in program order, so its activation arena is liveness-aliased: that is how it shows here)
+    assert chained.stats(32)["activation_bytes"] < 0.5 * lanes.stats(32)["activation_bytes"]
+    torch.cuda.synchronize()
+    for n, u, v in zip(NAMES, ref, got):
+        assert torch.equal(u, v), n
+        assert torch.equal(u[:16], u[16:]), ("copies", n)
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    outs = []
+    for i in range(9):
+        s = streams[i % 3]
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            outs.append(chained(*xs))
+    torch.cuda.synchronize()
+    for i, o in enumerate(outs):
+        for n, u, v in zip(NAMES, ref, o):
+            assert torch.equal(u, v), (i, n)
+    u8 = lambda t: (t * 255.0).round().clamp(0, 255).to(torch.uint8).contiguous().pin_memory()
+    hb = (u8(host[0]), u8(host[1]), host[2].pin_memory(), host[3].pin_memory())
+    direct = [t.cpu().clone() for t in lanes(*(t.cuda() for t in hb))]
+    pipe = HostPipeline(chained)
+    n_out = 0
+    for host_out in pipe.run_stream((hb for _ in range(7)), inflight=3):
+        for n, h, d in zip(NAMES, host_out, direct):
+            assert torch.equal(h, d), (n_out, n)
+        n_out += 1
+    assert n_out == 7
+
+
 def test_plan_cache_is_bounded(hrp_lib, monkeypatch):
     """A caller that varies the batch size cannot grow device memory without bound: plans other than the nominal chunk
     are evicted LRU (HRP_MAX_PLANS), and an evicted batch size is simply re-planned with the same results."""

@@ -46,11 +46,11 @@ for _ in range(3):
     best = min(best, e0.elapsed_time(e1) / 40)
 print(f"{which} B={B}: {best * 1e3:7.1f} us  {io / best / 1e6:7.1f} GB/s  [{buf.value.decode()}]")
 if len(sys.argv) > 4 and variant == 1:
-    tl = torch.zeros(8 * 8 * 16, dtype=torch.int64, device="cuda")
+    tl = torch.zeros(8 * 8 * 16 + 1, dtype=torch.int64, device="cuda")
     _lib.check(L.hrp_conv_set_timeline(op.handle, C.c_void_p(tl.data_ptr())))
     op.run()
     torch.cuda.synchronize()
-    t = tl.cpu().view(8, 8, 16)
+    t = tl[:-1].cpu().view(8, 8, 16)
     names = ["P.start", "P.empty0", "P.issued", "M.tmemfree", "M.full0", "M.lastcommit", "E.top", "E.tmemfull", "E.stagok",
              "E.done", "S.ready", "S.issued", "S.drained"]
     t0 = int(t[0, 0][t[0, 0] > 0].min())

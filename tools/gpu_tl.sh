@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for d in 0 1 4; do
-HRP_CONV_DBG=$d timeout 300 python tools/profile_model.py profile 512 > gpurun_out/profile_kuka512.txt 2>&1
-echo -n "dbg=$d "; grep "final_layer" gpurun_out/per_op_kuka_512.tsv | cut -c1-140
-done
+timeout 600 python tools/bench_conv.py 512 > gpurun_out/bench_conv512.txt 2>&1
+cat gpurun_out/bench_conv512.txt
+HRP_CONV_WRES=0 timeout 600 python tools/bench_conv.py 512 > gpurun_out/bench_conv512_nowres.txt 2>&1
+grep "final\|rn 256->1024\|rn 64->256\|rn 1024" gpurun_out/bench_conv512_nowres.txt

@@ -1,6 +1,7 @@
 """Summarise an ncu launch list (gpu__time_duration, sm__pipe_tensor_cycles_active, dram bytes per launch) of one bench
 step: per-kernel-family share of the step, time-weighted tensor-pipe utilisation (whole step / conv kernels only) and
-DRAM traffic.    python tools/ncu_launch_table.py launches.csv [out.json]"""
+DRAM traffic.    python tools/ncu_launch_table.py launches.csv [out.json [traffic.json per_op.tsv source-label]]
+(traffic.json is the file bench.py reads for roofline.traffic: the step's DRAM bytes next to its algorithmic bytes)"""
 import collections
 import csv
 import json
@@ -37,3 +38,8 @@ if len(sys.argv) > 2:
                "tensor_pipe_pct_step": tot_p / tot_t, "tensor_pipe_pct_conv": cp / max(ct, 1),
                "families": {k: {"launches": a[0], "us": a[1] / 1e3, "tensor_pipe_pct": a[2] / max(a[1], 1), "dram_mb": a[3] / 1e6}
                             for k, a in agg.items()}}, open(sys.argv[2], "w"), indent=1)
+if len(sys.argv) > 4:
+    alg = sum(float(r["bytes"]) for r in csv.DictReader(open(sys.argv[4]), delimiter="\t") if r["kind"] == "conv")
+    json.dump({"robot": "kuka", "batch": 512, "kernels": len(per), "dram_bytes_per_step": tot_b,
+               "algorithmic_bytes_per_step": alg, "source": sys.argv[5] if len(sys.argv) > 5 else sys.argv[1]},
+              open(sys.argv[3], "w"))
