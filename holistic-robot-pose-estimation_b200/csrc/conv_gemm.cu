@@ -415,14 +415,21 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
 // epilogue warps (two per TMEM lane quarter) drain the accumulators.  Per-tile fixed costs (TMEM allocation,
 // barrier init, descriptor fetch, launch) are paid once per CTA.
 // ------------------------------------------------------------------------------------------------------
-constexpr int kThreadsP = 352;      // warp 0 producer, warp 1 MMA, warps 2..9 epilogue, warp 10 TMA-store
+// warp 0 producer, warp 1 MMA, warps 2..9 epilogue, warp 10 TMA-store, warp 11 second producer.
+// Two producers: ONE thread running the ring protocol (wait for the slot, expect_tx, cp.async.bulk.tensor, bookkeeping)
+// sustains one load per ~550-650 cycles whatever the box size (tools/probe_tma.py, profiles/r02_probe_tma.txt: the raw
+// instruction issues every ~75 cycles and the engine delivers > 70 B/cycle/SM, but the per-slot handshake serialises the
+// thread), i.e. 16 KiB stages arrive at ~26 B/cycle/SM while the MMAs of a stage (N = 128, K = 64) take 257 cycles: every
+// persistent kernel with short stages was bound by its producer THREAD.  Two threads in two warps alternate stages and
+// reach ~48 B/cycle/SM.
+constexpr int kThreadsP = 384;
 constexpr int kEpiThreadsP = 256;
 // The soft-argmax fold (EPI_HEAD) has no store warp.  Its epilogue is ~1000 instructions per warp and tile, but it is NOT
 // what bounds the layer: with the epilogue reduced to the accumulator read the kernel still takes 848 of its 960 us at
 // 512 images, and sixteen epilogue warps instead of eight changed nothing (profiles/r02_exp_final_fold.txt) -- the A
 // stream (64 KB per 128 x 128 tile, re-fetched by the four N-tile CTAs) arrives at ~19 B/cycle/SM.
 constexpr int kEpiWarpsHead = 8;
-constexpr int kThreadsPHead = 64 + 32 * kEpiWarpsHead;
+constexpr int kThreadsPHead = 64 + 32 * kEpiWarpsHead + 32;  // (+ the second producer warp: the last one)
 template <int EPI> struct PersistShape {
   static constexpr int epi_warps = (EPI == 4) ? kEpiWarpsHead : kEpiThreadsP / 32;
   static constexpr int threads = (EPI == 4) ? kThreadsPHead : kThreadsP;
@@ -445,11 +452,12 @@ template <int CK, int EPI>
 __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persistent(const __grid_constant__ ConvMaps maps,
                                                                      const __grid_constant__ ConvParams p,
                                                                      const PersistCfg cfg) {
-  constexpr int SUB = 64 / CK;
   constexpr int A_SUB_BYTES = kTileM * CK * 2;
   constexpr int KSTEPS = CK / 16;
   constexpr uint32_t LAYOUT = (CK == 64) ? 2u : (CK == 32) ? 4u : 6u;
   constexpr uint32_t SBO = 8 * CK * 2;
+  constexpr int WARP_P2 = PersistShape<EPI>::threads / 32 - 1;  // second producer warp
+  const int SUB = cfg.sub;                     // k-blocks (CK channels of one tap) per stage: (64 / CK) x 1 or 2
 
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = smem_align1024(smem_dyn);
@@ -539,10 +547,20 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
   const int ph = phase >> 1, pw = phase & 1;                           \
   const int c_base = n_blk * n_tile;
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (elect_one()) {
-      if (wres) {
+  if (warp == 0 || warp == WARP_P2) {
+    // ===================== TMA producers: warp 0 (+ warp WARP_P2 when cfg.nprod == 2) =====================
+    // Stage g of the CTA (counted over all its tiles) is issued by producer g % nprod; both walk the same sequence and
+    // skip the other one's stages.  Producer 0 also fetches the resident weights and the residual / addend tiles.
+    const int me = (warp == 0) ? 0 : 1;
+    if (me < cfg.nprod && elect_one()) {
+      // Layers with TMA-fetched residual / addend tiles split the roles instead: producer 0 streams the operands,
+      // producer 1 fetches the addend tiles -- it is the one that has to wait for a staging entry to drain, and the
+      // operand stream no longer stops behind that wait.
+      const bool res_role = has_res && cfg.nprod == 2;
+      const bool two = cfg.nprod == 2 && !res_role;
+      const int res_owner = res_role ? 1 : 0;
+      uint32_t g = 0;
+      if (wres && me == 0) {
         // the packed weights of this CTA's N tile stay in shared memory for the CTA's lifetime.  With several N tiles the
         // grid is a multiple of n_tiles (host), so every tile this CTA walks (blockIdx.x + i * gridDim.x) has the same
         // n_blk = blockIdx.x % n_tiles: the A tiles stream through the pipeline alone and the L2 -> SM traffic halves.
@@ -596,31 +614,42 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
                               c_base + j * cko, w0 >> cfg.up_sh[a], h0 >> cfg.up_sh[a], n0);
           }
         };
-        if (has_res && nstag >= 2) load_residual();
-        tl_stamp(p.timeline, li, 0);
-        for (int it = 0; it < n_iters; ++it) {
-          mbar_wait(&bars->empty[s], par ^ 1);
-          if (it == 0) tl_stamp(p.timeline, li, 1);
+        if (has_res && nstag >= 2 && me == res_owner) load_residual();
+        if (res_role && me == 1) {
+          if (nstag == 1) load_residual();
+          continue;
+        }
+        if (me == 0) tl_stamp(p.timeline, li, 0);
+        for (int it = 0; it < n_iters; ++it, ++g) {
+          const bool mine = !two || (int)(g & 1u) == me;
+          if (mine) {
+            mbar_wait(&bars->empty[s], par ^ 1);
+            if (it == 0 && me == 0) tl_stamp(p.timeline, li, 1);
+          }
           uint8_t* sa = pipe_base + (size_t)s * stage_bytes;
           uint8_t* sb = sa + a_region;
           if (vsh) {
             // one (channel chunk, dw) per iteration: an A buffer of bh+2 image rows serves the three dh taps
-            mbar_expect_tx(&bars->full[s], (uint32_t)(cfg.a_bytes + (wres ? 0 : 3 * b_sub_bytes)));
-            tma_load_4d(sa, &maps.av, &bars->full[s], cc * CK, w0 + dwi - 1, h0 - 1, n0);
-            if (!wres)
-              for (int dhi = 0; dhi < 3; ++dhi)
-                tma_load_2d(sb + dhi * b_sub_bytes, &maps.b, &bars->full[s], ((dhi * 3 + dwi) * p.cpt + cc) * CK, brow);
+            if (mine) {
+              mbar_expect_tx(&bars->full[s], (uint32_t)(cfg.a_bytes + (wres ? 0 : 3 * b_sub_bytes)));
+              tma_load_4d(sa, &maps.av, &bars->full[s], cc * CK, w0 + dwi - 1, h0 - 1, n0);
+              if (!wres)
+                for (int dhi = 0; dhi < 3; ++dhi)
+                  tma_load_2d(sb + dhi * b_sub_bytes, &maps.b, &bars->full[s], ((dhi * 3 + dwi) * p.cpt + cc) * CK, brow);
+            }
             if (++dwi == 3) {
               dwi = 0;
               ++cc;
             }
           } else {
             const int nsub = min(SUB, nkb - it * SUB);
-            mbar_expect_tx(&bars->full[s], (uint32_t)(nsub * (A_SUB_BYTES + (wres ? 0 : b_sub_bytes))));
+            if (mine) mbar_expect_tx(&bars->full[s], (uint32_t)(nsub * (A_SUB_BYTES + (wres ? 0 : b_sub_bytes))));
             for (int j = 0; j < nsub; ++j) {
-              tma_load_4d(sa + j * A_SUB_BYTES, &maps.a[p.tap_map[tap]], &bars->full[s], cc * CK,
-                          w0 + p.tap_dw[tap] + tpw, h0 + p.tap_dh[tap] + tph, n0);
-              if (!wres) tma_load_2d(sb + j * b_sub_bytes, &maps.b, &bars->full[s], (it * SUB + j) * CK, brow);
+              if (mine) {
+                tma_load_4d(sa + j * A_SUB_BYTES, &maps.a[p.tap_map[tap]], &bars->full[s], cc * CK,
+                            w0 + p.tap_dw[tap] + tpw, h0 + p.tap_dh[tap] + tph, n0);
+                if (!wres) tma_load_2d(sb + j * b_sub_bytes, &maps.b, &bars->full[s], (it * SUB + j) * CK, brow);
+              }
               if (++cc == p.cpt) {
                 cc = 0;
                 ++tap;
@@ -632,8 +661,8 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
             par ^= 1;
           }
         }
-        tl_stamp(p.timeline, li, 2);
-        if (has_res && nstag == 1) load_residual();
+        if (me == 0) tl_stamp(p.timeline, li, 2);
+        if (has_res && nstag == 1 && me == res_owner) load_residual();
       }
     }
   } else if (warp == 1) {
@@ -1334,10 +1363,16 @@ int conv_encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* 
   const CUtensorMapSwizzle sw = (ck == 64)   ? CU_TENSOR_MAP_SWIZZLE_128B
                                 : (ck == 32) ? CU_TENSOR_MAP_SWIZZLE_64B
                                              : CU_TENSOR_MAP_SWIZZLE_32B;
+  // (HRP_TMA_L2PROMO=0|64|128|256 overrides the L2 promotion size: probing aid, tools/probe_tma.py)
+  static const int promo_env = (getenv("HRP_TMA_L2PROMO") != nullptr) ? atoi(getenv("HRP_TMA_L2PROMO")) : 256;
+  const CUtensorMapL2promotion promo = (promo_env == 0)     ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                       : (promo_env == 64)  ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                       : (promo_env == 128) ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                            : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
                   reinterpret_cast<const cuuint64_t*>(dims), reinterpret_cast<const cuuint64_t*>(strides_bytes),
-                  reinterpret_cast<const cuuint32_t*>(box), estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  reinterpret_cast<const cuuint32_t*>(box), estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, promo,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
     return HRP_ERR_CUDA;
@@ -1558,28 +1593,68 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed, con
     const bool multi_ok = p.n_tiles > 1 && p.nphase == 1 && grid_nt * 20 >= num_sms * 19 &&
                           (long long)p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles >= 2LL * num_sms;
     c.wres = ((p.n_tiles == 1 || multi_ok) && p.nphase == 1 && wbytes <= 80 * 1024 && !(e2 != nullptr && e2[0] == '0')) ? 1 : 0;
-    c.a_bytes = c.vsh ? (p.bh + 2) * p.bw * p.ck * 2 : kStageABytes;
-    c.a_region = (c.a_bytes + 1023) / 1024 * 1024;
-    const int b_region = c.wres ? 0 : (c.vsh ? 3 * b_sub : p.n_tile * 128);
-    c.stage_bytes = c.a_region + b_region;
+    // ---- pipeline geometry -------------------------------------------------------------------------------------
+    // A stage holds kmul x 64 channels' worth of k-blocks (kmul x 16 KiB of A, plus the matching weight sub-tiles unless
+    // the weights are resident).  One ring handshake (wait for the slot, expect_tx, TMA burst) costs the producer thread
+    // ~550-650 cycles however many bytes it moves, and the MMA issuer pays a similar price per stage it waits for
+    // (tools/probe_tma.py, profiles/r02_probe_tma.txt, profiles/r02_persist_timelines.txt): with 16 KiB stages the
+    // 1x1 layers ran at ~900 cycles per stage against 257 cycles of MMAs.  So: the BIGGEST stage that still leaves two
+    // of them in flight (kmul = 4, 2, 1; HRP_CONV_KSTAGE pins it), two producer threads taking alternate stages.
+    const char* e6 = getenv("HRP_CONV_KSTAGE");
+    const char* e7 = getenv("HRP_CONV_NPROD");
+    const char* e4 = getenv("HRP_CONV_NSTAG");
+    const int units = (p.ntaps * p.cpt) / (64 / p.ck);   // whole 64-channel units of K per tile
     c.pipe_offset = c.wres ? (wbytes + 1023) / 1024 * 1024 : 0;
-    if (c.vsh) {
-      uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.Ws, (uint64_t)p.Hs, (uint64_t)p.B};
-      uint64_t strides[3] = {(uint64_t)p.Cin * 2, (uint64_t)p.Win * p.Cin * 2, (uint64_t)p.Hin * p.Win * p.Cin * 2};
-      uint32_t box[4] = {(uint32_t)p.ck, (uint32_t)p.bw, (uint32_t)(p.bh + 2), 1u};
-      int rc = conv_encode_map(&plan->maps.av, in, 4, dims, strides, box, p.ck);
-      if (rc != HRP_OK) return rc;
-    }
     const int pipe_avail = avail - c.pipe_offset;
+    auto stage_bytes_of = [&](int kmul) {
+      const int a_bytes = c.vsh ? (p.bh + 2) * p.bw * p.ck * 2 : kStageABytes * kmul;
+      const int a_region = (a_bytes + 1023) / 1024 * 1024;
+      return a_region + (c.wres ? 0 : (c.vsh ? 3 * b_sub : p.n_tile * 128 * kmul));
+    };
     // Staging ring: the residual / addend tiles of tile i + nstag - 1 are fetched (by TMA, into the ring entry the output
     // tile will be built in) while tile i is in the epilogue, so with a residual the ring depth is the prefetch distance
     // and must cover a DRAM round trip (~2 tile periods on short-K layers): 4 entries when they fit, else 2, else 1.
-    const char* e4 = getenv("HRP_CONV_NSTAG");
-    int nstag = (stag_bytes > 0 && p.n_tile <= 128) ? ((has_res && !(e4 != nullptr && e4[0] == '2')) ? 4 : 2) : 1;
-    int st = (pipe_avail - nstag * entry) / c.stage_bytes;
-    while (st < 3 && nstag > 1) {
-      nstag >>= 1;
-      st = (pipe_avail - nstag * entry) / c.stage_bytes;
+    auto pick_nstag = [&](int ent, int sbytes, int min_st, int* st_out) {
+      int nstag = (stag_bytes > 0 && p.n_tile <= 128) ? ((has_res && !(e4 != nullptr && e4[0] == '2')) ? 4 : 2) : 1;
+      int st = (pipe_avail - nstag * ent) / sbytes;
+      while (st < min_st && nstag > 1) {
+        nstag >>= 1;
+        st = (pipe_avail - nstag * ent) / sbytes;
+      }
+      *st_out = st;
+      return nstag;
+    };
+    int kmul = 1, st = 0, nstag = 1;
+    {
+      // (default 16 KiB stages: measured over the whole network -- profiles/r02_exp_producer.txt -- bigger stages win on
+      //  the K = 256 / 512 1x1 layers (layer4 conv3 132 -> 114 us) and lose where they leave two slots or swallow the whole
+      //  K (layer2 conv3 192 -> 281 us); the sum is a wash.  HRP_CONV_KSTAGE=2|4 allows them.)
+      const int kpin = (e6 != nullptr) ? atoi(e6) : 1;
+      // candidates, biggest first; a stage never spans more than the tile's K
+      for (int km : {4, 2, 1}) {
+        if (c.vsh && km > 1) continue;
+        if (km > 1 && km > units) continue;
+        if (kpin > 0 && km != kpin && !(km == 1)) continue;
+        // big stages keep the staging ring they would have had with 16 KiB stages when >= 2 stages still fit beside it;
+        // 16 KiB stages want >= 3
+        int st_k = 0;
+        int ns_ref = pick_nstag(entry, stage_bytes_of(1), 3, &st_k);
+        if (km == 1) {
+          kmul = 1; st = st_k; nstag = ns_ref;
+          break;
+        }
+        const int ns_min = (ns_ref >= 2) ? 2 : ns_ref;   // (never below two entries where the small-stage plan had them)
+        int ns = ns_ref;
+        int st2 = (pipe_avail - ns * entry) / stage_bytes_of(km);
+        while (st2 < 2 && ns > ns_min) {
+          ns >>= 1;
+          st2 = (pipe_avail - ns * entry) / stage_bytes_of(km);
+        }
+        if (st2 >= 2) {
+          kmul = km; st = st2; nstag = ns;
+          break;
+        }
+      }
     }
     if (st < 2 && staged) {
       // the addend slots do not fit beside a 2-stage pipeline: keep pre[0] by TMA, gather the others (generic loads)
@@ -1587,12 +1662,24 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed, con
       memset(c.add_off, 0, sizeof(c.add_off));
       memset(c.up_off, 0, sizeof(c.up_off));
       entry = stag_bytes;
+      kmul = 1;
       nstag = (stag_bytes > 0 && p.n_tile <= 128) ? 2 : 1;
-      st = (pipe_avail - nstag * entry) / c.stage_bytes;
+      st = (pipe_avail - nstag * entry) / stage_bytes_of(1);
       while (st < 3 && nstag > 1) {
         nstag >>= 1;
-        st = (pipe_avail - nstag * entry) / c.stage_bytes;
+        st = (pipe_avail - nstag * entry) / stage_bytes_of(1);
       }
+    }
+    c.sub = (64 / p.ck) * kmul;
+    c.a_bytes = c.vsh ? (p.bh + 2) * p.bw * p.ck * 2 : kStageABytes * kmul;
+    c.a_region = (c.a_bytes + 1023) / 1024 * 1024;
+    c.stage_bytes = stage_bytes_of(kmul);
+    if (c.vsh) {
+      uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.Ws, (uint64_t)p.Hs, (uint64_t)p.B};
+      uint64_t strides[3] = {(uint64_t)p.Cin * 2, (uint64_t)p.Win * p.Cin * 2, (uint64_t)p.Hin * p.Win * p.Cin * 2};
+      uint32_t box[4] = {(uint32_t)p.ck, (uint32_t)p.bw, (uint32_t)(p.bh + 2), 1u};
+      int rc = conv_encode_map(&plan->maps.av, in, 4, dims, strides, box, p.ck);
+      if (rc != HRP_OK) return rc;
     }
     HRP_REQUIRE(st >= 1, "layer does not fit in shared memory");
     c.res_tma = (has_res && (p.os == 1 || staged)) ? 1 : 0;
@@ -1600,6 +1687,9 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed, con
     c.entry_bytes = entry;
     c.stages = std::min(8, st);
     c.nstag = nstag;
+    // two producers need >= 2 stages: with ONE slot a producer revisits it every second phase and a parity wait cannot
+    // tell "two phases ago" from "now" (with >= 2 slots the in-order consumer bounds the distance to one phase)
+    c.nprod = (c.stages >= 2 && !(e7 != nullptr && e7[0] == '1')) ? 2 : 1;
     c.stag_offset = c.pipe_offset + c.stages * c.stage_bytes;
     c.bar_offset = c.stag_offset + nstag * entry;
     c.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles * p.nphase;

@@ -17,6 +17,16 @@ int hrp_probe_desc_shift(int32_t ck, int32_t rows, int32_t shift, int32_t bo_mod
 /* hardware probe: cycles for `warps` (1, 4 or 8) warps of one CTA to issue `reps` tcgen05.ld.32x32b.x32 each (4 KiB per
  * instruction), waiting after every load (wait_each = 1) or only at the end; dev_out2[0] = cycles */
 int hrp_probe_tmem_ld_rate(int32_t warps, int32_t reps, int32_t wait_each, long long* dev_out2);
+/* hardware probe: TMA tiled-load rate per SM for the conv kernels' A-operand boxes {64 ch, bw, bh, bn} (16 KiB, 128 rows of
+ * 128 B at stride C * 2 B) of an NHWC bf16 tensor, `depth` loads in flight per CTA, `share` CTAs reading the same tiles;
+ * rows > 0: 2-D box {64 ch, rows pixels} on the (B*H*W, C) view instead; producers: low byte = 1 or 2 issuing threads (two warps), second byte = wait flavour (0 try_wait spin, 1 test_wait spin, 2 try_wait with a 0 ns suspend hint); dev_out[0] = cycles CTA 0 needed for `iters` loads */
+int hrp_probe_tma_rate(const void* act, int32_t B, int32_t H, int32_t W, int32_t C, int32_t bw, int32_t bh, int32_t bn,
+                       int32_t depth, int32_t iters, int32_t share, int32_t ctas, int32_t rows, int32_t producers,
+                       long long* dev_out);
+/* hardware probe: one thread issues n back-to-back 2-D TMA loads of {64 ch, rows} boxes on one mbarrier;
+ * dev_out = {cycles until the last one has issued, cycles until all bytes have landed} (mean over reps - 1 rounds) */
+int hrp_probe_tma_issue(const void* act, int64_t npix, int32_t C, int32_t rows, int32_t n, int32_t reps, int32_t ctas,
+                        long long* dev_out);
 #ifdef __cplusplus
 }
 #endif

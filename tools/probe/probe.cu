@@ -3,6 +3,7 @@
 // and to decide which layers can be tensor-bound at all.
 #include "hrp_probe.h"
 #include "hrp_common.cuh"
+#include "conv.h"
 
 namespace hrp {
 
@@ -225,6 +226,218 @@ extern "C" int hrp_probe_tmem_ld_rate(int32_t warps, int32_t reps, int32_t wait_
   using namespace hrp;
   HRP_REQUIRE((warps == 1 || warps == 4 || warps == 8) && reps > 0 && dev_out2 != nullptr, "bad args");
   tmem_ld_rate_kernel<<<1, warps * 32, 0>>>(reps, wait_each, dev_out2);
+  HRP_CUDA_CHECK(cudaGetLastError());
+  HRP_CUDA_CHECK(cudaDeviceSynchronize());
+  return HRP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Probe 4: TMA tiled-load rate of ONE SM as the convolution kernels use it.  Tensor = NHWC bf16 activations
+// (B, H, W, C); every load is the 4-D box {64 channels, bw, bh, bn} (128 pixels x 128 bytes = 16 KiB, SWIZZLE_128B), i.e.
+// 128 rows of 128 B whose stride in memory is C * 2 bytes.  One producer thread keeps `depth` loads in flight through a
+// ring of shared-memory buffers (full / empty mbarriers); a consumer thread releases a buffer as soon as it has landed.
+// Tiles are walked like the persistent kernel does: tile t = cta / share + i * (grid / share), and for each tile the
+// C / 64 channel blocks in turn (share > 1: `share` neighbouring CTAs read the same tiles at the same time).
+// dev_out[0] = cycles of CTA 0 for `iters` loads.
+// ------------------------------------------------------------------------------------------------------
+namespace hrp {
+// wait flavours for the ring probe: 0 = mbar_wait (try_wait spin, the kernels' default), 1 = test_wait spin (never
+// suspends), 2 = try_wait with an explicit suspend-time hint of 0 ns
+__device__ __forceinline__ void probe_wait(uint64_t* bar, uint32_t parity, int mode) {
+  if (mode == 0) {
+    mbar_wait(bar, parity);
+    return;
+  }
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  while (!done) {
+    if (mode == 1)
+      asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}\n"
+                   : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    else
+      asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, P1;\n\t}\n"
+                   : "=r"(done) : "r"(addr), "r"(parity), "r"(0u) : "memory");
+  }
+}
+__global__ void __launch_bounds__(96) tma_rate_kernel(const __grid_constant__ CUtensorMap map, int depth, int iters, int kblocks,
+                                                      int tiles_w, int tiles_h, int tiles_total, int bw, int bh, int bn, int share,
+                                                      int rank2, int box_bytes, int producers, int wait_mode, long long* out) {
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = smem_align1024(smem_dyn);
+  __shared__ uint64_t full[16], empty[16];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < depth; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&map);
+  }
+  __syncthreads();
+  const int group = blockIdx.x / share, ngroups = gridDim.x / share;
+  const long long t0 = clock64();
+  const int trace0 = 600;  // first traced load (steady state)
+  if (threadIdx.x == 0 || (producers == 2 && threadIdx.x == 64)) {
+    // (no divisions in the loop: the coordinates advance with wrap-around counters -- an integer division costs the
+    //  issuing thread more than a TMA instruction does)
+    const int me = (threadIdx.x == 0) ? 0 : 1;
+    int s = me;
+    uint32_t par = 0;
+    int kb = 0;
+    int t = group % tiles_total;
+    int tw = t % tiles_w, th = (t / tiles_w) % tiles_h, tn = t / (tiles_w * tiles_h);
+    const int rows = box_bytes / 128;
+    const int step_w = ngroups % tiles_w, step_h = (ngroups / tiles_w) % tiles_h, step_n = ngroups / (tiles_w * tiles_h);
+    const int n_tiles_n = tiles_total / (tiles_w * tiles_h);
+    long long tw_wait = 0, tw_exp = 0, tw_tma = 0;
+    for (int i = me; i < iters; i += producers) {
+      const long long c0 = clock64();
+      probe_wait(&empty[s], par ^ 1, wait_mode);
+      const long long c1 = clock64();
+      mbar_expect_tx(&full[s], (uint32_t)box_bytes);
+      const long long c2 = clock64();
+      if (rank2) {
+        tma_load_2d(smem + (size_t)s * box_bytes, &map, &full[s], kb * 64, t * rows);
+      } else {
+        tma_load_4d(smem + (size_t)s * box_bytes, &map, &full[s], kb * 64, tw * bw, th * bh, tn * bn);
+      }
+      const long long c3 = clock64();
+      if (blockIdx.x == 0 && i >= trace0 && i < trace0 + 96) {
+        out[8 + (i - trace0) * 4 + 0] = c1 - t0;
+        out[8 + (i - trace0) * 4 + 1] = c3 - t0;
+      }
+      tw_wait += c1 - c0;
+      tw_exp += c2 - c1;
+      tw_tma += c3 - c2;
+      for (int r = 0; r < producers; ++r)
+        if (++kb == kblocks) {
+          kb = 0;
+          t += ngroups;
+          if (t >= tiles_total) t -= tiles_total;
+          tw += step_w;
+          if (tw >= tiles_w) { tw -= tiles_w; ++th; }
+          th += step_h;
+          if (th >= tiles_h) { th -= tiles_h; ++tn; }
+          tn += step_n;
+          if (tn >= n_tiles_n) tn -= n_tiles_n;
+        }
+      s += producers;
+      if (s >= depth) {
+        s -= depth;
+        par ^= 1;
+      }
+    }
+    if (blockIdx.x == 0 && me == 0) {  // where the issuing thread spends its time (cycles summed over its loads)
+      out[1] = tw_wait;
+      out[2] = tw_exp;
+      out[3] = tw_tma;
+    }
+  } else if (threadIdx.x == 32) {
+    int s = 0;
+    uint32_t par = 0;
+    for (int i = 0; i < iters; ++i) {
+      probe_wait(&full[s], par, wait_mode);
+      if (blockIdx.x == 0 && i >= trace0 && i < trace0 + 96) out[8 + (i - trace0) * 4 + 2] = clock64() - t0;
+      mbar_arrive(&empty[s]);
+      if (++s == depth) {
+        s = 0;
+        par ^= 1;
+      }
+    }
+    if (blockIdx.x == 0) out[0] = clock64() - t0;
+  }
+}
+}  // namespace hrp
+
+// rows: 0 -> 4-D box {64, bw, bh, bn} (128 pixels); > 0 -> 2-D box {64 channels, rows pixels} on the (B*H*W, C) view
+extern "C" int hrp_probe_tma_rate(const void* act, int32_t B, int32_t H, int32_t W, int32_t C, int32_t bw, int32_t bh,
+                                  int32_t bn, int32_t depth, int32_t iters, int32_t share, int32_t ctas, int32_t rows,
+                                  int32_t producers, long long* dev_out) {
+  using namespace hrp;
+  HRP_REQUIRE(act != nullptr && C % 64 == 0 && bw * bh * bn == 128 && depth >= 1 && depth <= 13 && share >= 1 &&
+                  ctas % share == 0 && W % bw == 0 && H % bh == 0 && B % bn == 0 && rows >= 0 && rows <= 256 &&
+                  ((producers & 0xff) == 1 || ((producers & 0xff) == 2 && depth % 2 == 0)),
+              "bad args");
+  CUtensorMap map;
+  int rc;
+  const int box_bytes = (rows > 0 ? rows : 128) * 128;
+  const long long npix = (long long)B * H * W;
+  if (rows > 0) {
+    uint64_t dims[2] = {(uint64_t)C, (uint64_t)npix};
+    uint64_t strides[1] = {(uint64_t)C * 2};
+    uint32_t box[2] = {64u, (uint32_t)rows};
+    rc = conv_encode_map(&map, act, 2, dims, strides, box, 64);
+  } else {
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+    uint32_t box[4] = {64u, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
+    rc = conv_encode_map(&map, act, 4, dims, strides, box, 64);
+  }
+  if (rc != HRP_OK) return rc;
+  HRP_REQUIRE(depth * box_bytes <= 220 * 1024, "ring does not fit in shared memory");
+  const int smem = depth * box_bytes + 1024;
+  cudaFuncSetAttribute(tma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int tiles_w = W / bw, tiles_h = H / bh;
+  const int tiles_total = rows > 0 ? (int)(npix / rows) : tiles_w * tiles_h * (B / bn);
+  tma_rate_kernel<<<ctas, 96, smem>>>(map, depth, iters, C / 64, tiles_w, tiles_h, tiles_total, bw, bh, bn, share,
+                                      rows > 0 ? 1 : 0, box_bytes, producers & 0xff, (producers >> 8) & 0xff, dev_out);
+  HRP_CUDA_CHECK(cudaGetLastError());
+  HRP_CUDA_CHECK(cudaDeviceSynchronize());
+  return HRP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Probe 5: raw issue cost of cp.async.bulk.tensor for ONE thread: n back-to-back 2-D loads of {64 ch, rows} boxes into n
+// shared-memory slots, all completing on one mbarrier.  dev_out[0] = cycles until the last instruction has issued,
+// dev_out[1] = cycles until all bytes have landed (CTA 0; every CTA does the same on its own tiles).
+// ------------------------------------------------------------------------------------------------------
+namespace hrp {
+__global__ void __launch_bounds__(32) tma_issue_kernel(const __grid_constant__ CUtensorMap map, int n, int rows, int reps,
+                                                       long long* out) {
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = smem_align1024(smem_dyn);
+  __shared__ uint64_t bar;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&map);
+    long long t_issue = 0, t_done = 0;
+    for (int r = 0; r < reps; ++r) {
+      const long long t0 = clock64();
+      mbar_expect_tx(&bar, (uint32_t)(n * rows * 128));
+#pragma unroll 1
+      for (int i = 0; i < n; ++i)
+        tma_load_2d(smem + (size_t)i * rows * 128, &map, &bar, 0, ((int)blockIdx.x * n + i + r * 37) * rows);
+      const long long t1 = clock64();
+      mbar_wait(&bar, (uint32_t)(r & 1));
+      const long long t2 = clock64();
+      if (r > 0) {
+        t_issue += t1 - t0;
+        t_done += t2 - t0;
+      }
+    }
+    if (blockIdx.x == 0) {
+      out[0] = t_issue / (reps - 1);
+      out[1] = t_done / (reps - 1);
+    }
+  }
+}
+}  // namespace hrp
+
+extern "C" int hrp_probe_tma_issue(const void* act, int64_t npix, int32_t C, int32_t rows, int32_t n, int32_t reps,
+                                   int32_t ctas, long long* dev_out) {
+  using namespace hrp;
+  HRP_REQUIRE(act != nullptr && C % 64 == 0 && rows >= 8 && rows <= 256 && n >= 1 && n * rows * 128 <= 220 * 1024 && reps >= 2,
+              "bad args");
+  CUtensorMap map;
+  uint64_t dims[2] = {(uint64_t)C, (uint64_t)npix};
+  uint64_t strides[1] = {(uint64_t)C * 2};
+  uint32_t box[2] = {64u, (uint32_t)rows};
+  int rc = conv_encode_map(&map, act, 2, dims, strides, box, 64);
+  if (rc != HRP_OK) return rc;
+  const int smem = n * rows * 128 + 1024;
+  cudaFuncSetAttribute(tma_issue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  tma_issue_kernel<<<ctas, 32, smem>>>(map, n, rows, reps, dev_out);
   HRP_CUDA_CHECK(cudaGetLastError());
   HRP_CUDA_CHECK(cudaDeviceSynchronize());
   return HRP_OK;
