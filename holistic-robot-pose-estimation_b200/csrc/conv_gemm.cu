@@ -429,7 +429,12 @@ constexpr int kEpiThreadsP = 256;
 // 512 images, and sixteen epilogue warps instead of eight changed nothing (profiles/r02_exp_final_fold.txt) -- the A
 // stream (64 KB per 128 x 128 tile, re-fetched by the four N-tile CTAs) arrives at ~19 B/cycle/SM.
 constexpr int kEpiWarpsHead = 8;
-constexpr int kThreadsPHead = 64 + 32 * kEpiWarpsHead + 32;  // (+ the second producer warp: the last one)
+// soft-argmax fold: warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue, warp 10 second producer, warp 11 second MMA
+// issuer (no store warp).  Two issuers = two independent pipelines (PersistCfg::dual): even tiles run through producer 0
+// -> first half of the stage ring -> issuer A, odd tiles through producer 1 -> second half -> issuer B; the TMEM
+// accumulators alternate by tile anyway.  Each serial actor pays its ~600-900 cycles per stage handshake on every
+// second tile only.
+constexpr int kThreadsPHead = 64 + 32 * kEpiWarpsHead + 64;
 template <int EPI> struct PersistShape {
   static constexpr int epi_warps = (EPI == 4) ? kEpiWarpsHead : kEpiThreadsP / 32;
   static constexpr int threads = (EPI == 4) ? kThreadsPHead : kThreadsP;
@@ -456,7 +461,10 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
   constexpr int KSTEPS = CK / 16;
   constexpr uint32_t LAYOUT = (CK == 64) ? 2u : (CK == 32) ? 4u : 6u;
   constexpr uint32_t SBO = 8 * CK * 2;
-  constexpr int WARP_P2 = PersistShape<EPI>::threads / 32 - 1;  // second producer warp
+  constexpr int WARP_P2 = (EPI == EPI_HEAD) ? 2 + kEpiWarpsHead : 11;      // second producer warp
+  constexpr int WARP_M2 = (EPI == EPI_HEAD) ? 3 + kEpiWarpsHead : -1;      // second MMA issuer warp (fold kernel only)
+  const bool dual = (EPI == EPI_HEAD) && cfg.dual != 0;                    // two independent (producer, ring, issuer) pipelines
+  const int ring = dual ? cfg.stages / 2 : cfg.stages;                     // slots per pipeline
   const int SUB = cfg.sub;                     // k-blocks (CK channels of one tap) per stage: (64 / CK) x 1 or 2
 
   extern __shared__ uint8_t smem_dyn[];
@@ -557,8 +565,9 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
       // producer 1 fetches the addend tiles -- it is the one that has to wait for a staging entry to drain, and the
       // operand stream no longer stops behind that wait.
       const bool res_role = has_res && cfg.nprod == 2;
-      const bool two = cfg.nprod == 2 && !res_role;
+      const bool two = cfg.nprod == 2 && !res_role && !dual;
       const int res_owner = res_role ? 1 : 0;
+      const int sbase = (dual && me == 1) ? ring : 0;   // dual: this producer's half of the ring
       uint32_t g = 0;
       if (wres && me == 0) {
         // the packed weights of this CTA's N tile stay in shared memory for the CTA's lifetime.  With several N tiles the
@@ -614,6 +623,7 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
                               c_base + j * cko, w0 >> cfg.up_sh[a], h0 >> cfg.up_sh[a], n0);
           }
         };
+        if (dual && (li & 1) != me) continue;   // the other pipeline's tile
         if (has_res && nstag >= 2 && me == res_owner) load_residual();
         if (res_role && me == 1) {
           if (nstag == 1) load_residual();
@@ -622,20 +632,21 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
         if (me == 0) tl_stamp(p.timeline, li, 0);
         for (int it = 0; it < n_iters; ++it, ++g) {
           const bool mine = !two || (int)(g & 1u) == me;
+          const int sl = sbase + s;
           if (mine) {
-            mbar_wait(&bars->empty[s], par ^ 1);
+            mbar_wait(&bars->empty[sl], par ^ 1);
             if (it == 0 && me == 0) tl_stamp(p.timeline, li, 1);
           }
-          uint8_t* sa = pipe_base + (size_t)s * stage_bytes;
+          uint8_t* sa = pipe_base + (size_t)sl * stage_bytes;
           uint8_t* sb = sa + a_region;
           if (vsh) {
             // one (channel chunk, dw) per iteration: an A buffer of bh+2 image rows serves the three dh taps
             if (mine) {
-              mbar_expect_tx(&bars->full[s], (uint32_t)(cfg.a_bytes + (wres ? 0 : 3 * b_sub_bytes)));
-              tma_load_4d(sa, &maps.av, &bars->full[s], cc * CK, w0 + dwi - 1, h0 - 1, n0);
+              mbar_expect_tx(&bars->full[sl], (uint32_t)(cfg.a_bytes + (wres ? 0 : 3 * b_sub_bytes)));
+              tma_load_4d(sa, &maps.av, &bars->full[sl], cc * CK, w0 + dwi - 1, h0 - 1, n0);
               if (!wres)
                 for (int dhi = 0; dhi < 3; ++dhi)
-                  tma_load_2d(sb + dhi * b_sub_bytes, &maps.b, &bars->full[s], ((dhi * 3 + dwi) * p.cpt + cc) * CK, brow);
+                  tma_load_2d(sb + dhi * b_sub_bytes, &maps.b, &bars->full[sl], ((dhi * 3 + dwi) * p.cpt + cc) * CK, brow);
             }
             if (++dwi == 3) {
               dwi = 0;
@@ -643,12 +654,12 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
             }
           } else {
             const int nsub = min(SUB, nkb - it * SUB);
-            if (mine) mbar_expect_tx(&bars->full[s], (uint32_t)(nsub * (A_SUB_BYTES + (wres ? 0 : b_sub_bytes))));
+            if (mine) mbar_expect_tx(&bars->full[sl], (uint32_t)(nsub * (A_SUB_BYTES + (wres ? 0 : b_sub_bytes))));
             for (int j = 0; j < nsub; ++j) {
               if (mine) {
-                tma_load_4d(sa + j * A_SUB_BYTES, &maps.a[p.tap_map[tap]], &bars->full[s], cc * CK,
+                tma_load_4d(sa + j * A_SUB_BYTES, &maps.a[p.tap_map[tap]], &bars->full[sl], cc * CK,
                             w0 + p.tap_dw[tap] + tpw, h0 + p.tap_dh[tap] + tph, n0);
-                if (!wres) tma_load_2d(sb + j * b_sub_bytes, &maps.b, &bars->full[s], (it * SUB + j) * CK, brow);
+                if (!wres) tma_load_2d(sb + j * b_sub_bytes, &maps.b, &bars->full[sl], (it * SUB + j) * CK, brow);
               }
               if (++cc == p.cpt) {
                 cc = 0;
@@ -656,7 +667,7 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
               }
             }
           }
-          if (++s == stages) {
+          if (++s == ring) {
             s = 0;
             par ^= 1;
           }
@@ -665,9 +676,11 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
         if (has_res && nstag == 1 && me == res_owner) load_residual();
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer: warp-uniform loop, one elected lane issues the tcgen05 instructions ==========
-    {
+  } else if (warp == 1 || warp == WARP_M2) {
+    // ===================== MMA issuer(s): warp-uniform loop, one elected lane issues the tcgen05 instructions ==========
+    const int mw = (warp == 1) ? 0 : 1;
+    if (mw == 0 || dual) {
+      const int sbase = (dual && mw == 1) ? ring : 0;
       const uint32_t idesc = make_idesc_bf16(kTileM, (uint32_t)n_tile);
       // descriptor = constant high word | (constant low word + smem byte address >> 4): one 32-bit add per operand
       // on the uniform datapath (shared-memory addresses stay below 2^18, so the 14-bit field never carries)
@@ -684,19 +697,21 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
       uint32_t par = 0;
       int li = 0;
       for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x, ++li) {
+        if (dual && (li & 1) != mw) continue;   // the other pipeline's tile
         const int abuf = li & 1;
         mbar_wait(&bars->tmem_empty[abuf], (uint32_t)(((li >> 1) & 1) ^ 1));  // epilogue drained this accumulator
         tc_fence_after();
-        if (lane == 0) tl_stamp(p.timeline, li, 3);
+        if (lane == 0 && mw == 0) tl_stamp(p.timeline, li, 3);
         // K steps round-robin over `ksplit` accumulators (summed by the epilogue)
         const uint32_t tacc0 = tmem_base + (uint32_t)(abuf * ksplit * n_tile);
         int cc = 0, dwi = 0;
         uint32_t mi = 0;
         for (int it = 0; it < n_iters; ++it) {
-          mbar_wait(&bars->full[s], par);
+          const int sl = sbase + s;
+          mbar_wait(&bars->full[sl], par);
           tc_fence_after();
-          if (it == 0 && lane == 0) tl_stamp(p.timeline, li, 4);
-          const uint32_t a_it = pipe_units + (uint32_t)s * stage_units;
+          if (it == 0 && lane == 0 && mw == 0) tl_stamp(p.timeline, li, 4);
+          const uint32_t a_it = pipe_units + (uint32_t)sl * stage_units;
           const uint32_t b_it = a_it + aregion_units;
           if (vsh) {
             const uint32_t bw_it = wres_units + (uint32_t)(dwi * p.cpt + cc) * bsub_units;
@@ -713,7 +728,7 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
                   ++mi;
                 }
               }
-              umma_commit(&bars->empty[s]);
+              umma_commit(&bars->empty[sl]);
               if (it == n_iters - 1) umma_commit(&bars->tmem_full[abuf]);
             }
             mi = (uint32_t)((it + 1) * 3 * KSTEPS);
@@ -736,14 +751,14 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
                   ++mi;
                 }
               }
-              umma_commit(&bars->empty[s]);
+              umma_commit(&bars->empty[sl]);
               if (it == n_iters - 1) umma_commit(&bars->tmem_full[abuf]);
             }
             mi = (uint32_t)(min((it + 1) * SUB, nkb) * KSTEPS);
           }
           __syncwarp();
-          if (it == n_iters - 1 && lane == 0) tl_stamp(p.timeline, li, 5);
-          if (++s == stages) {
+          if (it == n_iters - 1 && lane == 0 && mw == 0) tl_stamp(p.timeline, li, 5);
+          if (++s == ring) {
             s = 0;
             par ^= 1;
           }
@@ -1690,6 +1705,12 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed, con
     // two producers need >= 2 stages: with ONE slot a producer revisits it every second phase and a parity wait cannot
     // tell "two phases ago" from "now" (with >= 2 slots the in-order consumer bounds the distance to one phase)
     c.nprod = (c.stages >= 2 && !(e7 != nullptr && e7[0] == '1')) ? 2 : 1;
+    // soft-argmax fold: two independent pipelines (see kThreadsPHead) when each gets at least two slots
+    {
+      const char* e8 = getenv("HRP_CONV_DUAL");
+      c.dual = (plan->epi == EPI_HEAD && c.nprod == 2 && c.stages >= 4 && !(e8 != nullptr && e8[0] == '0')) ? 1 : 0;
+      if (c.dual) c.stages &= ~1;
+    }
     c.stag_offset = c.pipe_offset + c.stages * c.stage_bytes;
     c.bar_offset = c.stag_offset + nstag * entry;
     c.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles * p.nphase;
