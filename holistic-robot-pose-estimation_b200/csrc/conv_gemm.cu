@@ -45,6 +45,11 @@ __device__ __forceinline__ void tl_stamp(long long* tl, int tile_local, int ev) 
 constexpr int EPI_PLAIN = 0;  // y = [relu](acc*scale + bias)
 constexpr int EPI_PRE = 1;    // + up to three same-resolution addends before the ReLU (residual / fuse partials)
 constexpr int EPI_FULL = 2;   // + nearest-upsampled addends, post-ReLU addend, pooled output
+// (persistent kernel only) the same two flavours with EVERY addend TMA-staged in the ring entry: separate instantiations,
+// because the generic kernel carrying both the staged and the gathering code paths is ~90 KB of SASS and its epilogue
+// warps spent 40 % of their time in instruction-fetch stalls (ncu stall_no_inst, profiles/r02_ncu_stalls_s2fuse_b512.txt)
+constexpr int EPI_PRE_ST = 5;
+constexpr int EPI_FULL_ST = 6;
 constexpr int EPI_RES = 3;    // + exactly one residual, TMA-prefetched into the staging tile (no per-row predicates or
                               //   global loads: the generic flavours spend ~60 issue slots per 8 channels on them)
 constexpr int EPI_HEAD = 4;   // persistent kernel only: logits -> per-warp soft-argmax partials, nothing is stored
@@ -490,9 +495,11 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
   const int n_iters = vsh ? 3 * p.cpt : (nkb + SUB - 1) / SUB;
   const int cko = p.cko;
   const int nblk_full = n_tile / cko;
-  constexpr bool GENERIC = (EPI == EPI_PRE || EPI == EPI_FULL);
-  const bool has_res = (EPI == EPI_RES) || (GENERIC && cfg.res_tma != 0);
-  const bool staged = GENERIC && cfg.staged != 0;   // every addend is a TMA box in the ring entry (PersistCfg)
+  constexpr bool staged = (EPI == EPI_PRE_ST || EPI == EPI_FULL_ST);  // every addend is a TMA box in the ring entry (PersistCfg)
+  constexpr bool FULLISH = (EPI == EPI_FULL || EPI == EPI_FULL_ST);
+  constexpr bool GENERIC = (EPI == EPI_PRE || EPI == EPI_FULL || staged);
+  constexpr bool ROLLED = staged;   // epilogue walks 8 columns at a time in a rolled loop (see the epilogue)
+  const bool has_res = (EPI == EPI_RES) || staged || (GENERIC && cfg.res_tma != 0);
   const int entry_bytes = cfg.entry_bytes;          // ring entry = output / pre[0] slot (stag_bytes) + addend slots
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
 
@@ -597,27 +604,30 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
           const int blk = kTileM * cko * 2;
           uint32_t bytes = (uint32_t)(nb * blk);
           if (staged) {
-#pragma unroll
+#pragma unroll 1
             for (int i = 0; i < 3; ++i)
               if (cfg.add_off[i] != 0) bytes += (uint32_t)(nb * blk);
-#pragma unroll
+#pragma unroll 1
             for (int a = 0; a < 3; ++a)
               if (cfg.up_off[a] != 0) bytes += (uint32_t)(nb * cfg.up_bw[a] * cfg.up_bh[a] * p.bn * cko * 2);
           }
           mbar_expect_tx(&bars->res_full[sbuf], bytes);
           const CUtensorMap* mr = (phase == 0) ? &maps.r : &maps.rp[phase - 1];
+#pragma unroll 1
           for (int j = 0; j < nb; ++j)
             tma_load_4d(entry + (size_t)j * blk, mr, &bars->res_full[sbuf], c_base + j * cko, w0, h0, n0);
           if (staged) {
-#pragma unroll
+#pragma unroll 1
             for (int i = 0; i < 3; ++i)
               if (cfg.add_off[i] != 0)
+#pragma unroll 1
                 for (int j = 0; j < nb; ++j)
                   tma_load_4d(entry + cfg.add_off[i] + (size_t)j * blk, &maps.add[i], &bars->res_full[sbuf], c_base + j * cko,
                               w0, h0, n0);
-#pragma unroll
+#pragma unroll 1
             for (int a = 0; a < 3; ++a)
               if (cfg.up_off[a] != 0)
+#pragma unroll 1
                 for (int j = 0; j < nb; ++j)
                   tma_load_4d(entry + cfg.up_off[a] + (size_t)j * cfg.up_blk[a], &maps.upm[a], &bars->res_full[sbuf],
                               c_base + j * cko, w0 >> cfg.up_sh[a], h0 >> cfg.up_sh[a], n0);
@@ -799,7 +809,7 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
                               (uint32_t)((2 ^ (sw & 3)) << 4), (uint32_t)((3 ^ (sw & 3)) << 4)};
     const uint32_t blk_bytes = (uint32_t)(kTileM * cko * 2);
     const bool do_store = (EPI == EPI_RES || EPI == EPI_PLAIN) || (p.out != nullptr);
-    const bool pool = (EPI == EPI_FULL) && (p.pool_out != nullptr);
+    const bool pool = (EPI == EPI_FULL) && (p.pool_out != nullptr);   // (never together with staged addends)
     int li = 0;
     for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x, ++li) {
       HRP_DECODE_TILE(tile)
@@ -827,7 +837,7 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
       const bf16* pre2 = (GENERIC && p.pre[2] != nullptr) ? p.pre[2] + opix * p.Cout + c_base : nullptr;
       const bf16* upp[3] = {nullptr, nullptr, nullptr};
       const bf16* postp = nullptr;
-      if (EPI == EPI_FULL) {
+      if (EPI == EPI_FULL) {   // (gathering flavour only)
 #pragma unroll
         for (int a = 0; a < 3; ++a)
           if (p.up[a] != nullptr) {
@@ -837,8 +847,8 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
           }
         if (p.post != nullptr) postp = p.post + opix * p.Cout + c_base;
       }
-      const bool relu_in_cvt = p.relu && !(EPI == EPI_FULL && (p.post != nullptr || pool));
-      const bool relu_explicit = (EPI == EPI_FULL) && p.relu && !relu_in_cvt;
+      const bool relu_in_cvt = p.relu && !(FULLISH && (p.post != nullptr || pool));
+      const bool relu_explicit = FULLISH && p.relu && !relu_in_cvt;
       uint8_t* const stage_row = stag_base + (size_t)sbuf * entry_bytes + (size_t)row * (cko * 2);
       // staged nearest-upsampled addends: this thread's pixel of the low-resolution box and its swizzle phase
       const uint8_t* up_row[3] = {nullptr, nullptr, nullptr};
@@ -872,9 +882,13 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
 
 #pragma unroll 1
       for (int c0 = half * 32; c0 < c_lim; c0 += 8 * PersistShape<EPI>::epi_warps) {
-        uint32_t acc[32];
-        tmem_ld32(taddr + (uint32_t)c0, acc);
-        tmem_ld_wait();
+        uint32_t acc[ROLLED ? 8 : 32];
+        if (ROLLED) {
+          tmem_ld8(taddr + (uint32_t)c0, reinterpret_cast<uint32_t(&)[8]>(acc[0]));  // (rolled 8-column loop below)
+        } else {
+          tmem_ld32(taddr + (uint32_t)c0, reinterpret_cast<uint32_t(&)[32]>(acc[0]));
+          tmem_ld_wait();
+        }
         if (EPI == EPI_HEAD) {
           if (p.dbg & 4) continue;  // (ablation: accumulator read only)
           // Soft-argmax fold.  This thread owns pixel (h, w) of image n0 (tile = two image rows: bw 64, bh 2, bn 1) and the
@@ -945,32 +959,57 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
           }
           continue;
         }
-        for (int ks = 1; ks < ksplit; ++ks) {  // partial sums of the K-split accumulators
-          uint32_t part[32];
-          tmem_ld32(taddr + (uint32_t)(ks * n_tile + c0), part);
-          tmem_ld_wait();
+        if (!ROLLED) {
+          for (int ks = 1; ks < ksplit; ++ks) {  // partial sums of the K-split accumulators
+            uint32_t part[32];
+            tmem_ld32(taddr + (uint32_t)(ks * n_tile + c0), part);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __uint_as_float(part[i]));
+            for (int i = 0; i < (ROLLED ? 8 : 32); ++i)
+              acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __uint_as_float(part[i]));
+          }
         }
         uint8_t* const chunk_base = stage_row + (size_t)(c0 >> cko_shift) * blk_bytes +
                                     (((uint32_t)((c0 & (cko - 1)) >> 3) ^ (uint32_t)(sw & 4)) << 4);
-#pragma unroll
+        // Eight columns at a time.  The plain / residual / gathering flavours unroll the four groups of a 32-column
+        // accumulator load (the gathers want all their global loads in flight at once); the staged flavours (up to six
+        // shared-memory addends per group) run them as a ROLLED loop over 8-column TMEM loads, the next one in flight while
+        // the current group is processed: unrolled, their epilogue alone was ~50 KB of SASS streaming through the
+        // instruction caches (ncu: 40 % of the warp stalls were instruction fetches; 32 -> 64 fuse conv 126 -> 80 us).
+        uint32_t nxt[8];
+#pragma unroll(ROLLED ? 1 : 4)
         for (int g = 0; g < 4; ++g) {
           const int cg = c0 + g * 8;
+          const int ab = ROLLED ? 0 : g * 8;   // this group's accumulator registers
+          if (ROLLED) {
+            tmem_ld_wait();   // group g has landed (in acc for g == 0, in nxt otherwise): only now may it be read
+            if (g > 0) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) acc[i] = nxt[i];
+            }
+            if (g < 3) tmem_ld8(taddr + (uint32_t)(cg + 8), nxt);
+            for (int ks = 1; ks < ksplit; ++ks) {  // partial sums of the K-split accumulators (probing aid)
+              uint32_t part[8];
+              tmem_ld8(taddr + (uint32_t)(ks * n_tile + cg), part);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 8; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __uint_as_float(part[i]));
+            }
+          }
           float v[8];
           const float4 s0 = *reinterpret_cast<const float4*>(sc + cg);
           const float4 s1 = *reinterpret_cast<const float4*>(sc + cg + 4);
           const float4 b0 = *reinterpret_cast<const float4*>(sh_ + cg);
           const float4 b1 = *reinterpret_cast<const float4*>(sh_ + cg + 4);
-          v[0] = fmaf(__uint_as_float(acc[g * 8 + 0]), s0.x, b0.x);
-          v[1] = fmaf(__uint_as_float(acc[g * 8 + 1]), s0.y, b0.y);
-          v[2] = fmaf(__uint_as_float(acc[g * 8 + 2]), s0.z, b0.z);
-          v[3] = fmaf(__uint_as_float(acc[g * 8 + 3]), s0.w, b0.w);
-          v[4] = fmaf(__uint_as_float(acc[g * 8 + 4]), s1.x, b1.x);
-          v[5] = fmaf(__uint_as_float(acc[g * 8 + 5]), s1.y, b1.y);
-          v[6] = fmaf(__uint_as_float(acc[g * 8 + 6]), s1.z, b1.z);
-          v[7] = fmaf(__uint_as_float(acc[g * 8 + 7]), s1.w, b1.w);
-          uint4* const sptr = reinterpret_cast<uint4*>(chunk_base + goff[g]);
+          v[0] = fmaf(__uint_as_float(acc[ab + 0]), s0.x, b0.x);
+          v[1] = fmaf(__uint_as_float(acc[ab + 1]), s0.y, b0.y);
+          v[2] = fmaf(__uint_as_float(acc[ab + 2]), s0.z, b0.z);
+          v[3] = fmaf(__uint_as_float(acc[ab + 3]), s0.w, b0.w);
+          v[4] = fmaf(__uint_as_float(acc[ab + 4]), s1.x, b1.x);
+          v[5] = fmaf(__uint_as_float(acc[ab + 5]), s1.y, b1.y);
+          v[6] = fmaf(__uint_as_float(acc[ab + 6]), s1.z, b1.z);
+          v[7] = fmaf(__uint_as_float(acc[ab + 7]), s1.w, b1.w);
+          uint4* const sptr = reinterpret_cast<uint4*>(chunk_base + (ROLLED ? (((uint32_t)g ^ (uint32_t)(sw & 3)) << 4) : goff[g]));
           if (EPI != EPI_PLAIN) {
             if (has_res) add_bf16x8(v, *sptr);  // residual prefetched by TMA (zero-filled outside the tensor)
             if (staged) {
@@ -978,7 +1017,7 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
               const uint8_t* const sp8 = reinterpret_cast<const uint8_t*>(sptr);
               if (cfg.add_off[0] != 0) add_bf16x8(v, *reinterpret_cast<const uint4*>(sp8 + cfg.add_off[0]));
               if (cfg.add_off[1] != 0) add_bf16x8(v, *reinterpret_cast<const uint4*>(sp8 + cfg.add_off[1]));
-              if (EPI == EPI_FULL) {
+              if (FULLISH) {
                 const uint32_t blk_i = (uint32_t)(c0 >> cko_shift);
                 const uint32_t chunk = (uint32_t)((c0 & (cko - 1)) >> 3) + (uint32_t)g;
 #pragma unroll
@@ -1002,7 +1041,7 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
           }
-          if (EPI == EPI_FULL && p.post != nullptr) {
+          if (FULLISH && p.post != nullptr) {
             if (staged) add_bf16x8(v, *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(sptr) + cfg.add_off[2]));
             else if (valid) add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(postp + cg)));
           }
@@ -1410,6 +1449,9 @@ static void set_smem_attr_once() {
     HRP_SET_ATTR_P(32, EPI_PLAIN); HRP_SET_ATTR_P(32, EPI_PRE); HRP_SET_ATTR_P(32, EPI_FULL); HRP_SET_ATTR_P(32, EPI_RES);
     HRP_SET_ATTR_P(64, EPI_PLAIN); HRP_SET_ATTR_P(64, EPI_PRE); HRP_SET_ATTR_P(64, EPI_FULL); HRP_SET_ATTR_P(64, EPI_RES);
     HRP_SET_ATTR_P(64, EPI_HEAD);
+    HRP_SET_ATTR_P(16, EPI_PRE_ST); HRP_SET_ATTR_P(16, EPI_FULL_ST);
+    HRP_SET_ATTR_P(32, EPI_PRE_ST); HRP_SET_ATTR_P(32, EPI_FULL_ST);
+    HRP_SET_ATTR_P(64, EPI_PRE_ST); HRP_SET_ATTR_P(64, EPI_FULL_ST);
 #undef HRP_SET_ATTR_P
   });
 }
@@ -1770,7 +1812,9 @@ int conv_plan_launch(const ConvPlan& plan, cudaStream_t stream) {
   do {                                                        \
     if (plan.epi == EPI_PLAIN) HRP_LAUNCH_P(CKV, EPI_PLAIN);   \
     else if (plan.epi == EPI_RES) HRP_LAUNCH_P(CKV, EPI_RES);  \
+    else if (plan.epi == EPI_PRE && plan.pcfg.staged) HRP_LAUNCH_P(CKV, EPI_PRE_ST);  \
     else if (plan.epi == EPI_PRE) HRP_LAUNCH_P(CKV, EPI_PRE);  \
+    else if (plan.pcfg.staged) HRP_LAUNCH_P(CKV, EPI_FULL_ST); \
     else HRP_LAUNCH_P(CKV, EPI_FULL);                         \
   } while (0)
     if (p.ck == 64) HRP_LAUNCH_P_CK(64);
