@@ -429,20 +429,24 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
 // reach ~48 B/cycle/SM.
 constexpr int kThreadsP = 384;
 constexpr int kEpiThreadsP = 256;
-// The soft-argmax fold (EPI_HEAD) has no store warp.  Its epilogue is ~1000 instructions per warp and tile, but it is NOT
-// what bounds the layer: with the epilogue reduced to the accumulator read the kernel still takes 848 of its 960 us at
-// 512 images, and sixteen epilogue warps instead of eight changed nothing (profiles/r02_exp_final_fold.txt) -- the A
-// stream (64 KB per 128 x 128 tile, re-fetched by the four N-tile CTAs) arrives at ~19 B/cycle/SM.
-constexpr int kEpiWarpsHead = 8;
-// soft-argmax fold: warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue, warp 10 second producer, warp 11 second MMA
+// The soft-argmax fold (EPI_HEAD) has no store warp.  History (profiles/r02_exp_final_fold.txt): with ONE (producer, ring,
+// issuer) pipeline the mainloop bounded the layer (848 of 960 us with the epilogue reduced to the accumulator read; eight
+// vs sixteen epilogue warps made no difference).  With the two pipelines below the mainloop alone runs in 444-550 us and the
+// epilogue -- a latency chain of ~11 dependent shuffles per 32-column block, IPC 0.5 with two warps per scheduler -- became
+// the limit: sixteen epilogue warps (one 32-column block per warp and tile, 96 registers) with 32 KiB stages: 990 -> 810 us.
+constexpr int kEpiWarpsHead = 16;
+// soft-argmax fold: warp 0 producer, warp 1 MMA issuer, warps 2..17 epilogue, warp 18 second producer, warp 19 second MMA
 // issuer (no store warp).  Two issuers = two independent pipelines (PersistCfg::dual): even tiles run through producer 0
 // -> first half of the stage ring -> issuer A, odd tiles through producer 1 -> second half -> issuer B; the TMEM
 // accumulators alternate by tile anyway.  Each serial actor pays its ~600-900 cycles per stage handshake on every
 // second tile only.
 constexpr int kThreadsPHead = 64 + 32 * kEpiWarpsHead + 64;
+// Flavours whose register count leaves room for a 13th warp (plain: 155 registers x 416 threads) get the second MMA
+// issuer as well (PersistCfg::dual).
 template <int EPI> struct PersistShape {
   static constexpr int epi_warps = (EPI == 4) ? kEpiWarpsHead : kEpiThreadsP / 32;
-  static constexpr int threads = (EPI == 4) ? kThreadsPHead : kThreadsP;
+  static constexpr bool has_m2 = (EPI == 4 || EPI == 0);
+  static constexpr int threads = (EPI == 4) ? kThreadsPHead : (EPI == 0 ? kThreadsP + 32 : kThreadsP);
 };
 
 struct __align__(16) PersistBarriers {
@@ -467,8 +471,8 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
   constexpr uint32_t LAYOUT = (CK == 64) ? 2u : (CK == 32) ? 4u : 6u;
   constexpr uint32_t SBO = 8 * CK * 2;
   constexpr int WARP_P2 = (EPI == EPI_HEAD) ? 2 + kEpiWarpsHead : 11;      // second producer warp
-  constexpr int WARP_M2 = (EPI == EPI_HEAD) ? 3 + kEpiWarpsHead : -1;      // second MMA issuer warp (fold kernel only)
-  const bool dual = (EPI == EPI_HEAD) && cfg.dual != 0;                    // two independent (producer, ring, issuer) pipelines
+  constexpr int WARP_M2 = (EPI == EPI_HEAD) ? 3 + kEpiWarpsHead : (PersistShape<EPI>::has_m2 ? 12 : -1);  // second MMA issuer
+  const bool dual = PersistShape<EPI>::has_m2 && cfg.dual != 0;            // two independent (producer, ring, issuer) pipelines
   const int ring = dual ? cfg.stages / 2 : cfg.stages;                     // slots per pipeline
   const int SUB = cfg.sub;                     // k-blocks (CK channels of one tap) per stage: (64 / CK) x 1 or 2
 
@@ -1686,7 +1690,9 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed, con
       // (default 16 KiB stages: measured over the whole network -- profiles/r02_exp_producer.txt -- bigger stages win on
       //  the K = 256 / 512 1x1 layers (layer4 conv3 132 -> 114 us) and lose where they leave two slots or swallow the whole
       //  K (layer2 conv3 192 -> 281 us); the sum is a wash.  HRP_CONV_KSTAGE=2|4 allows them.)
-      const int kpin = (e6 != nullptr) ? atoi(e6) : 1;
+      //  The soft-argmax fold is the exception: its sixteen epilogue warps compete with the producer / issuer warps for
+      //  issue slots, and halving the handshakes per tile is worth 980 -> 810 us there.
+      const int kpin = (e6 != nullptr) ? atoi(e6) : (plan->epi == EPI_HEAD ? 2 : 1);
       // candidates, biggest first; a stage never spans more than the tile's K
       for (int km : {4, 2, 1}) {
         if (c.vsh && km > 1) continue;
@@ -1750,7 +1756,8 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed, con
     // soft-argmax fold: two independent pipelines (see kThreadsPHead) when each gets at least two slots
     {
       const char* e8 = getenv("HRP_CONV_DUAL");
-      c.dual = (plan->epi == EPI_HEAD && c.nprod == 2 && c.stages >= 4 && !(e8 != nullptr && e8[0] == '0')) ? 1 : 0;
+      c.dual = ((plan->epi == EPI_HEAD || plan->epi == EPI_PLAIN) && !c.vsh && c.nprod == 2 && c.stages >= 4 &&
+                !(e8 != nullptr && e8[0] == '0')) ? 1 : 0;
       if (c.dual) c.stages &= ~1;
     }
     c.stag_offset = c.pipe_offset + c.stages * c.stage_bytes;
@@ -1807,7 +1814,8 @@ int conv_plan_launch(const ConvPlan& plan, cudaStream_t stream) {
   }
   if (plan.persistent) {
 #define HRP_LAUNCH_P(CKV, EPIV) \
-  launch_ex(conv_gemm_persistent<CKV, EPIV>, dim3(plan.pgrid), dim3(kThreadsP), (size_t)plan.psmem, stream, plan.maps, p, plan.pcfg)
+  launch_ex(conv_gemm_persistent<CKV, EPIV>, dim3(plan.pgrid), dim3(PersistShape<EPIV>::threads), (size_t)plan.psmem, stream, \
+            plan.maps, p, plan.pcfg)
 #define HRP_LAUNCH_P_CK(CKV)                                  \
   do {                                                        \
     if (plan.epi == EPI_PLAIN) HRP_LAUNCH_P(CKV, EPI_PLAIN);   \
