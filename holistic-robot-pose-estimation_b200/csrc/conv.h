@@ -92,7 +92,8 @@ struct PersistCfg {
   int ksplit;        // accumulators per tile: K steps round-robin over them to hide the dependent-MMA latency
   int sub;           // k-blocks (ck channels of one tap) per pipeline stage
   int nprod;         // TMA producer threads (1 or 2, in two warps): stage g is issued by producer g % nprod
-  int dual;          // fold kernel: two independent (producer, half ring, MMA issuer) pipelines, tiles alternate between them
+  int dual;          // two independent (producer, half ring, MMA issuer) pipelines, tiles alternate between them
+  int res_store;     // the TMA-store warp fetches the residual / addend tiles (else a producer does)
   // Staged addends: the generic epilogue flavours (PRE / FULL) gather their addends with 16-byte loads at pixel stride --
   // ~60 issue slots and 32 L1 sectors per 8 channels and addend.  With `staged` every addend tile is fetched by TMA into
   // the staging-ring entry of its output tile (same swizzled box layout as the output / residual slot, so the epilogue

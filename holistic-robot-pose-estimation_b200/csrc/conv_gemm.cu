@@ -445,8 +445,8 @@ constexpr int kThreadsPHead = 64 + 32 * kEpiWarpsHead + 64;
 // issuer as well (PersistCfg::dual).
 template <int EPI> struct PersistShape {
   static constexpr int epi_warps = (EPI == 4) ? kEpiWarpsHead : kEpiThreadsP / 32;
-  static constexpr bool has_m2 = (EPI == 4 || EPI == 0);
-  static constexpr int threads = (EPI == 4) ? kThreadsPHead : (EPI == 0 ? kThreadsP + 32 : kThreadsP);
+  static constexpr bool has_m2 = (EPI == 4 || EPI == 0 || EPI == 3 || EPI == 5 || EPI == 6);  // not the gathering flavours (164 registers)
+  static constexpr int threads = (EPI == 4) ? kThreadsPHead : (has_m2 ? kThreadsP + 32 : kThreadsP);
 };
 
 struct __align__(16) PersistBarriers {
@@ -566,6 +566,49 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
   const int ph = phase >> 1, pw = phase & 1;                           \
   const int c_base = n_blk * n_tile;
 
+  // TMA fetch of tile `tile_`'s residual / addend tiles into staging-ring entry `sbuf_` (the caller knows the entry is free)
+  auto fetch_addends = [&](int tile_, int sbuf_) {
+    HRP_DECODE_TILE(tile_)
+    (void)th; (void)tw; (void)tn; (void)ph; (void)pw;
+    int nb = 0;
+    for (int j = 0; j < nblk_full && c_base + j * cko < p.Cout; ++j) ++nb;
+    uint8_t* const entry = stag_base + (size_t)sbuf_ * entry_bytes;
+    const int blk = kTileM * cko * 2;
+    uint32_t bytes = (uint32_t)(nb * blk);
+    if (staged) {
+#pragma unroll 1
+      for (int i = 0; i < 3; ++i)
+        if (cfg.add_off[i] != 0) bytes += (uint32_t)(nb * blk);
+#pragma unroll 1
+      for (int a = 0; a < 3; ++a)
+        if (cfg.up_off[a] != 0) bytes += (uint32_t)(nb * cfg.up_bw[a] * cfg.up_bh[a] * p.bn * cko * 2);
+    }
+    mbar_expect_tx(&bars->res_full[sbuf_], bytes);
+    const CUtensorMap* mr = (phase == 0) ? &maps.r : &maps.rp[phase - 1];
+#pragma unroll 1
+    for (int j = 0; j < nb; ++j)
+      tma_load_4d(entry + (size_t)j * blk, mr, &bars->res_full[sbuf_], c_base + j * cko, w0, h0, n0);
+    if (staged) {
+#pragma unroll 1
+      for (int i = 0; i < 3; ++i)
+        if (cfg.add_off[i] != 0)
+#pragma unroll 1
+          for (int j = 0; j < nb; ++j)
+            tma_load_4d(entry + cfg.add_off[i] + (size_t)j * blk, &maps.add[i], &bars->res_full[sbuf_], c_base + j * cko, w0,
+                        h0, n0);
+#pragma unroll 1
+      for (int a = 0; a < 3; ++a)
+        if (cfg.up_off[a] != 0)
+#pragma unroll 1
+          for (int j = 0; j < nb; ++j)
+            tma_load_4d(entry + cfg.up_off[a] + (size_t)j * cfg.up_blk[a], &maps.upm[a], &bars->res_full[sbuf_],
+                        c_base + j * cko, w0 >> cfg.up_sh[a], h0 >> cfg.up_sh[a], n0);
+    }
+  };
+  // Who fetches them: the TMA-store warp (cfg.res_store, default) -- it is the thread that learns first that an entry has
+  // drained, and both producers stay free for the two operand rings --, else producer 1 (or the only producer).
+  const bool res_store = has_res && cfg.res_store != 0;
+
   if (warp == 0 || warp == WARP_P2) {
     // ===================== TMA producers: warp 0 (+ warp WARP_P2 when cfg.nprod == 2) =====================
     // Stage g of the CTA (counted over all its tiles) is issued by producer g % nprod; both walk the same sequence and
@@ -575,7 +618,7 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
       // Layers with TMA-fetched residual / addend tiles split the roles instead: producer 0 streams the operands,
       // producer 1 fetches the addend tiles -- it is the one that has to wait for a staging entry to drain, and the
       // operand stream no longer stops behind that wait.
-      const bool res_role = has_res && cfg.nprod == 2;
+      const bool res_role = has_res && !res_store && cfg.nprod == 2;
       const bool two = cfg.nprod == 2 && !res_role && !dual;
       const int res_owner = res_role ? 1 : 0;
       const int sbase = (dual && me == 1) ? ring : 0;   // dual: this producer's half of the ring
@@ -600,45 +643,12 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
         const int brow = (p.shared_phase ? 0 : phase * p.cout_pad) + c_base;
         const int tph = p.shared_phase ? 0 : ph, tpw = p.shared_phase ? 0 : pw;
         int tap = 0, cc = 0, dwi = 0;
+        if (dual && (li & 1) != me) continue;   // the other pipeline's tile
         auto load_residual = [&]() {
           mbar_wait(&bars->stag_free[sbuf], spar ^ 1);  // the store that last used this entry has drained
-          int nb = 0;
-          for (int j = 0; j < nblk_full && c_base + j * cko < p.Cout; ++j) ++nb;
-          uint8_t* const entry = stag_base + (size_t)sbuf * entry_bytes;
-          const int blk = kTileM * cko * 2;
-          uint32_t bytes = (uint32_t)(nb * blk);
-          if (staged) {
-#pragma unroll 1
-            for (int i = 0; i < 3; ++i)
-              if (cfg.add_off[i] != 0) bytes += (uint32_t)(nb * blk);
-#pragma unroll 1
-            for (int a = 0; a < 3; ++a)
-              if (cfg.up_off[a] != 0) bytes += (uint32_t)(nb * cfg.up_bw[a] * cfg.up_bh[a] * p.bn * cko * 2);
-          }
-          mbar_expect_tx(&bars->res_full[sbuf], bytes);
-          const CUtensorMap* mr = (phase == 0) ? &maps.r : &maps.rp[phase - 1];
-#pragma unroll 1
-          for (int j = 0; j < nb; ++j)
-            tma_load_4d(entry + (size_t)j * blk, mr, &bars->res_full[sbuf], c_base + j * cko, w0, h0, n0);
-          if (staged) {
-#pragma unroll 1
-            for (int i = 0; i < 3; ++i)
-              if (cfg.add_off[i] != 0)
-#pragma unroll 1
-                for (int j = 0; j < nb; ++j)
-                  tma_load_4d(entry + cfg.add_off[i] + (size_t)j * blk, &maps.add[i], &bars->res_full[sbuf], c_base + j * cko,
-                              w0, h0, n0);
-#pragma unroll 1
-            for (int a = 0; a < 3; ++a)
-              if (cfg.up_off[a] != 0)
-#pragma unroll 1
-                for (int j = 0; j < nb; ++j)
-                  tma_load_4d(entry + cfg.up_off[a] + (size_t)j * cfg.up_blk[a], &maps.upm[a], &bars->res_full[sbuf],
-                              c_base + j * cko, w0 >> cfg.up_sh[a], h0 >> cfg.up_sh[a], n0);
-          }
+          fetch_addends(tile, sbuf);
         };
-        if (dual && (li & 1) != me) continue;   // the other pipeline's tile
-        if (has_res && nstag >= 2 && me == res_owner) load_residual();
+        if (has_res && !res_store && nstag >= 2 && me == res_owner) load_residual();
         if (res_role && me == 1) {
           if (nstag == 1) load_residual();
           continue;
@@ -687,7 +697,7 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
           }
         }
         if (me == 0) tl_stamp(p.timeline, li, 2);
-        if (has_res && nstag == 1 && me == res_owner) load_residual();
+        if (has_res && !res_store && nstag == 1 && me == res_owner) load_residual();
       }
     }
   } else if (warp == 1 || warp == WARP_M2) {
@@ -782,6 +792,10 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
   } else if (EPI != EPI_HEAD && warp == 10) {
     // ===================== TMA-store warp: drains finished staging buffers, never stalls the epilogue ==========
     if (p.out != nullptr && elect_one()) {
+      if (res_store) {  // the first nstag tiles find their entries free
+        int t0 = blockIdx.x;
+        for (int b = 0; b < nstag && t0 < cfg.total_tiles; ++b, t0 += gridDim.x) fetch_addends(t0, b);
+      }
       int li = 0;
       for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x, ++li) {
         HRP_DECODE_TILE(tile)
@@ -799,7 +813,12 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
         tl_stamp(p.timeline, li, 11);
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem read by the TMA unit: buffer reusable
         tl_stamp(p.timeline, li, 12);
-        mbar_arrive(&bars->stag_free[sbuf]);
+        if (res_store) {  // the entry has drained: fetch the addends of the tile that will be built in it next
+          const int nt = tile + nstag * (int)gridDim.x;
+          if (nt < cfg.total_tiles) fetch_addends(nt, sbuf);
+        } else {
+          mbar_arrive(&bars->stag_free[sbuf]);
+        }
       }
     }
   } else {
@@ -1756,7 +1775,11 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed, con
     // soft-argmax fold: two independent pipelines (see kThreadsPHead) when each gets at least two slots
     {
       const char* e8 = getenv("HRP_CONV_DUAL");
-      c.dual = ((plan->epi == EPI_HEAD || plan->epi == EPI_PLAIN) && !c.vsh && c.nprod == 2 && c.stages >= 4 &&
+      const char* e9 = getenv("HRP_CONV_RES_STORE");
+      const bool k_has_res = plan->epi == EPI_RES || staged || c.res_tma != 0;   // (= the kernel's has_res)
+      c.res_store = (k_has_res && !(e9 != nullptr && e9[0] == '0')) ? 1 : 0;
+      const bool m2 = plan->epi == EPI_HEAD || plan->epi == EPI_PLAIN || plan->epi == EPI_RES || staged;
+      c.dual = (m2 && (!k_has_res || c.res_store) && !c.vsh && c.nprod == 2 && c.stages >= 4 &&
                 !(e8 != nullptr && e8[0] == '0')) ? 1 : 0;
       if (c.dual) c.stages &= ~1;
     }
