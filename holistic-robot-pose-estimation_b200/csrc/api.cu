@@ -150,9 +150,10 @@ int hrp_conv_describe(const hrp_conv* conv, char* buf, int64_t buflen) {
     snprintf(buf, (size_t)buflen, "halo pair=%d T=%d bands=%d ring=%d NR=%d smem=%d grid=%u", pl.hp.pair, pl.hp.T, pl.hp.n_abuf,
              pl.hp.nring, pl.hp.NR, pl.halo_smem, pl.halo_grid);
   else if (pl.persistent)
-    snprintf(buf, (size_t)buflen, "persistent epi=%d n_tile=%d stages=%d sub=%d nprod=%d nstag=%d vsh=%d wres=%d smem=%d grid=%u",
-             pl.epi, pl.p.n_tile, pl.pcfg.stages, pl.pcfg.sub, pl.pcfg.nprod, pl.pcfg.nstag, pl.pcfg.vsh, pl.pcfg.wres,
-             pl.psmem, pl.pgrid);
+    snprintf(buf, (size_t)buflen,
+             "persistent epi=%d n_tile=%d stages=%d sub=%d nprod=%d dual=%d res_store=%d staged=%d nstag=%d vsh=%d wres=%d smem=%d grid=%u",
+             pl.epi, pl.p.n_tile, pl.pcfg.stages, pl.pcfg.sub, pl.pcfg.nprod, pl.pcfg.dual, pl.pcfg.res_store, pl.pcfg.staged,
+             pl.pcfg.nstag, pl.pcfg.vsh, pl.pcfg.wres, pl.psmem, pl.pgrid);
   else
     snprintf(buf, (size_t)buflen, "tile epi=%d n_tile=%d stages=%d smem=%d grid=%u", pl.epi, pl.p.n_tile, pl.stages,
              pl.smem_bytes, pl.grid.x * pl.grid.z);

@@ -329,6 +329,52 @@ def test_persistent_conv_vs_torch(case, hrp_lib):
         assert diff <= 2.0 ** -6 * max(1.0, ref.abs().max().item()), f"{name}[{tag}]: persistent vs tile differ by {diff}"
 
 
+@pytest.mark.parametrize("cfg", [
+    {"HRP_CONV_NPROD": "1", "HRP_CONV_DUAL": "0", "HRP_CONV_RES_STORE": "0"},   # one producer does everything
+    {"HRP_CONV_DUAL": "0", "HRP_CONV_RES_STORE": "0"},                          # second producer fetches the addends
+    {"HRP_CONV_DUAL": "0"},                                                     # store warp fetches them, one ring
+    {"HRP_CONV_KSTAGE": "2"},                                                   # 32 KiB stages
+], ids=["one_producer", "addend_producer", "store_warp_addends", "big_stages"])
+def test_persistent_pipeline_organisation_does_not_change_a_bit(cfg, hrp_lib, monkeypatch):
+    """The persistent kernel's default organisation (two producers feeding two stage rings with two MMA issuers, the
+    TMA-store warp fetching residual / addend tiles) only changes WHO moves the data and when: every accumulator still
+    receives the same MMAs in the same order, so each simpler organisation must give identical bits.  Covers the plain,
+    residual and staged-addend flavours on shapes with more tiles than SMs and >= 4 stages."""
+    import ctypes as C
+    from horopose_b200 import _lib, ops
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(23)
+    B, Cin, H, Cout = 40, 256, 16, 256
+    x = _nhwc(_bf16_round(torch.randn(B, Cin, H, H, generator=g)).cuda())
+    w = _bf16_round(torch.randn(Cout, Cin, 1, 1, generator=g) / Cin ** 0.5)
+    res = _nhwc(_bf16_round(torch.randn(B, Cout, H, H, generator=g)).cuda())
+    xs = _nhwc(_bf16_round(torch.randn(B, 32, 2 * H, 2 * H, generator=g)).cuda())       # 3x3 stride-2 32 -> 64 fuse conv
+    ws = _bf16_round(torch.randn(64, 32, 3, 3, generator=g) / 288 ** 0.5)
+    pre = _nhwc(_bf16_round(torch.randn(B, 64, H, H, generator=g)).cuda())
+    up = _nhwc(_bf16_round(torch.randn(B, 64, H // 2, H // 2, generator=g)).cuda())
+
+    def run_all():
+        outs, descs = [], []
+        for kw in (dict(x=x, weight=w, relu=True), dict(x=x, weight=w, relu=True, pre=[res]),
+                   dict(x=xs, weight=ws, stride=2, pad=1, relu=True, pre=[pre], up=[(up, 1)])):
+            op = ops.ConvOp(kw.pop("x"), kw.pop("weight"), **kw)
+            _lib.check(L.hrp_conv_set_variant(op.handle, C.c_int32(1)))
+            buf = C.create_string_buffer(256)
+            _lib.check(L.hrp_conv_describe(op.handle, buf, 256))
+            descs.append(buf.value.decode())
+            outs.append(op.run().clone())
+        torch.cuda.synchronize()
+        return outs, descs
+
+    ref, ref_desc = run_all()
+    assert all("persistent" in d for d in ref_desc), ref_desc
+    for k, v in cfg.items():
+        monkeypatch.setenv(k, v)
+    got, got_desc = run_all()
+    for a, b, d0, d1 in zip(ref, got, ref_desc, got_desc):
+        assert torch.equal(a, b), (d0, d1)
+
+
 def test_persistent_full_epilogue_deconv_and_pool(hrp_lib):
     """Persistent kernel on the remaining epilogue / geometry classes: nearest-upsampled + post addends (EPI_FULL), the
     4-phase deconv, and the pooled fp32 output."""
