@@ -126,6 +126,7 @@ struct HaloParams {
   const bf16* res;       // residual addend (pre[0]) or null
   bf16* out;
   long long* tl;         // debug timeline (globaltimer stamps of the first 8 CTAs), null in production
+  int dbg;               // ablation (HRP_HALO_DBG=1): epilogue reduced to the accumulator read
 };
 
 struct ConvPlan {

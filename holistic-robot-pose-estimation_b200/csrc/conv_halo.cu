@@ -376,6 +376,23 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
 #pragma unroll
       for (int c0 = 0; c0 < NOUT; c0 += 32) tmem_ld32(taddr + (uint32_t)c0, reinterpret_cast<uint32_t(&)[32]>(acc_all[c0]));
       tmem_ld_wait();
+      if (hp.dbg & 1) {  // (ablation: no arithmetic, no shared-memory traffic -- the protocol is kept)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&bars->acc_empty[acc]);
+          mbar_arrive(&bars->ring_ready[buf]);
+        }
+        it.next(hp);
+        if (it.valid(hp)) it.next(hp);
+        tc += 2;
+        buf += 2;
+        if (buf >= NB) {
+          buf -= NB;
+          rpar ^= 1;
+        }
+        continue;
+      }
 #pragma unroll
       for (int c0 = 0; c0 < NOUT; c0 += 32) {
         const uint32_t* a = acc_all + c0;
@@ -624,6 +641,7 @@ int conv_halo_launch(const ConvPlan& plan, cudaStream_t stream) {
   halo_attr_once();
   HaloParams h = plan.hp;
   h.tl = plan.p.timeline;
+  h.dbg = (getenv("HRP_HALO_DBG") != nullptr) ? atoi(getenv("HRP_HALO_DBG")) : 0;
   const bool res = (h.res != nullptr);
 #define HRP_HALO_LAUNCH(CKV, NV, RV, PV, MAPB) \
   launch_ex(conv_halo_kernel<CKV, NV, RV, PV>, dim3(plan.halo_grid), dim3(kHaloThreads), (size_t)plan.halo_smem, stream, \
