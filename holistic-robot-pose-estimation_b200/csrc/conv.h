@@ -84,7 +84,8 @@ struct PersistCfg {
   int stag_offset;   // byte offset of the staging buffers
   int bar_offset;    // byte offset of the barriers (scale/shift follow them)
   int total_tiles;   // m tiles x n tiles x phases
-  int tmem_cols;     // allocated TMEM columns (power of two >= 2*n_tile)
+  int tmem_cols;     // allocated TMEM columns (power of two >= nacc * ksplit * n_tile)
+  int nacc;          // accumulator tiles in the TMEM ring (2 or 4)
   int tw_shift, th_shift;  // log2 of tiles_w / tiles_h (tile decode without divisions)
   int vsh;           // vertical tap sharing: one (bh+2)-row A buffer per (channel chunk, dw)
   int wres;          // packed weights of the (single) N tile resident in shared memory

@@ -452,8 +452,8 @@ template <int EPI> struct PersistShape {
 struct __align__(16) PersistBarriers {
   uint64_t full[8];
   uint64_t empty[8];
-  uint64_t tmem_full[2];
-  uint64_t tmem_empty[2];
+  uint64_t tmem_full[4];
+  uint64_t tmem_empty[4];
   uint64_t res_full[4];
   uint64_t stag_free[4];
   uint64_t stag_ready[4];
@@ -487,6 +487,9 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
   const int nstag_shift = (nstag == 4) ? 2 : (nstag == 2) ? 1 : 0;
   const bool vsh = cfg.vsh != 0, wres = cfg.wres != 0;
   const int ksplit = cfg.ksplit;               // accumulators per tile (1, 2 or 4)
+  // accumulator ring in TMEM: 2 or 4 tiles (4 when 4 x ksplit x n_tile <= 512 columns): the MMA issuers run up to three
+  // tiles ahead of the epilogue instead of one -- with two pipelines each of them owns two accumulators
+  const int nacc = cfg.nacc, nacc_shift = (nacc == 4) ? 2 : 1;
   const uint32_t ksmask = (uint32_t)ksplit - 1u;
   uint8_t* const pipe_base = smem + cfg.pipe_offset;  // resident weights (if any) live in front of the stages
   uint8_t* const stag_base = smem + cfg.stag_offset;
@@ -514,7 +517,7 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
       mbar_init(&bars->full[s], 1);
       mbar_init(&bars->empty[s], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&bars->tmem_full[i], 1);
       mbar_init(&bars->tmem_empty[i], PersistShape<EPI>::epi_warps);  // one arrival per epilogue warp
     }
@@ -722,8 +725,8 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
       int li = 0;
       for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x, ++li) {
         if (dual && (li & 1) != mw) continue;   // the other pipeline's tile
-        const int abuf = li & 1;
-        mbar_wait(&bars->tmem_empty[abuf], (uint32_t)(((li >> 1) & 1) ^ 1));  // epilogue drained this accumulator
+        const int abuf = li & (nacc - 1);
+        mbar_wait(&bars->tmem_empty[abuf], (uint32_t)(((li >> nacc_shift) & 1) ^ 1));  // epilogue drained this accumulator
         tc_fence_after();
         if (lane == 0 && mw == 0) tl_stamp(p.timeline, li, 3);
         // K steps round-robin over `ksplit` accumulators (summed by the epilogue)
@@ -837,7 +840,7 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
     for (int tile = blockIdx.x; tile < cfg.total_tiles; tile += gridDim.x, ++li) {
       HRP_DECODE_TILE(tile)
       (void)th; (void)tw; (void)tn;
-      const int abuf = li & 1;
+      const int abuf = li & (nacc - 1);
       const int sbuf = li & (nstag - 1);
       const uint32_t spar = (uint32_t)((li >> nstag_shift) & 1);
       bool valid = true;
@@ -894,7 +897,7 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
       const float* sh_ = sb_smem + p.cout_pad + c_base;
 
       if (warp == 2 && lane == 0) tl_stamp(p.timeline, li, 6);
-      mbar_wait(&bars->tmem_full[abuf], (uint32_t)((li >> 1) & 1));
+      mbar_wait(&bars->tmem_full[abuf], (uint32_t)((li >> nacc_shift) & 1));
       tc_fence_after();
       if (warp == 2 && lane == 0) tl_stamp(p.timeline, li, 7);
       if (do_store) {
@@ -1801,8 +1804,10 @@ int conv_plan_finalize(ConvPlan* plan, const bf16* in, const bf16* w_packed, con
     const int n_mma = p.ntaps * p.cpt * (p.ck / 16);
     while (ks > 1 && n_mma < 2 * ks) ks >>= 1;  // every accumulator must receive at least one MMA (no stale TMEM)
     c.ksplit = ks;
+    const char* e10 = getenv("HRP_CONV_NACC");
+    c.nacc = (4 * ks * p.n_tile <= 512 && !(e10 != nullptr && e10[0] == '2')) ? 4 : 2;
     int cols = 32;
-    while (cols < 2 * ks * p.n_tile) cols <<= 1;
+    while (cols < c.nacc * ks * p.n_tile) cols <<= 1;
     c.tmem_cols = cols;
     plan->psmem = c.bar_offset + tail;
     plan->pgrid = (unsigned)std::min(c.total_tiles, (c.wres && p.n_tiles > 1) ? grid_nt : num_sms);
