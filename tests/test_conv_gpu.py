@@ -196,6 +196,11 @@ def test_maxpool_and_bridges(hrp_lib):
     mp = ops.maxpool3x3s2(xn)
     ref = F.max_pool2d(x, 3, 2, 1).permute(0, 2, 3, 1)
     assert torch.equal(mp.float(), ref)
+    # the network's size and a ragged one
+    for shape in ((3, 64, 128, 128), (2, 16, 12, 20)):
+        y = _bf16_round(torch.randn(*shape, generator=g)).cuda()
+        got = ops.maxpool3x3s2(ops.nchw_to_nhwc_bf16(y))
+        assert torch.equal(got.float(), F.max_pool2d(y, 3, 2, 1).permute(0, 2, 3, 1)), shape
 
 
 # ---- halo-tile kernel (conv_halo.cu): 3x3 stride-1 convs with Cin = Cout in {32, 64} ----
