@@ -41,6 +41,32 @@ __device__ __forceinline__ void tl_stamp(long long* tl, int tile_local, int ev) 
   if (t >= 0 && t < 8) tl[(blockIdx.x * 8 + t) * 16 + ev] = clock64();
 }
 
+// Column sums of an 8-value-per-lane tile over the 32 lanes of a warp in 9 shuffles instead of 40: at each of the first
+// three butterfly levels a lane keeps the half of its values whose index bit matches its lane bit and sends the other half
+// (8 -> 4 -> 2 -> 1 values), two plain levels finish.  Afterwards every lane holds the full sum of column
+// ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1); the tree is fixed, so the result is reproducible.
+__device__ __forceinline__ float warp_colsum8(const float (&a)[8], int lane) {
+  const bool h16 = (lane & 16) != 0;
+  float k0 = h16 ? a[4] : a[0], k1 = h16 ? a[5] : a[1], k2 = h16 ? a[6] : a[2], k3 = h16 ? a[7] : a[3];
+  const float s0 = h16 ? a[0] : a[4], s1 = h16 ? a[1] : a[5], s2 = h16 ? a[2] : a[6], s3 = h16 ? a[3] : a[7];
+  k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+  k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+  k2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+  k3 += __shfl_xor_sync(0xffffffffu, s3, 16);
+  const bool h8 = (lane & 8) != 0;
+  float m0 = h8 ? k2 : k0, m1 = h8 ? k3 : k1;
+  const float t0 = h8 ? k0 : k2, t1 = h8 ? k1 : k3;
+  m0 += __shfl_xor_sync(0xffffffffu, t0, 8);
+  m1 += __shfl_xor_sync(0xffffffffu, t1, 8);
+  const bool h4 = (lane & 4) != 0;
+  float r = h4 ? m1 : m0;
+  const float u = h4 ? m0 : m1;
+  r += __shfl_xor_sync(0xffffffffu, u, 4);
+  r += __shfl_xor_sync(0xffffffffu, r, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;
+}
+
 // Epilogue flavours (template parameter EPI): the common case carries no addends and no per-row predicates at all.
 constexpr int EPI_PLAIN = 0;  // y = [relu](acc*scale + bias)
 constexpr int EPI_PRE = 1;    // + up to three same-resolution addends before the ReLU (residual / fuse partials)
@@ -368,22 +394,15 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
           // reproducibility: the within-warp tree is fixed, and on the path the pooled maps are 8x8 = two warps per
           // image, i.e. exactly two atomicAdd contributions per (image, channel) onto a zeroed accumulator -- fp32
           // addition is commutative, so their arrival order cannot change the result (tests: bitwise replay)
+          float pv[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float x = valid ? v[i] : 0.f;
-            x += __shfl_xor_sync(0xffffffffu, x, 16);
-            x += __shfl_xor_sync(0xffffffffu, x, 8);
-            x += __shfl_xor_sync(0xffffffffu, x, 4);
-            x += __shfl_xor_sync(0xffffffffu, x, 2);
-            x += __shfl_xor_sync(0xffffffffu, x, 1);
-            v[i] = x;
-          }
+          for (int i = 0; i < 8; ++i) pv[i] = valid ? v[i] : 0.f;
+          const float csum = warp_colsum8(pv, lane);
           const int n_warp = n0 + ((q * 32) >> (p.bw_shift + p.bh_shift));
-          float mine = 0.f;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) mine = (lane == i) ? v[i] : mine;
-          if (lane < 8 && n_warp < p.B)
-            atomicAdd(p.pool_out + (size_t)n_warp * p.Cout + c_base + cg + lane, mine * p.pool_scale);
+          if ((lane & 3) == 0 && n_warp < p.B)
+            atomicAdd(p.pool_out + (size_t)n_warp * p.Cout + c_base + cg + (((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 +
+                                                                            ((lane >> 2) & 1)),
+                      csum * p.pool_scale);
         }
       }
     }
@@ -1087,22 +1106,15 @@ __global__ void __launch_bounds__(PersistShape<EPI>::threads, 1) conv_gemm_persi
             *sptr = o;
           }
           if (pool) {
+            float pv[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float x = valid ? v[i] : 0.f;
-              x += __shfl_xor_sync(0xffffffffu, x, 16);
-              x += __shfl_xor_sync(0xffffffffu, x, 8);
-              x += __shfl_xor_sync(0xffffffffu, x, 4);
-              x += __shfl_xor_sync(0xffffffffu, x, 2);
-              x += __shfl_xor_sync(0xffffffffu, x, 1);
-              v[i] = x;
-            }
+            for (int i = 0; i < 8; ++i) pv[i] = valid ? v[i] : 0.f;
+            const float csum = warp_colsum8(pv, lane);
             const int n_warp = n0 + ((q * 32) >> (p.bw_shift + p.bh_shift));
-            float mine = 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) mine = (lane == i) ? v[i] : mine;
-            if (lane < 8 && n_warp < p.B)
-              atomicAdd(p.pool_out + (size_t)n_warp * p.Cout + c_base + cg + lane, mine * p.pool_scale);
+            if ((lane & 3) == 0 && n_warp < p.B)
+              atomicAdd(p.pool_out + (size_t)n_warp * p.Cout + c_base + cg + (((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 +
+                                                                              ((lane >> 2) & 1)),
+                        csum * p.pool_scale);
           }
         }
       }
