@@ -492,6 +492,7 @@ int hrp_head(const hrp_head_args* a, void* stream) {
   p.image_size = a->image_size;
   p.depth_factor = a->depth_factor;
   p.heatmap = reinterpret_cast<const bf16*>(a->heatmap);
+  p.heatmap_f32 = a->heatmap_fp32 != 0 ? 1 : 0;
   p.chunks = head_default_chunks(a->B);
   p.counters = reinterpret_cast<unsigned int*>(a->workspace);
   p.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(a->workspace) +
@@ -523,8 +524,8 @@ int hrp_head_backward_heatmap(const void* heatmap, const float* uvd, const float
   const float* partials = reinterpret_cast<const float*>(reinterpret_cast<const char*>(workspace) +
                                                          ((size_t)B * sizeof(unsigned int) + 255) / 256 * 256);
   return launch_head_backward_heatmap(reinterpret_cast<const bf16*>(heatmap), partials, uvd, grad_uvd, B, nkpt, ref_kpt,
-                                      fix_root, head_default_chunks(B), out_fp32 != 0, grad_heatmap,
-                                      reinterpret_cast<cudaStream_t>(stream));
+                                      fix_root, head_default_chunks(B), (out_fp32 & 1) != 0, grad_heatmap,
+                                      reinterpret_cast<cudaStream_t>(stream), (out_fp32 & 2) != 0);
 }
 
 int hrp_copy_device(void* dst, const void* src, int64_t bytes, void* stream) {

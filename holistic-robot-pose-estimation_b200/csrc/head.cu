@@ -908,6 +908,50 @@ __device__ __forceinline__ void softmax_merge(float& m, float& S, float& Sx, flo
   m = M;
 }
 
+// Everything after the streaming loop of a head CTA: merge the 8 depth-vector lanes of each keypoint and the pixel slots,
+// publish the per-chunk partials, and let the last CTA of the image finish the sample.
+__device__ __forceinline__ void head_chunk_finish(const HeadParams& p, HeadSmem& sm, int b, int chunk, int nk, int slots,
+                                                  int slot, int k, int vec, bool kvalid, float m, float S, float Sx, float Sy,
+                                                  float Sz) {
+#pragma unroll
+  for (int off = 1; off < 8; off <<= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, off), S2 = __shfl_xor_sync(0xffffffffu, S, off);
+    const float Sx2 = __shfl_xor_sync(0xffffffffu, Sx, off), Sy2 = __shfl_xor_sync(0xffffffffu, Sy, off);
+    const float Sz2 = __shfl_xor_sync(0xffffffffu, Sz, off);
+    softmax_merge(m, S, Sx, Sy, Sz, m2, S2, Sx2, Sy2, Sz2);
+  }
+  if (vec == 0 && kvalid) {
+    float* d = sm.part[slot][k];
+    d[0] = m; d[1] = S; d[2] = Sx; d[3] = Sy; d[4] = Sz;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < nk) {
+    const int kk = threadIdx.x;
+    float M = -INFINITY, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+    for (int s = 0; s < slots; ++s) {
+      const float* pp = sm.part[s][kk];
+      softmax_merge(M, a1, a2, a3, a4, pp[0], pp[1], pp[2], pp[3], pp[4]);
+    }
+    float* dst = p.partials + (((size_t)b * p.chunks + chunk) * nk + kk) * 5;
+    __stcg(dst, M);
+    __stcg(dst + 1, a1);
+    __stcg(dst + 2, a2);
+    __stcg(dst + 3, a3);
+    __stcg(dst + 4, a4);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int ticket = atomicAdd(p.counters + b, 1u);
+    sm.is_last = (ticket == (unsigned int)p.chunks - 1u);
+    if (sm.is_last) p.counters[b] = 0u;  // self-reset for the next launch
+  }
+  __syncthreads();
+  if (!sm.is_last) return;
+  __threadfence();
+  head_finalize(p, sm, b);
+}
+
 // Streaming layout: thread t of a CTA owns the 16-byte vector (t mod vpp) of a pixel row -- a fixed (keypoint, 8-bin
 // depth vector) -> 5 fp32 accumulators -- and walks the pixels slot, slot + slots, ... (slot = t / vpp); a warp reads
 // 512 contiguous bytes per load instruction.
@@ -991,44 +1035,99 @@ __global__ void __launch_bounds__(kHeadMaxThreads, 3) head_kernel(const __grid_c
       accumulate(raw, chunk * ppc + pix);
     }
   }
-  // merge the 8 depth-vector lanes of each keypoint, then the pixel slots through shared memory
+  head_chunk_finish(p, sm, b, chunk, nk, slots, slot, k, vec, kvalid, m, S, Sx, Sy, Sz);
+}
+
+// The same kernel for fp32 logits (HeadParams::heatmap_f32: the standalone operator on a caller's fp32 heatmap, no bf16
+// rounding of the logits): a thread's 8 depth bins are two 16-byte vectors, otherwise the identical mapping, order of
+// operations and tail.  Twice the bytes per logit, so it is HBM-bound at twice the time; the network path never uses it.
+__global__ void __launch_bounds__(kHeadMaxThreads, 3) head_kernel_f32(const __grid_constant__ HeadParams p) {
+  __shared__ HeadSmem sm;
+  const int nk = p.nkpt;
+  const int vpp = nk * 8;
+  const int slots = (int)blockDim.x / vpp;
+  const int slot = (int)threadIdx.x / vpp;
+  const int kv = (int)threadIdx.x - slot * vpp;
+  const int k = kv >> 3;
+  const bool kvalid = (slot < slots);
+  const int vec = kv & 7;
+  const int b = blockIdx.x / p.chunks, chunk = blockIdx.x - b * p.chunks;
+  const int ppc = 4096 / p.chunks;
+  const float dbase = (float)(vec * 8);
+  const uint4* base = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.heatmap) +
+                                                     ((size_t)b * 4096 + (size_t)chunk * ppc) * (size_t)(nk * 64)) +
+                      (size_t)(k * 8 + vec) * 2;
+  const size_t pstride = (size_t)vpp * 2;   // 16-byte vectors per pixel
+  float m = -INFINITY, S = 0.f, Sx = 0.f, Sy = 0.f, Sz = 0.f;
+  if (kvalid) {
+    constexpr int UNROLL = 2;
+    int pix = slot;
+    for (; pix + (UNROLL - 1) * slots < ppc; pix += UNROLL * slots) {
+      uint4 raw[UNROLL][2];
 #pragma unroll
-  for (int off = 1; off < 8; off <<= 1) {
-    const float m2 = __shfl_xor_sync(0xffffffffu, m, off), S2 = __shfl_xor_sync(0xffffffffu, S, off);
-    const float Sx2 = __shfl_xor_sync(0xffffffffu, Sx, off), Sy2 = __shfl_xor_sync(0xffffffffu, Sy, off);
-    const float Sz2 = __shfl_xor_sync(0xffffffffu, Sz, off);
-    softmax_merge(m, S, Sx, Sy, Sz, m2, S2, Sx2, Sy2, Sz2);
-  }
-  if (vec == 0 && kvalid) {
-    float* d = sm.part[slot][k];
-    d[0] = m; d[1] = S; d[2] = Sx; d[3] = Sy; d[4] = Sz;
-  }
-  __syncthreads();
-  if ((int)threadIdx.x < nk) {
-    const int kk = threadIdx.x;
-    float M = -INFINITY, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
-    for (int s = 0; s < slots; ++s) {
-      const float* pp = sm.part[s][kk];
-      softmax_merge(M, a1, a2, a3, a4, pp[0], pp[1], pp[2], pp[3], pp[4]);
+      for (int u = 0; u < UNROLL; ++u) {
+        raw[u][0] = ld_stream(base + (size_t)(pix + u * slots) * pstride);
+        raw[u][1] = ld_stream(base + (size_t)(pix + u * slots) * pstride + 1);
+      }
+      float vmax = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const uint32_t xs[8] = {raw[u][0].x, raw[u][0].y, raw[u][0].z, raw[u][0].w, raw[u][1].x, raw[u][1].y, raw[u][1].z, raw[u][1].w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) vmax = fmaxf(vmax, __uint_as_float(xs[i]));
+      }
+      vmax *= kLog2e;
+      if (vmax > m) {
+        const float f = exp2f(m - vmax);
+        S *= f; Sx *= f; Sy *= f; Sz *= f;
+        m = vmax;
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int gp = chunk * ppc + pix + u * slots;
+        const float fw = (float)(gp & 63), fh = (float)(gp >> 6);
+        const uint32_t xs[8] = {raw[u][0].x, raw[u][0].y, raw[u][0].z, raw[u][0].w, raw[u][1].x, raw[u][1].y, raw[u][1].z, raw[u][1].w};
+        float s8 = 0.f, sz8 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float e = ex2_ftz(fmaf(__uint_as_float(xs[i]), kLog2e, -m));
+          s8 += e;
+          sz8 = fmaf(e, dbase + (float)i, sz8);
+        }
+        S += s8;
+        Sx = fmaf(s8, fw, Sx);
+        Sy = fmaf(s8, fh, Sy);
+        Sz += sz8;
+      }
     }
-    float* dst = p.partials + (((size_t)b * p.chunks + chunk) * nk + kk) * 5;
-    __stcg(dst, M);
-    __stcg(dst + 1, a1);
-    __stcg(dst + 2, a2);
-    __stcg(dst + 3, a3);
-    __stcg(dst + 4, a4);
+    for (; pix < ppc; pix += slots) {   // ragged tail
+      const uint4 r0 = ld_stream(base + (size_t)pix * pstride), r1 = ld_stream(base + (size_t)pix * pstride + 1);
+      const uint32_t xs[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+      float vmax = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) vmax = fmaxf(vmax, __uint_as_float(xs[i]));
+      vmax *= kLog2e;
+      if (vmax > m) {
+        const float f = exp2f(m - vmax);
+        S *= f; Sx *= f; Sy *= f; Sz *= f;
+        m = vmax;
+      }
+      const int gp = chunk * ppc + pix;
+      const float fw = (float)(gp & 63), fh = (float)(gp >> 6);
+      float s8 = 0.f, sz8 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float e = ex2_ftz(fmaf(__uint_as_float(xs[i]), kLog2e, -m));
+        s8 += e;
+        sz8 = fmaf(e, dbase + (float)i, sz8);
+      }
+      S += s8;
+      Sx = fmaf(s8, fw, Sx);
+      Sy = fmaf(s8, fh, Sy);
+      Sz += sz8;
+    }
   }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int ticket = atomicAdd(p.counters + b, 1u);
-    sm.is_last = (ticket == (unsigned int)p.chunks - 1u);
-    if (sm.is_last) p.counters[b] = 0u;  // self-reset for the next launch
-  }
-  __syncthreads();
-  if (!sm.is_last) return;
-  __threadfence();
-  head_finalize(p, sm, b);
+  head_chunk_finish(p, sm, b, chunk, nk, slots, slot, k, vec, kvalid, m, S, Sx, Sy, Sz);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1108,7 +1207,7 @@ struct HeadBwdParams {
   void* grad_out;
 };
 
-template <bool F32>
+template <bool F32, bool F32IN>
 __global__ void __launch_bounds__(kHeadMaxThreads) head_bwd_heatmap_kernel(const HeadBwdParams p) {
   const int nk = p.nkpt;
   const int vpp = nk * 8;
@@ -1135,19 +1234,29 @@ __global__ void __launch_bounds__(kHeadMaxThreads) head_bwd_heatmap_kernel(const
   const float Ew = (uq[0] + 0.5f) * 64.0f, Eh = (uq[1] + 0.5f) * 64.0f, Ed = fixed_d ? 0.0f : (uq[2] + 0.5f) * 64.0f;
   const float dbase = (float)(vec * 8) - Ed;
   const size_t row0 = ((size_t)b * 4096 + (size_t)chunk * ppc);
-  const uint4* src = reinterpret_cast<const uint4*>(p.heatmap + row0 * (size_t)(nk * 64)) + kv;
+  const uint4* src = F32IN ? reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.heatmap) + row0 * (size_t)(nk * 64)) + 2 * kv
+                           : reinterpret_cast<const uint4*>(p.heatmap + row0 * (size_t)(nk * 64)) + kv;
+  const size_t pstride = F32IN ? (size_t)vpp * 2 : (size_t)vpp;
   for (int pix = slot; pix < ppc; pix += slots) {
     const int gp = chunk * ppc + pix;
     const float cwh = fmaf(gu, (float)(gp & 63) - Ew, gv * ((float)(gp >> 6) - Eh));
-    const uint4 raw = ld_stream(src + (size_t)pix * vpp);
-    const uint32_t xs[4] = {raw.x, raw.y, raw.z, raw.w};
     float g[8];
+    if (F32IN) {
+      const uint4 r0 = ld_stream(src + (size_t)pix * pstride), r1 = ld_stream(src + (size_t)pix * pstride + 1);
+      const uint32_t xs[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float p0 = ex2_ftz(fmaf(bf16lo_to_f32(xs[i]), kLog2e, -M)) * invS;
-      const float p1 = ex2_ftz(fmaf(bf16hi_to_f32(xs[i]), kLog2e, -M)) * invS;
-      g[2 * i] = p0 * fmaf(gd, dbase + (float)(2 * i), cwh);
-      g[2 * i + 1] = p1 * fmaf(gd, dbase + (float)(2 * i + 1), cwh);
+      for (int i = 0; i < 8; ++i)
+        g[i] = ex2_ftz(fmaf(__uint_as_float(xs[i]), kLog2e, -M)) * invS * fmaf(gd, dbase + (float)i, cwh);
+    } else {
+      const uint4 raw = ld_stream(src + (size_t)pix * pstride);
+      const uint32_t xs[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float p0 = ex2_ftz(fmaf(bf16lo_to_f32(xs[i]), kLog2e, -M)) * invS;
+        const float p1 = ex2_ftz(fmaf(bf16hi_to_f32(xs[i]), kLog2e, -M)) * invS;
+        g[2 * i] = p0 * fmaf(gd, dbase + (float)(2 * i), cwh);
+        g[2 * i + 1] = p1 * fmaf(gd, dbase + (float)(2 * i + 1), cwh);
+      }
     }
     const size_t vidx = (row0 + pix) * (size_t)vpp + kv;  // index of this 8-logit vector
     if (F32) {
@@ -1167,7 +1276,7 @@ __global__ void __launch_bounds__(kHeadMaxThreads) head_bwd_heatmap_kernel(const
 
 int launch_head_backward_heatmap(const bf16* heatmap, const float* partials, const float* uvd, const float* grad_uvd, int B,
                                  int nkpt, int ref_kpt, int fix_root, int chunks, bool out_fp32, void* grad_out,
-                                 cudaStream_t s) {
+                                 cudaStream_t s, bool in_fp32) {
   HRP_REQUIRE(B > 0 && nkpt > 0 && nkpt <= kMaxKpt && chunks > 0 && 4096 % chunks == 0, "bad head-backward dims");
   HRP_REQUIRE(ref_kpt >= 0 && ref_kpt < nkpt, "reference keypoint out of range");
   const int vpp = nkpt * 8;
@@ -1184,8 +1293,14 @@ int launch_head_backward_heatmap(const bf16* heatmap, const float* partials, con
   p.uvd = uvd;
   p.grad_uvd = grad_uvd;
   p.grad_out = grad_out;
-  if (out_fp32) head_bwd_heatmap_kernel<true><<<B * chunks, threads, 0, s>>>(p);
-  else head_bwd_heatmap_kernel<false><<<B * chunks, threads, 0, s>>>(p);
+  if (in_fp32) {
+    HRP_REQUIRE(out_fp32, "fp32 logits give an fp32 gradient");
+    head_bwd_heatmap_kernel<true, true><<<B * chunks, threads, 0, s>>>(p);
+  } else if (out_fp32) {
+    head_bwd_heatmap_kernel<true, false><<<B * chunks, threads, 0, s>>>(p);
+  } else {
+    head_bwd_heatmap_kernel<false, false><<<B * chunks, threads, 0, s>>>(p);
+  }
   count_launch();
   HRP_CUDA_CHECK(cudaGetLastError());
   return HRP_OK;
@@ -1213,7 +1328,8 @@ int launch_head(const HeadParams& p, cudaStream_t s) {
   const int threads = (slots * vpp + 31) / 32 * 32;
   HRP_REQUIRE(vpp <= kHeadMaxThreads && threads <= kHeadMaxThreads && slots <= kHeadMaxSlots,
               "too many keypoints for the head kernel");
-  head_kernel<<<p.B * p.chunks, threads, 0, s>>>(p);
+  if (p.heatmap_f32) head_kernel_f32<<<p.B * p.chunks, threads, 0, s>>>(p);
+  else head_kernel<<<p.B * p.chunks, threads, 0, s>>>(p);
   count_launch();
   HRP_CUDA_CHECK(cudaGetLastError());
   return HRP_OK;

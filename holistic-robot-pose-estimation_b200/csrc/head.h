@@ -39,6 +39,7 @@ struct HeadParams {
   float image_size, depth_factor;
   // soft-argmax input: bf16 heatmap logits, pixel-major (B, 64*64, nkpt*64): channel = k*64 + d
   const bf16* heatmap;
+  int heatmap_f32;          // the logits are fp32 in the same pixel-major layout (standalone operator only)
   int chunks;               // CTAs per image
   float* partials;          // workspace (B, chunks, nkpt, 5)
   unsigned int* counters;   // workspace (B) zero-initialised; self-resetting
@@ -82,7 +83,7 @@ size_t head_partials_elems(int B, int nkpt, int chunks);
 int head_default_chunks(int B);
 int launch_head_backward_heatmap(const bf16* heatmap, const float* partials, const float* uvd, const float* grad_uvd, int B,
                                  int nkpt, int ref_kpt, int fix_root, int chunks, bool out_fp32, void* grad_out,
-                                 cudaStream_t s);
+                                 cudaStream_t s, bool in_fp32 = false);
 
 struct FkParams {
   int B, rot_dim, root, use_b2c;

@@ -2,10 +2,13 @@
 
 forward(out, K=..., root_trans=...) takes the reference's heatmap-logit tensor (B, nkpt*64, 64, 64) (channel =
 k*64 + d) and returns (pred_uvd_jts (B,nkpt,3), pred_xyz_jts (B,nkpt,3)).  The logits are bridged to the kernel's
-pixel-major bf16 layout (one extra pass; inside the full model the final conv writes that layout directly).
+pixel-major layout (one extra pass) as fp32 (default) or rounded to bf16 (`logits_dtype="bf16"`: the type the network's
+final conv would store; inside the full model there is no hand-off, the fold consumes the fp32 accumulators).
 When the logits require a gradient (training), the soft-argmax backward runs on the GPU as well (`_IntegralUVD`).
 """
 from __future__ import annotations
+
+import os
 
 import ctypes as C
 
@@ -21,7 +24,7 @@ class HeadArgs(C.Structure):
                 ("heatmap", C.c_void_p), ("K", C.c_void_p), ("root_depth", C.c_void_p), ("robot", C.c_void_p),
                 ("pose", C.c_void_p), ("rot", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
                 ("uvd", C.c_void_p), ("xyz_int", C.c_void_p), ("root_uv", C.c_void_p), ("trans", C.c_void_p),
-                ("xyz_fk", C.c_void_p), ("uv_int", C.c_void_p), ("uv_fk", C.c_void_p)]
+                ("xyz_fk", C.c_void_p), ("uv_int", C.c_void_p), ("uv_fk", C.c_void_p), ("heatmap_fp32", C.c_int32)]
 
 
 _workspaces = {}
@@ -42,8 +45,9 @@ def _workspace(device, B, nkpt):
 
 def run_head(heatmap_nhwc, K, root_depth, *, nkpt, ref_kpt, fix_root=True, image_size=256.0, depth_factor=1.3,
              robot=None, pose=None, rot=None, want_uv=False, workspace=None):
-    """heatmap_nhwc: (B,64,64,nkpt*64) bf16 CUDA.  Returns dict of fp32 CUDA tensors."""
-    assert heatmap_nhwc.is_cuda and heatmap_nhwc.dtype == torch.bfloat16 and heatmap_nhwc.is_contiguous()
+    """heatmap_nhwc: (B,64,64,nkpt*64) CUDA, bf16 (the layout the final convolution writes) or fp32 (a caller's logits,
+    no rounding).  Returns dict of fp32 CUDA tensors."""
+    assert heatmap_nhwc.is_cuda and heatmap_nhwc.dtype in (torch.bfloat16, torch.float32) and heatmap_nhwc.is_contiguous()
     B = heatmap_nhwc.shape[0]
     dev = heatmap_nhwc.device
     K = K.detach().to(device=dev, dtype=torch.float32).contiguous()
@@ -54,6 +58,7 @@ def run_head(heatmap_nhwc, K, root_depth, *, nkpt, ref_kpt, fix_root=True, image
     a.B, a.nkpt, a.ref_kpt, a.fix_root = B, nkpt, ref_kpt, int(fix_root)
     a.image_size, a.depth_factor = float(image_size), float(depth_factor)
     a.heatmap, a.K, a.root_depth = heatmap_nhwc.data_ptr(), K.data_ptr(), root_depth.data_ptr()
+    a.heatmap_fp32 = int(heatmap_nhwc.dtype == torch.float32)
     keep = [K, root_depth]
     if robot is not None and pose is not None:
         pose = pose.detach().to(device=dev, dtype=torch.float32).contiguous()
@@ -83,8 +88,8 @@ class _IntegralUVD(torch.autograd.Function):
     the forward left in its (private, saved) workspace -- one heatmap read and one gradient write."""
 
     @staticmethod
-    def forward(ctx, out, K, root_depth, nkpt, rootid, fixroot, image_size, depth_factor):
-        hm = ops.nchw_to_nhwc_bf16(out.detach().float().contiguous(), cpad=out.shape[1])
+    def forward(ctx, out, K, root_depth, nkpt, rootid, fixroot, image_size, depth_factor, fp32_logits=True):
+        hm = _pixel_major(out, fp32_logits)
         need = C.c_int64(0)
         check(_lib.lib().hrp_head_workspace_bytes(out.shape[0], nkpt, C.byref(need)))
         ws = torch.zeros(need.value, dtype=torch.uint8, device=out.device)
@@ -105,8 +110,18 @@ class _IntegralUVD(torch.autograd.Function):
             check(_lib.lib().hrp_head_backward_heatmap(
                 C.c_void_p(hm.data_ptr()), C.c_void_p(uvd.data_ptr()), C.c_void_p(g.data_ptr()), C.c_void_p(ws.data_ptr()),
                 C.c_int64(ws.numel()), C.c_int32(B), C.c_int32(nkpt), C.c_int32(rootid), C.c_int32(int(fixroot)),
-                C.c_int32(1), C.c_void_p(grad.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
-        return grad.permute(0, 3, 1, 2).reshape(shape), None, None, None, None, None, None, None
+                C.c_int32(3 if hm.dtype == torch.float32 else 1), C.c_void_p(grad.data_ptr()),
+                C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return grad.permute(0, 3, 1, 2).reshape(shape), None, None, None, None, None, None, None, None
+
+
+def _pixel_major(out, fp32_logits):
+    """The reference's heatmap (B, nkpt*64, 64, 64) -> pixel-major (B, 64, 64, nkpt*64): fp32 as given (one transposing
+    copy), or rounded to bf16 -- the layout and type the network's final convolution would write."""
+    x = out.detach().float()
+    if fp32_logits:
+        return x.reshape(x.shape[0], -1, 64, 64).permute(0, 2, 3, 1).contiguous()
+    return ops.nchw_to_nhwc_bf16(x.contiguous(), cpad=out.shape[1])
 
 
 def _inv_intrinsics(K):
@@ -146,6 +161,11 @@ class HeatmapIntegralPose(torch.nn.Module):
         self.bbox_3d_shape = torch.tensor(bbox_3d_shape).float()
         self.depth_factor = self.bbox_3d_shape[2] * 1e-3   # integral.py:91-93 (an fp32 tensor product)
         self.image_size = kwargs["image_size"]
+        # fp32 logits are consumed as fp32 (exactly the reference's arithmetic up to the order of the sums); "bf16" rounds
+        # them first to what the network's final convolution stores and halves the bytes the kernel reads
+        self.logits_dtype = kwargs.get("logits_dtype", os.environ.get("HRP_INTEGRAL_LOGITS", "fp32"))
+        if self.logits_dtype not in ("fp32", "bf16"):
+            raise ValueError("logits_dtype must be 'fp32' or 'bf16'")
 
     def forward(self, out, flip_test=False, **kwargs):
         K, root_trans = kwargs["K"], kwargs["root_trans"]
@@ -157,10 +177,11 @@ class HeatmapIntegralPose(torch.nn.Module):
             K = K.to(out.device).float()
             root_trans = root_trans.to(out.device).float()
             uvd = _IntegralUVD.apply(out, K.detach(), root_trans[:, 2].detach(), self.num_joints, self.rootid,
-                                     bool(self.fixroot), float(self.image_size), float(self.depth_factor))
+                                     bool(self.fixroot), float(self.image_size), float(self.depth_factor),
+                                     self.logits_dtype == "fp32")
             xyz = _uvd_to_xyz(uvd, float(self.image_size), _inv_intrinsics(K), root_trans, float(self.depth_factor))
             return uvd, xyz
-        hm = ops.nchw_to_nhwc_bf16(out.detach().float().contiguous(), cpad=out.shape[1])
+        hm = _pixel_major(out, self.logits_dtype == "fp32")
         r = run_head(hm, K, root_trans[:, 2].to(out.device), nkpt=self.num_joints, ref_kpt=self.rootid,
                      fix_root=self.fixroot, image_size=float(self.image_size), depth_factor=float(self.depth_factor))
         return r["uvd"], r["xyz_int"]

@@ -194,6 +194,8 @@ typedef struct hrp_head_args {
   float* xyz_fk;           /* (B,nkpt,3) or NULL */
   float* uv_int;           /* (B,nkpt,2) or NULL: projection of xyz_int with K */
   float* uv_fk;            /* (B,nkpt,2) or NULL */
+  int32_t heatmap_fp32;    /* 0: `heatmap` is bf16 (the layout the final convolution writes); 1: fp32, same pixel-major layout
+                              (a caller's fp32 logits, no rounding: twice the bytes, twice the time) */
 } hrp_head_args;
 
 int hrp_head_workspace_bytes(int32_t B, int32_t nkpt, int64_t* bytes);
@@ -202,7 +204,8 @@ int hrp_head(const hrp_head_args* args, void* stream);
  * HeatmapIntegralPose.forward (lib/utils/integral.py:97-135) in training (lib/core/function.py:253-311).
  * Must follow hrp_head on the SAME heatmap and workspace (it re-uses the per-chunk softmax statistics the forward
  * left there).  uvd: the forward's output; grad_uvd (B,nkpt,3) fp32; grad_heatmap: layout of `heatmap`, bf16
- * (out_fp32 = 0) or fp32 (out_fp32 = 1). */
+ * (out_fp32 = 0) or fp32 (out_fp32 = 1); out_fp32 = 3: `heatmap` itself is fp32 (heatmap_fp32 = 1 in the forward) and
+ * so is the gradient. */
 int hrp_head_backward_heatmap(const void* heatmap, const float* uvd, const float* grad_uvd, const void* workspace,
                               int64_t workspace_bytes, int32_t B, int32_t nkpt, int32_t ref_kpt, int32_t fix_root,
                               int32_t out_fp32, void* grad_heatmap, void* stream);
