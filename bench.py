@@ -166,7 +166,7 @@ def main():
     ap.add_argument("--global-batch", type=int, default=GLOBAL_BATCH)
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch of the weak-scaling variant")
     ap.add_argument("--overlap", type=int, default=0,
-                    help="independent steps in flight per GPU (caller streams = plan replicas); 0 = auto: 3 up to 128 "
+                    help="independent steps in flight per GPU (caller streams = plan replicas); 0 = auto: 3 up to 96 "
                          "images per GPU (a 64-image step cannot fill 148 SMs by itself), 2 up to 256, else 1")
     ap.add_argument("--robot", default=ROBOT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -321,9 +321,9 @@ def main():
 
     def default_overlap(b):
         """Independent steps kept in flight per GPU (caller streams = plan replicas).  Measured
-        (profiles/r02_exp_small_shards.txt): 3 steps of single-lane PDL graphs beat one 5-lane graph by 6-9 % at 64-128
+        (profiles/r02_exp_small_shards.txt): 2-3 steps of single-lane PDL graphs beat one 5-lane graph by 6-9 % at 64-128
         images and 2 steps by 2-3 % at 256; at 512 every kernel fills the GPU and one step in flight is as fast."""
-        return 3 if b <= 128 else (2 if b <= 256 else 1)
+        return 3 if b <= 96 else (2 if b <= 256 else 1)   # (128 images: 2 and 3 tie on the device, 2 is better end to end)
 
     def batch_of(mode):
         if mode == "strong":
