@@ -709,6 +709,11 @@ struct HeadSmem {
   float pts[kMaxKpt * 3];
   float depth;
   int is_last;
+  // copies of the robot table and of the regressors' small matrices for the single-thread tail of head_finalize: read
+  // from global memory they were ~100 dependent first-touch loads on ONE thread (~100 us per sample, on the critical
+  // path of every forward)
+  RobotTable rb;
+  float regA[2][kMaxDof][kMaxDof];
 };
 
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
@@ -747,6 +752,17 @@ __device__ __noinline__ void head_finalize(const HeadParams& p, HeadSmem& sm, in
   const int tid = threadIdx.x;
   const int nk = p.nkpt;
   const RobotTable* rb = p.robot;
+  if (rb != nullptr) {  // stage the tables of the serial tail (all threads, coalesced)
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(rb);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.rb);
+    for (int i = tid; i < (int)(sizeof(RobotTable) / 4); i += blockDim.x) dst[i] = __ldg(src + i);
+    if (p.xf != nullptr) {
+      for (int i = tid; i < kMaxDof * kMaxDof; i += blockDim.x) {
+        (&sm.regA[0][0][0])[i] = __ldg(&p.reg_pose->A[0][0] + i);
+        (&sm.regA[1][0][0])[i] = __ldg(&p.reg_rot->A[0][0] + i);
+      }
+    }
+  }
   // (a) merge the per-chunk partial sums of every keypoint -> uvd (integral.py:114-135)
   if (tid < nk) {
     float M = -INFINITY;
@@ -852,7 +868,7 @@ __device__ __noinline__ void head_finalize(const HeadParams& p, HeadSmem& sm, in
       float nx[kMaxDof];
       for (int i = 0; i < dof; ++i) {
         float dlt = sm.reg_a[i];
-        for (int j = 0; j < dof; ++j) dlt = fmaf(p.reg_pose->A[i][j], pose[j], dlt);
+        for (int j = 0; j < dof; ++j) dlt = fmaf(sm.regA[0][i][j], pose[j], dlt);
         nx[i] = pose[i] + dlt;
       }
       for (int i = 0; i < dof; ++i) pose[i] = nx[i];
@@ -861,7 +877,7 @@ __device__ __noinline__ void head_finalize(const HeadParams& p, HeadSmem& sm, in
       float nx[6];
       for (int i = 0; i < 6; ++i) {
         float dlt = sm.reg_a[dof + i];
-        for (int j = 0; j < 6; ++j) dlt = fmaf(p.reg_rot->A[i][j], rot[j], dlt);
+        for (int j = 0; j < 6; ++j) dlt = fmaf(sm.regA[1][i][j], rot[j], dlt);
         nx[i] = rot[i] + dlt;
       }
       for (int i = 0; i < 6; ++i) rot[i] = nx[i];
@@ -877,7 +893,7 @@ __device__ __noinline__ void head_finalize(const HeadParams& p, HeadSmem& sm, in
   if (p.rot != nullptr)
     for (int i = 0; i < 6; ++i) p.rot[(size_t)b * 6 + i] = rot[i];
   // FK (full_net.py:380-383)
-  fk_tree(rb, pose, sm.T, 1);
+  fk_tree(&sm.rb, pose, sm.T, 1);
   float R[9], b2c[12];
   rot6d_to_rows(rot, R);
   for (int r = 0; r < 3; ++r) {
@@ -886,7 +902,7 @@ __device__ __noinline__ void head_finalize(const HeadParams& p, HeadSmem& sm, in
     b2c[r * 4 + 2] = R[r * 3 + 2];
     b2c[r * 4 + 3] = tr[r];
   }
-  fk_keypoints(rb, sm.T, 1, b2c, p.ref_kpt, sm.pts);
+  fk_keypoints(&sm.rb, sm.T, 1, b2c, p.ref_kpt, sm.pts);
   for (int k = 0; k < nk; ++k) {
     if (p.xyz_fk != nullptr)
       for (int r = 0; r < 3; ++r) p.xyz_fk[((size_t)b * nk + k) * 3 + r] = sm.pts[k * 3 + r];
