@@ -39,6 +39,31 @@ if len(sys.argv) > 2:
                "families": {k: {"launches": a[0], "us": a[1] / 1e3, "tensor_pipe_pct": a[2] / max(a[1], 1), "dram_mb": a[3] / 1e6}
                             for k, a in agg.items()}}, open(sys.argv[2], "w"), indent=1)
 if len(sys.argv) > 4:
+    # per-network split: the launch list of a single-lane plan is in program order, i.e. launch 2 + i is op i of the per-op
+    # table (2 input-packing kernels first, the head kernel last); checked through the kernel family of every op
+    ops = list(csv.DictReader(open(sys.argv[4]), delimiter="\t"))
+    order = []
+    for r in rows:
+        if r[0] not in order:
+            order.append(r[0])
+    first = next(i for i, k in enumerate(order) if "pack_input" not in names[k])
+    fam = {"tile": "conv_gemm_kernel", "persist": "conv_gemm_persistent", "halo": "conv_halo_kernel"}
+    ok = len(order) - first - 1 == len(ops) and all(
+        names[order[first + j]].startswith(fam.get(o["variant"], "")) for j, o in enumerate(ops) if o["kind"] == "conv")
+    if ok:
+        groups = collections.OrderedDict((g, [0.0, 0.0]) for g in ("rootnet_backbone (HRNet-w32)", "reg_backbone (ResNet-50)",
+                                                                     "deconv head + final layer"))
+        for j, o in enumerate(ops):
+            m = per[order[first + j]]
+            g = ("rootnet_backbone (HRNet-w32)" if o["name"].startswith("rootnet_backbone") else
+                 "reg_backbone (ResNet-50)" if o["name"].startswith("reg_backbone") else "deconv head + final layer")
+            groups[g][0] += m.get(T, 0.0)
+            groups[g][1] += m.get(T, 0.0) * m.get(P, 0.0)
+        print("time-weighted tensor-pipe activity by network (launch order = program order of the single-lane plan):")
+        for g, (t_, p_) in groups.items():
+            print(f"  {g:32s} {t_ / 1e3:9.1f} us  {t_ / tot_t * 100:5.1f}% of the step   tensor pipe {p_ / max(t_, 1):5.1f} %")
+    else:
+        print("(launch list does not align with the per-op table: no per-network split)")
     alg = sum(float(r["bytes"]) for r in csv.DictReader(open(sys.argv[4]), delimiter="\t") if r["kind"] == "conv")
     json.dump({"robot": "kuka", "batch": 512, "kernels": len(per), "dram_bytes_per_step": tot_b,
                "algorithmic_bytes_per_step": alg, "source": sys.argv[5] if len(sys.argv) > 5 else sys.argv[1]},
