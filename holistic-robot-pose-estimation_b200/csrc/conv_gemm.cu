@@ -433,13 +433,14 @@ __global__ void __launch_bounds__(kNumThreads) conv_gemm_kernel(const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Persistent variant: one CTA per SM loops over output tiles.  The TMA producer runs ahead across tile
-// boundaries, the accumulator is double-buffered in TMEM (MMA of tile i+1 overlaps the epilogue of tile i), the
-// residual tile (pre[0]) is prefetched by TMA into the output staging buffer and updated in place, and eight
-// epilogue warps (two per TMEM lane quarter) drain the accumulators.  Per-tile fixed costs (TMEM allocation,
+// Persistent variant: one CTA per SM loops over output tiles.  The TMA producers run ahead across tile
+// boundaries, the accumulators form a ring of two or four tiles in TMEM (the MMAs of the next tiles overlap the epilogue
+// of tile i), the residual / addend tiles are prefetched by TMA into the output staging ring and updated in place, and
+// eight epilogue warps (two per TMEM lane quarter) drain the accumulators.  Per-tile fixed costs (TMEM allocation,
 // barrier init, descriptor fetch, launch) are paid once per CTA.
 // ------------------------------------------------------------------------------------------------------
-// warp 0 producer, warp 1 MMA, warps 2..9 epilogue, warp 10 TMA-store, warp 11 second producer.
+// warp 0 producer, warp 1 MMA, warps 2..9 epilogue, warp 10 TMA-store (+ addend fetches), warp 11 second producer,
+// warp 12 second MMA issuer (flavours with PersistShape::has_m2).
 // Two producers: ONE thread running the ring protocol (wait for the slot, expect_tx, cp.async.bulk.tensor, bookkeeping)
 // sustains one load per ~550-650 cycles whatever the box size (tools/probe_tma.py, profiles/r02_probe_tma.txt: the raw
 // instruction issues every ~75 cycles and the engine delivers > 70 B/cycle/SM, but the per-slot handshake serialises the
